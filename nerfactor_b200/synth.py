@@ -1,0 +1,143 @@
+"""Seeded synthetic scenes, weights and batches.
+
+There is no network for datasets or checkpoints, so every benchmark and parity
+test runs on random-init networks of the reference architecture and synthetic
+geometry of the reference batch layout
+(nerfactor/datasets/nerf_shape.py:72-95: id_, hw, rayo, rayd, rgb, alpha, xyz,
+normal, lvis).  Pure NumPy; no oracle, no CUDA.
+"""
+import math
+
+import numpy as np
+
+CAM_ANGLE_X = 0.6911  # Blender-synthetic-like horizontal FoV
+
+
+def look_at_c2w(radius=4.0, azimuth_deg=30.0, elevation_deg=30.0):
+    """Camera-to-world 4x4 (OpenGL convention: camera looks down -z, +y up),
+    the layout of metadata['cam_transform_mat'] (datasets/nerf.py:146-148)."""
+    az, el = math.radians(azimuth_deg), math.radians(elevation_deg)
+    eye = radius * np.array(
+        [math.cos(el) * math.cos(az), math.cos(el) * math.sin(az), math.sin(el)])
+    fwd = -eye / np.linalg.norm(eye)
+    up = np.array([0., 0., 1.])
+    right = np.cross(fwd, up)
+    right /= np.linalg.norm(right)
+    true_up = np.cross(right, fwd)
+    c2w = np.eye(4)
+    c2w[:3, 0], c2w[:3, 1], c2w[:3, 2], c2w[:3, 3] = right, true_up, -fwd, eye
+    return c2w
+
+
+def glorot_uniform(rng, fan_in, fan_out):
+    """Keras Dense default (nerfactor/networks/mlp.py:34)."""
+    lim = math.sqrt(6.0 / (fan_in + fan_out))
+    return rng.uniform(-lim, lim, size=(fan_in, fan_out)).astype(np.float32)
+
+
+def init_mlp(rng, in_dim, widths, act, skip_at=None, bias_std=0.0):
+    """Parameter dict {'layers': [(W[in,out], b[out])...], 'act', 'skip_at'} with
+    the input sizes Keras would infer for mlp.Network (mlp.py:39-50)."""
+    layers, d = [], in_dim
+    for i, w in enumerate(widths):
+        W = glorot_uniform(rng, d, w)
+        b = (rng.standard_normal(w) * bias_std).astype(np.float32)
+        layers.append((W, b))
+        d = w + in_dim if (skip_at is not None and i in skip_at) else w
+    return {'layers': layers, 'act': list(act) if act else [None] * len(widths),
+            'skip_at': skip_at}
+
+
+def embed_dims(n_freqs, in_dims=3):
+    return in_dims * (1 + 2 * n_freqs)
+
+
+def make_stage_b_params(seed=0, brdf='microfacet', light_hw=(16, 32), width=128,
+                        depth=4, skip_at=2, n_freqs_xyz=10, n_freqs_ldir=4,
+                        n_freqs_rusink=2, z_dim=3, bias_std=0.05):
+    """Random-init NeRFactor networks (nerfactor.py:128-167, shape.py:79-94,
+    brdf.py:57-66, nerfactor_microfacet.py:108-114) + light (nerfactor.py:367-375)."""
+    rng = np.random.default_rng(seed)
+    dx, dl, dr = embed_dims(n_freqs_xyz), embed_dims(n_freqs_ldir), \
+        embed_dims(n_freqs_rusink)
+    trunk = lambda d_in: init_mlp(
+        rng, d_in, [width] * depth, ['relu'] * depth, [skip_at], bias_std)
+    p = {}
+    p['normal_mlp'] = trunk(dx)
+    p['normal_out'] = init_mlp(rng, width, [3], [None], None, bias_std)
+    p['lvis_mlp'] = trunk(dx + dl)
+    p['lvis_out'] = init_mlp(rng, width, [1], ['sigmoid'], None, bias_std)
+    p['albedo_mlp'] = trunk(dx)
+    p['albedo_out'] = init_mlp(rng, width, [3], ['sigmoid'], None, bias_std)
+    p['brdf_z_mlp'] = trunk(dx)
+    if brdf == 'microfacet':
+        p['brdf_z_out'] = init_mlp(rng, width, [1], ['sigmoid'], None, bias_std)
+    else:
+        p['brdf_z_out'] = init_mlp(rng, width, [z_dim], [None], None, bias_std)
+        p['brdf_mlp'] = trunk(z_dim + dr)
+        p['brdf_out'] = init_mlp(rng, width, [1], ['softplus'], None, bias_std)
+    p['light'] = rng.uniform(0., 1., size=light_hw + (3,)).astype(np.float32)
+    return p
+
+
+def make_nerf_params(seed=0, width=256, enc_depth=8, n_freqs_xyz=10,
+                     bias_std=0.05, sigma_gain=40.0, sigma_bias=8.0):
+    """Random-init NeRF sigma networks (models/nerf.py:53-71: enc = 8x256 ReLU
+    with the input re-concatenated after layer enc_depth//2, sigma_out =
+    Dense(1)); coarse and fine copies (nerf.py:42-47).  A glorot-init field is a
+    thin uniform fog, so the output layer is rescaled (sigma_gain) and shifted
+    (sigma_bias) to give a scene-like field: ~1/3 of space occupied, per-step
+    opacities of a few tenths."""
+    rng = np.random.default_rng(seed)
+    dx = embed_dims(n_freqs_xyz)
+    p = {}
+    for pref in ('coarse_', 'fine_'):
+        p[pref + 'enc'] = init_mlp(
+            rng, dx, [width] * enc_depth, ['relu'] * enc_depth,
+            [enc_depth // 2], bias_std)
+        so = init_mlp(rng, width, [1], [None], None, 0.0)
+        so['layers'][0] = ((so['layers'][0][0] * sigma_gain).astype(np.float32),
+                           np.full((1,), sigma_bias, np.float32))
+        p[pref + 'sigma_out'] = so
+    return p
+
+
+def make_stage_b_batch(seed, n_rays, n_lights, fg_frac=0.75, cam_loc=None):
+    """The 9-tuple `Model.call` consumes (SURVEY 8d 'Stage B inputs')."""
+    rng = np.random.default_rng(seed)
+    if cam_loc is None:
+        cam_loc = look_at_c2w()[:3, 3]
+    xyz = rng.uniform(-1., 1., size=(n_rays, 3))
+    r = rng.uniform(0.5, 1.5, size=(n_rays, 1))
+    xyz = xyz / np.maximum(np.linalg.norm(xyz, axis=1, keepdims=True), 1e-3) * r
+    normal = xyz / np.linalg.norm(xyz, axis=1, keepdims=True) + \
+        0.1 * rng.standard_normal((n_rays, 3))
+    normal /= np.linalg.norm(normal, axis=1, keepdims=True)
+    alpha = (rng.uniform(size=(n_rays, 1)) < fg_frac).astype(np.float32)
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    id_ = np.array([b'synth_000'] * n_rays)
+    hw = np.tile(np.array([[n_rays, 1]], np.int32), (n_rays, 1))
+    rayo = np.tile(f32(cam_loc)[None, :], (n_rays, 1))
+    rayd = f32(xyz) - rayo
+    rgb = rng.uniform(0., 1., size=(n_rays, 3))
+    lvis = rng.uniform(0., 1., size=(n_rays, n_lights))
+    return (id_, hw, rayo, f32(rayd), f32(rgb), f32(alpha), f32(xyz), f32(normal),
+            f32(lvis))
+
+
+def make_probes(seed, n_probes, light_hw=(16, 32)):
+    """Synthetic HDR light probes: exp(N(0, 1.5^2)) clipped to [0, 200]."""
+    rng = np.random.default_rng(seed)
+    x = np.exp(rng.normal(0., 1.5, size=(n_probes,) + tuple(light_hw) + (3,)))
+    return np.clip(x, 0., 200.).astype(np.float32)
+
+
+def light_index_map(envmap_hw, light_hw):
+    """Nearest-pixel map from each of the light_hw[0]*light_hw[1] directions to a
+    pixel of a (smaller or equal) env-map (SURVEY 8d caveat on L): identity when
+    the two grids agree."""
+    eh, ew = envmap_hw
+    lh, lw = light_hw
+    ii = (np.arange(lh) * eh) // lh
+    jj = (np.arange(lw) * ew) // lw
+    return (ii[:, None] * ew + jj[None, :]).reshape(-1).astype(np.int32)
