@@ -1,0 +1,223 @@
+/*
+ * nerfactor_b200 -- C ABI of the B200-native NeRFactor render-and-relight hot path.
+ *
+ * The reference (google/nerfactor) is pure Python/TensorFlow: it has no FFI.  The
+ * drop-in seam is its Python class/function surface; each entry
+ * point below is what a binding for one reference function would call, and cites
+ * the reference code it replaces (paths relative to the reference root).
+ *
+ * Conventions (SURVEY.md 8b "Ownership / Errors / Threading"):
+ *   - every pointer named *_d is DEVICE memory owned by the caller (contiguous,
+ *     row-major, fp32 unless noted); the library never allocates or frees device
+ *     memory; packed weights live in a caller-provided device buffer
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*);
+ *     nothing synchronises the device
+ *   - every export returns 0 on success or a negative NF_ERR_* code;
+ *     nf_last_error_string(ctx) describes the last failure; no C++ exception
+ *     crosses the boundary
+ *   - thread-compatible per nf_ctx; one process per GPU
+ */
+#ifndef NERFACTOR_B200_H_
+#define NERFACTOR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NF_OK 0
+#define NF_ERR_INVALID_ARG (-1)
+#define NF_ERR_UNSUPPORTED (-2)
+#define NF_ERR_CUDA (-3)
+#define NF_ERR_NO_DEVICE (-4)
+
+/* activations of a Dense layer (nerfactor/networks/mlp.py:31-35) */
+#define NF_ACT_NONE 0
+#define NF_ACT_RELU 1
+#define NF_ACT_SIGMOID 2
+#define NF_ACT_SOFTPLUS 3
+
+/* what a row of the MLP input is built from (fused prologue) */
+#define NF_MLP_POINT 0 /* embed(xyz)                       normal/albedo/brdf_z nets */
+#define NF_MLP_LVIS 1  /* embed(xyz) ++ embed(surf2l)      light-visibility net      */
+#define NF_MLP_BRDF 2  /* z ++ embed(rusink(l, v))         frozen learned-BRDF net   */
+#define NF_MLP_SIGMA 3 /* embed(o + t d)                   NeRF sigma net            */
+
+/* arithmetic of the Dense contractions */
+#define NF_PREC_FP32 0 /* CUDA-core FFMA, fp32 throughout (parity / small nets)   */
+#define NF_PREC_F16 1  /* tcgen05 kind::f16, fp16 operands, fp32 accumulate in TMEM */
+#define NF_PREC_BF16 2 /* tcgen05 kind::f16, bf16 operands, fp32 accumulate in TMEM */
+
+typedef struct nf_ctx nf_ctx;
+typedef struct nf_mlp nf_mlp;
+
+/* ---- context / errors ---------------------------------------------------- */
+int nf_version(void);
+/* device < 0: use the current device. Fails with NF_ERR_NO_DEVICE when no
+ * sm_100 GPU is present (the product path never falls back to the CPU). */
+int nf_ctx_create(nf_ctx** out, int device);
+int nf_ctx_destroy(nf_ctx* ctx);
+const char* nf_last_error_string(const nf_ctx* ctx);
+int nf_ctx_sm_count(const nf_ctx* ctx);
+
+/* ---- networks -------------------------------------------------------------
+ * nf_mlp mirrors one `mlp.Network(widths, act, skip_at)` trunk plus its output
+ * `mlp.Network([out_dim], act=[out_act])` head (nerfactor/networks/mlp.py:24-50;
+ * built at nerfactor/models/shape.py:79-94, nerfactor.py:128-167, brdf.py:57-66,
+ * nerf.py:53-71).  Host weights are Keras-layout fp32: W[l] is [in_l, out_l]
+ * row-major, b[l] is [out_l]; l = 0..depth-1 are the trunk layers (ReLU), l = depth
+ * is the head.  The layer after `skip_at` takes concat(hidden, input) (mlp.py:46-49).
+ */
+typedef struct nf_mlp_desc {
+  int kind;      /* NF_MLP_*                                                    */
+  int in_dim;    /* width of the embedded input (63 / 90 / 18)                  */
+  int width;     /* hidden width (128 or 256)                                   */
+  int depth;     /* trunk layers (4 or 8)                                       */
+  int skip_at;   /* index of the layer whose output is concatenated with input  */
+  int out_dim;   /* head outputs (1..4)                                         */
+  int out_act;   /* NF_ACT_* of the head                                        */
+  int n_freqs_a; /* positional-encoding octaves of the first input (xyz/rusink) */
+  int n_freqs_b; /* octaves of the second input (light direction), LVIS only    */
+  int z_dim;     /* latent width prepended to the input, BRDF only              */
+  const float* const* W; /* depth + 1 host pointers                             */
+  const float* const* b; /* depth + 1 host pointers                             */
+} nf_mlp_desc;
+
+/* Packs the weights on the host (fp32 Keras layout for the FFMA kernels + the
+ * swizzle-free K-major fp16/bf16 images and fp32 per-ray blocks the tcgen05
+ * kernels read).  The handle owns only host memory. */
+int nf_mlp_create(nf_ctx* ctx, const nf_mlp_desc* desc, nf_mlp** out);
+int nf_mlp_destroy(nf_mlp* mlp);
+/* Bytes of device memory the caller must provide for the packed weights. */
+size_t nf_mlp_device_bytes(const nf_mlp* mlp);
+/* cudaMemcpyAsync of the packed image into caller memory (256-byte aligned);
+ * the handle remembers `dst_d` for the forward calls. */
+int nf_mlp_upload(nf_ctx* ctx, nf_mlp* mlp, void* dst_d, void* stream);
+
+/* ---- Stage B: per-point networks -------------------------------------------
+ * out[n, out_dim] = head(trunk(embed(xyz_scale * xyz)))
+ * replaces Model._pred_normal_at  nerfactor/models/shape.py:196-211 (caller adds eps)
+ *          Model._pred_albedo_at  nerfactor/models/nerfactor.py:377-396 (caller: affine)
+ *          Model._pred_brdf_at    nerfactor/models/nerfactor.py:398-411
+ *          (and chunk_apply shape.py:184-194, Embedder embedder.py:46-47)          */
+int nf_point_mlp_fwd(nf_ctx* ctx, const nf_mlp* mlp, const float* xyz_d, int n,
+                     float xyz_scale, float* out_d, int precision, void* stream);
+
+/* lvis[n, L] = sigmoid(head(trunk(embed(xyz_scale*xyz) ++ embed(l2n(lxyz - xyz)))))
+ * replaces Model._calc_ldir  nerfactor/models/shape.py:128-135 (never materialised)
+ *          Model._pred_lvis_at nerfactor/models/shape.py:213-237                  */
+int nf_lvis_fwd(nf_ctx* ctx, const nf_mlp* mlp, const float* xyz_d, int n,
+                float xyz_scale, const float* lxyz_d, int n_lights, float* lvis_d,
+                int precision, void* stream);
+
+/* spec[n, L] = front_lit ? softplus(head(trunk(z ++ embed(rusink)))) : 0
+ * with rusink = dir2rusink(R l2n(lxyz - xyz), R l2n(cam - xyz)), R = world2local(normal)
+ * replaces Model._eval_brdf_at nerfactor/models/nerfactor.py:413-457 (up to `spec`),
+ *          gen_world2local nerfactor/util/geom.py:119-149, dir2rusink geom.py:152-192 */
+int nf_brdf_learned_fwd(nf_ctx* ctx, const nf_mlp* mlp, const float* xyz_d,
+                        const float* normal_d, const float* cam_d, const float* z_d,
+                        int n, const float* lxyz_d, int n_lights, float* spec_d,
+                        int precision, void* stream);
+
+/* ---- Stage B: rendering equation -------------------------------------------
+ * rgb[n, E, 3] = tonemap(sum_l brdf[n,l,:] * lvis[n,l]*[cos>0] * light[e, idx(l), :]
+ *                        * cos[n,l] * area[l])
+ * replaces Model._render / integrate  nerfactor/models/nerfactor.py:315-365 and the
+ * BRDF evaluation that feeds it:
+ *   brdf_kind 0: Microfacet.__call__  brdf/microfacet/microfacet.py:30-111
+ *                (rough_d [n,1], f0)   via nerfactor_microfacet.py:116-124
+ *   brdf_kind 1: albedo/pi + spec*scale  nerfactor/models/nerfactor.py:457-461
+ *                (spec_d [n,L] from nf_brdf_learned_fwd)
+ * `normal_d` is the raw network output + eps; it is safe-l2-normalised inside
+ * (nerfactor.py:212).  light_idx_d (may be NULL = identity) maps a light direction
+ * to an env-map pixel.  tonemap = clip[0,1] then optional linear2srgb
+ * (nerfactor/util/img.py:140-163).                                              */
+typedef struct nf_integrate_args {
+  int n, n_lights, n_envmaps, envmap_pixels;
+  int brdf_kind;          /* 0 microfacet, 1 learned (spec) */
+  int linear2srgb;        /* nerfactor.ini:76 */
+  float f0;               /* fresnel_f0 (microfacet) */
+  float spec_scale;       /* learned_brdf_scale */
+  const float* xyz_d;     /* [n,3] */
+  const float* normal_d;  /* [n,3] */
+  const float* cam_d;     /* [n,3] ray origins = camera location */
+  const float* albedo_d;  /* [n,3] */
+  const float* rough_d;   /* [n,1]  (kind 0) */
+  const float* spec_d;    /* [n,L]  (kind 1) */
+  const float* lvis_d;    /* [n,L] */
+  const float* lxyz_d;    /* [L,3] */
+  const float* lareas_d;  /* [L] */
+  const float* light_d;   /* [E, envmap_pixels, 3] (already clipped >= 0) */
+  const int32_t* light_idx_d; /* [L] or NULL */
+  float* rgb_d;           /* [n, E, 3] */
+} nf_integrate_args;
+int nf_integrate_fwd(nf_ctx* ctx, const nf_integrate_args* args, void* stream);
+
+/* One-light-at-a-time relighting: rgb_olat[n, L, 3] for the L env-maps
+ * olat_inten * onehot(l) + ambient (nerfactor/models/nerfactor.py:71-84, 348-354),
+ * same argument block (light_d / n_envmaps ignored). */
+int nf_integrate_olat_fwd(nf_ctx* ctx, const nf_integrate_args* args, float olat_inten,
+                          float ambient, float* rgb_olat_d, void* stream);
+
+/* ---- Stage A: rays, sigma march, compositing --------------------------------
+ * rayo/rayd[h*w, 3] (fp64 math, fp32 store, ray n = y*w + x, no half-pixel offset)
+ * replaces Dataset._gen_rays nerfactor/datasets/nerf.py:172-193 (ndc=False, spp=1).
+ * c2w: 16 HOST doubles (row-major 4x4).  normalize != 0 additionally applies
+ * tf.linalg.l2_normalize (geometry_from_nerf.py:100) to rayd.                     */
+int nf_gen_rays(nf_ctx* ctx, const double* c2w_host, double cam_angle_x, int h, int w,
+                int normalize, float* rayo_d, float* rayd_d, void* stream);
+
+/* z[n, S]: t = linspace(0,1,S); z = near(1-t) + far t (or linear in disparity);
+ * optional stratified perturbation with caller-supplied uniforms u_d[n,S]
+ * replaces nerf.Model.gen_z nerfactor/models/nerf.py:120-136                     */
+int nf_gen_z(nf_ctx* ctx, float near, float far, int n_samples, int n_rays,
+             int lin_in_disp, const float* perturb_u_d, float* z_d, void* stream);
+
+/* sigma[n, S] = in_bbox ? relu(sigma_out(enc(embed(o + z d)))) : 0
+ * replaces eval_sigma_mlp nerfactor/geometry_from_nerf.py:322-350 (+ check_bounds
+ * :365-378; bbox = 6 floats x0,x1,y0,y1,z0,z1 on the HOST, or NULL)               */
+int nf_sigma_fwd(nf_ctx* ctx, const nf_mlp* mlp, const float* rayo_d,
+                 const float* rayd_d, const float* z_d, int n_rays, int n_samples,
+                 const float* bbox_host, float* sigma_d, int precision, void* stream);
+
+/* Same as nf_sigma_fwd plus normal[n,S,3] = -l2_normalize(d sigma / d xyz)
+ * replaces the GradientTape.batch_jacobian block geometry_from_nerf.py:285-305     */
+int nf_sigma_normal_fwd(nf_ctx* ctx, const nf_mlp* mlp, const float* rayo_d,
+                        const float* rayd_d, const float* z_d, int n_rays,
+                        int n_samples, const float* bbox_host, float* sigma_d,
+                        float* normal_d, void* stream);
+
+/* weights[n,S] (optional), occu[n], depth[n], surf[n,3] (optional),
+ * exp_normal[n,3] (optional, needs normal_d [n,S,3])
+ * replaces nerf.Model.accumulate_sigma nerfactor/models/nerf.py:184-212 (noise 0) and
+ * the reductions geometry_from_nerf.py:312-317, :134                              */
+int nf_composite(nf_ctx* ctx, const float* sigma_d, const float* z_d,
+                 const float* rayo_d, const float* rayd_d, const float* normal_d,
+                 int n_rays, int n_samples, float* weights_d, float* occu_d,
+                 float* depth_d, float* surf_d, float* exp_normal_d, void* stream);
+
+/* z_all[n, S_c + S_f] = sort(concat(z_c, inv_transform_sample(mid(z_c), w[1:-1])))
+ * replaces nerf.Model.gen_z_fine nerfactor/models/nerf.py:138-147 and
+ * inv_transform_sample nerfactor/util/math.py:71-94 (det=True)                    */
+int nf_gen_z_fine(nf_ctx* ctx, const float* z_coarse_d, const float* weights_d,
+                  int n_rays, int n_coarse, int n_fine, float* z_all_d, void* stream);
+
+/* Light-visibility march set-up: for every (point, light) pair writes the ray
+ * origin/direction (surf, l2_normalize(lxyz - surf)) and front-lit flag
+ * ((surf2l . normal) > 0), replaces geometry_from_nerf.py:196-215.                */
+int nf_lvis_rays(nf_ctx* ctx, const float* surf_d, const float* normal_d, int n_pts,
+                 const float* lxyz_d, int n_lights, float* rayo_d, float* rayd_d,
+                 uint8_t* front_lit_d, void* stream);
+
+/* ---- diagnostics (no reference counterpart) ---------------------------------
+ * One 128x128xK tcgen05 tile: out[128,128] = a[128,K] * b[128,K]^T through the same
+ * TMEM / shared-memory operand layouts the fused kernels use (bring-up check).   */
+int nf_selftest_umma(nf_ctx* ctx, const float* a_d, const float* b_d, int K,
+                     int swap_lbo_sbo, float* out_d, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NERFACTOR_B200_H_ */

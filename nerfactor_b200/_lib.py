@@ -1,0 +1,360 @@
+"""ctypes binding of libnerfactor_b200.so (the C ABI in include/nerfactor_b200.h).
+
+PyTorch is only the owner of device memory and streams here: every wrapper
+passes raw device pointers and the current CUDA stream to the library.  There is
+no CPU or PyTorch fallback: a missing library or a missing sm_100 GPU raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libnerfactor_b200.so')
+
+NF_OK = 0
+ERRORS = {-1: 'NF_ERR_INVALID_ARG', -2: 'NF_ERR_UNSUPPORTED', -3: 'NF_ERR_CUDA',
+          -4: 'NF_ERR_NO_DEVICE'}
+ACT = {None: 0, 'relu': 1, 'sigmoid': 2, 'softplus': 3}
+KIND = {'point': 0, 'lvis': 1, 'brdf': 2, 'sigma': 3}
+PREC = {'fp32': 0, 'f16': 1, 'bf16': 2}
+
+# every symbol include/nerfactor_b200.h declares (tests check the .so exports all)
+EXPORTS = [
+    'nf_version', 'nf_ctx_create', 'nf_ctx_destroy', 'nf_last_error_string',
+    'nf_ctx_sm_count', 'nf_mlp_create', 'nf_mlp_destroy', 'nf_mlp_device_bytes',
+    'nf_mlp_upload', 'nf_point_mlp_fwd', 'nf_lvis_fwd', 'nf_brdf_learned_fwd',
+    'nf_integrate_fwd', 'nf_integrate_olat_fwd', 'nf_gen_rays', 'nf_gen_z',
+    'nf_sigma_fwd', 'nf_sigma_normal_fwd', 'nf_composite', 'nf_gen_z_fine',
+    'nf_lvis_rays', 'nf_selftest_umma']
+
+
+class NfError(RuntimeError):
+    pass
+
+
+class MlpDesc(C.Structure):
+    _fields_ = [('kind', C.c_int), ('in_dim', C.c_int), ('width', C.c_int),
+                ('depth', C.c_int), ('skip_at', C.c_int), ('out_dim', C.c_int),
+                ('out_act', C.c_int), ('n_freqs_a', C.c_int), ('n_freqs_b', C.c_int),
+                ('z_dim', C.c_int), ('W', C.POINTER(C.c_void_p)),
+                ('b', C.POINTER(C.c_void_p))]
+
+
+class IntegrateArgs(C.Structure):
+    _fields_ = [('n', C.c_int), ('n_lights', C.c_int), ('n_envmaps', C.c_int),
+                ('envmap_pixels', C.c_int), ('brdf_kind', C.c_int),
+                ('linear2srgb', C.c_int), ('f0', C.c_float), ('spec_scale', C.c_float),
+                ('xyz_d', C.c_void_p), ('normal_d', C.c_void_p), ('cam_d', C.c_void_p),
+                ('albedo_d', C.c_void_p), ('rough_d', C.c_void_p), ('spec_d', C.c_void_p),
+                ('lvis_d', C.c_void_p), ('lxyz_d', C.c_void_p), ('lareas_d', C.c_void_p),
+                ('light_d', C.c_void_p), ('light_idx_d', C.c_void_p), ('rgb_d', C.c_void_p)]
+
+
+_lib = None
+
+
+def load_library():
+    """Loads the shared library (no GPU needed to load / inspect symbols)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NfError(
+            'libnerfactor_b200.so is not built: run `python -c "import '
+            '__graft_entry__ as g; g.build()"` (nerfactor_b200/csrc/build.sh). '
+            'There is no CPU fallback.')
+    lib = C.CDLL(LIB_PATH)
+    vp, i, f, d = C.c_void_p, C.c_int, C.c_float, C.c_double
+    lib.nf_version.restype = i
+    lib.nf_ctx_create.argtypes = [C.POINTER(vp), i]
+    lib.nf_ctx_destroy.argtypes = [vp]
+    lib.nf_last_error_string.argtypes = [vp]
+    lib.nf_last_error_string.restype = C.c_char_p
+    lib.nf_ctx_sm_count.argtypes = [vp]
+    lib.nf_mlp_create.argtypes = [vp, C.POINTER(MlpDesc), C.POINTER(vp)]
+    lib.nf_mlp_destroy.argtypes = [vp]
+    lib.nf_mlp_device_bytes.argtypes = [vp]
+    lib.nf_mlp_device_bytes.restype = C.c_size_t
+    lib.nf_mlp_upload.argtypes = [vp, vp, vp, vp]
+    lib.nf_point_mlp_fwd.argtypes = [vp, vp, vp, i, f, vp, i, vp]
+    lib.nf_lvis_fwd.argtypes = [vp, vp, vp, i, f, vp, i, vp, i, vp]
+    lib.nf_brdf_learned_fwd.argtypes = [vp, vp, vp, vp, vp, vp, i, vp, i, vp, i, vp]
+    lib.nf_integrate_fwd.argtypes = [vp, C.POINTER(IntegrateArgs), vp]
+    lib.nf_integrate_olat_fwd.argtypes = [vp, C.POINTER(IntegrateArgs), f, f, vp, vp]
+    lib.nf_gen_rays.argtypes = [vp, C.POINTER(d), d, i, i, i, vp, vp, vp]
+    lib.nf_gen_z.argtypes = [vp, f, f, i, i, i, vp, vp, vp]
+    lib.nf_sigma_fwd.argtypes = [vp, vp, vp, vp, vp, i, i, C.POINTER(f), vp, i, vp]
+    lib.nf_sigma_normal_fwd.argtypes = [vp, vp, vp, vp, vp, i, i, C.POINTER(f), vp, vp, vp]
+    lib.nf_composite.argtypes = [vp, vp, vp, vp, vp, vp, i, i, vp, vp, vp, vp, vp, vp]
+    lib.nf_gen_z_fine.argtypes = [vp, vp, vp, i, i, i, vp, vp]
+    lib.nf_lvis_rays.argtypes = [vp, vp, vp, i, vp, i, vp, vp, vp, vp]
+    lib.nf_selftest_umma.argtypes = [vp, vp, vp, i, i, vp, vp]
+    for name in EXPORTS:
+        if name not in ('nf_last_error_string', 'nf_mlp_device_bytes'):
+            getattr(lib, name).restype = i
+    _lib = lib
+    return lib
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), 'need a contiguous CUDA tensor'
+    return C.c_void_p(t.data_ptr())
+
+
+def _f32(t):
+    assert t.dtype == torch.float32, 'fp32 tensor expected'
+    return _ptr(t)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Context:
+    """nf_ctx wrapper; one per process / GPU."""
+
+    def __init__(self, device=None):
+        self.lib = load_library()
+        if not torch.cuda.is_available():
+            raise NfError('no CUDA device: nerfactor_b200 has no CPU fallback')
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = torch.device('cuda', device)
+        h = C.c_void_p()
+        rc = self.lib.nf_ctx_create(C.byref(h), int(device))
+        if rc != NF_OK:
+            raise NfError('nf_ctx_create failed: %s (an sm_100 GPU is required)'
+                          % ERRORS.get(rc, rc))
+        self.h = h
+
+    def check(self, rc):
+        if rc != NF_OK:
+            msg = self.lib.nf_last_error_string(self.h).decode()
+            raise NfError('%s: %s' % (ERRORS.get(rc, rc), msg))
+
+    @property
+    def sm_count(self):
+        return self.lib.nf_ctx_sm_count(self.h)
+
+    def __del__(self):
+        try:
+            if getattr(self, 'h', None):
+                self.lib.nf_ctx_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+_default_ctx = None
+
+
+def default_context():
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context()
+    return _default_ctx
+
+
+class PackedMlp:
+    """nf_mlp wrapper: packs a trunk + head on the host and uploads it into a
+    torch-owned device buffer."""
+
+    def __init__(self, ctx, kind, layers, skip_at, out_act, n_freqs_a=0, n_freqs_b=0,
+                 z_dim=0):
+        """layers: [(W[in,out], b[out]) ...] fp32 NumPy, trunk layers then head."""
+        self.ctx = ctx
+        depth = len(layers) - 1
+        Ws = [np.ascontiguousarray(w, dtype=np.float32) for w, _ in layers]
+        bs = [np.ascontiguousarray(b, dtype=np.float32) for _, b in layers]
+        self._keep = (Ws, bs)
+        d = MlpDesc()
+        d.kind, d.in_dim, d.width = KIND[kind], Ws[0].shape[0], Ws[0].shape[1]
+        d.depth, d.skip_at = depth, skip_at
+        d.out_dim, d.out_act = Ws[-1].shape[1], ACT[out_act]
+        d.n_freqs_a, d.n_freqs_b, d.z_dim = n_freqs_a, n_freqs_b, z_dim
+        Wp = (C.c_void_p * (depth + 1))(*[w.ctypes.data for w in Ws])
+        bp = (C.c_void_p * (depth + 1))(*[b.ctypes.data for b in bs])
+        d.W, d.b = Wp, bp
+        self.kind, self.out_dim, self.depth, self.width = kind, d.out_dim, depth, d.width
+        h = C.c_void_p()
+        ctx.check(ctx.lib.nf_mlp_create(ctx.h, C.byref(d), C.byref(h)))
+        self.h = h
+        nbytes = ctx.lib.nf_mlp_device_bytes(h)
+        self.buf = torch.empty(nbytes + 256, dtype=torch.uint8, device=ctx.device)
+        off = (-self.buf.data_ptr()) % 256
+        self.dev_ptr = self.buf.data_ptr() + off
+        ctx.check(ctx.lib.nf_mlp_upload(ctx.h, h, C.c_void_p(self.dev_ptr), _stream()))
+
+    def __del__(self):
+        try:
+            if getattr(self, 'h', None):
+                self.ctx.lib.nf_mlp_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------ forward ops
+
+def point_mlp_fwd(ctx, mlp, xyz, xyz_scale=1.0, precision='fp32'):
+    n = xyz.shape[0]
+    out = torch.empty((n, mlp.out_dim), dtype=torch.float32, device=xyz.device)
+    ctx.check(ctx.lib.nf_point_mlp_fwd(ctx.h, mlp.h, _f32(xyz), n, float(xyz_scale),
+                                       _f32(out), PREC[precision], _stream()))
+    return out
+
+
+def lvis_fwd(ctx, mlp, xyz, lxyz, xyz_scale=1.0, precision='f16'):
+    n, L = xyz.shape[0], lxyz.shape[0]
+    out = torch.empty((n, L), dtype=torch.float32, device=xyz.device)
+    ctx.check(ctx.lib.nf_lvis_fwd(ctx.h, mlp.h, _f32(xyz), n, float(xyz_scale), _f32(lxyz),
+                                  L, _f32(out), PREC[precision], _stream()))
+    return out
+
+
+def brdf_learned_fwd(ctx, mlp, xyz, normal, cam, z, lxyz, precision='f16'):
+    n, L = xyz.shape[0], lxyz.shape[0]
+    out = torch.empty((n, L), dtype=torch.float32, device=xyz.device)
+    ctx.check(ctx.lib.nf_brdf_learned_fwd(
+        ctx.h, mlp.h, _f32(xyz), _f32(normal), _f32(cam), _f32(z), n, _f32(lxyz), L,
+        _f32(out), PREC[precision], _stream()))
+    return out
+
+
+def _integrate_args(xyz, normal, cam, albedo, lvis, lxyz, lareas, rough=None, spec=None,
+                    light=None, light_idx=None, rgb=None, f0=0.04, spec_scale=1.0,
+                    linear2srgb=True):
+    a = IntegrateArgs()
+    a.n, a.n_lights = xyz.shape[0], lxyz.shape[0]
+    a.brdf_kind = 0 if spec is None else 1
+    a.linear2srgb, a.f0, a.spec_scale = int(linear2srgb), float(f0), float(spec_scale)
+    a.xyz_d, a.normal_d, a.cam_d = _f32(xyz), _f32(normal), _f32(cam)
+    a.albedo_d, a.lvis_d = _f32(albedo), _f32(lvis)
+    a.rough_d = _f32(rough) if rough is not None else None
+    a.spec_d = _f32(spec) if spec is not None else None
+    a.lxyz_d, a.lareas_d = _f32(lxyz), _f32(lareas)
+    if light is not None:
+        a.n_envmaps, a.envmap_pixels = light.shape[0], light.shape[1]
+        a.light_d = _f32(light)
+    a.light_idx_d = _ptr(light_idx) if light_idx is not None else None
+    a.rgb_d = _f32(rgb) if rgb is not None else None
+    return a
+
+
+def integrate_fwd(ctx, xyz, normal, cam, albedo, lvis, lxyz, lareas, light, rough=None,
+                  spec=None, light_idx=None, f0=0.04, spec_scale=1.0, linear2srgb=True):
+    """light: [E, P, 3] (clipped >= 0). Returns rgb [n, E, 3]."""
+    n, E = xyz.shape[0], light.shape[0]
+    rgb = torch.empty((n, E, 3), dtype=torch.float32, device=xyz.device)
+    if light_idx is not None:
+        assert light_idx.dtype == torch.int32
+    a = _integrate_args(xyz, normal, cam, albedo, lvis, lxyz, lareas, rough, spec, light,
+                        light_idx, rgb, f0, spec_scale, linear2srgb)
+    ctx.check(ctx.lib.nf_integrate_fwd(ctx.h, C.byref(a), _stream()))
+    return rgb
+
+
+def integrate_olat_fwd(ctx, xyz, normal, cam, albedo, lvis, lxyz, lareas, olat_inten,
+                       ambient, rough=None, spec=None, f0=0.04, spec_scale=1.0,
+                       linear2srgb=True):
+    n, L = xyz.shape[0], lxyz.shape[0]
+    out = torch.empty((n, L, 3), dtype=torch.float32, device=xyz.device)
+    a = _integrate_args(xyz, normal, cam, albedo, lvis, lxyz, lareas, rough, spec, None,
+                        None, None, f0, spec_scale, linear2srgb)
+    ctx.check(ctx.lib.nf_integrate_olat_fwd(ctx.h, C.byref(a), float(olat_inten),
+                                            float(ambient), _f32(out), _stream()))
+    return out
+
+
+def gen_rays(ctx, c2w, cam_angle_x, h, w, normalize=False):
+    c2w = np.ascontiguousarray(np.asarray(c2w, dtype=np.float64).reshape(16))
+    rayo = torch.empty((h * w, 3), dtype=torch.float32, device=ctx.device)
+    rayd = torch.empty((h * w, 3), dtype=torch.float32, device=ctx.device)
+    ctx.check(ctx.lib.nf_gen_rays(
+        ctx.h, c2w.ctypes.data_as(C.POINTER(C.c_double)), float(cam_angle_x), h, w,
+        int(normalize), _f32(rayo), _f32(rayd), _stream()))
+    return rayo, rayd
+
+
+def gen_z(ctx, near, far, n_samples, n_rays, lin_in_disp=False, perturb_u=None):
+    z = torch.empty((n_rays, n_samples), dtype=torch.float32, device=ctx.device)
+    ctx.check(ctx.lib.nf_gen_z(ctx.h, float(near), float(far), n_samples, n_rays,
+                               int(lin_in_disp),
+                               _f32(perturb_u) if perturb_u is not None else None,
+                               _f32(z), _stream()))
+    return z
+
+
+def _bbox(bbox):
+    if bbox is None:
+        return None
+    arr = (C.c_float * 6)(*[float(v) for v in bbox])
+    return arr
+
+
+def sigma_fwd(ctx, mlp, rayo, rayd, z, bbox=None, precision='f16'):
+    n, S = z.shape
+    sigma = torch.empty((n, S), dtype=torch.float32, device=z.device)
+    bb = _bbox(bbox)
+    ctx.check(ctx.lib.nf_sigma_fwd(ctx.h, mlp.h, _f32(rayo), _f32(rayd), _f32(z), n, S,
+                                   bb, _f32(sigma), PREC[precision], _stream()))
+    return sigma
+
+
+def sigma_normal_fwd(ctx, mlp, rayo, rayd, z, bbox=None):
+    n, S = z.shape
+    sigma = torch.empty((n, S), dtype=torch.float32, device=z.device)
+    normal = torch.empty((n, S, 3), dtype=torch.float32, device=z.device)
+    bb = _bbox(bbox)
+    ctx.check(ctx.lib.nf_sigma_normal_fwd(ctx.h, mlp.h, _f32(rayo), _f32(rayd), _f32(z), n,
+                                          S, bb, _f32(sigma), _f32(normal), _stream()))
+    return sigma, normal
+
+
+def composite(ctx, sigma, z, rayo, rayd, normal=None, want_weights=True, want_surf=True):
+    n, S = sigma.shape
+    dev = sigma.device
+    weights = torch.empty((n, S), dtype=torch.float32, device=dev) if want_weights else None
+    occu = torch.empty((n,), dtype=torch.float32, device=dev)
+    depth = torch.empty((n,), dtype=torch.float32, device=dev)
+    surf = torch.empty((n, 3), dtype=torch.float32, device=dev) if want_surf else None
+    en = torch.empty((n, 3), dtype=torch.float32, device=dev) if normal is not None else None
+    ctx.check(ctx.lib.nf_composite(
+        ctx.h, _f32(sigma), _f32(z), _f32(rayo), _f32(rayd),
+        _f32(normal) if normal is not None else None, n, S,
+        _f32(weights) if weights is not None else None, _f32(occu), _f32(depth),
+        _f32(surf) if surf is not None else None, _f32(en) if en is not None else None,
+        _stream()))
+    return weights, occu, depth, surf, en
+
+
+def gen_z_fine(ctx, z_coarse, weights, n_fine):
+    n, Sc = z_coarse.shape
+    z_all = torch.empty((n, Sc + n_fine), dtype=torch.float32, device=z_coarse.device)
+    ctx.check(ctx.lib.nf_gen_z_fine(ctx.h, _f32(z_coarse), _f32(weights), n, Sc, n_fine,
+                                    _f32(z_all), _stream()))
+    return z_all
+
+
+def lvis_rays(ctx, surf, normal, lxyz):
+    n, L = surf.shape[0], lxyz.shape[0]
+    dev = surf.device
+    rayo = torch.empty((n * L, 3), dtype=torch.float32, device=dev)
+    rayd = torch.empty((n * L, 3), dtype=torch.float32, device=dev)
+    fl = torch.empty((n * L,), dtype=torch.uint8, device=dev)
+    ctx.check(ctx.lib.nf_lvis_rays(ctx.h, _f32(surf), _f32(normal), n, _f32(lxyz), L,
+                                   _f32(rayo), _f32(rayd), _ptr(fl), _stream()))
+    return rayo, rayd, fl.view(n, L)
+
+
+def selftest_umma(ctx, a, b, swap_lbo_sbo=False):
+    """a, b: [128, K] fp32 CUDA tensors -> a @ b.T through one tcgen05 tile."""
+    K = a.shape[1]
+    out = torch.empty((128, 128), dtype=torch.float32, device=a.device)
+    ctx.check(ctx.lib.nf_selftest_umma(ctx.h, _f32(a), _f32(b), K, int(swap_lbo_sbo),
+                                       _f32(out), _stream()))
+    return out

@@ -1,0 +1,690 @@
+// tcgen05 fused skip-MLP forward for the per-(point, light) networks
+// (light visibility: nerfactor/models/shape.py:213-237; learned BRDF:
+// nerfactor/models/nerfactor.py:413-457), sm_100a only.
+//
+// Design (DESIGN.md "K2"):
+//  * persistent CTA per SM, 12 warps: warp 0 = MMA issuer (+TMEM owner), warps
+//    4-7 and 8-11 = two worker groups, each owning one 128-row tile at a time
+//    (one tile = 128 consecutive light directions of ONE surface point).
+//  * the Dense chain never leaves the SM: accumulators D[128x128] fp32 live in
+//    TMEM; the bias+ReLU epilogue reads D with tcgen05.ld, packs to fp16/bf16 and
+//    writes the next layer's A operand back to TMEM with tcgen05.st; the MMA
+//    reads A from TMEM and the weights (B) from shared memory, where the whole
+//    network is resident (loaded once per CTA with cp.async.bulk).
+//  * the xyz part of the input (63 of 90 columns, identical for all rows of a
+//    tile) is folded into a per-point fp32 bias: beff = b + W[:63]^T embed(xyz),
+//    computed on the CUDA cores once per point; the tensor cores only contract
+//    the per-light columns (27 -> K = 32) and the hidden layers.  Same maths as
+//    x @ W + b, fewer MMA flops, and the 2^9-frequency features stay in fp32.
+//  * the two groups ping-pong: while one group runs its epilogue the other
+//    group's MMAs occupy the tensor pipe.
+#include "nf_common.cuh"
+
+namespace {
+
+constexpr int TC_WIDTH = 128;
+constexpr int TC_THREADS = 384;
+constexpr int TMEM_COLS = 512;
+constexpr int GRP_COLS = 256;      // TMEM columns per worker group
+constexpr int COL_D = 0;           // D accumulator: 128 fp32 columns
+constexpr int COL_AH = 128;        // hidden activations: 64 columns (128 x 16-bit)
+constexpr int COL_AE = 192;        // per-row embedding: <= 16 columns (32 x 16-bit)
+
+// ------------------------------------------------------------------ PTX glue
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void group_bar(int id) {  // 128-thread named barrier
+  asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]   (kind::f16: fp16 or bf16 operands, fp32 accumulate)
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+#define TC_LD32(r, addr)                                                                         \
+  asm volatile(                                                                                  \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                  \
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                  \
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"  \
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),      \
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),  \
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),            \
+        "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),            \
+        "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])             \
+      : "r"(addr))
+
+#define TC_ST16(addr, r)                                                                         \
+  asm volatile(                                                                                  \
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "                                            \
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(addr),    \
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),    \
+      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]),          \
+      "r"(r[15])                                                                                 \
+      : "memory")
+
+#define TC_ST8(addr, r)                                                                          \
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(addr), \
+               "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]),      \
+               "r"(r[7])                                                                         \
+               : "memory")
+
+// pack two fp32 into one 16-bit pair register: lo -> bits [0,16), hi -> bits [16,32)
+template <int BF16, int RELU>
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  uint32_t d;
+  if (BF16) {
+    if (RELU) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  } else {
+    if (RELU) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    else asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  }
+  return d;
+}
+
+// K-major, swizzle-free shared-memory operand descriptor (cute UMMA::SmemDescriptor):
+// core matrix = 8 rows x 16 bytes, rows 16 B apart; SBO = bytes between 8-row groups
+// along N, LBO = bytes between core matrices along K.
+__device__ __forceinline__ uint64_t make_b_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  return d;                // base_offset 0, lbo_mode 0, layout SWIZZLE_NONE
+}
+// kind::f16 instruction descriptor: D=f32, A/B = f16|bf16, K-major, M=128, N=128
+__device__ __forceinline__ uint32_t make_idesc(int bf16, int n) {
+  uint32_t fmt = bf16 ? 1u : 0u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+// ------------------------------------------------------------- kernel params
+struct TcParams {
+  const uint8_t* blob;   // packed network (device)
+  size_t off_img;        // B-operand images (fp16 or bf16), see nf_tc_pack
+  size_t off_aux;        // fp32 side block
+  int kind;              // NF_MLP_LVIS | NF_MLP_BRDF
+  int n;                 // surface points
+  int L;                 // light directions
+  int nr;                // per-point input columns folded into the bias (63 | z_dim)
+  int n_freqs_a, n_freqs_b, z_dim;
+  int out_act;
+  float xyz_scale;
+  const float* xyz;      // [n,3]
+  const float* lxyz;     // [L,3]
+  const float* normal;   // BRDF: [n,3]
+  const float* cam;      // BRDF: [n,3]
+  const float* zlat;     // BRDF: [n,z_dim]
+  float* out;            // [n, L]
+};
+
+// fp32 side block layout (floats): see nf_tc_pack
+constexpr int AUX_B = 0;                    // b0..b3: 4 x 128
+constexpr int AUX_WOUT = 4 * 128;           // w_out: 128
+constexpr int AUX_BOUT = 5 * 128;           // b_out: 1 (padded to 4)
+constexpr int AUX_WX0 = 5 * 128 + 4;        // W0 rows [0, nr): nr_pad x 128
+// followed by Wx3: W3 rows [128, 128 + nr): nr_pad x 128
+
+template <int KIND>
+struct KindCfg;
+template <>
+struct KindCfg<NF_MLP_LVIS> {
+  static constexpr int KE = 32;       // per-row embedding K (27 padded)
+  static constexpr int NR_PAD = 64;   // per-point columns (63 padded)
+};
+template <>
+struct KindCfg<NF_MLP_BRDF> {
+  static constexpr int KE = 16;       // 15 padded
+  static constexpr int NR_PAD = 8;    // z_dim <= 8
+};
+
+template <int KIND>
+constexpr int img_halves() {
+  return (KindCfg<KIND>::KE + 128 + 128 + 128 + KindCfg<KIND>::KE) * TC_WIDTH;
+}
+
+template <int KIND>
+struct SmemLayout {
+  static constexpr int KE = KindCfg<KIND>::KE;
+  static constexpr int NR_PAD = KindCfg<KIND>::NR_PAD;
+  static constexpr size_t img_bytes = (size_t)img_halves<KIND>() * 2;
+  static constexpr size_t aux_floats = AUX_WX0 + 2 * (size_t)NR_PAD * 128;
+  static constexpr size_t off_img = 0;
+  static constexpr size_t off_aux = img_bytes;
+  static constexpr size_t off_beff = off_aux + aux_floats * 4;          // [2 groups][2][128]
+  static constexpr size_t off_e = off_beff + 2 * 2 * 128 * 4;           // [2 groups][64]
+  static constexpr size_t off_lx = off_e + 2 * 64 * 4;                  // float4 [Lmax]
+  static constexpr int LMAX = 1024;
+  static constexpr size_t off_bar = off_lx + (size_t)LMAX * 16;
+  static constexpr size_t total = off_bar + 128;
+};
+
+template <int KIND, int BF16>
+__global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const TcParams p) {
+  using SL = SmemLayout<KIND>;
+  constexpr int KE = SL::KE;
+  constexpr int NR_PAD = SL::NR_PAD;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* s_img = smem + SL::off_img;
+  float* s_aux = reinterpret_cast<float*>(smem + SL::off_aux);
+  float* s_beff = reinterpret_cast<float*>(smem + SL::off_beff);
+  float* s_e = reinterpret_cast<float*>(smem + SL::off_e);
+  float4* s_lx = reinterpret_cast<float4*>(smem + SL::off_lx);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SL::off_bar);
+  uint64_t* bar_w = bars + 0;          // weights landed
+  uint64_t* bar_a = bars + 1;          // [2] A operand ready (128 arrivals)
+  uint64_t* bar_d = bars + 3;          // [2] D accumulator ready (tcgen05.commit)
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunks = (p.L + 127) / 128;
+
+  // ---------------------------------------------------------------- set-up
+  if (threadIdx.x == 0) {
+    mbar_init(bar_w, 1);
+    mbar_init(bar_a + 0, 128); mbar_init(bar_a + 1, 128);
+    mbar_init(bar_d + 0, 1); mbar_init(bar_d + 1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(s_tmem)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int l = threadIdx.x; l < p.L; l += blockDim.x)
+    s_lx[l] = make_float4(p.lxyz[l * 3], p.lxyz[l * 3 + 1], p.lxyz[l * 3 + 2], 0.f);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+  if (threadIdx.x == 0) {
+    const uint32_t aux_bytes = (uint32_t)(SL::aux_floats * 4);
+    mbar_expect_tx(bar_w, (uint32_t)SL::img_bytes + aux_bytes);
+    // TMA bulk copies (UBLKCP): whole network -> shared memory, once per CTA
+    const uint8_t* gi = p.blob + p.off_img;
+    for (size_t o = 0; o < SL::img_bytes; o += 32768) {
+      size_t nb = SL::img_bytes - o < 32768 ? SL::img_bytes - o : 32768;
+      bulk_g2s(s_img + o, gi + o, (uint32_t)nb, bar_w);
+    }
+    const uint8_t* ga = p.blob + p.off_aux;
+    for (size_t o = 0; o < aux_bytes; o += 32768) {
+      size_t nb = aux_bytes - o < 32768 ? aux_bytes - o : 32768;
+      bulk_g2s(reinterpret_cast<uint8_t*>(s_aux) + o, ga + o, (uint32_t)nb, bar_w);
+    }
+  }
+  mbar_wait(bar_w, 0);
+
+  // unit of work = one surface point; group G takes points G, G + 2*grid, ...
+  const int n_groups = gridDim.x * 2;
+  auto group_points = [&](int g) {
+    int G = blockIdx.x * 2 + g;
+    return G < p.n ? (p.n - 1 - G) / n_groups + 1 : 0;
+  };
+
+  if (warp == 0) {
+    // =============================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(BF16, TC_WIDTH);
+      const uint32_t lbo = TC_WIDTH * 16, sbo = 128;
+      const uint32_t img0 = smem_u32(s_img);
+      // segment byte offsets inside the image: [KE | 128 | 128 | 128 | KE] x 128 x 2 B
+      const uint32_t seg_off[5] = {0u, (uint32_t)KE * 256u, (uint32_t)(KE + 128) * 256u,
+                                   (uint32_t)(KE + 256) * 256u, (uint32_t)(KE + 384) * 256u};
+      const int nt0 = group_points(0) * chunks, nt1 = group_points(1) * chunks;
+      const int nt_max = nt0 > nt1 ? nt0 : nt1;
+      uint32_t ph[2] = {0u, 0u};
+      for (int it = 0; it < nt_max; ++it) {
+        for (int layer = 0; layer < 4; ++layer) {
+          for (int g = 0; g < 2; ++g) {
+            if (it >= (g == 0 ? nt0 : nt1)) continue;
+            mbar_wait(bar_a + g, ph[g]);
+            ph[g] ^= 1u;
+            tc_fence_after();
+            const uint32_t tb = tmem_base + g * GRP_COLS;
+            const uint32_t d_t = tb + COL_D;
+            if (layer == 0) {
+#pragma unroll
+              for (int k = 0; k < KE / 16; ++k)
+                tc_mma_ts(d_t, tb + COL_AE + k * 8,
+                          make_b_desc(img0 + seg_off[0] + k * 2 * lbo, lbo, sbo), idesc, k > 0);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                tc_mma_ts(d_t, tb + COL_AH + k * 8,
+                          make_b_desc(img0 + seg_off[layer] + k * 2 * lbo, lbo, sbo), idesc, k > 0);
+              if (layer == 3) {
+#pragma unroll
+                for (int k = 0; k < KE / 16; ++k)
+                  tc_mma_ts(d_t, tb + COL_AE + k * 8,
+                            make_b_desc(img0 + seg_off[4] + k * 2 * lbo, lbo, sbo), idesc, 1u);
+              }
+            }
+            tc_commit(bar_d + g);
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================================================== workers
+    const int g = (warp - 4) >> 2;            // group 0 | 1
+    const int wq = warp & 3;                  // TMEM lane quarter this warp may access
+    const int t = wq * 32 + lane;             // row of the tile == TMEM lane
+    const int tg = t;                         // thread index inside the group
+    const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
+    const uint32_t tb = tmem_base + g * GRP_COLS + lane_addr;
+    float* beff0 = s_beff + g * 256;
+    float* beff3 = beff0 + 128;
+    float* e_s = s_e + g * 64;
+    const float* Wx0 = s_aux + AUX_WX0;
+    const float* Wx3 = Wx0 + NR_PAD * 128;
+    const int G = blockIdx.x * 2 + g;
+    uint32_t phd = 0u;
+
+    for (int pt = G; pt < p.n; pt += n_groups) {
+      // ---------------------------------------------- per-point (once per L lights)
+      const f3 x = ld3(p.xyz + (size_t)pt * 3);
+      f3 fr_t, fr_b, fr_n, v_loc;
+      if (KIND == NF_MLP_LVIS) {
+        // embed(xyz_scale * xyz): embedder.py:46-47
+        if (tg < 3) e_s[tg] = (tg == 0 ? x.x : (tg == 1 ? x.y : x.z)) * p.xyz_scale;
+        else if (tg < 3 + 3 * p.n_freqs_a) {
+          int idx = tg - 3, f = idx / 3, c = idx % 3;
+          float xv = (c == 0 ? x.x : (c == 1 ? x.y : x.z)) * p.xyz_scale;
+          float s, co;
+          sincosf(xv * (float)(1 << f), &s, &co);
+          e_s[3 + 6 * f + c] = s;
+          e_s[3 + 6 * f + 3 + c] = co;
+        }
+      } else {
+        if (tg < p.z_dim) e_s[tg] = p.zlat[(size_t)pt * p.z_dim + tg];
+        world2local_dev(ld3(p.normal + (size_t)pt * 3), fr_t, fr_b, fr_n);   // geom.py:119-149
+        f3 v = l2n(ld3(p.cam + (size_t)pt * 3) - x, 1e-6f);                   // shape.py:137-144
+        v_loc = mk3(dot3(fr_t, v), dot3(fr_b, v), dot3(fr_n, v));             // nerfactor.py:418
+      }
+      group_bar(1 + g);
+      {
+        float a0 = s_aux[AUX_B + 0 * 128 + tg], a3 = s_aux[AUX_B + 3 * 128 + tg];
+        for (int k = 0; k < p.nr; ++k) {
+          float ev = e_s[k];
+          a0 = fmaf(ev, Wx0[k * 128 + tg], a0);
+          a3 = fmaf(ev, Wx3[k * 128 + tg], a3);
+        }
+        beff0[tg] = a0;
+        beff3[tg] = a3;
+      }
+      group_bar(1 + g);
+
+      for (int c = 0; c < chunks; ++c) {
+        const int li = c * 128 + t;
+        const int lc = li < p.L ? li : p.L - 1;
+        // ------------------------------------------------ per-row embedding -> A_e
+        float mask = 1.f;
+        {
+          float4 lp = s_lx[lc];
+          f3 d = l2n(mk3(lp.x, lp.y, lp.z) - x, 1e-6f);                       // shape.py:128-135
+          float v[KE];
+#pragma unroll
+          for (int i = 0; i < KE; ++i) v[i] = 0.f;
+          f3 q;
+          int nf;
+          if (KIND == NF_MLP_LVIS) { q = d; nf = 4; }
+          else {
+            f3 l_loc = mk3(dot3(fr_t, d), dot3(fr_b, d), dot3(fr_n, d));      // nerfactor.py:419
+            mask = l_loc.z > 0.f ? 1.f : 0.f;                                 // :429-432
+            q = dir2rusink_dev(l_loc, v_loc);                                 // geom.py:152-192
+            nf = 2;
+          }
+          v[0] = q.x; v[1] = q.y; v[2] = q.z;
+          float sx, cx, sy, cy, sz, cz;
+          sincosf(q.x, &sx, &cx); sincosf(q.y, &sy, &cy); sincosf(q.z, &sz, &cz);
+#pragma unroll
+          for (int f = 0; f < (KIND == NF_MLP_LVIS ? 4 : 2); ++f) {
+            if (f < nf) {
+              v[3 + 6 * f + 0] = sx; v[3 + 6 * f + 1] = sy; v[3 + 6 * f + 2] = sz;
+              v[3 + 6 * f + 3] = cx; v[3 + 6 * f + 4] = cy; v[3 + 6 * f + 5] = cz;
+              // double-angle step to the next octave
+              float nsx = 2.f * sx * cx, ncx = 1.f - 2.f * sx * sx;
+              float nsy = 2.f * sy * cy, ncy = 1.f - 2.f * sy * sy;
+              float nsz = 2.f * sz * cz, ncz = 1.f - 2.f * sz * sz;
+              sx = nsx; cx = ncx; sy = nsy; cy = ncy; sz = nsz; cz = ncz;
+            }
+          }
+          uint32_t pk[KE / 2];
+#pragma unroll
+          for (int i = 0; i < KE / 2; ++i) pk[i] = pack2<BF16, 0>(v[2 * i], v[2 * i + 1]);
+          if (KE == 32) { TC_ST16(tb + COL_AE, pk); }
+          else { TC_ST8(tb + COL_AE, pk); }
+        }
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(bar_a + g);
+
+        // ------------------------------------------------ layers 0..2: epilogue -> A_h
+        for (int layer = 0; layer < 3; ++layer) {
+          const float* bias = layer == 0 ? beff0 : (s_aux + AUX_B + layer * 128);
+          mbar_wait(bar_d + g, phd);
+          phd ^= 1u;
+          tc_fence_after();
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            uint32_t r[32];
+            TC_LD32(r, tb + COL_D + cc * 32);
+            tc_wait_ld();
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float2 bb = *reinterpret_cast<const float2*>(bias + cc * 32 + 2 * i);
+              pk[i] = pack2<BF16, 1>(__uint_as_float(r[2 * i]) + bb.x,
+                                     __uint_as_float(r[2 * i + 1]) + bb.y);
+            }
+            TC_ST16(tb + COL_AH + cc * 16, pk);
+          }
+          tc_wait_st();
+          tc_fence_before();
+          mbar_arrive(bar_a + g);
+        }
+        // ------------------------------------------------ layer 3 + head
+        mbar_wait(bar_d + g, phd);
+        phd ^= 1u;
+        tc_fence_after();
+        float acc = 0.f;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          uint32_t r[32];
+          TC_LD32(r, tb + COL_D + cc * 32);
+          tc_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float h = fmaxf(__uint_as_float(r[i]) + beff3[cc * 32 + i], 0.f);
+            acc = fmaf(h, s_aux[AUX_WOUT + cc * 32 + i], acc);
+          }
+        }
+        float o = acc + s_aux[AUX_BOUT];
+        o = apply_act(p.out_act, o) * mask;
+        if (li < p.L) p.out[(size_t)pt * p.L + li] = o;
+      }
+    }
+  }
+
+  // ---------------------------------------------------------------- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS)
+                 : "memory");
+  }
+}
+
+
+// ------------------------------------------------------------------ bring-up test
+// One CTA: D[128x128] = A[128xK] * B[128xK]^T with A written to TMEM by tcgen05.st
+// (the layout the epilogue uses) and B in the swizzle-free K-major image.
+// a_host/b_host are row-major fp32 [128][K]; out is D row-major [128][128].
+__global__ void __launch_bounds__(128, 1)
+umma_selftest_kernel(const float* __restrict__ a, const float* __restrict__ b, int K,
+                     int swap_lbo_sbo, float* __restrict__ out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint16_t* img = reinterpret_cast<uint16_t*>(smem);            // [K/8][128][8]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (size_t)K * 128 * 2);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = threadIdx.x;
+  for (int i = t; i < K * 128; i += 128) {
+    int n = i / K, k = i % K;
+    __half h = __float2half_rn(b[n * K + k]);
+    img[((size_t)(k / 8) * 128 + n) * 8 + (k % 8)] = *reinterpret_cast<uint16_t*>(&h);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (t == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+  const uint32_t tb = tmem_base + ((uint32_t)(warp * 32) << 16);
+  // A row t -> TMEM lane t, columns 128.. (16-bit pairs)
+  for (int c0 = 0; c0 < K / 2; c0 += 8) {
+    uint32_t pk[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      pk[i] = pack2<0, 0>(a[t * K + 2 * (c0 + i)], a[t * K + 2 * (c0 + i) + 1]);
+    TC_ST8(tb + 128 + c0, pk);
+  }
+  tc_wait_st();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (t == 0) {
+    uint32_t lbo = 128 * 16, sbo = 128;
+    if (swap_lbo_sbo) { uint32_t x = lbo; lbo = sbo; sbo = x; }
+    const uint32_t idesc = make_idesc(0, 128);
+    for (int k = 0; k < K / 16; ++k)
+      tc_mma_ts(tmem_base, tmem_base + 128 + k * 8,
+                make_b_desc(smem_u32(img) + k * 2 * 128 * 16, lbo, sbo), idesc, k > 0);
+    tc_commit(bar);
+  }
+  mbar_wait(bar, 0);
+  tc_fence_after();
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) {
+    uint32_t r[32];
+    TC_LD32(r, tb + cc * 32);
+    tc_wait_ld();
+    for (int i = 0; i < 32; ++i) out[t * 128 + cc * 32 + i] = __uint_as_float(r[i]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+  }
+}
+
+// host float -> fp16 / bf16 bits (round to nearest even)
+uint16_t f2h_bits(float f) {
+  __half h = __float2half_rn(f);
+  uint16_t b;
+  memcpy(&b, &h, 2);
+  return b;
+}
+uint16_t f2bf_bits(float f) {
+  __nv_bfloat16 h = __float2bfloat16_rn(f);
+  uint16_t b;
+  memcpy(&b, &h, 2);
+  return b;
+}
+
+template <int KIND, int BF16>
+int launch_tc(nf_ctx* ctx, const nf_mlp* m, const TcParams& p, cudaStream_t st) {
+  using SL = SmemLayout<KIND>;
+  NF_CHECK_ARG(ctx, SL::total <= ctx->smem_optin, "shared memory budget exceeded");
+  NF_CUDA(ctx, cudaFuncSetAttribute(mlp_tc_kernel<KIND, BF16>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SL::total));
+  int grid = ctx->sm_count;
+  int need = (p.n + 1) / 2;
+  if (grid > need) grid = need;
+  mlp_tc_kernel<KIND, BF16><<<grid, TC_THREADS, SL::total, st>>>(p);
+  NF_LAUNCH_CHECK(ctx);
+  return NF_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// Host packing.  For the per-(point, light) networks (width 128, depth 4, skip
+// after layer 2) append to the blob:
+//   image (fp16) ++ image (bf16): segments [W0e | W1 | W2 | W3h | W3e], each
+//     stored K-major without swizzle as [K/8][N=128][8] 16-bit values, i.e. the
+//     element (n, k) of B = W^T sits at ((k/8)*128 + n)*16 + (k%8)*2 bytes.
+//     W0e / W3e are the rows of W0 / W3 that multiply the per-row embedding
+//     (light direction or Rusinkiewicz encoding), zero-padded to KE rows.
+//   aux (fp32): b0..b3 [4][128], w_out [128], b_out [4], Wx0 [NR_PAD][128],
+//     Wx3 [NR_PAD][128] = the rows of W0 / W3 that multiply the per-point columns.
+int nf_tc_pack(nf_mlp* m) {
+  const nf_mlp_desc& d = m->d;
+  const bool pair_kind = d.kind == NF_MLP_LVIS || d.kind == NF_MLP_BRDF;
+  if (!pair_kind || d.width != 128 || d.depth != 4 || d.skip_at != 2 || d.out_dim != 1) return NF_OK;
+  const int KE = d.kind == NF_MLP_LVIS ? 32 : 16;
+  const int NR_PAD = d.kind == NF_MLP_LVIS ? 64 : 8;
+  const int nr = d.kind == NF_MLP_LVIS ? 3 * (1 + 2 * d.n_freqs_a) : d.z_dim;
+  const int ne = d.in_dim - nr;  // per-row columns
+  if (ne > KE || nr > NR_PAD) return NF_OK;  // unusual spec: FP32 path only
+  if (d.kind == NF_MLP_LVIS && d.n_freqs_b != 4) return NF_OK;
+  if (d.kind == NF_MLP_BRDF && d.n_freqs_a != 2) return NF_OK;
+  const float* W[5];
+  const float* B[5];
+  for (int l = 0; l <= 4; ++l) { W[l] = d.W[l]; B[l] = d.b[l]; }
+  const size_t halves = (size_t)(KE + 384 + KE) * 128;
+  const size_t aux_floats = AUX_WX0 + 2 * (size_t)NR_PAD * 128;
+  size_t base = (m->blob.size() + 255) / 256 * 256;
+  m->off_tc_f16 = base;
+  m->off_tc_bf16 = base + (halves * 2 + 255) / 256 * 256;
+  m->off_tc_aux = m->off_tc_bf16 + (halves * 2 + 255) / 256 * 256;
+  m->tc_bytes = halves * 2;
+  m->tc_aux_bytes = aux_floats * 4;
+  m->blob.resize(m->off_tc_aux + (m->tc_aux_bytes + 255) / 256 * 256, 0);
+  uint16_t* img16 = reinterpret_cast<uint16_t*>(m->blob.data() + m->off_tc_f16);
+  uint16_t* imgbf = reinterpret_cast<uint16_t*>(m->blob.data() + m->off_tc_bf16);
+  float* aux = reinterpret_cast<float*>(m->blob.data() + m->off_tc_aux);
+  // segment s: rows of Keras W[l] (layout [K_l][128]) starting at row r0, count kc, padded to kp
+  struct Seg { int l, r0, kc, kp; };
+  const Seg segs[5] = {{0, nr, ne, KE}, {1, 0, 128, 128}, {2, 0, 128, 128}, {3, 0, 128, 128},
+                       {3, 128 + nr, ne, KE}};
+  size_t seg_base = 0;
+  for (int s = 0; s < 5; ++s) {
+    const Seg& sg = segs[s];
+    for (int k = 0; k < sg.kp; ++k)
+      for (int n = 0; n < 128; ++n) {
+        float v = k < sg.kc ? W[sg.l][(size_t)(sg.r0 + k) * 128 + n] : 0.f;
+        size_t idx = seg_base + ((size_t)(k / 8) * 128 + n) * 8 + (k % 8);
+        img16[idx] = f2h_bits(v);
+        imgbf[idx] = f2bf_bits(v);
+      }
+    seg_base += (size_t)sg.kp * 128;
+  }
+  for (int l = 0; l < 4; ++l) memcpy(aux + AUX_B + l * 128, B[l], 128 * sizeof(float));
+  for (int c = 0; c < 128; ++c) aux[AUX_WOUT + c] = W[4][c];  // [128][1]
+  aux[AUX_BOUT] = B[4][0];
+  for (int k = 0; k < nr; ++k) {
+    memcpy(aux + AUX_WX0 + (size_t)k * 128, W[0] + (size_t)k * 128, 128 * sizeof(float));
+    memcpy(aux + AUX_WX0 + (size_t)(NR_PAD + k) * 128, W[3] + (size_t)(128 + k) * 128,
+           128 * sizeof(float));
+  }
+  return NF_OK;
+}
+
+static int tc_common(nf_ctx* ctx, const nf_mlp* m, int precision, TcParams& p) {
+  NF_CHECK_ARG(ctx, m->dev, "network not uploaded (call nf_mlp_upload first)");
+  NF_CHECK_ARG(ctx, precision == NF_PREC_F16 || precision == NF_PREC_BF16, "bad precision");
+  if (m->tc_bytes == 0)
+    return nf_set_error(ctx, NF_ERR_UNSUPPORTED,
+                        "no tcgen05 kernel for this network shape (need width 128, depth 4, "
+                        "skip_at 2, out_dim 1); use NF_PREC_FP32");
+  memset(&p, 0, sizeof(p));
+  p.blob = (const uint8_t*)m->dev;
+  p.off_img = precision == NF_PREC_BF16 ? m->off_tc_bf16 : m->off_tc_f16;
+  p.off_aux = m->off_tc_aux;
+  p.kind = m->d.kind;
+  p.n_freqs_a = m->d.n_freqs_a; p.n_freqs_b = m->d.n_freqs_b; p.z_dim = m->d.z_dim;
+  p.out_act = m->d.out_act;
+  return NF_OK;
+}
+
+int nf_tc_lvis_launch(nf_ctx* ctx, const nf_mlp* m, const float* xyz, int n, float xyz_scale,
+                      const float* lxyz, int L, float* lvis, int precision, cudaStream_t st) {
+  TcParams p;
+  int rc = tc_common(ctx, m, precision, p);
+  if (rc != NF_OK) return rc;
+  NF_CHECK_ARG(ctx, L <= 1024, "n_lights > 1024 not supported by the tcgen05 kernel");
+  if (n == 0) return NF_OK;
+  p.n = n; p.L = L; p.nr = 3 * (1 + 2 * m->d.n_freqs_a); p.xyz_scale = xyz_scale;
+  p.xyz = xyz; p.lxyz = lxyz; p.out = lvis;
+  return precision == NF_PREC_BF16 ? launch_tc<NF_MLP_LVIS, 1>(ctx, m, p, st)
+                                   : launch_tc<NF_MLP_LVIS, 0>(ctx, m, p, st);
+}
+
+int nf_tc_brdf_launch(nf_ctx* ctx, const nf_mlp* m, const float* xyz, const float* normal,
+                      const float* cam, const float* z, int n, const float* lxyz, int L,
+                      float* spec, int precision, cudaStream_t st) {
+  TcParams p;
+  int rc = tc_common(ctx, m, precision, p);
+  if (rc != NF_OK) return rc;
+  NF_CHECK_ARG(ctx, L <= 1024, "n_lights > 1024 not supported by the tcgen05 kernel");
+  if (n == 0) return NF_OK;
+  p.n = n; p.L = L; p.nr = m->d.z_dim; p.xyz_scale = 1.f;
+  p.xyz = xyz; p.lxyz = lxyz; p.normal = normal; p.cam = cam; p.zlat = z; p.out = spec;
+  return precision == NF_PREC_BF16 ? launch_tc<NF_MLP_BRDF, 1>(ctx, m, p, st)
+                                   : launch_tc<NF_MLP_BRDF, 0>(ctx, m, p, st);
+}
+
+int nf_tc_sigma_launch(nf_ctx* ctx, const nf_mlp*, const float*, const float*, const float*, int,
+                       int, const float*, float*, int, cudaStream_t) {
+  return nf_set_error(ctx, NF_ERR_UNSUPPORTED,
+                      "nf_sigma_fwd: tcgen05 path for the 8x256 sigma network not built yet");
+}
+
+// Diagnostics (not part of the reference surface): single-tile tcgen05 self-test.
+extern "C" int nf_selftest_umma(nf_ctx* ctx, const float* a_d, const float* b_d, int K,
+                                int swap_lbo_sbo, float* out_d, void* stream) {
+  NF_CHECK_ARG(ctx, a_d && b_d && out_d && K >= 16 && K <= 128 && K % 16 == 0, "bad argument");
+  size_t sm = (size_t)K * 128 * 2 + 64;
+  NF_CUDA(ctx, cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  umma_selftest_kernel<<<1, 128, sm, (cudaStream_t)stream>>>(a_d, b_d, K, swap_lbo_sbo, out_d);
+  NF_LAUNCH_CHECK(ctx);
+  return NF_OK;
+}

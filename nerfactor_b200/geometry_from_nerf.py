@@ -1,0 +1,93 @@
+"""Mirror of nerfactor/geometry_from_nerf.py (Stage A): camera -> surface march
+(`compute_depth_and_normal`), surface -> light march (`compute_light_visibility`),
+`eval_sigma_mlp`, plus `march_single_pass`, the single-pass S-sample march the
+headline benchmark times.  Script-level flags of the reference
+(`FLAGS.mlp_chunk`, `lpix_chunk`, `light_h`, `lvis_far`, `scene_bbox`,
+`occu_thres`) are keyword arguments here."""
+import numpy as np
+import torch
+
+from . import _lib
+from .brdf.renderer import gen_light_xyz
+
+
+def parse_bbox(scene_bbox):
+    """geometry_from_nerf.py:365-371: 'x_min,x_max,y_min,y_max,z_min,z_max' or None."""
+    if scene_bbox is None or scene_bbox == '':
+        return None
+    if isinstance(scene_bbox, str):
+        return [float(v) for v in scene_bbox.split(',')]
+    return [float(v) for v in scene_bbox]
+
+
+def eval_sigma_mlp(model, rayo, rayd, z, use_fine=False, scene_bbox=None, precision=None):
+    """geometry_from_nerf.py:322-350 on the samples o + z d (never materialised):
+    relu(sigma_out(enc(embed(p)))), 0 outside the bounding box."""
+    prec = precision or model.precision
+    return _lib.sigma_fwd(model.ctx, model.packed_sigma(use_fine), rayo, rayd, z,
+                          parse_bbox(scene_bbox), prec)
+
+
+def march_single_pass(model, rayo, rayd, n_samples, use_fine=False, perturb_u=None,
+                      scene_bbox=None, precision=None, want_weights=False):
+    """gen_z (nerf.py:120-136) -> sigma (gfn.py:322-350) -> weights (nerf.py:184-212)
+    -> occu / depth (gfn.py:312-315) -> surf = rayo + rayd * depth (gfn.py:134)."""
+    ctx = model.ctx
+    n = rayo.shape[0]
+    z = _lib.gen_z(ctx, model.near, model.far, n_samples, n, False, perturb_u)
+    sigma = eval_sigma_mlp(model, rayo, rayd, z, use_fine, scene_bbox, precision)
+    w, occu, depth, surf, _ = _lib.composite(ctx, sigma, z, rayo, rayd,
+                                             want_weights=want_weights)
+    return {'z': z, 'sigma': sigma, 'weights': w, 'occu': occu, 'depth': depth,
+            'surf': surf}
+
+
+def compute_depth_and_normal(model, rayo, rayd, config, scene_bbox=None, precision=None):
+    """geometry_from_nerf.py:249-319 -> (occu[N], exp_depth[N], exp_normal[N,3])."""
+    ctx = model.ctx
+    n_c = 64 + config.getint('DEFAULT', 'n_samples_coarse')
+    n_f = 64 + config.getint('DEFAULT', 'n_samples_fine')
+    lin = config.getboolean('DEFAULT', 'lin_in_disp')
+    near, far = config.getfloat('DEFAULT', 'near'), config.getfloat('DEFAULT', 'far')
+    n = rayo.shape[0]
+    z = _lib.gen_z(ctx, near, far, n_c, n, lin, None)
+    sigma = eval_sigma_mlp(model, rayo, rayd, z, False, scene_bbox, precision)
+    w, _, _, _, _ = _lib.composite(ctx, sigma, z, rayo, rayd, want_surf=False)
+    z = _lib.gen_z_fine(ctx, z, w, n_f)
+    sigma, normal = _lib.sigma_normal_fwd(ctx, model.packed_sigma(True), rayo, rayd, z,
+                                          parse_bbox(scene_bbox))
+    _, occu, depth, _, exp_normal = _lib.composite(
+        ctx, sigma, z, rayo, rayd, normal=normal, want_weights=False, want_surf=False)
+    return occu, depth, exp_normal
+
+
+def compute_light_visibility(model, surf, normal, config, lvis_near=.1, lvis_far=1.,
+                             light_h=16, scene_bbox=None, precision=None, lxyz=None,
+                             pair_chunk=1 << 20):
+    """geometry_from_nerf.py:177-246 -> lvis_hit [M, L] (device tensor).  All lights
+    are marched together in chunks of (point, light) pairs instead of the
+    reference's 512-iteration Python loop; back-lit pairs stay 0."""
+    ctx = model.ctx
+    n_c = 64 + config.getint('DEFAULT', 'n_samples_coarse')
+    n_f = 64 + config.getint('DEFAULT', 'n_samples_fine')
+    lin = config.getboolean('DEFAULT', 'lin_in_disp')
+    if lxyz is None:
+        lxyz, _ = gen_light_xyz(light_h, 2 * light_h)
+    lxyz = torch.as_tensor(np.asarray(lxyz, np.float32).reshape(-1, 3)).to(ctx.device)
+    m, L = surf.shape[0], lxyz.shape[0]
+    rayo, rayd, fl = _lib.lvis_rays(ctx, surf, normal, lxyz)
+    idx = torch.nonzero(fl.reshape(-1), as_tuple=False)[:, 0]
+    lvis = torch.zeros((m * L,), dtype=torch.float32, device=ctx.device)
+    for i in range(0, idx.numel(), pair_chunk):
+        sel = idx[i:i + pair_chunk]
+        o, d = rayo.index_select(0, sel).contiguous(), rayd.index_select(0, sel).contiguous()
+        k = o.shape[0]
+        z = _lib.gen_z(ctx, lvis_near, lvis_far, n_c, k, lin, None)
+        sigma = eval_sigma_mlp(model, o, d, z, False, scene_bbox, precision)
+        w, _, _, _, _ = _lib.composite(ctx, sigma, z, o, d, want_surf=False)
+        z = _lib.gen_z_fine(ctx, z, w, n_f)
+        sigma = eval_sigma_mlp(model, o, d, z, True, scene_bbox, precision)
+        _, occu, _, _, _ = _lib.composite(ctx, sigma, z, o, d, want_weights=False,
+                                          want_surf=False)
+        lvis.index_copy_(0, sel, 1. - occu)
+    return lvis.reshape(m, L)

@@ -1,0 +1,33 @@
+"""Mirror of nerfactor/models/nerfactor_microfacet.py: analytic GGX BRDF with a
+predicted scalar roughness (z_dim = 1, sigmoid head) instead of the learned latent."""
+from ..brdf.microfacet import Microfacet
+from ..networks import mlp
+from .nerfactor import Model as NeRFactorModel
+
+
+class Model(NeRFactorModel):
+    def _init_brdf_dims(self):
+        self.z_dim = 1                      # nerfactor_microfacet.py:38
+        self.normalize_brdf_z = False
+
+    def _init_brdf_model(self, params):
+        self.brdf_model = None              # no learned prior in this variant
+
+    def _init_embedder(self):
+        """nerfactor_microfacet.py:102-106: grandparent's embedders (no rusink)."""
+        return super(NeRFactorModel, self)._init_embedder()
+
+    def _init_net(self):
+        """nerfactor_microfacet.py:108-114: roughness head gets a sigmoid."""
+        net = super()._init_net()
+        net['brdf_z_out'] = mlp.Network([self.z_dim], act=['sigmoid'])
+        return net
+
+    def _eval_brdf_at(self, pts2l, pts2c, normal, albedo, brdf_prop, pts=None, cam=None):
+        """nerfactor_microfacet.py:116-124: the GGX lobe is evaluated inside the
+        rendering-equation kernel; hand it the roughness and f0."""
+        fresnel_f0 = self.config.getfloat('DEFAULT', 'fresnel_f0')
+        return {'microfacet': Microfacet(f0=fresnel_f0), 'rough': brdf_prop.contiguous()}
+
+    def _brdf_kernel_args(self, brdf):
+        return {'rough': brdf['rough'], 'f0': brdf['microfacet'].f0}

@@ -1,0 +1,111 @@
+"""CPU-side checks of the C-ABI library and the host mirror (no GPU needed):
+the .so loads, exports every symbol include/nerfactor_b200.h declares, refuses to
+create a context without a GPU, and packs weights on the host."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from nerfactor_b200 import _lib, synth, config as nfconfig
+from nerfactor_b200.networks import mlp
+from nerfactor_b200.networks.embedder import Embedder
+from nerfactor_b200.brdf.renderer import gen_light_xyz
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, 'include', 'nerfactor_b200.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(nf_[a-z0-9_]+)\s*\(', src)))
+
+
+def test_library_exports_every_header_symbol():
+    lib = _lib.load_library()
+    syms = _header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), 'missing export %s' % s
+    assert sorted(_lib.EXPORTS) == syms
+    assert lib.nf_version() == 100
+
+
+def test_no_gpu_means_no_context():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    lib = _lib.load_library()
+    h = C.c_void_p()
+    assert lib.nf_ctx_create(C.byref(h), -1) == -4          # NF_ERR_NO_DEVICE
+    with pytest.raises(_lib.NfError):
+        _lib.Context()
+
+
+def _desc(kind, layers, skip_at, out_act, **kw):
+    d = _lib.MlpDesc()
+    Ws = [np.ascontiguousarray(w) for w, _ in layers]
+    bs = [np.ascontiguousarray(b) for _, b in layers]
+    depth = len(layers) - 1
+    d.kind, d.in_dim, d.width = _lib.KIND[kind], Ws[0].shape[0], Ws[0].shape[1]
+    d.depth, d.skip_at, d.out_dim = depth, skip_at, Ws[-1].shape[1]
+    d.out_act = _lib.ACT[out_act]
+    d.n_freqs_a, d.n_freqs_b, d.z_dim = kw.get('a', 0), kw.get('b', 0), kw.get('z', 0)
+    d.W = (C.c_void_p * (depth + 1))(*[w.ctypes.data for w in Ws])
+    d.b = (C.c_void_p * (depth + 1))(*[b.ctypes.data for b in bs])
+    return d, (Ws, bs)
+
+
+def test_host_weight_packing_sizes_and_errors():
+    lib = _lib.load_library()
+    p = synth.make_stage_b_params(0, 'learned')
+    lv = p['lvis_mlp']['layers'] + p['lvis_out']['layers']
+    d, keep = _desc('lvis', lv, 2, 'sigmoid', a=10, b=4)
+    h = C.c_void_p()
+    assert lib.nf_mlp_create(None, C.byref(d), C.byref(h)) == 0
+    nbytes = lib.nf_mlp_device_bytes(h)
+    fp32 = sum(w.size + b.size for w, b in lv) * 4
+    tc = 2 * (32 + 384 + 32) * 128 * 2 + (644 + 2 * 64 * 128) * 4
+    assert fp32 + tc <= nbytes <= fp32 + tc + 16 * 256
+    lib.nf_mlp_destroy(h)
+    # wrong embedding spec -> invalid argument, no handle
+    d2, keep2 = _desc('lvis', lv, 2, 'sigmoid', a=9, b=4)
+    assert lib.nf_mlp_create(None, C.byref(d2), C.byref(h)) == -1
+    # sigma net 8x256 packs too (fp32 image only for now)
+    nerf = synth.make_nerf_params(0)
+    sg = nerf['coarse_enc']['layers'] + nerf['coarse_sigma_out']['layers']
+    d3, keep3 = _desc('sigma', sg, 4, None, a=10)
+    assert lib.nf_mlp_create(None, C.byref(d3), C.byref(h)) == 0
+    assert lib.nf_mlp_device_bytes(h) >= sum(w.size + b.size for w, b in sg) * 4
+    lib.nf_mlp_destroy(h)
+
+
+def test_network_mirror_shapes():
+    net = mlp.Network([128] * 4, act=['relu'] * 4, skip_at=[2]).build(90)
+    ks = [l.kernel.shape for l in net.layers]
+    assert ks == [(90, 128), (128, 128), (128, 128), (218, 128)]     # mlp.py:39-50
+    enc = mlp.Network([256] * 8, act=['relu'] * 8, skip_at=[4]).build(63)
+    assert enc.layers[5].kernel.shape == (319, 256)                  # nerf.py:53-59
+    assert Embedder(in_dims=3, log2_max_freq=9, n_freqs=10).out_dims == 63
+    assert Embedder(in_dims=3, log2_max_freq=3, n_freqs=4).out_dims == 27
+    with pytest.raises(NotImplementedError):
+        net(np.zeros((1, 90), np.float32))
+
+
+def test_gen_light_xyz_mirror_matches_pinned_reference(golden_dir):
+    ref = np.load(os.path.join(golden_dir, 'ref_pinned.npz'))
+    for h, w in ((16, 32), (2, 8), (16, 64)):
+        xyz, areas = gen_light_xyz(h, w)
+        assert np.array_equal(xyz, ref['lxyz_%dx%d' % (h, w)])
+        assert np.array_equal(areas, ref['lareas_%dx%d' % (h, w)])
+
+
+def test_default_configs_match_reference_ini_values():
+    c = nfconfig.default_config('nerfactor')
+    assert c.getint('DEFAULT', 'mlp_width') == 128 and c.getint('DEFAULT', 'mlp_skip_at') == 2
+    assert c.getfloat('DEFAULT', 'albedo_slope') == 0.77
+    m = nfconfig.default_config('nerfactor_microfacet')
+    assert m.getfloat('DEFAULT', 'fresnel_f0') == 0.04
+    n = nfconfig.default_config('nerf')
+    assert n.getint('DEFAULT', 'enc_depth') == 8 and n.getint('DEFAULT', 'mlp_width') == 256

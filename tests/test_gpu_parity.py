@@ -1,0 +1,238 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.
+
+Tolerances: fp32 kernels 1e-5 (rel-L2); tcgen05 f16 path: rendered RGB within the
+north-star's 1e-4 relative L2; bit-exact for ray generation / pixel indexing."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import brdf as obrdf, stage_a, stage_b, networks as onets
+from nerfactor_b200 import synth, config as nfconfig
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_l2(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+@pytest.fixture(scope='module')
+def ctx():
+    from nerfactor_b200 import _lib
+    return _lib.default_context()
+
+
+def dev(x, ctx, dtype=torch.float32):
+    return torch.as_tensor(np.ascontiguousarray(x), dtype=dtype).to(ctx.device)
+
+
+# ------------------------------------------------------------------- Stage A
+@pytest.mark.parametrize('hw', [(64, 64), (800, 800), (37, 53)])
+def test_gen_rays_bit_exact(ctx, hw):
+    from nerfactor_b200 import _lib
+    h, w = hw
+    c2w = synth.look_at_c2w(4.0, 30.0, 30.0)
+    ro, rd = stage_a.gen_rays(c2w, synth.CAM_ANGLE_X, h, w)
+    go, gd = _lib.gen_rays(ctx, c2w, synth.CAM_ANGLE_X, h, w)
+    assert np.array_equal(go.cpu().numpy(), ro.reshape(-1, 3))
+    assert np.array_equal(gd.cpu().numpy(), rd.reshape(-1, 3))     # ray n = y*W + x
+
+
+def _nerf_model(ctx, seed=3, precision='fp32'):
+    from nerfactor_b200.models.nerf import Model
+    return Model(nfconfig.default_config('nerf'), params=synth.make_nerf_params(seed),
+                 ctx=ctx, precision=precision)
+
+
+def _rays(ctx, h, w):
+    from nerfactor_b200 import _lib
+    return _lib.gen_rays(ctx, synth.look_at_c2w(), synth.CAM_ANGLE_X, h, w, normalize=True)
+
+
+def test_march_single_pass_fp32_vs_oracle_and_golden(ctx, golden_dir):
+    from nerfactor_b200 import geometry_from_nerf as gfn
+    g = np.load(os.path.join(golden_dir, 'oracle_stage_a.npz'))
+    model = _nerf_model(ctx, int(g['seed_nerf']))
+    ro, rd = _rays(ctx, 8, 8)
+    out = gfn.march_single_pass(model, ro, rd, 32, precision='fp32', want_weights=True)
+    assert rel_l2(out['sigma'].cpu(), g['sp_sigma']) < 2e-5
+    assert rel_l2(out['weights'].cpu(), g['sp_weights']) < 2e-5
+    assert rel_l2(out['depth'].cpu(), g['sp_depth']) < 1e-5
+    assert rel_l2(out['occu'].cpu(), g['sp_occu']) < 1e-5
+    assert rel_l2(out['surf'].cpu(), g['sp_surf']) < 1e-5
+
+
+def test_gen_z_and_gen_z_fine_vs_oracle(ctx):
+    from nerfactor_b200 import _lib
+    rng = np.random.default_rng(0)
+    n, sc, sf = 257, 40, 56
+    u = rng.uniform(size=(n, sc)).astype(np.float32)
+    z_o = stage_a.gen_z(2., 6., sc, n, perturb_u=u)
+    z_g = _lib.gen_z(ctx, 2., 6., sc, n, False, dev(u, ctx))
+    assert np.allclose(z_g.cpu().numpy(), z_o.numpy(), atol=1e-6)
+    w = rng.uniform(size=(n, sc)).astype(np.float32) ** 4
+    w[:5] = 0.                                            # empty rays: denom -> eps
+    zf_o = stage_a.gen_z_fine(z_o, torch.tensor(w), sf)
+    zf_g = _lib.gen_z_fine(ctx, z_g, dev(w, ctx), sf)
+    got = zf_g.cpu().numpy()
+    assert np.all(np.diff(got, axis=1) >= 0)              # sortedness
+    assert np.allclose(got, zf_o.numpy(), atol=2e-5)
+
+
+def test_composite_weights_vs_oracle(ctx):
+    from nerfactor_b200 import _lib
+    rng = np.random.default_rng(1)
+    n, s = 300, 77
+    sigma = (rng.standard_normal((n, s)) * 5).astype(np.float32)
+    z = np.sort(rng.uniform(2, 6, (n, s)).astype(np.float32), axis=1)
+    rd = rng.standard_normal((n, 3)).astype(np.float32)
+    ro = rng.standard_normal((n, 3)).astype(np.float32)
+    nrm = rng.standard_normal((n, s, 3)).astype(np.float32)
+    w_o = stage_a.accumulate_sigma(torch.tensor(sigma), torch.tensor(z), torch.tensor(rd))
+    w, occu, depth, surf, en = _lib.composite(
+        ctx, dev(sigma, ctx), dev(z, ctx), dev(ro, ctx), dev(rd, ctx), dev(nrm, ctx))
+    assert np.allclose(w.cpu().numpy(), w_o.numpy(), atol=2e-6)
+    assert np.allclose(occu.cpu().numpy(), w_o.sum(-1).numpy(), atol=1e-5)
+    assert np.allclose(depth.cpu().numpy(), (w_o * torch.tensor(z)).sum(-1).numpy(), atol=2e-5)
+    en_o = (w_o[:, :, None] * torch.tensor(nrm)).sum(-2).numpy()
+    assert np.allclose(en.cpu().numpy(), en_o, atol=2e-5)
+
+
+def test_light_visibility_march_fp32_vs_oracle(ctx):
+    from nerfactor_b200 import geometry_from_nerf as gfn
+    model = _nerf_model(ctx, 3)
+    cfg = nfconfig.default_config('nerf', n_samples_coarse=-32, n_samples_fine=-16)
+    rng = np.random.default_rng(5)
+    surf = rng.uniform(-1, 1, (24, 3)).astype(np.float32)
+    nrm = rng.standard_normal((24, 3)).astype(np.float32)
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    lx, _ = obrdf.gen_light_xyz(2, 4)
+    model.precision = 'fp32'
+    got = gfn.compute_light_visibility(model, dev(surf, ctx), dev(nrm, ctx), cfg, lxyz=lx)
+    nerf = synth.make_nerf_params(3)
+    exp = stage_a.compute_light_visibility(nerf, torch.tensor(surf), torch.tensor(nrm), lx,
+                                           n_samples_coarse=-32, n_samples_fine=-16)
+    assert np.allclose(got.cpu().numpy(), exp.numpy(), atol=3e-4)
+
+
+# ------------------------------------------------------------------- Stage B
+def _stage_b(ctx, brdf, lh, lw, seed=7, precision='f16', **kw):
+    name = 'nerfactor_microfacet' if brdf == 'microfacet' else 'nerfactor'
+    from importlib import import_module
+    Model = import_module('nerfactor_b200.models.' + name).Model
+    params = synth.make_stage_b_params(seed, brdf, light_hw=(lh, lw))
+    cfg = nfconfig.default_config(name, light_h=lh)
+    m = Model(cfg, params=params, ctx=ctx, precision=precision, **kw)
+    lxyz, lareas = obrdf.gen_light_xyz(lh, lw)
+    m.set_lights(lxyz.reshape(-1, 3), lareas.reshape(-1))
+    m.light_res = (lh, lw)
+    om = stage_b.StageB(params, {'brdf': brdf}, lxyz=lxyz, lareas=lareas)
+    return m, om, params
+
+
+@pytest.mark.parametrize('brdf', ['microfacet', 'learned'])
+@pytest.mark.parametrize('precision', ['fp32', 'f16'])
+def test_model_call_matches_golden(ctx, golden_dir, brdf, precision):
+    """Config-1-like case (96 rays, L=16): full Model.call vs the frozen oracle vectors."""
+    g = np.load(os.path.join(golden_dir, 'oracle_stage_b_%s.npz' % brdf))
+    lh, lw = int(g['lh']), int(g['lw'])
+    m, _, _ = _stage_b(ctx, brdf, lh, lw, int(g['seed_params']), precision)
+    batch = synth.make_stage_b_batch(int(g['seed_batch']), int(g['n_rays']), lh * lw)
+    probes = synth.make_probes(int(g['seed_probes']), 3, (lh, lw))
+    for i, p in enumerate(probes):
+        m.novel_probes['p%d' % i] = p
+    pred, gt, lk, _ = m.call(batch, 'test', relight_probes=True)
+    tol_net = 1e-5 if precision == 'fp32' else 3e-3
+    assert rel_l2(pred['normal'].cpu(), g['normal']) < 1e-5
+    assert rel_l2(pred['albedo'].cpu(), g['albedo']) < 1e-5
+    assert rel_l2(pred['brdf'].cpu(), g['brdf']) < 1e-5
+    assert rel_l2(pred['lvis'].cpu(), g['lvis']) < tol_net
+    tol_rgb = 1e-5 if precision == 'fp32' else 1e-4      # north-star bar on RGB
+    assert rel_l2(pred['rgb'].cpu(), g['rgb']) < tol_rgb
+    assert rel_l2(pred['rgb_probes'].cpu(), g['rgb_relit']) < tol_rgb
+    bg = batch[5][:, 0] == 0
+    assert np.all(pred['rgb'].cpu().numpy()[bg] == 0)    # background rows stay zero
+
+
+@pytest.mark.parametrize('brdf', ['microfacet', 'learned'])
+def test_stage_b_l512_rgb_within_1e4(ctx, brdf):
+    """Reference-native light grid (16x32 = 512 lights), ragged N (not a tile multiple)."""
+    m, om, _ = _stage_b(ctx, brdf, 16, 32, seed=21, precision='f16')
+    batch = synth.make_stage_b_batch(22, 203, 512)
+    pred, _, _, _ = m.call(batch, 'test', relight_olat=True)
+    opred, _, _ = om.call(batch, 'test', relight_lights=om.novel_olat((16, 32))[:40])
+    assert rel_l2(pred['rgb'].cpu(), opred['rgb']) < 1e-4
+    assert rel_l2(pred['lvis'].cpu(), opred['lvis']) < 3e-3
+    assert rel_l2(pred['rgb_olat'].cpu().numpy()[:, :40], opred['rgb_relit']) < 1e-4
+
+
+def test_lvis_and_brdf_kernels_fp32_vs_f16_vs_oracle(ctx):
+    from nerfactor_b200 import _lib
+    m, om, params = _stage_b(ctx, 'learned', 16, 32, seed=5, precision='f16')
+    rng = np.random.default_rng(9)
+    n = 70
+    xyz = rng.uniform(-1.2, 1.2, (n, 3)).astype(np.float32)
+    xt = dev(xyz, ctx)
+    surf2l = om.calc_ldir(torch.tensor(xyz))
+    lv_o = om.pred_lvis_at(torch.tensor(xyz), surf2l).numpy()
+    mlp_l = m._packed_mlp('lvis', 'lvis', n_freqs_a=10, n_freqs_b=4)
+    lv32 = _lib.lvis_fwd(ctx, mlp_l, xt, m.lxyz, 1.0, 'fp32').cpu().numpy()
+    lv16 = _lib.lvis_fwd(ctx, mlp_l, xt, m.lxyz, 1.0, 'f16').cpu().numpy()
+    lvbf = _lib.lvis_fwd(ctx, mlp_l, xt, m.lxyz, 1.0, 'bf16').cpu().numpy()
+    assert np.abs(lv32 - lv_o).max() < 2e-5
+    assert np.abs(lv16 - lv_o).max() < 4e-3 and rel_l2(lv16, lv_o) < 1.5e-3
+    assert np.abs(lvbf - lv_o).max() < 3e-2 and rel_l2(lvbf, lv_o) < 1e-2
+
+
+def test_empty_and_all_background(ctx):
+    m, _, _ = _stage_b(ctx, 'microfacet', 2, 8)
+    batch = list(synth.make_stage_b_batch(3, 33, 16))
+    batch[5] = np.zeros_like(batch[5])                     # alpha = 0 everywhere
+    pred, _, _, _ = m.call(tuple(batch), 'test')
+    assert pred['rgb'].shape == (33, 3) and float(pred['rgb'].abs().sum()) == 0.
+    with pytest.raises(ValueError):
+        m.call(tuple(batch), 'predict')                    # models/base.py:107-110
+
+
+def test_loss_matches_oracle(ctx):
+    m, om, _ = _stage_b(ctx, 'learned', 2, 8, seed=7, precision='fp32')
+    batch = synth.make_stage_b_batch(11, 64, 16)
+    nfg = int((batch[5][:, 0] > 0).sum())
+    noise = (0.01 * np.random.default_rng(2).standard_normal((nfg, 3))).astype(np.float32)
+    pred, gt, lk, _ = m.call(batch, 'train', xyz_noise=noise)
+    loss = m.compute_loss(pred, gt, **lk)
+    opred, ogt, olk = om.call(batch, 'train', xyz_noise=noise)
+    oloss = om.compute_loss(opred, ogt, **olk)
+    assert np.allclose(loss.cpu().numpy(), oloss.numpy(), atol=2e-6, rtol=1e-4)
+
+
+def test_full_size_properties(ctx):
+    """800x800-scale properties the oracle cannot check in seconds: linearity of the
+    rendering equation in the env-map before tonemapping, permutation equivariance
+    over rays, and OLAT consistency (sum of OLAT renders == white-light render)."""
+    from nerfactor_b200 import _lib
+    m, _, _ = _stage_b(ctx, 'microfacet', 16, 32, seed=31)
+    n = 20000
+    batch = synth.make_stage_b_batch(32, n, 512, fg_frac=1.0)
+    xyz, nrm, cam = dev(batch[6], ctx), dev(batch[7], ctx), dev(batch[2], ctx)
+    albedo = dev(np.full((n, 3), .5, np.float32), ctx)
+    rough = dev(np.full((n, 1), .4, np.float32), ctx)
+    lvis = m._pred_lvis_at(xyz)
+    args = dict(lxyz=m.lxyz, lareas=m.lareas, rough=rough, f0=0.04, linear2srgb=False)
+    la = torch.rand((1, 512, 3), device=ctx.device) * 1e-3     # small: stay below the clip
+    lb = torch.rand((1, 512, 3), device=ctx.device) * 1e-3
+    ra = _lib.integrate_fwd(ctx, xyz, nrm, cam, albedo, lvis, light=la, **args)
+    rb = _lib.integrate_fwd(ctx, xyz, nrm, cam, albedo, lvis, light=lb, **args)
+    rab = _lib.integrate_fwd(ctx, xyz, nrm, cam, albedo, lvis, light=la + lb, **args)
+    assert rel_l2((ra + rb).cpu(), rab.cpu()) < 1e-5
+    perm = torch.randperm(n, device=ctx.device)
+    lvis_p = m._pred_lvis_at(xyz[perm].contiguous())
+    assert torch.equal(lvis_p, lvis[perm])                  # rays are independent
+    olat = _lib.integrate_olat_fwd(ctx, xyz, nrm, cam, albedo, lvis, olat_inten=1e-3,
+                                   ambient=0., **args)
+    white = _lib.integrate_fwd(ctx, xyz, nrm, cam, albedo, lvis,
+                               light=torch.full((1, 512, 3), 1e-3, device=ctx.device), **args)
+    assert rel_l2(olat.sum(1).cpu(), white[:, 0].cpu()) < 1e-4
