@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""Headline benchmark: rays/sec of the render-and-relight hot path.
+
+A step = one full view of BASELINE.json configs[1] ("lego_3072 geometry: 800x800,
+128 spp, 512 light dirs, microfacet BRDF"): ray generation -> 128-sample sigma-MLP
+march -> surface points (Stage A), then normal / light-visibility / albedo /
+roughness MLPs, GGX BRDF and the 512-light rendering equation (Stage B) -> sRGB.
+Synthetic data, random-init networks of the reference architecture.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N > 1 runs under torchrun (one rank per GPU): every rank renders its own full view
+(weak scaling, north star "rays shard naturally"), and one NCCL all-gather per
+step assembles all images on every rank.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_SIGMA = 982528       # per sample  
+FLOP_LVIS = 144640        # per (ray, light)
+FLOP_POINT = 131328       # per ray, normal / albedo nets (rough: 130816)
+FALLBACK_PEAKS = {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--imh', type=int, default=800)
+    ap.add_argument('--imw', type=int, default=800)
+    ap.add_argument('--spp', type=int, default=128, help='sigma-MLP samples per ray')
+    ap.add_argument('--light-h', type=int, default=16)
+    ap.add_argument('--sigma-precision', default=os.environ.get('NF_SIGMA_PREC', 'auto'))
+    ap.add_argument('--cpu-sample-rays', type=int, default=2048)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        d['source'] = 'measured (MEASURED_PEAKS.json)'
+        return d
+    d = dict(FALLBACK_PEAKS)
+    d['source'] = 'fallback (B200_PROFILING.md)'
+    return d
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop = index, [], threading.Event()
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop.is_set():
+            try:
+                o = subprocess.run(
+                    ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                     '--format=csv,noheader,nounits'], capture_output=True, text=True,
+                    timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([x.strip() for x in o.split(',')])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unsampled']}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names)
+                   if any(r[3 + i].lower().startswith('active') for r in self.rows)]
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(self.rows[0][1]),
+                'power_w_max': max(float(r[2]) for r in self.rows), 'reasons': reasons,
+                'samples': len(self.rows)}
+
+
+# ------------------------------------------------------------------ reference arm
+def cpu_reference_rays_per_s(args, n_rays, steps, warmup):
+    """The oracle (op-for-op CPU restatement of the reference; TF cannot run here) on a
+    bounded sample of the same workload: n_rays rays at the same S and L."""
+    from oracle import stage_a, stage_b, brdf as obrdf
+    from nerfactor_b200 import synth
+    torch.set_num_threads(os.cpu_count())
+    lh = args.light_h
+    params = synth.make_stage_b_params(0, 'microfacet', light_hw=(lh, 2 * lh))
+    nerf = synth.make_nerf_params(0)
+    lxyz, lareas = obrdf.gen_light_xyz(lh, 2 * lh)
+    om = stage_b.StageB(params, {'brdf': 'microfacet'}, lxyz=lxyz, lareas=lareas)
+    rayo, rayd = stage_a.gen_rays(synth.look_at_c2w(), synth.CAM_ANGLE_X, args.imh, args.imw)
+    sel = np.linspace(0, args.imh * args.imw - 1, n_rays).astype(np.int64)
+    ro = torch.tensor(rayo.reshape(-1, 3)[sel])
+    rd = stage_a.l2_normalize(torch.tensor(rayd.reshape(-1, 3)[sel]), 1)
+
+    def step():
+        a = stage_a.march_single_pass(nerf, ro, rd, 2., 6., args.spp, use_fine=True)
+        alpha = torch.clamp(a['occu'], 0., 1.)[:, None]
+        xyz = a['surf'] * alpha
+        z3 = torch.zeros((n_rays, 3))
+        batch = (None, None, ro, rd, z3, alpha, xyz, z3, torch.zeros((n_rays, 2 * lh * lh)))
+        return om.call(batch, 'test')[0]['rgb']
+
+    with torch.no_grad():
+        for _ in range(warmup):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        dt = (time.perf_counter() - t0) / steps
+    return n_rays / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    n = args.cpu_sample_rays
+    rps, dt = cpu_reference_rays_per_s(args, n, max(1, args.steps), max(1, min(args.warmup, 1)))
+    sample = '%d of %d rays per step, same S=%d and L=%d' % (
+        n, args.imh * args.imw, args.spp, 2 * args.light_h ** 2)
+    line = {
+        'impl': 'reference', 'metric': 'rays/sec', 'value': rps, 'unit': 'rays/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(args, 'cpu'),
+        'cpu_baseline': {'value': rps, 'unit': 'rays/s', 'cores': os.cpu_count(),
+                         'kind': 'port', 'sample': sample},
+        'e2e': {'value': rps, 'unit': 'rays/s', 'h2d_bytes_per_step': 0,
+                'd2h_bytes_per_step': 0},
+        'note': 'restated reference (PyTorch-CPU oracle); TensorFlow 2.2 is not installable here'}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, sigma_prec):
+    return {'workload': 'configs[1]: %dx%d view, %d sigma-MLP samples/ray (single pass), '
+                        '%d light dirs, microfacet BRDF' % (
+                            args.imw, args.imh, args.spp, 2 * args.light_h ** 2),
+            'rays_per_view': args.imh * args.imw, 'samples_per_ray': args.spp,
+            'light_dirs': 2 * args.light_h ** 2, 'brdf': 'microfacet',
+            'precision': {'sigma_mlp': sigma_prec, 'lvis_mlp': 'f16 operands / f32 accum',
+                          'point_mlps': 'f32', 'render': 'f32'},
+            'l2_policy': 'per-step working set (lvis 1.3 GB, sigma 0.33 GB) exceeds the 126 MB L2',
+            'parallelism': 'one view per GPU + all_gather of images'}
+
+
+# ------------------------------------------------------------------------ our arm
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        return run_reference(args)
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    from nerfactor_b200 import _lib, synth, config as nfconfig
+    from nerfactor_b200.models.nerfactor_microfacet import Model
+    from nerfactor_b200.models.nerf import Model as NerfModel
+    from nerfactor_b200.pipeline import ViewRenderer
+
+    ctx = _lib.Context(local)
+    lh = args.light_h
+    L = 2 * lh * lh
+    n_rays = args.imh * args.imw
+    sigma_prec = args.sigma_precision
+    nerf = NerfModel(nfconfig.default_config('nerf'), params=synth.make_nerf_params(0), ctx=ctx,
+                     precision='f16')
+    if sigma_prec == 'auto':
+        try:      # tcgen05 sigma kernel if this build has it, else the FP32 CUDA-core path
+            z = _lib.gen_z(ctx, 2., 6., 16, 128)
+            o = torch.zeros((128, 3), device=ctx.device)
+            _lib.sigma_fwd(ctx, nerf.packed_sigma(True), o, o, z, None, 'f16')
+            sigma_prec = 'f16'
+        except _lib.NfError:
+            sigma_prec = 'fp32'
+    nerf.precision = sigma_prec
+    model = Model(nfconfig.default_config('nerfactor_microfacet', light_h=lh),
+                  params=synth.make_stage_b_params(0, 'microfacet', light_hw=(lh, 2 * lh)),
+                  ctx=ctx, precision='f16')
+    vr = ViewRenderer(nerf, model, n_samples=args.spp, use_fine=True)
+    c2w = synth.look_at_c2w(4.0, 30.0 + 45.0 * rank, 30.0)      # one view per rank
+    light_host = torch.rand((lh, 2 * lh, 3)).pin_memory()
+    rgb_host = torch.empty((n_rays, 3)).pin_memory()
+    alpha_host = torch.empty((n_rays, 1)).pin_memory()
+    gathered = torch.empty((world * n_rays, 3), device=ctx.device) if world > 1 else None
+
+    def step_device():
+        pred = vr.render(c2w, synth.CAM_ANGLE_X, args.imh, args.imw)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, pred['rgb'].contiguous())
+        return pred
+
+    def step_e2e():
+        pred = vr.render_to_host(c2w, synth.CAM_ANGLE_X, args.imh, args.imw, light_host,
+                                 rgb_host, alpha_host)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, pred['rgb'].contiguous())
+        return pred
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ctx.launches
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=ctx.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.barrier()
+            ms = float(t.item())
+        return ms, ctx.launches - l0
+
+    with ClockSampler(local) as cs:
+        ms, launches = timed(step_device, args.steps, max(3, args.warmup))
+    clocks = cs.summary()
+    ms_step = ms / args.steps
+    value = world * n_rays / (ms_step * 1e-3)
+    ms_e2e, _ = timed(step_e2e, args.steps, 1)
+    e2e_value = world * n_rays / (ms_e2e / args.steps * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- per-kernel device times (CUDA events on the launching stream) + rooflines
+    pk = peaks()
+    a = vr.stage_a(c2w, synth.CAM_ANGLE_X, args.imh, args.imw)
+    mask = a['alpha'][:, 0] > 0
+    xyz_m = a['xyz'][mask].contiguous()
+    n_fg = int(xyz_m.shape[0])
+
+    def kt(fn, reps=3):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    rayo, rayd = a['rayo'], a['rayd']
+    z = _lib.gen_z(ctx, nerf.near, nerf.far, args.spp, n_rays)
+    t_sigma = kt(lambda: _lib.sigma_fwd(ctx, nerf.packed_sigma(True), rayo, rayd, z, None,
+                                        sigma_prec), 2 if sigma_prec == 'fp32' else 3)
+    t_lvis = kt(lambda: model._pred_lvis_at(xyz_m))
+    lvis = model._pred_lvis_at(xyz_m)
+    t_point = kt(lambda: model._pred_normal_at(xyz_m))
+    nrm = model._pred_normal_at(xyz_m)
+    alb = model._pred_albedo_at(xyz_m)
+    rough = model._pred_brdf_at(xyz_m)
+    cam = rayo[mask].contiguous()
+    light = model.light.reshape(1, -1, 3).contiguous()
+    t_int = kt(lambda: _lib.integrate_fwd(ctx, xyz_m, nrm, cam, alb, lvis, model.lxyz,
+                                          model.lareas, light, rough=rough, f0=0.04))
+    tensor_peak = pk['bf16_tflops_sustained']
+    rf_sigma = {'kernel': 'nf_sigma_fwd (%s)' % sigma_prec, 'bound': 'tensor',
+                'achieved': n_rays * args.spp * FLOP_SIGMA / (t_sigma * 1e-3) / 1e12,
+                'peak': tensor_peak, 'unit': 'TFLOP/s', 'ms': t_sigma, 'traffic': None}
+    rf_lvis = {'kernel': 'nf_lvis_fwd (mlp_tc_kernel f16)', 'bound': 'tensor',
+               'achieved': n_fg * L * FLOP_LVIS / (t_lvis * 1e-3) / 1e12,
+               'peak': tensor_peak, 'unit': 'TFLOP/s', 'ms': t_lvis, 'traffic': None}
+    rf_int = {'kernel': 'nf_integrate_fwd (microfacet)', 'bound': 'hbm',
+              'achieved': n_fg * (4 * L + 64 + 12) / (t_int * 1e-3) / 1e9,
+              'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'ms': t_int, 'traffic': None,
+              'note': 'ALU-bound with the analytic GGX lobe (SURVEY 7 hard parts)'}
+    rf_point = {'kernel': 'nf_point_mlp_fwd (fp32 FFMA)', 'bound': 'fp32-alu',
+                'achieved': n_fg * FLOP_POINT / (t_point * 1e-3) / 1e12, 'peak': None,
+                'unit': 'TFLOP/s', 'ms': t_point, 'traffic': None}
+    for r in (rf_sigma, rf_lvis, rf_int):
+        r['frac'] = r['achieved'] / r['peak']
+    dominant = max((rf_sigma, rf_lvis, rf_int), key=lambda r: r['ms'])
+    dominant = dict(dominant, peak_source=pk['source'] + ', sustained bf16 cuBLAS' if
+                    dominant['bound'] == 'tensor' else pk['source'])
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        rps, dt = cpu_reference_rays_per_s(args, args.cpu_sample_rays, 1, 1)
+        cpu = {'value': rps, 'unit': 'rays/s', 'cores': os.cpu_count(), 'kind': 'port',
+               'sample': '%d of %d rays, same S=%d and L=%d, 1 warm-up + 1 timed pass (%.1f s)'
+                         % (args.cpu_sample_rays, n_rays, args.spp, L, dt)}
+
+    line = {
+        'metric': 'rays/sec', 'value': value, 'unit': 'rays/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': max(3, args.warmup), 'ms_per_step': ms_step,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f16' if sigma_prec != 'fp32' else 'f32+f16', 'data': 'synthetic',
+        'config': workload_config(args, sigma_prec),
+        'e2e': {'value': e2e_value, 'unit': 'rays/s',
+                'h2d_bytes_per_step': int(light_host.numel() * 4 + 16 * 8 + 8),
+                'd2h_bytes_per_step': int(rgb_host.numel() * 4 + alpha_host.numel() * 4)},
+        'gpu_launches': launches, 'clocks': clocks,
+        'roofline': dominant,
+        'rooflines': [rf_sigma, rf_lvis, rf_int, rf_point],
+        'foreground_rays': n_fg,
+        'cpu_baseline': cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

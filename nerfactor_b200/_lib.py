@@ -130,11 +130,17 @@ class Context:
             raise NfError('nf_ctx_create failed: %s (an sm_100 GPU is required)'
                           % ERRORS.get(rc, rc))
         self.h = h
+        self.launches = 0      # kernels of this library enqueued so far
 
     def check(self, rc):
         if rc != NF_OK:
             msg = self.lib.nf_last_error_string(self.h).decode()
             raise NfError('%s: %s' % (ERRORS.get(rc, rc), msg))
+
+    def launch(self, rc):
+        """check() for calls that enqueue one of this library's kernels."""
+        self.launches += 1
+        self.check(rc)
 
     @property
     def sm_count(self):
@@ -203,23 +209,25 @@ class PackedMlp:
 def point_mlp_fwd(ctx, mlp, xyz, xyz_scale=1.0, precision='fp32'):
     n = xyz.shape[0]
     out = torch.empty((n, mlp.out_dim), dtype=torch.float32, device=xyz.device)
-    ctx.check(ctx.lib.nf_point_mlp_fwd(ctx.h, mlp.h, _f32(xyz), n, float(xyz_scale),
+    ctx.launch(ctx.lib.nf_point_mlp_fwd(ctx.h, mlp.h, _f32(xyz), n, float(xyz_scale),
                                        _f32(out), PREC[precision], _stream()))
     return out
 
 
 def lvis_fwd(ctx, mlp, xyz, lxyz, xyz_scale=1.0, precision='f16'):
+    lxyz = lxyz.reshape(-1, 3)
     n, L = xyz.shape[0], lxyz.shape[0]
     out = torch.empty((n, L), dtype=torch.float32, device=xyz.device)
-    ctx.check(ctx.lib.nf_lvis_fwd(ctx.h, mlp.h, _f32(xyz), n, float(xyz_scale), _f32(lxyz),
+    ctx.launch(ctx.lib.nf_lvis_fwd(ctx.h, mlp.h, _f32(xyz), n, float(xyz_scale), _f32(lxyz),
                                   L, _f32(out), PREC[precision], _stream()))
     return out
 
 
 def brdf_learned_fwd(ctx, mlp, xyz, normal, cam, z, lxyz, precision='f16'):
+    lxyz = lxyz.reshape(-1, 3)
     n, L = xyz.shape[0], lxyz.shape[0]
     out = torch.empty((n, L), dtype=torch.float32, device=xyz.device)
-    ctx.check(ctx.lib.nf_brdf_learned_fwd(
+    ctx.launch(ctx.lib.nf_brdf_learned_fwd(
         ctx.h, mlp.h, _f32(xyz), _f32(normal), _f32(cam), _f32(z), n, _f32(lxyz), L,
         _f32(out), PREC[precision], _stream()))
     return out
@@ -229,6 +237,7 @@ def _integrate_args(xyz, normal, cam, albedo, lvis, lxyz, lareas, rough=None, sp
                     light=None, light_idx=None, rgb=None, f0=0.04, spec_scale=1.0,
                     linear2srgb=True):
     a = IntegrateArgs()
+    lxyz, lareas = lxyz.reshape(-1, 3), lareas.reshape(-1)
     a.n, a.n_lights = xyz.shape[0], lxyz.shape[0]
     a.brdf_kind = 0 if spec is None else 1
     a.linear2srgb, a.f0, a.spec_scale = int(linear2srgb), float(f0), float(spec_scale)
@@ -254,18 +263,18 @@ def integrate_fwd(ctx, xyz, normal, cam, albedo, lvis, lxyz, lareas, light, roug
         assert light_idx.dtype == torch.int32
     a = _integrate_args(xyz, normal, cam, albedo, lvis, lxyz, lareas, rough, spec, light,
                         light_idx, rgb, f0, spec_scale, linear2srgb)
-    ctx.check(ctx.lib.nf_integrate_fwd(ctx.h, C.byref(a), _stream()))
+    ctx.launch(ctx.lib.nf_integrate_fwd(ctx.h, C.byref(a), _stream()))
     return rgb
 
 
 def integrate_olat_fwd(ctx, xyz, normal, cam, albedo, lvis, lxyz, lareas, olat_inten,
                        ambient, rough=None, spec=None, f0=0.04, spec_scale=1.0,
                        linear2srgb=True):
-    n, L = xyz.shape[0], lxyz.shape[0]
+    n, L = xyz.shape[0], lxyz.reshape(-1, 3).shape[0]
     out = torch.empty((n, L, 3), dtype=torch.float32, device=xyz.device)
     a = _integrate_args(xyz, normal, cam, albedo, lvis, lxyz, lareas, rough, spec, None,
                         None, None, f0, spec_scale, linear2srgb)
-    ctx.check(ctx.lib.nf_integrate_olat_fwd(ctx.h, C.byref(a), float(olat_inten),
+    ctx.launch(ctx.lib.nf_integrate_olat_fwd(ctx.h, C.byref(a), float(olat_inten),
                                             float(ambient), _f32(out), _stream()))
     return out
 
@@ -274,7 +283,7 @@ def gen_rays(ctx, c2w, cam_angle_x, h, w, normalize=False):
     c2w = np.ascontiguousarray(np.asarray(c2w, dtype=np.float64).reshape(16))
     rayo = torch.empty((h * w, 3), dtype=torch.float32, device=ctx.device)
     rayd = torch.empty((h * w, 3), dtype=torch.float32, device=ctx.device)
-    ctx.check(ctx.lib.nf_gen_rays(
+    ctx.launch(ctx.lib.nf_gen_rays(
         ctx.h, c2w.ctypes.data_as(C.POINTER(C.c_double)), float(cam_angle_x), h, w,
         int(normalize), _f32(rayo), _f32(rayd), _stream()))
     return rayo, rayd
@@ -282,7 +291,7 @@ def gen_rays(ctx, c2w, cam_angle_x, h, w, normalize=False):
 
 def gen_z(ctx, near, far, n_samples, n_rays, lin_in_disp=False, perturb_u=None):
     z = torch.empty((n_rays, n_samples), dtype=torch.float32, device=ctx.device)
-    ctx.check(ctx.lib.nf_gen_z(ctx.h, float(near), float(far), n_samples, n_rays,
+    ctx.launch(ctx.lib.nf_gen_z(ctx.h, float(near), float(far), n_samples, n_rays,
                                int(lin_in_disp),
                                _f32(perturb_u) if perturb_u is not None else None,
                                _f32(z), _stream()))
@@ -300,7 +309,7 @@ def sigma_fwd(ctx, mlp, rayo, rayd, z, bbox=None, precision='f16'):
     n, S = z.shape
     sigma = torch.empty((n, S), dtype=torch.float32, device=z.device)
     bb = _bbox(bbox)
-    ctx.check(ctx.lib.nf_sigma_fwd(ctx.h, mlp.h, _f32(rayo), _f32(rayd), _f32(z), n, S,
+    ctx.launch(ctx.lib.nf_sigma_fwd(ctx.h, mlp.h, _f32(rayo), _f32(rayd), _f32(z), n, S,
                                    bb, _f32(sigma), PREC[precision], _stream()))
     return sigma
 
@@ -310,7 +319,7 @@ def sigma_normal_fwd(ctx, mlp, rayo, rayd, z, bbox=None):
     sigma = torch.empty((n, S), dtype=torch.float32, device=z.device)
     normal = torch.empty((n, S, 3), dtype=torch.float32, device=z.device)
     bb = _bbox(bbox)
-    ctx.check(ctx.lib.nf_sigma_normal_fwd(ctx.h, mlp.h, _f32(rayo), _f32(rayd), _f32(z), n,
+    ctx.launch(ctx.lib.nf_sigma_normal_fwd(ctx.h, mlp.h, _f32(rayo), _f32(rayd), _f32(z), n,
                                           S, bb, _f32(sigma), _f32(normal), _stream()))
     return sigma, normal
 
@@ -323,7 +332,7 @@ def composite(ctx, sigma, z, rayo, rayd, normal=None, want_weights=True, want_su
     depth = torch.empty((n,), dtype=torch.float32, device=dev)
     surf = torch.empty((n, 3), dtype=torch.float32, device=dev) if want_surf else None
     en = torch.empty((n, 3), dtype=torch.float32, device=dev) if normal is not None else None
-    ctx.check(ctx.lib.nf_composite(
+    ctx.launch(ctx.lib.nf_composite(
         ctx.h, _f32(sigma), _f32(z), _f32(rayo), _f32(rayd),
         _f32(normal) if normal is not None else None, n, S,
         _f32(weights) if weights is not None else None, _f32(occu), _f32(depth),
@@ -335,7 +344,7 @@ def composite(ctx, sigma, z, rayo, rayd, normal=None, want_weights=True, want_su
 def gen_z_fine(ctx, z_coarse, weights, n_fine):
     n, Sc = z_coarse.shape
     z_all = torch.empty((n, Sc + n_fine), dtype=torch.float32, device=z_coarse.device)
-    ctx.check(ctx.lib.nf_gen_z_fine(ctx.h, _f32(z_coarse), _f32(weights), n, Sc, n_fine,
+    ctx.launch(ctx.lib.nf_gen_z_fine(ctx.h, _f32(z_coarse), _f32(weights), n, Sc, n_fine,
                                     _f32(z_all), _stream()))
     return z_all
 
@@ -346,7 +355,7 @@ def lvis_rays(ctx, surf, normal, lxyz):
     rayo = torch.empty((n * L, 3), dtype=torch.float32, device=dev)
     rayd = torch.empty((n * L, 3), dtype=torch.float32, device=dev)
     fl = torch.empty((n * L,), dtype=torch.uint8, device=dev)
-    ctx.check(ctx.lib.nf_lvis_rays(ctx.h, _f32(surf), _f32(normal), n, _f32(lxyz), L,
+    ctx.launch(ctx.lib.nf_lvis_rays(ctx.h, _f32(surf), _f32(normal), n, _f32(lxyz), L,
                                    _f32(rayo), _f32(rayd), _ptr(fl), _stream()))
     return rayo, rayd, fl.view(n, L)
 
@@ -355,6 +364,6 @@ def selftest_umma(ctx, a, b, swap_lbo_sbo=False):
     """a, b: [128, K] fp32 CUDA tensors -> a @ b.T through one tcgen05 tile."""
     K = a.shape[1]
     out = torch.empty((128, 128), dtype=torch.float32, device=a.device)
-    ctx.check(ctx.lib.nf_selftest_umma(ctx.h, _f32(a), _f32(b), K, int(swap_lbo_sbo),
+    ctx.launch(ctx.lib.nf_selftest_umma(ctx.h, _f32(a), _f32(b), K, int(swap_lbo_sbo),
                                        _f32(out), _stream()))
     return out

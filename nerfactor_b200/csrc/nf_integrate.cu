@@ -181,6 +181,7 @@ int check_args(nf_ctx* ctx, const nf_integrate_args* a) {
   NF_CHECK_ARG(ctx, a, "null args");
   NF_CHECK_ARG(ctx, a->n >= 0 && a->n_lights > 0 && a->n_lights <= 4096, "bad n / n_lights");
   NF_CHECK_ARG(ctx, a->brdf_kind == 0 || a->brdf_kind == 1, "bad brdf_kind");
+  if (a->n == 0) return NF_OK;
   NF_CHECK_ARG(ctx, a->xyz_d && a->normal_d && a->cam_d && a->albedo_d && a->lvis_d &&
                         a->lxyz_d && a->lareas_d, "null buffer");
   NF_CHECK_ARG(ctx, a->brdf_kind == 0 ? a->rough_d != nullptr : a->spec_d != nullptr,
@@ -195,9 +196,9 @@ extern "C" {
 int nf_integrate_fwd(nf_ctx* ctx, const nf_integrate_args* a, void* stream) {
   int rc = check_args(ctx, a);
   if (rc != NF_OK) return rc;
+  if (a->n == 0) return NF_OK;
   NF_CHECK_ARG(ctx, a->n_envmaps >= 1 && a->light_d && a->rgb_d, "missing env-maps / output");
   NF_CHECK_ARG(ctx, a->envmap_pixels >= 1, "bad envmap_pixels");
-  if (a->n == 0) return NF_OK;
   int ec = a->n_envmaps < E_CHUNK ? a->n_envmaps : E_CHUNK;
   size_t sm = sizeof(float4) * (size_t)a->n_lights * (1 + ec);
   NF_CHECK_ARG(ctx, sm <= ctx->smem_optin, "n_lights too large for shared memory");
@@ -214,9 +215,9 @@ int nf_integrate_olat_fwd(nf_ctx* ctx, const nf_integrate_args* a, float olat_in
                           float ambient, float* rgb_olat_d, void* stream) {
   int rc = check_args(ctx, a);
   if (rc != NF_OK) return rc;
+  if (a->n == 0) return NF_OK;
   NF_CHECK_ARG(ctx, rgb_olat_d, "null output");
   NF_CHECK_ARG(ctx, a->light_idx_d == nullptr, "OLAT needs the identity light map");
-  if (a->n == 0) return NF_OK;
   size_t sm = sizeof(float4) * (size_t)a->n_lights;
   NF_CUDA(ctx, cudaFuncSetAttribute(integrate_olat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   int blocks_needed = (a->n + WARPS - 1) / WARPS;

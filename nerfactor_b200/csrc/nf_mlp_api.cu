@@ -19,8 +19,10 @@ extern "C" {
 
 int nf_point_mlp_fwd(nf_ctx* ctx, const nf_mlp* mlp, const float* xyz_d, int n, float xyz_scale,
                      float* out_d, int precision, void* stream) {
-  NF_CHECK_ARG(ctx, mlp && xyz_d && out_d && n >= 0, "bad argument");
+  NF_CHECK_ARG(ctx, mlp && n >= 0, "bad argument");
   NF_CHECK_ARG(ctx, mlp->d.kind == NF_MLP_POINT, "network is not NF_MLP_POINT");
+  if (n == 0) return NF_OK;
+  NF_CHECK_ARG(ctx, xyz_d && out_d, "null buffer");
   if (precision != NF_PREC_FP32)
     return nf_set_error(ctx, NF_ERR_UNSUPPORTED,
                         "nf_point_mlp_fwd: the per-point networks run in NF_PREC_FP32 only");
@@ -30,8 +32,10 @@ int nf_point_mlp_fwd(nf_ctx* ctx, const nf_mlp* mlp, const float* xyz_d, int n, 
 
 int nf_lvis_fwd(nf_ctx* ctx, const nf_mlp* mlp, const float* xyz_d, int n, float xyz_scale,
                 const float* lxyz_d, int n_lights, float* lvis_d, int precision, void* stream) {
-  NF_CHECK_ARG(ctx, mlp && xyz_d && lxyz_d && lvis_d && n >= 0 && n_lights > 0, "bad argument");
+  NF_CHECK_ARG(ctx, mlp && lxyz_d && n >= 0 && n_lights > 0, "bad argument");
   NF_CHECK_ARG(ctx, mlp->d.kind == NF_MLP_LVIS && mlp->d.out_dim == 1, "network is not NF_MLP_LVIS");
+  if (n == 0) return NF_OK;
+  NF_CHECK_ARG(ctx, xyz_d && lvis_d, "null buffer");
   if (precision == NF_PREC_FP32)
     return nf_simt_launch(ctx, mlp, (long long)n * n_lights, n_lights, xyz_scale, xyz_d, lxyz_d,
                           nullptr, nullptr, nullptr, nullptr, lvis_d, (cudaStream_t)stream);
@@ -42,9 +46,11 @@ int nf_lvis_fwd(nf_ctx* ctx, const nf_mlp* mlp, const float* xyz_d, int n, float
 int nf_brdf_learned_fwd(nf_ctx* ctx, const nf_mlp* mlp, const float* xyz_d, const float* normal_d,
                         const float* cam_d, const float* z_d, int n, const float* lxyz_d,
                         int n_lights, float* spec_d, int precision, void* stream) {
-  NF_CHECK_ARG(ctx, mlp && xyz_d && normal_d && cam_d && z_d && lxyz_d && spec_d, "null argument");
+  NF_CHECK_ARG(ctx, mlp && lxyz_d, "null argument");
   NF_CHECK_ARG(ctx, n >= 0 && n_lights > 0, "bad sizes");
   NF_CHECK_ARG(ctx, mlp->d.kind == NF_MLP_BRDF && mlp->d.out_dim == 1, "network is not NF_MLP_BRDF");
+  if (n == 0) return NF_OK;
+  NF_CHECK_ARG(ctx, xyz_d && normal_d && cam_d && z_d && spec_d, "null buffer");
   if (precision == NF_PREC_FP32)
     return nf_simt_launch(ctx, mlp, (long long)n * n_lights, n_lights, 1.f, xyz_d, lxyz_d,
                           normal_d, cam_d, z_d, nullptr, spec_d, (cudaStream_t)stream);
@@ -55,9 +61,11 @@ int nf_brdf_learned_fwd(nf_ctx* ctx, const nf_mlp* mlp, const float* xyz_d, cons
 int nf_sigma_fwd(nf_ctx* ctx, const nf_mlp* mlp, const float* rayo_d, const float* rayd_d,
                  const float* z_d, int n_rays, int n_samples, const float* bbox_host,
                  float* sigma_d, int precision, void* stream) {
-  NF_CHECK_ARG(ctx, mlp && rayo_d && rayd_d && z_d && sigma_d, "null argument");
+  NF_CHECK_ARG(ctx, mlp, "null argument");
   NF_CHECK_ARG(ctx, n_rays >= 0 && n_samples > 0, "bad sizes");
   NF_CHECK_ARG(ctx, mlp->d.kind == NF_MLP_SIGMA && mlp->d.out_dim == 1, "network is not NF_MLP_SIGMA");
+  if (n_rays == 0) return NF_OK;
+  NF_CHECK_ARG(ctx, rayo_d && rayd_d && z_d && sigma_d, "null buffer");
   if (precision == NF_PREC_FP32)
     return nf_simt_launch(ctx, mlp, (long long)n_rays * n_samples, n_samples, 1.f, rayo_d, rayd_d,
                           z_d, nullptr, nullptr, bbox_host, sigma_d, (cudaStream_t)stream);

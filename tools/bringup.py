@@ -22,7 +22,7 @@ for K in (16, 32, 128):
     a = rng.integers(-4, 5, (128, K)).astype(np.float32)
     b = rng.integers(-4, 5, (128, K)).astype(np.float32)
     ref = a @ b.T
-    for swap in (0, 1):
+    for swap in (0,):
         try:
             got = _lib.selftest_umma(ctx, torch.tensor(a).cuda(), torch.tensor(b).cuda(), bool(swap))
             torch.cuda.synchronize()
