@@ -44,7 +44,7 @@ def parse():
     ap.add_argument('--spp', type=int, default=128, help='sigma-MLP samples per ray')
     ap.add_argument('--light-h', type=int, default=16)
     ap.add_argument('--sigma-precision', default=os.environ.get('NF_SIGMA_PREC', 'auto'))
-    ap.add_argument('--cpu-sample-rays', type=int, default=2048)
+    ap.add_argument('--cpu-sample-rays', type=int, default=1024)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     return ap.parse_args()
 
@@ -103,13 +103,25 @@ class ClockSampler:
                 'samples': len(self.rows)}
 
 
+def host_cores():
+    """Cores this process may actually use: affinity mask capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else os.cpu_count()
+    try:
+        q, per = open('/sys/fs/cgroup/cpu.max').read().split()
+        if q != 'max':
+            n = max(1, min(n, int(float(q) / float(per) + 0.5)))
+    except Exception:
+        pass
+    return n
+
+
 # ------------------------------------------------------------------ reference arm
 def cpu_reference_rays_per_s(args, n_rays, steps, warmup):
     """The oracle (op-for-op CPU restatement of the reference; TF cannot run here) on a
     bounded sample of the same workload: n_rays rays at the same S and L."""
     from oracle import stage_a, stage_b, brdf as obrdf
     from nerfactor_b200 import synth
-    torch.set_num_threads(os.cpu_count())
+    torch.set_num_threads(host_cores())
     lh = args.light_h
     params = synth.make_stage_b_params(0, 'microfacet', light_hw=(lh, 2 * lh))
     nerf = synth.make_nerf_params(0)
@@ -152,7 +164,7 @@ def run_reference(args):
         'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': workload_config(args, 'cpu'),
-        'cpu_baseline': {'value': rps, 'unit': 'rays/s', 'cores': os.cpu_count(),
+        'cpu_baseline': {'value': rps, 'unit': 'rays/s', 'cores': host_cores(),
                          'kind': 'port', 'sample': sample},
         'e2e': {'value': rps, 'unit': 'rays/s', 'h2d_bytes_per_step': 0,
                 'd2h_bytes_per_step': 0},
@@ -318,7 +330,7 @@ def main():
     cpu = None
     if not args.no_cpu_baseline:
         rps, dt = cpu_reference_rays_per_s(args, args.cpu_sample_rays, 1, 1)
-        cpu = {'value': rps, 'unit': 'rays/s', 'cores': os.cpu_count(), 'kind': 'port',
+        cpu = {'value': rps, 'unit': 'rays/s', 'cores': host_cores(), 'kind': 'port',
                'sample': '%d of %d rays, same S=%d and L=%d, 1 warm-up + 1 timed pass (%.1f s)'
                          % (args.cpu_sample_rays, n_rays, args.spp, L, dt)}
 

@@ -44,30 +44,38 @@ __device__ __forceinline__ PointCtx load_point(const nf_integrate_args& a, int i
 }
 
 // Returns the achromatic specular term and w = lvis*[cos>0]*cos*area for one pair.
+//
+// GGX lobe of brdf/microfacet/microfacet.py:30-111, algebraically reduced to one division:
+//   D = a2 chi_d / (pi cm^4 (a2 + tan^2)^2)  with tan^2 = (1 - cm^2)/cm^2
+//     = a2 chi_d / (pi u^2),  u = a2 cm^2 + 1 - cm^2           (cm^2 != 0; cm = 0 -> chi_d = 0)
+//   G = chi_g * g_view (per-point, view-side only), chi_g = [(h.v)/(n.v) > 0] = [(h.v)(n.v) > 0]
+//   spec = F G D / (4 |l.n| |v.n|) = F g_view a2 chi / (4 pi u^2 |l.n| |v.n|)   (0 if the
+//   denominator is 0, tf.math.divide_no_nan).
+// The reference re-normalises the already unit light direction inside Microfacet
+// (microfacet.py:46); that second normalisation is the identity to 1 ulp and is skipped.
 __device__ __forceinline__ void eval_pair(const nf_integrate_args& a, const PointCtx& c,
                                           float4 lx, float lvis, float spec_in,
                                           float& spec, float& w) {
-  f3 l1 = l2n(mk3(lx.x, lx.y, lx.z) - c.pt, 1e-6f);              // shape.py:128-135
+  f3 d = mk3(lx.x, lx.y, lx.z) - c.pt;
+  float inv = rsqrtf(fmaxf(dot3(d, d), 1e-6f));                  // shape.py:128-135
+  f3 l1 = d * inv;
   float cosv = dot3(l1, c.n1);                                   // nerfactor.py:325
   w = (cosv > 0.f ? lvis : 0.f) * cosv * lx.w;                   // :329-335 (lx.w = area)
   if (a.brdf_kind == 0) {
-    f3 l2 = l2n(l1, 1e-6f);                                      // microfacet.py:46
-    f3 h = l2n(l2 + c.v2, 1e-6f);                                // :51-52
-    float ldh = dot3(l2, h);
-    float om = 1.f - ldh;
+    f3 hs = l1 + c.v2;
+    f3 h = hs * rsqrtf(fmaxf(dot3(hs, hs), 1e-6f));              // microfacet.py:51-52
+    float om = 1.f - dot3(l1, h);
     float om2 = om * om;
     float f = a.f0 + (1.f - a.f0) * (om2 * om2 * om);            // :106-111
     float cm = dot3(h, c.n2);                                    // :96
-    float chi_d = cm > 0.f ? 1.f : 0.f;
     float cm2 = cm * cm;
-    float tm2 = divide_no_nan(1.f - cm2, cm2);
-    float t = c.alpha2_sq + tm2;
-    float d = divide_no_nan(c.alpha2_sq * chi_d, NF_PI_F * (cm2 * cm2) * (t * t));  // :101-103
+    float u = fmaf(c.alpha2_sq, cm2, 1.f - cm2);
     float hv = dot3(h, c.v2);                                    // :78
-    float chi_g = divide_no_nan(hv, c.cos_v) > 0.f ? 1.f : 0.f;  // :80-81
-    float g = chi_g * c.g_view;
-    float ldn = dot3(l2, c.n2);
-    spec = divide_no_nan(f * g * d, 4.f * fabsf(ldn) * c.abs_vn);  // :58-61
+    bool on = (cm > 0.f) && (hv * c.cos_v > 0.f);                // chi_d, chi_g (:80-81, :97)
+    float ldn = dot3(l1, c.n2);
+    float den = (4.f * NF_PI_F) * (u * u) * (fabsf(ldn) * c.abs_vn);
+    float num = f * (c.g_view * c.alpha2_sq);
+    spec = (on && den != 0.f) ? __fdividef(num, den) : 0.f;      // :58-61
   } else {
     spec = spec_in * a.spec_scale;                               // nerfactor.py:460
   }

@@ -19,8 +19,10 @@
 //  * the two groups ping-pong: while one group runs its epilogue the other
 //    group's MMAs occupy the tensor pipe.
 #include "nf_common.cuh"
+#include "nf_tc_ptx.cuh"
 
 namespace {
+using namespace nftc;
 
 constexpr int TC_WIDTH = 128;
 constexpr int TC_THREADS = 384;
@@ -29,124 +31,6 @@ constexpr int GRP_COLS = 256;      // TMEM columns per worker group
 constexpr int COL_D = 0;           // D accumulator: 128 fp32 columns
 constexpr int COL_AH = 128;        // hidden activations: 64 columns (128 x 16-bit)
 constexpr int COL_AE = 192;        // per-row embedding: <= 16 columns (32 x 16-bit)
-
-// ------------------------------------------------------------------ PTX glue
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {
-  }
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-          smem_u32(dst)),
-      "l"(src), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
-}
-__device__ __forceinline__ void group_bar(int id) {  // 128-thread named barrier
-  asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                   smem_u32(bar))
-               : "memory");
-}
-// D[tmem] (+)= A[tmem] * B[smem desc]   (kind::f16: fp16 or bf16 operands, fp32 accumulate)
-__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
-                                          uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
-#define TC_LD32(r, addr)                                                                         \
-  asm volatile(                                                                                  \
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                  \
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                  \
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"  \
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),      \
-        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),  \
-        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),            \
-        "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),            \
-        "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])             \
-      : "r"(addr))
-
-#define TC_ST16(addr, r)                                                                         \
-  asm volatile(                                                                                  \
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "                                            \
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(addr),    \
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),    \
-      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]),          \
-      "r"(r[15])                                                                                 \
-      : "memory")
-
-#define TC_ST8(addr, r)                                                                          \
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(addr), \
-               "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]),      \
-               "r"(r[7])                                                                         \
-               : "memory")
-
-// pack two fp32 into one 16-bit pair register: lo -> bits [0,16), hi -> bits [16,32)
-template <int BF16, int RELU>
-__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
-  uint32_t d;
-  if (BF16) {
-    if (RELU) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-    else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-  } else {
-    if (RELU) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-    else asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-  }
-  return d;
-}
-
-// K-major, swizzle-free shared-memory operand descriptor (cute UMMA::SmemDescriptor):
-// core matrix = 8 rows x 16 bytes, rows 16 B apart; SBO = bytes between 8-row groups
-// along N, LBO = bytes between core matrices along K.
-__device__ __forceinline__ uint64_t make_b_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
-  return d;                // base_offset 0, lbo_mode 0, layout SWIZZLE_NONE
-}
-// kind::f16 instruction descriptor: D=f32, A/B = f16|bf16, K-major, M=128, N=128
-__device__ __forceinline__ uint32_t make_idesc(int bf16, int n) {
-  uint32_t fmt = bf16 ? 1u : 0u;
-  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
-}
 
 // ------------------------------------------------------------- kernel params
 struct TcParams {
@@ -418,18 +302,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const TcParams p)
           phd ^= 1u;
           tc_fence_after();
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
-            uint32_t r[32];
-            TC_LD32(r, tb + COL_D + cc * 32);
+          for (int c2 = 0; c2 < 2; ++c2) {
+            uint32_t r0[32], r1[32];
+            TC_LD32(r0, tb + COL_D + c2 * 64);
+            TC_LD32(r1, tb + COL_D + c2 * 64 + 32);
             tc_wait_ld();
             uint32_t pk[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              float2 bb = *reinterpret_cast<const float2*>(bias + cc * 32 + 2 * i);
-              pk[i] = pack2<BF16, 1>(__uint_as_float(r[2 * i]) + bb.x,
-                                     __uint_as_float(r[2 * i + 1]) + bb.y);
+              float2 bb = *reinterpret_cast<const float2*>(bias + c2 * 64 + 2 * i);
+              pk[i] = pack2<BF16, 1>(__uint_as_float(r0[2 * i]) + bb.x,
+                                     __uint_as_float(r0[2 * i + 1]) + bb.y);
             }
-            TC_ST16(tb + COL_AH + cc * 16, pk);
+            TC_ST16(tb + COL_AH + c2 * 32, pk);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float2 bb = *reinterpret_cast<const float2*>(bias + c2 * 64 + 32 + 2 * i);
+              pk[i] = pack2<BF16, 1>(__uint_as_float(r1[2 * i]) + bb.x,
+                                     __uint_as_float(r1[2 * i + 1]) + bb.y);
+            }
+            TC_ST16(tb + COL_AH + c2 * 32 + 16, pk);
           }
           tc_wait_st();
           tc_fence_before();
@@ -441,14 +333,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const TcParams p)
         tc_fence_after();
         float acc = 0.f;
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          uint32_t r[32];
-          TC_LD32(r, tb + COL_D + cc * 32);
+        for (int c2 = 0; c2 < 2; ++c2) {
+          uint32_t r0[32], r1[32];
+          TC_LD32(r0, tb + COL_D + c2 * 64);
+          TC_LD32(r1, tb + COL_D + c2 * 64 + 32);
           tc_wait_ld();
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            float h = fmaxf(__uint_as_float(r[i]) + beff3[cc * 32 + i], 0.f);
-            acc = fmaf(h, s_aux[AUX_WOUT + cc * 32 + i], acc);
+            float h = fmaxf(__uint_as_float(r0[i]) + beff3[c2 * 64 + i], 0.f);
+            acc = fmaf(h, s_aux[AUX_WOUT + c2 * 64 + i], acc);
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float h = fmaxf(__uint_as_float(r1[i]) + beff3[c2 * 64 + 32 + i], 0.f);
+            acc = fmaf(h, s_aux[AUX_WOUT + c2 * 64 + 32 + i], acc);
           }
         }
         float o = acc + s_aux[AUX_BOUT];
@@ -575,8 +473,11 @@ int launch_tc(nf_ctx* ctx, const nf_mlp* m, const TcParams& p, cudaStream_t st) 
 //     (light direction or Rusinkiewicz encoding), zero-padded to KE rows.
 //   aux (fp32): b0..b3 [4][128], w_out [128], b_out [4], Wx0 [NR_PAD][128],
 //     Wx3 [NR_PAD][128] = the rows of W0 / W3 that multiply the per-point columns.
+int nf_sigma_tc_pack(nf_mlp* m);  // nf_sigma_tc.cu
+
 int nf_tc_pack(nf_mlp* m) {
   const nf_mlp_desc& d = m->d;
+  if (d.kind == NF_MLP_SIGMA) return nf_sigma_tc_pack(m);
   const bool pair_kind = d.kind == NF_MLP_LVIS || d.kind == NF_MLP_BRDF;
   if (!pair_kind || d.width != 128 || d.depth != 4 || d.skip_at != 2 || d.out_dim != 1) return NF_OK;
   const int KE = d.kind == NF_MLP_LVIS ? 32 : 16;
@@ -670,12 +571,6 @@ int nf_tc_brdf_launch(nf_ctx* ctx, const nf_mlp* m, const float* xyz, const floa
   p.xyz = xyz; p.lxyz = lxyz; p.normal = normal; p.cam = cam; p.zlat = z; p.out = spec;
   return precision == NF_PREC_BF16 ? launch_tc<NF_MLP_BRDF, 1>(ctx, m, p, st)
                                    : launch_tc<NF_MLP_BRDF, 0>(ctx, m, p, st);
-}
-
-int nf_tc_sigma_launch(nf_ctx* ctx, const nf_mlp*, const float*, const float*, const float*, int,
-                       int, const float*, float*, int, cudaStream_t) {
-  return nf_set_error(ctx, NF_ERR_UNSUPPORTED,
-                      "nf_sigma_fwd: tcgen05 path for the 8x256 sigma network not built yet");
 }
 
 // Diagnostics (not part of the reference surface): single-tile tcgen05 self-test.

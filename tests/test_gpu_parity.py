@@ -65,6 +65,44 @@ def test_march_single_pass_fp32_vs_oracle_and_golden(ctx, golden_dir):
     assert rel_l2(out['surf'].cpu(), g['sp_surf']) < 1e-5
 
 
+@pytest.mark.parametrize('shape', [(8, 8, 32), (37, 5, 128), (50, 41, 77)])
+def test_sigma_tcgen05_vs_fp32_kernel_and_oracle(ctx, shape):
+    """tcgen05 f16 sigma kernel (ragged tile counts, S not a tile divisor) against the
+    FP32 kernel; the FP32 kernel against the oracle; bbox masking is exact."""
+    from nerfactor_b200 import _lib
+    h, w, S = shape
+    model = _nerf_model(ctx, 3)
+    ro, rd = _rays(ctx, h, w)
+    z = _lib.gen_z(ctx, 2., 6., S, h * w)
+    mlp_s = model.packed_sigma(True)
+    s32 = _lib.sigma_fwd(ctx, mlp_s, ro, rd, z, None, 'fp32')
+    s16 = _lib.sigma_fwd(ctx, mlp_s, ro, rd, z, None, 'f16')
+    sbf = _lib.sigma_fwd(ctx, mlp_s, ro, rd, z, None, 'bf16')
+    assert rel_l2(s16.cpu(), s32.cpu()) < 3e-3
+    assert rel_l2(sbf.cpu(), s32.cpu()) < 3e-2
+    if h * w * S <= 4096:
+        pts = (ro[:, None, :] + rd[:, None, :] * z[:, :, None]).reshape(-1, 3).cpu()
+        so = stage_a.eval_sigma_mlp(synth.make_nerf_params(3), pts, True).reshape(h * w, S)
+        assert rel_l2(s32.cpu(), so) < 5e-5
+    bb = [-1., 1., -1., 1., -1., 1.]
+    pts = ro[:, None, :] + rd[:, None, :] * z[:, :, None]
+    outside = ((pts < -1.) | (pts > 1.)).any(-1)
+    for prec in ('fp32', 'f16'):
+        sb = _lib.sigma_fwd(ctx, mlp_s, ro, rd, z, bb, prec)
+        assert float(sb[outside].abs().max()) == 0.
+        ref = s32 if prec == 'fp32' else s16
+        assert torch.equal(sb[~outside], ref[~outside])
+    _, occ32, d32, _, _ = _lib.composite(ctx, s32, z, ro, rd)
+    _, occ16, d16, _, _ = _lib.composite(ctx, s16, z, ro, rd)
+    # fp16 operands: sigma is good to ~1e-3 relative; depth / occupancy follow, except on
+    # the rare ray whose LAST sample has sigma within rounding of 0: its delta is 1e10
+    # (nerf.py:188-191), so alpha_last jumps between 0 and 1 -- a discontinuity of the
+    # reference algorithm itself.  Hence percentiles, not max.
+    dd, do = (d32 - d16).abs(), (occ32 - occ16).abs()
+    assert float(dd.mean()) < 3e-3 and float(torch.quantile(dd, 0.99)) < 2e-2
+    assert float(torch.quantile(do, 0.99)) < 5e-3
+
+
 def test_gen_z_and_gen_z_fine_vs_oracle(ctx):
     from nerfactor_b200 import _lib
     rng = np.random.default_rng(0)
