@@ -195,6 +195,10 @@ def main():
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
+        # keep stdout to the single JSON line: NCCL's banner / debug output goes to stderr
+        if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
+            os.environ['NCCL_DEBUG'] = 'WARN'
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     from nerfactor_b200 import _lib, synth, config as nfconfig

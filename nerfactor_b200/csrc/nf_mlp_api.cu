@@ -73,13 +73,4 @@ int nf_sigma_fwd(nf_ctx* ctx, const nf_mlp* mlp, const float* rayo_d, const floa
                             precision, (cudaStream_t)stream);
 }
 
-int nf_sigma_normal_fwd(nf_ctx* ctx, const nf_mlp* mlp, const float* rayo_d, const float* rayd_d,
-                        const float* z_d, int n_rays, int n_samples, const float* bbox_host,
-                        float* sigma_d, float* normal_d, void* stream) {
-  (void)mlp; (void)rayo_d; (void)rayd_d; (void)z_d; (void)n_rays; (void)n_samples;
-  (void)bbox_host; (void)sigma_d; (void)normal_d; (void)stream;
-  return nf_set_error(ctx, NF_ERR_UNSUPPORTED,
-                      "nf_sigma_normal_fwd: d sigma / d xyz kernel not built yet (SURVEY 8a a7)");
-}
-
 }  // extern "C"

@@ -103,6 +103,42 @@ def test_sigma_tcgen05_vs_fp32_kernel_and_oracle(ctx, shape):
     assert float(torch.quantile(do, 0.99)) < 5e-3
 
 
+def test_sigma_normal_kernel_vs_oracle_autograd(ctx):
+    """-l2_normalize(d relu(sigma) / d xyz) (geometry_from_nerf.py:285-300) vs torch autograd."""
+    from nerfactor_b200 import _lib
+    model = _nerf_model(ctx, 3)
+    ro, rd = _rays(ctx, 7, 9)
+    S = 19                                             # 63 x 19 rows: ragged last CTA
+    z = _lib.gen_z(ctx, 2., 6., S, 63)
+    sig, nrm = _lib.sigma_normal_fwd(ctx, model.packed_sigma(True), ro, rd, z)
+    pts = (ro[:, None, :] + rd[:, None, :] * z[:, :, None]).reshape(-1, 3).cpu()
+    so, no = stage_a.sigma_and_normal(synth.make_nerf_params(3), pts)
+    assert rel_l2(sig.cpu().reshape(-1), so.reshape(-1)) < 5e-5
+    got, exp = nrm.cpu().reshape(-1, 3).numpy(), no.numpy()
+    live = np.linalg.norm(exp, axis=1) > 0.5           # where relu is active
+    assert live.sum() > 100
+    assert np.abs(got[live] - exp[live]).max() < 2e-3
+    assert np.abs(got[~live]).max() < 1e-6             # zero gradient -> zero normal
+    # the fp32 forward inside the gradient kernel equals the plain fp32 kernel
+    s32 = _lib.sigma_fwd(ctx, model.packed_sigma(True), ro, rd, z, None, 'fp32')
+    assert rel_l2(sig.cpu(), s32.cpu()) < 1e-6
+
+
+def test_compute_depth_and_normal_vs_golden(ctx, golden_dir):
+    """Hierarchical camera->surface march (geometry_from_nerf.py:249-319), 32 + 48 samples."""
+    from nerfactor_b200 import geometry_from_nerf as gfn
+    g = np.load(os.path.join(golden_dir, 'oracle_stage_a.npz'))
+    model = _nerf_model(ctx, int(g['seed_nerf']))
+    ro, rd = _rays(ctx, 8, 8)
+    cfg = nfconfig.default_config('nerf', n_samples_coarse=-32, n_samples_fine=-16)
+    occu, depth, normal = gfn.compute_depth_and_normal(model, ro, rd, cfg, precision='fp32')
+    d = np.abs(depth.cpu().numpy() - g['h_depth'])
+    assert np.median(d) < 1e-4 and np.quantile(d, 0.95) < 5e-3
+    assert np.abs(occu.cpu().numpy() - g['h_occu']).max() < 1e-3
+    dn = np.abs(normal.cpu().numpy() - g['h_normal']).max(axis=1)
+    assert np.median(dn) < 1e-3 and np.quantile(dn, 0.95) < 2e-2
+
+
 def test_gen_z_and_gen_z_fine_vs_oracle(ctx):
     from nerfactor_b200 import _lib
     rng = np.random.default_rng(0)
