@@ -107,7 +107,9 @@ __global__ void __launch_bounds__(NTHREADS) mlp_simt_kernel(const SimtParams p) 
     } else if (p.kind == NF_MLP_SIGMA) {
       f3 o = ld3(p.xyz + ray * 3), d = ld3(p.aux0 + ray * 3);
       float z = live ? p.aux1[g] : 0.f;
-      f3 pt = mk3(o.x + d.x * z, o.y + d.y * z, o.z + d.z * z);   // gfn.py:264
+      // pts = rayo + rayd * z (gfn.py:264): multiply then add, like the TF / oracle ops
+      f3 pt = mk3(__fadd_rn(o.x, __fmul_rn(d.x, z)), __fadd_rn(o.y, __fmul_rn(d.y, z)),
+                  __fadd_rn(o.z, __fmul_rn(d.z, z)));
       if (live && sub < 3) {
         float pc = sub == 0 ? pt.x : (sub == 1 ? pt.y : pt.z);
         embed_comp(xr, 0, sub, pc, p.n_freqs_a);

@@ -247,6 +247,48 @@ def test_stage_b_l512_rgb_within_1e4(ctx, brdf):
     assert rel_l2(pred['rgb_olat'].cpu().numpy()[:, :40], opred['rgb_relit']) < 1e-4
 
 
+def test_config3_learned_brdf_1024_lights_on_16x32_envmap(ctx):
+    """BASELINE configs[2]: learned-MERL BRDF, L = 1024 light directions (16x64 grid) looking
+    up a 16x32 HDR env-map through the nearest-pixel index map (SURVEY 8d caveat on L)."""
+    from nerfactor_b200.models.nerfactor import Model
+    params = synth.make_stage_b_params(41, 'learned', light_hw=(16, 32))
+    lxyz, lareas = obrdf.gen_light_xyz(16, 64)
+    idx = synth.light_index_map((16, 32), (16, 64))
+    m = Model(nfconfig.default_config('nerfactor'), params=params, ctx=ctx, precision='f16')
+    m.set_lights(lxyz.reshape(-1, 3), lareas.reshape(-1), light_idx=idx)
+    om = stage_b.StageB(params, {'brdf': 'learned'}, lxyz=lxyz, lareas=lareas, light_idx=idx)
+    batch = synth.make_stage_b_batch(42, 77, 1024)
+    probes = synth.make_probes(43, 2, (16, 32))
+    for i, p_ in enumerate(probes):
+        m.novel_probes['hdr%d' % i] = p_
+    pred, _, _, _ = m.call(batch, 'test', relight_probes=True)
+    opred, _, _ = om.call(batch, 'test', relight_lights=[p_ for p_ in probes])
+    assert pred['lvis'].shape == (77, 1024)
+    assert rel_l2(pred['rgb'].cpu(), opred['rgb']) < 1e-4
+    assert rel_l2(pred['rgb_probes'].cpu(), opred['rgb_relit']) < 1e-4
+
+
+def test_config5_relight_sweep_eight_envmaps(ctx):
+    """BASELINE configs[4] per-GPU slice: one view relit under 8 env-maps in one call
+    (two passes of four inside nf_integrate_fwd)."""
+    m, om, _ = _stage_b(ctx, 'learned', 16, 32, seed=51, precision='f16')
+    batch = synth.make_stage_b_batch(52, 150, 512)
+    probes = synth.make_probes(53, 8, (16, 32))
+    for i, p_ in enumerate(probes):
+        m.novel_probes['env%d' % i] = p_
+    pred, _, _, _ = m.call(batch, 'test', relight_probes=True)
+    opred, _, _ = om.call(batch, 'test', relight_lights=[p_ for p_ in probes])
+    assert pred['rgb_probes'].shape == (150, 8, 3)
+    assert rel_l2(pred['rgb_probes'].cpu(), opred['rgb_relit']) < 1e-4
+    # overrides of test.py:91-132: global albedo override and BRDF-latent override
+    z = np.array([0.01, -0.02, 0.005], np.float32)
+    alb = np.array([0.3, 0.5, 0.7], np.float32)
+    p2, _, _, _ = m.call(batch, 'test', albedo_override=alb, brdf_z_override=z)
+    o2, _, _ = om.call(batch, 'test', albedo_override=alb, brdf_z_override=z)
+    assert rel_l2(p2['rgb'].cpu(), o2['rgb']) < 1e-4
+    assert rel_l2(p2['albedo'].cpu(), o2['albedo']) < 1e-6
+
+
 def test_lvis_and_brdf_kernels_fp32_vs_f16_vs_oracle(ctx):
     from nerfactor_b200 import _lib
     m, om, params = _stage_b(ctx, 'learned', 16, 32, seed=5, precision='f16')
