@@ -1,0 +1,208 @@
+"""Differentiable train-mode forward of the NeRFactor models.
+
+A train step works on `n_rays_per_step` = 1024 rays (nerfactor.ini:93), i.e. 0.5 M
+(ray, light) rows -- three orders of magnitude less than a test-time view.  The Dense
+contractions (>99.9 % of the step's FLOPs) run in this library's CUDA kernels through
+`DenseFn` (nf_dense_fwd / nf_dense_bwd); the O(N L) element-wise rendering math around
+them is expressed in torch ops on the device so torch.autograd provides its adjoint,
+with the reference's custom gradients (nerfactor/util/math.py:24-60) kept as explicit
+autograd Functions.  Forward values equal the fused inference kernels' (same formulas).
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+
+
+# ------------------------------------------------------------------ Dense layers
+
+class DenseFn(torch.autograd.Function):
+    """act([x1 | x2] @ w + b) through nf_dense_fwd / nf_dense_bwd."""
+
+    @staticmethod
+    def forward(ctx, x1, x2, w, b, act):
+        c = _lib.default_context()
+        x1 = x1.contiguous()
+        x2c = None if x2 is None else x2.contiguous()
+        w, b = w.contiguous(), b.contiguous()
+        if w.data_ptr() % 16:            # cp.async needs 16-byte aligned weight rows
+            w = w.clone()
+        y = _lib.dense_fwd(c, x1, x2c, w, b, act)
+        ctx.save_for_backward(x1, x2c if x2c is not None else x1.new_empty(0), w, y)
+        ctx.has_x2, ctx.act = x2c is not None, act
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x1, x2, w, y = ctx.saved_tensors
+        x2 = x2 if ctx.has_x2 else None
+        c = _lib.default_context()
+        n1, n2 = ctx.needs_input_grad[0], ctx.has_x2 and ctx.needs_input_grad[1]
+        dx1, dx2, dw, db = _lib.dense_bwd(c, x1, x2, w, y, dy.contiguous(), ctx.act, n1, n2)
+        return dx1, dx2, dw, db, None
+
+
+def _pad_to4(n):
+    return (n + 3) // 4 * 4
+
+
+def mlp_apply(x, layers, acts, skip_at):
+    """mlp.Network.__call__ (nerfactor/networks/mlp.py:39-50) + seq.Network for the head.
+    layers: [(W[in,out], b[out]), ...] torch tensors (Keras layout).  Inputs / outputs
+    whose width is not a multiple of 4 are zero-padded for the kernels (and sliced back)."""
+    in_dim = x.shape[1]
+    in_pad = _pad_to4(in_dim)
+    xp = F.pad(x, (0, in_pad - in_dim)) if in_pad != in_dim else x
+    h, h_skip = xp, None
+    for i, ((w, b), act) in enumerate(zip(layers, acts)):
+        n = w.shape[1]
+        n_pad = _pad_to4(n)
+        if h_skip is not None:                      # layer after the skip: [hidden | input]
+            wh, wx = w[:w.shape[0] - in_dim], w[w.shape[0] - in_dim:]
+            wx = F.pad(wx, (0, 0, 0, in_pad - in_dim))
+            wfull = torch.cat((wh, wx), 0)
+            x1, x2 = h, h_skip
+        else:
+            wfull = F.pad(w, (0, 0, 0, h.shape[1] - w.shape[0])) if h.shape[1] != w.shape[0] else w
+            x1, x2 = h, None
+        if n_pad != n:
+            wfull = F.pad(wfull, (0, n_pad - n))
+            bfull = F.pad(b, (0, n_pad - n))
+        else:
+            bfull = b
+        y = DenseFn.apply(x1, x2, wfull, bfull, act)
+        h = y[:, :n] if n_pad != n else y
+        h_skip = xp if (skip_at is not None and i in skip_at) else None
+    return h
+
+
+def embed(x, n_freqs):
+    """nerfactor/networks/embedder.py:46-47."""
+    out = [x]
+    for k in range(n_freqs):
+        out += [torch.sin(x * float(2 ** k)), torch.cos(x * float(2 ** k))]
+    return torch.cat(out, -1)
+
+
+# ------------------------------------------------------- TF semantics with custom grads
+
+def safe_l2_normalize(x, axis, eps=1e-6):
+    """nerfactor/util/math.py:63-64 (tf.linalg.l2_normalize)."""
+    sq = torch.sum(x * x, dim=axis, keepdim=True)
+    return x * torch.rsqrt(torch.clamp(sq, min=eps))
+
+
+class SafeAcos(torch.autograd.Function):
+    """nerfactor/util/math.py:42-60."""
+
+    @staticmethod
+    def forward(ctx, x):
+        xc = torch.clamp(x, -1., 1.)
+        ctx.save_for_backward(xc)
+        return torch.acos(xc)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (xc,) = ctx.saved_tensors
+        denom = torch.sqrt(1. - xc ** 2 + 1e-6) + 1e-6
+        return dy * (-1. / denom)
+
+
+class SafeAtan2(torch.autograd.Function):
+    """nerfactor/util/math.py:24-39: z = atan2(x, y)."""
+
+    @staticmethod
+    def forward(ctx, x, y):
+        ctx.save_for_backward(x, y)
+        return torch.atan2(x, y)
+
+    @staticmethod
+    def backward(ctx, dz):
+        x, y = ctx.saved_tensors
+        denom = x ** 2 + y ** 2 + 1e-6
+        return dz * (y / denom), dz * (-x / denom)
+
+
+def divide_no_nan(a, b):
+    a, b = torch.broadcast_tensors(a, b)
+    safe = torch.where(b == 0, torch.ones_like(b), b)
+    return torch.where(b == 0, torch.zeros_like(a), a / safe)
+
+
+def gen_world2local(normal, eps=1e-6):
+    """nerfactor/util/geom.py:119-149."""
+    normal = safe_l2_normalize(normal, 1)
+    z = (torch.tensor((0., 0., 1.), device=normal.device) + eps)[None, :].expand_as(normal)
+    t = safe_l2_normalize(torch.linalg.cross(normal, z), 1)
+    b = safe_l2_normalize(torch.linalg.cross(normal, t), 1)
+    return torch.stack((t, b, normal), dim=1)
+
+
+def dir2rusink(a, b):
+    """nerfactor/util/geom.py:152-192."""
+    a = safe_l2_normalize(a, 1)
+    b = safe_l2_normalize(b, 1)
+    h = safe_l2_normalize((a + b) / 2, 1)
+    theta_h = SafeAcos.apply(h[:, 2])
+    phi_h = SafeAtan2.apply(h[:, 1], h[:, 0])
+    binormal = torch.tensor((0., 1., 0.), device=a.device)
+    normal = torch.tensor((0., 0., 1.), device=a.device)
+
+    def rot_vec(vector, axis, angle):
+        cos_ang, sin_ang = torch.cos(angle).reshape(-1), torch.sin(angle).reshape(-1)
+        axis = axis.reshape(1, 3)
+        return vector * cos_ang[:, None] + \
+            axis * (vector @ axis.t()) * (1 - cos_ang)[:, None] + \
+            torch.linalg.cross(axis.expand_as(vector), vector) * sin_ang[:, None]
+
+    diff = rot_vec(rot_vec(b, normal, -phi_h), binormal, -theta_h)
+    theta_d = SafeAcos.apply(diff[:, 2])
+    at = SafeAtan2.apply(diff[:, 1], diff[:, 0])
+    phi_d = at - torch.floor(at / math.pi) * math.pi          # tf.math.floormod
+    return torch.stack((phi_d, theta_h, theta_d), dim=1)
+
+
+def microfacet_brdf(pts2l, pts2c, normal, albedo, rough, f0):
+    """brdf/microfacet/microfacet.py:30-111."""
+    pts2l = safe_l2_normalize(pts2l, 2)
+    pts2c = safe_l2_normalize(pts2c, 1)
+    normal = safe_l2_normalize(normal, 1)
+    h = safe_l2_normalize(pts2l + pts2c[:, None, :], 2)
+    f = f0 + (1 - f0) * (1 - torch.einsum('ijk,ijk->ij', pts2l, h)) ** 5
+    alpha = rough ** 2
+    cos_theta_m = torch.einsum('ijk,ik->ij', h, normal)
+    chi = (cos_theta_m > 0).to(h.dtype)
+    cm2 = cos_theta_m ** 2
+    tm2 = divide_no_nan(1 - cm2, cm2)
+    d = divide_no_nan(alpha ** 2 * chi, math.pi * cm2 ** 2 * (alpha ** 2 + tm2) ** 2)
+    cos_theta_v = torch.einsum('ij,ij->i', normal, pts2c)
+    div = divide_no_nan(torch.einsum('ijk,ik->ij', h, pts2c), cos_theta_v[:, None])
+    chi_g = (div > 0).to(h.dtype)
+    cv2 = torch.clamp(cos_theta_v ** 2, 0., 1.)
+    tv2 = torch.clamp(divide_no_nan(1 - cv2, cv2), min=0.)
+    g = divide_no_nan(chi_g * 2, 1 + torch.sqrt(1 + alpha ** 2 * tv2[:, None]))
+    l_dot_n = torch.einsum('ijk,ik->ij', pts2l, normal)
+    denom = 4 * torch.abs(l_dot_n) * torch.abs(cos_theta_v)[:, None]
+    spec = divide_no_nan(f * g * d, denom)
+    return spec[:, :, None] + (albedo / math.pi)[:, None, :]
+
+
+def linear2srgb(x):
+    """nerfactor/util/img.py:140-163."""
+    x = torch.clamp(x, 0., 1.)
+    # pow(0, 1/2.4) has an infinite derivative: TF evaluates it too and selects afterwards
+    nonlin = 1.055 * torch.pow(torch.clamp(x, min=1e-30), 1 / 2.4) - 0.055
+    return torch.where(x <= 0.0031308, x * 12.92, nonlin)
+
+
+def render(lvis, brdf, surf2l, normal, light_flat, lareas, srgb):
+    """nerfactor/models/nerfactor.py:315-342 for one env-map."""
+    cos = torch.einsum('ijk,ik->ij', surf2l, normal)
+    front_lit = (cos > 0).to(cos.dtype)
+    lv = front_lit * lvis
+    contrib = brdf * (lv[:, :, None] * light_flat[None, :, :]) * cos[:, :, None] * \
+        lareas.reshape(1, -1, 1)
+    rgb = torch.clamp(torch.sum(contrib, dim=1), 0., 1.)
+    return linear2srgb(rgb) if srgb else rgb

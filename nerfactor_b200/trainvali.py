@@ -1,0 +1,276 @@
+"""Mirror of the train / validation step of nerfactor/trainvali.py (:110-127 optimizer,
+:273-295 distributed_train_step, :301-317 vali step) for the shape and NeRFactor models.
+
+    trainer = Trainer(model, config)          # model: nerfactor_b200.models.{shape,nerfactor,...}
+    loss = trainer.train_step(batch)          # forward (train mode) + backward + AMSGrad
+    trainer.sync_to_model()                   # push weights back for the inference kernels
+
+Data parallelism (trainvali.py:259-295, MirroredStrategy): one process per GPU; each rank
+gets its own rays, the per-ray loss is divided by the GLOBAL batch size
+(tf.nn.compute_average_loss, :282-283) and the flat gradient buffer is summed with ONE
+NCCL all-reduce before the optimizer step.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import autodiff as ad
+from .models.shape import to_device
+
+
+class Trainer:
+    def __init__(self, model, config=None, world_size=1, rank=0):
+        self.model = model
+        self.ctx = model.ctx
+        self.device = model.device
+        cfg = config or model.config
+        self.lr0 = cfg.getfloat('DEFAULT', 'lr', fallback=5e-3)
+        self.lr_decay_steps = cfg.getint('DEFAULT', 'lr_decay_steps', fallback=500_000)
+        self.lr_decay_rate = cfg.getfloat('DEFAULT', 'lr_decay_rate', fallback=0.1)
+        self.world_size, self.rank = world_size, rank
+        self.iterations = 0
+        # ---- flat parameter buffer: every trainable Dense kernel / bias, then the light
+        self.names, shapes = [], []
+        for net_name, net in model.net.items():
+            for li, layer in enumerate(net.layers):
+                if layer.trainable:
+                    self.names += [(net_name, li, 'kernel'), (net_name, li, 'bias')]
+                    shapes += [layer.kernel.shape, layer.bias.shape]
+        self.has_light = hasattr(model, '_light')
+        if self.has_light:
+            self.names.append(('light', 0, 'light'))
+            shapes.append(tuple(model._light.shape))
+        sizes = [int(np.prod(s)) for s in shapes]
+        # every view starts on a 16-byte boundary (the kernels stream weights with cp.async 16)
+        padded = [(n + 3) // 4 * 4 for n in sizes]
+        self.offsets = np.concatenate(([0], np.cumsum(padded))).astype(np.int64)
+        total = int(self.offsets[-1])
+        self.flat = torch.zeros(total, device=self.device)
+        for (net_name, li, kind), off, shp in zip(self.names, self.offsets[:-1], shapes):
+            if kind == 'light':
+                src = model._light
+            else:
+                layer = model.net[net_name].layers[li]
+                src = torch.as_tensor(getattr(layer, kind))
+            self.flat[off:off + src.numel()] = src.reshape(-1).to(self.device)
+        self.shapes = shapes
+        self.m = torch.zeros_like(self.flat)
+        self.v = torch.zeros_like(self.flat)
+        self.vhat = torch.zeros_like(self.flat)
+        # frozen BRDF prior (nerfactor.py:58-60), device copies
+        self.brdf_layers = None
+        if getattr(model, 'brdf_model', None) is not None:
+            bm = model.brdf_model
+            self.brdf_layers = [(to_device(w, self.device), to_device(b, self.device))
+                                for w, b in bm.net['brdf_mlp'].weights() + bm.net['brdf_out'].weights()]
+
+    # ------------------------------------------------------------------ params
+    def views(self, flat=None):
+        """name -> tensor views of the flat buffer (autograd leaf = the flat buffer)."""
+        flat = self.flat if flat is None else flat
+        out = {}
+        for (net_name, li, kind), off, shp in zip(self.names, self.offsets[:-1], self.shapes):
+            n = int(np.prod(shp))
+            out[(net_name, li, kind)] = flat[off:off + n].view(*shp)
+        return out
+
+    def net_layers(self, views, name):
+        """[(W, b), ...] of trunk + head `name` ('normal', 'lvis', 'albedo', 'brdf_z')."""
+        layers = []
+        for part in ('_mlp', '_out'):
+            net = self.model.net[name + part]
+            for li, layer in enumerate(net.layers):
+                key = (name + part, li, 'kernel')
+                if key in views:
+                    layers.append((views[key], views[(name + part, li, 'bias')]))
+                else:      # frozen layer
+                    layers.append((to_device(layer.kernel, self.device),
+                                   to_device(layer.bias, self.device)))
+        trunk = self.model.net[name + '_mlp']
+        head = self.model.net[name + '_out']
+        acts = [l.activation for l in trunk.layers] + [l.activation for l in head.layers]
+        return layers, acts, trunk.skip_at
+
+    def sync_to_model(self):
+        """Writes the trained weights back into model.net / model._light (re-packs lazily)."""
+        v = self.views()
+        for (net_name, li, kind), t in v.items():
+            if kind == 'light':
+                self.model._light = t.detach().clone()
+            else:
+                layer = self.model.net[net_name].layers[li]
+                arr = t.detach().cpu().numpy().copy()
+                if kind == 'kernel':
+                    layer.kernel = arr
+                else:
+                    layer.bias = arr
+        self.model.weights_changed()
+
+    def learning_rate(self):
+        """ExponentialDecay(lr, decay_steps, decay_rate), continuous (trainvali.py:113-117)."""
+        return self.lr0 * self.lr_decay_rate ** (self.iterations / self.lr_decay_steps)
+
+    # ------------------------------------------------------------------ forward
+    def _point(self, views, name, pts):
+        layers, acts, skip = self.net_layers(views, name)
+        e = ad.embed(self.model.xyz_scale * pts, self.model.embedder['xyz'].n_freqs)
+        return ad.mlp_apply(e, layers, acts, skip)
+
+    def _lvis(self, views, pts, surf2l):
+        layers, acts, skip = self.net_layers(views, 'lvis')
+        n, L = surf2l.shape[0], surf2l.shape[1]
+        m = self.model
+        e_x = ad.embed(m.xyz_scale * pts, m.embedder['xyz'].n_freqs)
+        e_l = ad.embed(surf2l.reshape(-1, 3), m.embedder['ldir'].n_freqs)
+        e = torch.cat((e_x[:, None, :].expand(n, L, e_x.shape[1]).reshape(n * L, -1), e_l), -1)
+        return ad.mlp_apply(e, layers, acts, skip).reshape(n, L)
+
+    def _brdf_learned(self, surf2l, surf2c, normal, albedo, z):
+        """nerfactor.py:413-461 (all pairs evaluated; back-lit ones are zeroed, :454-455)."""
+        m = self.model
+        n, L = surf2l.shape[0], surf2l.shape[1]
+        w2l = ad.gen_world2local(normal)
+        vdir = torch.einsum('jkl,jl->jk', w2l, surf2c)
+        ldir = torch.einsum('jkl,jnl->jnk', w2l, surf2l)
+        ldir_flat = ldir.reshape(-1, 3)
+        vdir_flat = vdir[:, None, :].expand(n, L, 3).reshape(-1, 3)
+        rusink = ad.dir2rusink(ldir_flat, vdir_flat)
+        z_flat = z[:, None, :].expand(n, L, z.shape[1]).reshape(n * L, -1)
+        front = (ldir_flat[:, 2] > 0).to(z.dtype)
+        e = torch.cat((z_flat, ad.embed(rusink, m.embedder['rusink'].n_freqs)), 1)
+        trunk = m.brdf_model.net['brdf_mlp']
+        acts = [l.activation for l in trunk.layers] + ['softplus']
+        spec = ad.mlp_apply(e, self.brdf_layers, acts, trunk.skip_at)[:, 0] * front
+        scale = m.config.getfloat('DEFAULT', 'learned_brdf_scale')
+        return albedo[:, None, :] / math.pi + (spec.reshape(n, L, 1) * scale).expand(n, L, 3)
+
+    def forward(self, flat, batch, mode, xyz_noise=None):
+        """Differentiable `Model.call` (shape.py:146-182 / nerfactor.py:181-313) + loss."""
+        m = self.model
+        views = self.views(flat)
+        dev = self.device
+        _, _, rayo, _, rgb, alpha, xyz, normal, lvis = batch
+        rayo, rgb, alpha, xyz, normal, lvis = [to_device(x, dev) for x in
+                                               (rayo, rgb, alpha, xyz, normal, lvis)]
+        is_shape = not hasattr(m, 'shape_mode')
+        jitter_std = m.config.getfloat('DEFAULT', 'xyz_jitter_std')
+        if is_shape:
+            sel = lambda x: x
+            ind = None
+        else:
+            mask = alpha[:, 0] > 0
+            ind = torch.nonzero(mask, as_tuple=False)[:, 0]
+            sel = lambda x: x.index_select(0, ind)
+        rayo_m, rgb_m, xyz_m, normal_m, lvis_m = [sel(x) for x in (rayo, rgb, xyz, normal, lvis)]
+        if xyz_noise is None and jitter_std > 0:
+            xyz_noise = torch.randn_like(xyz_m) * jitter_std
+        elif xyz_noise is not None:
+            xyz_noise = to_device(xyz_noise, dev)
+        lxyz = m.lxyz.reshape(1, -1, 3)
+        surf2l = ad.safe_l2_normalize(lxyz - xyz_m[:, None, :], 2)          # shape.py:128-135
+        xyz_j = None if xyz_noise is None else xyz_m + xyz_noise
+
+        n_full = alpha.shape[0]
+
+        def scatter(v):
+            if v is None or ind is None:
+                return v
+            out = torch.zeros((n_full,) + tuple(v.shape[1:]), dtype=v.dtype, device=dev)
+            return out.index_copy(0, ind, v)
+
+        if is_shape:
+            normal_pred = ad.safe_l2_normalize(self._point(views, 'normal', xyz_m) + 1e-6, 1)
+            normal_j = None
+            if xyz_j is not None and m.normal_smooth_weight > 0:
+                normal_j = ad.safe_l2_normalize(self._point(views, 'normal', xyz_j) + 1e-6, 1)
+            lvis_pred = self._lvis(views, xyz_m, surf2l)
+            lvis_j = None
+            if xyz_j is not None and m.lvis_smooth_weight > 0:
+                lvis_j = self._lvis(views, xyz_j, surf2l)
+            pred = {'normal': normal_pred, 'lvis': lvis_pred}
+            gt = {'normal': normal, 'lvis': lvis, 'alpha': alpha}
+            loss = m.compute_loss(pred, gt, normal_jitter=normal_j, lvis_jitter=lvis_j)
+            return loss, pred
+
+        surf2c = ad.safe_l2_normalize(rayo_m - xyz_m, 1)                     # shape.py:137-144
+        if m.shape_mode == 'nerf':
+            normal_pred, normal_j = normal_m, None
+            lvis_pred, lvis_j = torch.clamp(lvis_m, 1e-8, 1.), None
+        else:
+            normal_pred = self._point(views, 'normal', xyz_m) + 1e-6
+            normal_j = None if xyz_j is None else self._point(views, 'normal', xyz_j) + 1e-6
+            lvis_pred = self._lvis(views, xyz_m, surf2l)
+            lvis_j = None if xyz_j is None else self._lvis(views, xyz_j, surf2l)
+        normal_pred = ad.safe_l2_normalize(normal_pred, 1)
+        if normal_j is not None:
+            normal_j = ad.safe_l2_normalize(normal_j, 1)
+        slope = m.config.getfloat('DEFAULT', 'albedo_slope', fallback=0.7)
+        bias = m.config.getfloat('DEFAULT', 'albedo_bias', fallback=0.1)
+        albedo = slope * self._point(views, 'albedo', xyz_m) + bias
+        albedo_j = None if xyz_j is None else slope * self._point(views, 'albedo', xyz_j) + bias
+        z = self._point(views, 'brdf_z', xyz_m)
+        z_j = None if xyz_j is None else self._point(views, 'brdf_z', xyz_j)
+        if m.normalize_brdf_z:
+            z = ad.safe_l2_normalize(z, 1)
+            z_j = None if z_j is None else ad.safe_l2_normalize(z_j, 1)
+        if getattr(m, 'brdf_model', None) is not None:
+            brdf = self._brdf_learned(surf2l, surf2c, normal_pred, albedo, z)
+        else:
+            brdf = ad.microfacet_brdf(surf2l, surf2c, normal_pred, albedo, z,
+                                      m.config.getfloat('DEFAULT', 'fresnel_f0'))
+        light = torch.clamp(views[('light', 0, 'light')], min=0.)
+        light_flat = light.reshape(-1, 3)
+        if m.light_idx is not None:
+            light_flat = light_flat[m.light_idx.long()]
+        rgb_pred = ad.render(lvis_pred, brdf, surf2l, normal_pred, light_flat, m.lareas,
+                             m.config.getboolean('DEFAULT', 'linear2srgb'))
+        pred = {'rgb': scatter(rgb_pred), 'normal': scatter(normal_pred),
+                'lvis': scatter(lvis_pred), 'albedo': scatter(albedo), 'brdf': scatter(z)}
+        gt = {'rgb': scatter(rgb_m), 'normal': scatter(normal_m), 'lvis': scatter(lvis_m),
+              'alpha': alpha}
+        m_light = m._light
+        m._light = views[('light', 0, 'light')]       # compute_loss reads self.light (TV prior)
+        try:
+            loss = m.compute_loss(pred, gt, mode=mode, normal_jitter=scatter(normal_j),
+                                  lvis_jitter=scatter(lvis_j), brdf_prop_jitter=scatter(z_j),
+                                  albedo_jitter=scatter(albedo_j))
+        finally:
+            m._light = m_light
+        return loss, pred
+
+    # ------------------------------------------------------------------ steps
+    def loss_and_grad(self, batch, xyz_noise=None, global_batch=None):
+        """-> (per-ray loss [N], flat gradient of sum(loss) / global_batch)."""
+        flat = self.flat.detach().requires_grad_(True)
+        loss, _ = self.forward(flat, batch, 'train', xyz_noise)
+        gb = global_batch or (loss.shape[0] * self.world_size)
+        total = torch.sum(loss) / gb                      # tf.nn.compute_average_loss
+        (grad,) = torch.autograd.grad(total, flat)
+        return loss.detach(), grad
+
+    def train_step(self, batch, xyz_noise=None):
+        """trainvali.py:273-295: one optimizer iteration; returns the summed loss / global bs."""
+        loss, grad = self.loss_and_grad(batch, xyz_noise)
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(grad, op=dist.ReduceOp.SUM)   # gradient all-reduce (one flat buffer)
+        lr = self.learning_rate()
+        self.iterations += 1
+        _lib.adam_amsgrad_step(self.ctx, self.flat, grad.contiguous(), self.m, self.v, self.vhat,
+                               lr, self.iterations)
+        total = torch.sum(loss) / (loss.shape[0] * self.world_size)
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(total, op=dist.ReduceOp.SUM)
+        return total
+
+    @torch.no_grad()
+    def vali_step(self, batch):
+        """trainvali.py:301-317: forward in 'vali' mode through the fused inference kernels."""
+        self.sync_to_model()
+        pred, gt, loss_kwargs, _ = self.model.call(batch, 'vali')
+        if 'mode' not in loss_kwargs:
+            return self.model.compute_loss(pred, gt, **loss_kwargs)
+        return self.model.compute_loss(pred, gt, **loss_kwargs)

@@ -123,14 +123,43 @@ def gen_world2local(normal, eps=1e-6):
     return torch.stack((t, b, normal), dim=1)
 
 
+class _SafeAcos(torch.autograd.Function):
+    """nerfactor/util/math.py:42-60: acos(clip(x)) with the reference's custom gradient
+    -1 / (sqrt(1 - x_clip^2 + eps) + eps), eps = 1e-6."""
+
+    @staticmethod
+    def forward(ctx, x):
+        xc = torch.clamp(x, -1., 1.)
+        ctx.save_for_backward(xc)
+        return torch.acos(xc)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (xc,) = ctx.saved_tensors
+        return dy * (-1. / (torch.sqrt(1. - xc ** 2 + 1e-6) + 1e-6))
+
+
+class _SafeAtan2(torch.autograd.Function):
+    """nerfactor/util/math.py:24-39: atan2(x, y) with denominators x^2 + y^2 + eps."""
+
+    @staticmethod
+    def forward(ctx, x, y):
+        ctx.save_for_backward(x, y)
+        return torch.atan2(x, y)
+
+    @staticmethod
+    def backward(ctx, dz):
+        x, y = ctx.saved_tensors
+        denom = x ** 2 + y ** 2 + 1e-6
+        return dz * (y / denom), dz * (-x / denom)
+
+
 def safe_acos(x):
-    """nerfactor/util/math.py:42-60 forward: acos(clip(x, -1, 1))."""
-    return torch.acos(torch.clamp(x, -1., 1.))
+    return _SafeAcos.apply(x)
 
 
 def safe_atan2(x, y):
-    """nerfactor/util/math.py:24-39 forward: atan2(x, y)."""
-    return torch.atan2(x, y)
+    return _SafeAtan2.apply(x, y)
 
 
 def dir2rusink(a, b):

@@ -41,7 +41,10 @@ def linear2srgb(x):
     """nerfactor/util/img.py:140-163: pow on all elements, then select."""
     x = torch.clamp(x, 0., 1.)
     lin = x * 12.92
-    nonlin = 1.055 * torch.pow(x, 1 / 2.4) - (1.055 - 1)
+    # forward: identical to pow(x, 1/2.4) wherever that branch is selected; the floor only
+    # keeps the UNSELECTED branch's derivative finite at x = 0 (TF's pow gradient uses
+    # mul_no_nan there), so autograd gives the reference's gradient instead of 0 * inf
+    nonlin = 1.055 * torch.pow(torch.clamp(x, min=1e-30), 1 / 2.4) - (1.055 - 1)
     return torch.where(x <= 0.0031308, lin, nonlin)
 
 

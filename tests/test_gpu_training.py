@@ -1,0 +1,171 @@
+"""Training path (BASELINE configs[3] semantics at test size): Dense forward / backward
+kernels, AMSGrad kernel and the full train-step gradient against the oracle's autograd."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import stage_b, brdf as obrdf
+from nerfactor_b200 import synth, config as nfconfig
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_l2(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+@pytest.fixture(scope='module')
+def ctx():
+    from nerfactor_b200 import _lib
+    return _lib.default_context()
+
+
+@pytest.mark.parametrize('shape', [(1000, 92, 0, 128, 'relu'), (777, 128, 92, 128, 'relu'),
+                                   (513, 128, 0, 4, 'sigmoid'), (300, 256, 64, 256, 'relu'),
+                                   (130, 20, 0, 128, 'softplus'), (64, 128, 0, 4, None)])
+def test_dense_fwd_bwd_vs_torch(ctx, shape):
+    from nerfactor_b200 import autodiff as ad
+    m, k1, k2, n, act = shape
+    g = torch.Generator(device='cpu').manual_seed(m)
+    x1 = torch.randn((m, k1), generator=g).cuda().requires_grad_(True)
+    x2 = torch.randn((m, k2), generator=g).cuda().requires_grad_(True) if k2 else None
+    w = (torch.randn((k1 + k2, n), generator=g) * 0.1).cuda().requires_grad_(True)
+    b = (torch.randn((n,), generator=g) * 0.1).cuda().requires_grad_(True)
+    dy = torch.randn((m, n), generator=g).cuda()
+    y = ad.DenseFn.apply(x1, x2, w, b, act)
+    ins = [x1, w, b] + ([x2] if k2 else [])
+    grads = torch.autograd.grad(y, ins, dy)
+    xcat = (x1 if x2 is None else torch.cat((x1, x2), 1)).detach().double()
+    wd = w.detach().double()
+    pre = xcat @ wd + b.detach().double()
+    f = {'relu': torch.relu, 'sigmoid': torch.sigmoid, 'softplus': torch.nn.functional.softplus,
+         None: lambda t: t}[act]
+    yr = f(pre)
+    assert rel_l2(y.detach().cpu(), yr.cpu()) < 1e-5
+    # reference adjoint with act' evaluated on the kernel's own output (a pre-activation within
+    # rounding of 0 may flip the ReLU mask between fp32 and fp64; that is not a kernel error)
+    yk = y.detach().double()
+    dact = {'relu': (yk > 0).double(), 'sigmoid': yk * (1 - yk), 'softplus': 1 - torch.exp(-yk),
+            None: torch.ones_like(yk)}[act]
+    dz = dy.double() * dact
+    dx = dz @ wd.t()
+    ref = [dx[:, :k1], xcat.t() @ dz, dz.sum(0)] + ([dx[:, k1:]] if k2 else [])
+    for a, r in zip(grads, ref):
+        assert rel_l2(a.cpu(), r.cpu()) < 2e-5
+
+
+def test_amsgrad_kernel_vs_numpy(ctx):
+    from nerfactor_b200 import _lib
+    rng = np.random.default_rng(0)
+    n = 10007
+    p = rng.standard_normal(n).astype(np.float32)
+    pt = torch.tensor(p).cuda()
+    mt, vt, vh = [torch.zeros(n, device='cuda') for _ in range(3)]
+    pm, m, v, vhat = p.astype(np.float64), np.zeros(n), np.zeros(n), np.zeros(n)
+    b1, b2, eps = 0.9, 0.999, 1e-7
+    for step in range(1, 6):
+        g = rng.standard_normal(n).astype(np.float32) * (1.0 if step != 3 else 10.0)
+        lr = 5e-3 * 0.1 ** ((step - 1) / 500000)
+        _lib.adam_amsgrad_step(ctx, pt, torch.tensor(g).cuda(), mt, vt, vh, lr, step)
+        m = b1 * m + (1 - b1) * g
+        v = b2 * v + (1 - b2) * g.astype(np.float64) ** 2
+        vhat = np.maximum(vhat, v)
+        lr_t = lr * np.sqrt(1 - b2 ** step) / (1 - b1 ** step)
+        pm = pm - lr_t * m / (np.sqrt(vhat) + eps)
+    assert np.allclose(pt.cpu().numpy(), pm, atol=2e-6)
+
+
+def _models(ctx, brdf, lh=2, lw=8, seed=7, shape_mode='finetune'):
+    from importlib import import_module
+    name = 'nerfactor_microfacet' if brdf == 'microfacet' else 'nerfactor'
+    Model = import_module('nerfactor_b200.models.' + name).Model
+    params = synth.make_stage_b_params(seed, brdf, light_hw=(lh, lw))
+    cfg = nfconfig.default_config(name, light_h=lh, shape_mode=shape_mode)
+    m = Model(cfg, params=params, ctx=ctx, precision='fp32')
+    lxyz, lareas = obrdf.gen_light_xyz(lh, lw)
+    m.set_lights(lxyz.reshape(-1, 3), lareas.reshape(-1))
+    m.light_res = (lh, lw)
+    return m, params, (lxyz, lareas)
+
+
+def _oracle_grads(params, brdf, lights, batch, noise, shape_mode='finetune'):
+    tp = {}
+    leaves = {}
+    for k, v in params.items():
+        if k == 'light':
+            t = torch.tensor(v, requires_grad=True)
+            tp[k] = t
+            leaves[('light', 0, 'light')] = t
+        else:
+            layers = []
+            for li, (w, b) in enumerate(v['layers']):
+                wt, bt = torch.tensor(w, requires_grad=True), torch.tensor(b, requires_grad=True)
+                layers.append((wt, bt))
+                leaves[(k, li, 'kernel')], leaves[(k, li, 'bias')] = wt, bt
+            tp[k] = dict(v, layers=layers)
+    om = stage_b.StageB(tp, {'brdf': brdf, 'shape_mode': shape_mode}, lxyz=lights[0],
+                        lareas=lights[1])
+    pred, gt, lk = om.call(batch, 'train', xyz_noise=noise)
+    # nerfactor_microfacet.ini:71 sets brdf_smooth_weight = 0 (nerfactor.ini: 0.01)
+    wts = {'brdf_smooth_weight': 0.} if brdf == 'microfacet' else None
+    loss = om.compute_loss(pred, gt, weights=wts, **lk)
+    (loss.sum() / loss.shape[0]).backward()
+    return loss.detach(), leaves
+
+
+@pytest.mark.parametrize('brdf', ['microfacet', 'learned'])
+def test_train_step_gradient_vs_oracle_autograd(ctx, brdf):
+    from nerfactor_b200.trainvali import Trainer
+    m, params, lights = _models(ctx, brdf)
+    batch = synth.make_stage_b_batch(11, 48, 16)
+    nfg = int((batch[5][:, 0] > 0).sum())
+    noise = (0.01 * np.random.default_rng(2).standard_normal((nfg, 3))).astype(np.float32)
+    tr = Trainer(m)
+    loss, grad = tr.loss_and_grad(batch, xyz_noise=noise)
+    oloss, leaves = _oracle_grads(params, brdf, lights, batch, noise)
+    assert np.allclose(loss.cpu().numpy(), oloss.numpy(), atol=1e-5, rtol=1e-4)
+    gv = tr.views(grad)
+    checked = 0
+    for key, t in leaves.items():
+        if key not in gv:
+            assert key[0].startswith('brdf_mlp') or key[0].startswith('brdf_out')   # frozen prior
+            continue
+        ref = t.grad.numpy()
+        got = gv[key].cpu().numpy()
+        scale = max(np.abs(ref).max(), 1e-8)
+        assert np.abs(got - ref).max() / scale < 2e-3, key
+        checked += 1
+    assert checked >= 17
+
+
+def test_training_reduces_loss_and_syncs_back(ctx):
+    from nerfactor_b200.trainvali import Trainer
+    m, params, lights = _models(ctx, 'microfacet')
+    batch = synth.make_stage_b_batch(5, 64, 16, fg_frac=1.0)
+    tr = Trainer(m)
+    tr.lr0 = 1e-3
+    noise = np.zeros((64, 3), np.float32)
+    losses = [float(tr.train_step(batch, xyz_noise=noise)) for _ in range(25)]
+    assert losses[-1] < 0.9 * losses[0]
+    assert tr.iterations == 25
+    before = m.net['albedo_mlp'].layers[0].kernel.copy()
+    tr.sync_to_model()
+    assert not np.array_equal(before, m.net['albedo_mlp'].layers[0].kernel)
+    pred, _, _, _ = m.call(batch, 'test')          # fused kernels pick up the new weights
+    assert torch.isfinite(pred['rgb']).all()
+
+
+def test_shape_model_train_step(ctx):
+    """shape.py pre-training (normal + visibility MLPs, shape.py:239-277)."""
+    from nerfactor_b200.models.shape import Model
+    from nerfactor_b200.trainvali import Trainer
+    params = synth.make_stage_b_params(3, 'learned', light_hw=(2, 8))
+    m = Model(nfconfig.default_config('shape', light_h=2), params=params, ctx=ctx, precision='fp32')
+    batch = synth.make_stage_b_batch(9, 40, 8)          # light_h = 2 -> 2 x 4 lights
+    tr = Trainer(m)
+    noise = (0.01 * np.random.default_rng(1).standard_normal((40, 3))).astype(np.float32)
+    l0 = float(tr.train_step(batch, xyz_noise=noise))
+    for _ in range(15):
+        l1 = float(tr.train_step(batch, xyz_noise=noise))
+    assert np.isfinite(l0) and l1 < l0
