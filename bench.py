@@ -44,7 +44,7 @@ def parse():
     ap.add_argument('--spp', type=int, default=128, help='sigma-MLP samples per ray')
     ap.add_argument('--light-h', type=int, default=16)
     ap.add_argument('--sigma-precision', default=os.environ.get('NF_SIGMA_PREC', 'auto'))
-    ap.add_argument('--cpu-sample-rays', type=int, default=1024)
+    ap.add_argument('--cpu-sample-rays', type=int, default=8192)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     return ap.parse_args()
 
@@ -312,21 +312,39 @@ def main():
     t_int = kt(lambda: _lib.integrate_fwd(ctx, xyz_m, nrm, cam, alb, lvis, model.lxyz,
                                           model.lareas, light, rough=rough, f0=0.04))
     tensor_peak = pk['bf16_tflops_sustained']
+    alg_sigma = n_rays * args.spp * 4 * 2 + n_rays * 24          # z in, sigma out, rays
+    alg_lvis = n_fg * L * 4 + n_fg * 12
+    alg_int = n_fg * (4 * L + 64 + 12)
     rf_sigma = {'kernel': 'nf_sigma_fwd (%s)' % sigma_prec, 'bound': 'tensor',
                 'achieved': n_rays * args.spp * FLOP_SIGMA / (t_sigma * 1e-3) / 1e12,
-                'peak': tensor_peak, 'unit': 'TFLOP/s', 'ms': t_sigma, 'traffic': None}
+                'peak': tensor_peak, 'unit': 'TFLOP/s', 'ms': t_sigma, 'traffic': None,
+                'algorithmic_bytes': alg_sigma}
     rf_lvis = {'kernel': 'nf_lvis_fwd (mlp_tc_kernel f16)', 'bound': 'tensor',
                'achieved': n_fg * L * FLOP_LVIS / (t_lvis * 1e-3) / 1e12,
-               'peak': tensor_peak, 'unit': 'TFLOP/s', 'ms': t_lvis, 'traffic': None}
+               'peak': tensor_peak, 'unit': 'TFLOP/s', 'ms': t_lvis, 'traffic': None,
+               'algorithmic_bytes': alg_lvis}
     rf_int = {'kernel': 'nf_integrate_fwd (microfacet)', 'bound': 'hbm',
-              'achieved': n_fg * (4 * L + 64 + 12) / (t_int * 1e-3) / 1e9,
+              'achieved': alg_int / (t_int * 1e-3) / 1e9,
               'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'ms': t_int, 'traffic': None,
+              'algorithmic_bytes': alg_int,
               'note': 'ALU-bound with the analytic GGX lobe (SURVEY 7 hard parts)'}
     rf_point = {'kernel': 'nf_point_mlp_fwd (fp32 FFMA)', 'bound': 'fp32-alu',
                 'achieved': n_fg * FLOP_POINT / (t_point * 1e-3) / 1e12, 'peak': None,
                 'unit': 'TFLOP/s', 'ms': t_point, 'traffic': None}
     for r in (rf_sigma, rf_lvis, rf_int):
         r['frac'] = r['achieved'] / r['peak']
+    # DRAM bytes per launch from the committed ncu --set full capture of this exact workload
+    tpath = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        wl = tj['workload']
+        if (wl['imh'], wl['imw'], wl['spp'], wl['light_dirs']) == (args.imh, args.imw, args.spp, L):
+            for r, key in ((rf_sigma, 'sigma'), (rf_lvis, 'lvis'), (rf_int, 'integrate'),
+                           (rf_point, 'point')):
+                if key == 'sigma' and sigma_prec == 'fp32':
+                    continue
+                r['traffic'] = tj['kernels'][key]['dram_bytes']
+                r['traffic_source'] = tj['source']
     dominant = max((rf_sigma, rf_lvis, rf_int), key=lambda r: r['ms'])
     dominant = dict(dominant, peak_source=pk['source'] + ', sustained bf16 cuBLAS' if
                     dominant['bound'] == 'tensor' else pk['source'])
