@@ -50,7 +50,6 @@ struct TcParams {
   const float* cam;      // BRDF: [n,3]
   const float* zlat;     // BRDF: [n,z_dim]
   float* out;            // [n, L]
-  int dbg;               // bit0: skip the bias loads in the epilogue (latency experiment)
 };
 
 // fp32 side block layout (floats): see nf_tc_pack
@@ -311,20 +310,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const TcParams p)
             uint32_t pk[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              float2 bb = (p.dbg & 1) ? make_float2(0.f, 0.f)
-                                      : *reinterpret_cast<const float2*>(bias + c2 * 64 + 2 * i);
+              float2 bb = *reinterpret_cast<const float2*>(bias + c2 * 64 + 2 * i);
               pk[i] = pack2<BF16, 1>(__uint_as_float(r0[2 * i]) + bb.x,
                                      __uint_as_float(r0[2 * i + 1]) + bb.y);
             }
-            if (!(p.dbg & 2)) TC_ST16(tb + COL_AH + c2 * 32, pk);
+            TC_ST16(tb + COL_AH + c2 * 32, pk);
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              float2 bb = (p.dbg & 1) ? make_float2(0.f, 0.f)
-                                      : *reinterpret_cast<const float2*>(bias + c2 * 64 + 32 + 2 * i);
+              float2 bb = *reinterpret_cast<const float2*>(bias + c2 * 64 + 32 + 2 * i);
               pk[i] = pack2<BF16, 1>(__uint_as_float(r1[2 * i]) + bb.x,
                                      __uint_as_float(r1[2 * i + 1]) + bb.y);
             }
-            if (!(p.dbg & 2)) TC_ST16(tb + COL_AH + c2 * 32 + 16, pk);
+            TC_ST16(tb + COL_AH + c2 * 32 + 16, pk);
           }
           tc_wait_st();
           tc_fence_before();
@@ -557,7 +554,6 @@ int nf_tc_lvis_launch(nf_ctx* ctx, const nf_mlp* m, const float* xyz, int n, flo
   NF_CHECK_ARG(ctx, L <= 1024, "n_lights > 1024 not supported by the tcgen05 kernel");
   if (n == 0) return NF_OK;
   p.n = n; p.L = L; p.nr = 3 * (1 + 2 * m->d.n_freqs_a); p.xyz_scale = xyz_scale;
-  { const char* e = getenv("NF_DBG_LVIS"); p.dbg = e ? atoi(e) : 0; }
   p.xyz = xyz; p.lxyz = lxyz; p.out = lvis;
   return precision == NF_PREC_BF16 ? launch_tc<NF_MLP_LVIS, 1>(ctx, m, p, st)
                                    : launch_tc<NF_MLP_LVIS, 0>(ctx, m, p, st);

@@ -53,7 +53,6 @@ struct SigmaTcParams {
   float bbox[6];
   int use_bbox;
   float* sigma;          // [n_rays,S]
-  int dbg;               // bit0: producer copies half of each chunk (bandwidth experiment)
 };
 
 // bytes of the weight chunk for (layer, part): part 0/1 = hidden K-blocks, part 2 = input part
@@ -125,8 +124,8 @@ __global__ void __launch_bounds__(SG_THREADS, 1) sigma_tc_kernel(const SigmaTcPa
               const uint32_t bytes = part_bytes(part);
               const uint32_t slot = fill % SG_NSLOT;
               if (fill >= SG_NSLOT) mbar_wait(bar_empty + slot, ((fill / SG_NSLOT) - 1) & 1);
-              mbar_expect_tx(bar_full + slot, bytes >> (p.dbg & 1));
-              const uint32_t sl = (bytes / CL) >> (p.dbg & 1);
+              mbar_expect_tx(bar_full + slot, bytes);
+              const uint32_t sl = bytes / CL;
               uint8_t* dst = s_ring + (size_t)slot * SG_SLOT_BYTES + cta_rank * sl;
               const uint8_t* src = img + off + cta_rank * sl;
               if (CL > 1) bulk_g2s_mc(dst, src, sl, bar_full + slot, cta_mask);
@@ -428,7 +427,6 @@ int nf_tc_sigma_launch(nf_ctx* ctx, const nf_mlp* m, const float* rayo, const fl
   p.rayo = rayo; p.rayd = rayd; p.z = z; p.S = S; p.sigma = sigma;
   p.total = (long long)n_rays * S;
   if (bbox_host) { memcpy(p.bbox, bbox_host, sizeof(p.bbox)); p.use_bbox = 1; }
-  { const char* e = getenv("NF_DBG_SIGMA"); p.dbg = e ? atoi(e) : 0; }
   const long long tiles = (p.total + 127) / 128;
   static int cl_env = -1;
   if (cl_env < 0) {
