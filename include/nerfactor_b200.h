@@ -240,6 +240,9 @@ int nf_adam_amsgrad_step(nf_ctx* ctx, float* param_d, const float* grad_d, float
  * TMEM / shared-memory operand layouts the fused kernels use (bring-up check).   */
 int nf_selftest_umma(nf_ctx* ctx, const float* a_d, const float* b_d, int K,
                      int swap_lbo_sbo, float* out_d, void* stream);
+/* Same through one CTA-pair MMA (cta_group::2): out[256,128] = a[256,K] * b[128,K]^T.   */
+int nf_selftest_umma2(nf_ctx* ctx, const float* a_d, const float* b_d, int K, float* out_d,
+                      void* stream);
 
 #ifdef __cplusplus
 }

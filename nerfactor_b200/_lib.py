@@ -27,7 +27,7 @@ EXPORTS = [
     'nf_mlp_upload', 'nf_point_mlp_fwd', 'nf_lvis_fwd', 'nf_brdf_learned_fwd',
     'nf_integrate_fwd', 'nf_integrate_olat_fwd', 'nf_gen_rays', 'nf_gen_z',
     'nf_sigma_fwd', 'nf_sigma_normal_fwd', 'nf_composite', 'nf_gen_z_fine',
-    'nf_lvis_rays', 'nf_selftest_umma', 'nf_dense_fwd', 'nf_dense_bwd_workspace_bytes',
+    'nf_lvis_rays', 'nf_selftest_umma', 'nf_selftest_umma2', 'nf_dense_fwd', 'nf_dense_bwd_workspace_bytes',
     'nf_dense_bwd', 'nf_adam_amsgrad_step']
 
 
@@ -92,6 +92,7 @@ def load_library():
     lib.nf_gen_z_fine.argtypes = [vp, vp, vp, i, i, i, vp, vp]
     lib.nf_lvis_rays.argtypes = [vp, vp, vp, i, vp, i, vp, vp, vp, vp]
     lib.nf_selftest_umma.argtypes = [vp, vp, vp, i, i, vp, vp]
+    lib.nf_selftest_umma2.argtypes = [vp, vp, vp, i, vp, vp]
     ll = C.c_longlong
     lib.nf_dense_fwd.argtypes = [vp, vp, i, vp, i, vp, vp, ll, i, i, vp, vp]
     lib.nf_dense_bwd_workspace_bytes.argtypes = [ll, i, i, i]
@@ -415,3 +416,11 @@ def adam_amsgrad_step(ctx, param, grad, m, v, vhat, lr, step, beta1=0.9, beta2=0
     ctx.launch(ctx.lib.nf_adam_amsgrad_step(
         ctx.h, _f32(param), _f32(grad), _f32(m), _f32(v), _f32(vhat), param.numel(), float(lr),
         float(beta1), float(beta2), float(eps), int(step), _stream()))
+
+
+def selftest_umma2(ctx, a, b):
+    """a: [256, K], b: [128, K] fp32 CUDA tensors -> a @ b.T through one CTA-pair tcgen05 tile."""
+    K = a.shape[1]
+    out = torch.empty((256, 128), dtype=torch.float32, device=a.device)
+    ctx.launch(ctx.lib.nf_selftest_umma2(ctx.h, _f32(a), _f32(b), K, _f32(out), _stream()))
+    return out

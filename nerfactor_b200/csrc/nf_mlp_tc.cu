@@ -433,6 +433,65 @@ umma_selftest_kernel(const float* __restrict__ a, const float* __restrict__ b, i
   }
 }
 
+
+// ---- bring-up test of the CTA-pair MMA: D[256 x 128] = A[256 x K] * B[128 x K]^T ----------
+// cluster of 2 CTAs; CTA r holds rows [128 r, 128 r + 128) of A in its TMEM and rows
+// [64 r, 64 r + 64) of B in its shared memory ([K/8][64][8] K-major, no swizzle).
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+umma2_selftest_kernel(const float* __restrict__ a, const float* __restrict__ b, int K,
+                      float* __restrict__ out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint16_t* img = reinterpret_cast<uint16_t*>(smem);            // [K/8][64][8]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + (size_t)K * 64 * 2);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar + 1);
+  const int warp = threadIdx.x >> 5, t = threadIdx.x;
+  const uint32_t rank = cluster_ctarank();
+  for (int i = t; i < K * 64; i += 128) {
+    int n = i / K, k = i % K;
+    __half h = __float2half_rn(b[(rank * 64 + n) * K + k]);
+    img[((size_t)(k / 8) * 64 + n) * 8 + (k % 8)] = *reinterpret_cast<uint16_t*>(&h);
+  }
+  fence_proxy_async();
+  if (t == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 0) tc2_alloc(s_tmem, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+  const uint32_t tb = tmem_base + ((uint32_t)(warp * 32) << 16);
+  const float* arow = a + (size_t)(rank * 128 + t) * K;
+  for (int c0 = 0; c0 < K / 2; c0 += 8) {
+    uint32_t pk[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) pk[i] = pack2<0, 0>(arow[2 * (c0 + i)], arow[2 * (c0 + i) + 1]);
+    TC_ST8(tb + 128 + c0, pk);
+  }
+  tc_wait_st();
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  if (rank == 0 && t == 0) {
+    const uint32_t idesc = make_idesc_mn(0, 256, 128);
+    for (int k = 0; k < K / 16; ++k)
+      tc2_mma_ts(tmem_base, tmem_base + 128 + k * 8,
+                 make_b_desc(smem_u32(img) + k * 2 * 64 * 16, 64 * 16, 128), idesc, k > 0);
+    tc2_commit_mc(bar, 3);
+  }
+  mbar_wait(bar, 0);
+  tc_fence_after();
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) {
+    uint32_t r[32];
+    TC_LD32(r, tb + cc * 32);
+    tc_wait_ld();
+    for (int i = 0; i < 32; ++i) out[(size_t)(rank * 128 + t) * 128 + cc * 32 + i] = __uint_as_float(r[i]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 0) { __syncwarp(); tc2_dealloc(tmem_base, 256); }
+}
+
 // host float -> fp16 / bf16 bits (round to nearest even)
 uint16_t f2h_bits(float f) {
   __half h = __float2half_rn(f);
@@ -580,6 +639,16 @@ extern "C" int nf_selftest_umma(nf_ctx* ctx, const float* a_d, const float* b_d,
   size_t sm = (size_t)K * 128 * 2 + 64;
   NF_CUDA(ctx, cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   umma_selftest_kernel<<<1, 128, sm, (cudaStream_t)stream>>>(a_d, b_d, K, swap_lbo_sbo, out_d);
+  NF_LAUNCH_CHECK(ctx);
+  return NF_OK;
+}
+
+extern "C" int nf_selftest_umma2(nf_ctx* ctx, const float* a_d, const float* b_d, int K,
+                                 float* out_d, void* stream) {
+  NF_CHECK_ARG(ctx, a_d && b_d && out_d && K >= 16 && K <= 128 && K % 16 == 0, "bad argument");
+  size_t sm = (size_t)K * 64 * 2 + 64;
+  NF_CUDA(ctx, cudaFuncSetAttribute(umma2_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  umma2_selftest_kernel<<<2, 128, sm, (cudaStream_t)stream>>>(a_d, b_d, K, out_d);
   NF_LAUNCH_CHECK(ctx);
   return NF_OK;
 }

@@ -325,6 +325,322 @@ __global__ void __launch_bounds__(SG_THREADS, 1) sigma_tc_kernel(const SigmaTcPa
   }
 }
 
+
+// =====================================================================================
+// CTA-pair variant (cta_group::2): the two CTAs of a cluster each own one 128-sample tile
+// and HALF of every weight chunk (64 of the 128 output rows of an N-half); the leader CTA
+// issues M = 256 MMAs that read both halves, so every SM ingests half the weight bytes.
+// Barriers live at identical shared-memory offsets in both CTAs:
+//   full[s]      local    producer TMA of this CTA's half landed
+//   peerfull[s]  leader   forwarded by the peer CTA once ITS half landed
+//   empty[s], dfull[h], efree[b]   both   tcgen05.commit multicast from the leader
+//   aready[h], eready[b]           leader one arrival per epilogue / prologue warp of both CTAs
+// =====================================================================================
+constexpr int S2_NSLOT = 10;
+constexpr int S2_SLOT_BYTES = 16384;
+constexpr uint32_t S2_LBO = 64 * 16, S2_SBO = 128;
+constexpr size_t S2_OFF_RING = 0;
+constexpr size_t S2_OFF_E = S2_OFF_RING + (size_t)S2_NSLOT * S2_SLOT_BYTES;
+constexpr size_t S2_OFF_BIAS = S2_OFF_E + 2 * SG_E_BYTES;
+constexpr size_t S2_OFF_WOUT = S2_OFF_BIAS + 8 * 256 * 4;
+constexpr size_t S2_OFF_BOUT = S2_OFF_WOUT + 256 * 4;
+constexpr size_t S2_OFF_PART = S2_OFF_BOUT + 16;
+constexpr size_t S2_OFF_BAR = S2_OFF_PART + 128 * 4;
+// full[10] peerfull[10] empty[10] dfull[2] aready[2] eready[2] efree[2] bar_w = 39
+constexpr size_t S2_SMEM = S2_OFF_BAR + 48 * 8;
+
+template <int BF16>
+__global__ void __launch_bounds__(SG_THREADS, 1) sigma_tc2_kernel(const SigmaTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* s_ring = smem + S2_OFF_RING;
+  uint8_t* s_e = smem + S2_OFF_E;
+  const float* s_bias = reinterpret_cast<const float*>(smem + S2_OFF_BIAS);
+  const float* s_wout = reinterpret_cast<const float*>(smem + S2_OFF_WOUT);
+  const float* s_bout = reinterpret_cast<const float*>(smem + S2_OFF_BOUT);
+  float* s_part = reinterpret_cast<float*>(smem + S2_OFF_PART);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S2_OFF_BAR);
+  uint64_t* bar_full = bars;             // [10]
+  uint64_t* bar_peer = bars + 10;        // [10]
+  uint64_t* bar_empty = bars + 20;       // [10]
+  uint64_t* bar_dfull = bars + 30;       // [2]
+  uint64_t* bar_aready = bars + 32;      // [2]
+  uint64_t* bar_eready = bars + 34;      // [2]
+  uint64_t* bar_efree = bars + 36;       // [2]
+  uint64_t* bar_w = bars + 38;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 40);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int ntile = p.tiles_per_cta;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < S2_NSLOT; ++i) {
+      mbar_init(bar_full + i, 1); mbar_init(bar_peer + i, 1); mbar_init(bar_empty + i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_dfull + i, 1); mbar_init(bar_aready + i, 16);
+      mbar_init(bar_eready + i, 8); mbar_init(bar_efree + i, 1);
+    }
+    mbar_init(bar_w, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tc2_alloc(s_tmem, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+  if (threadIdx.x == 0) {
+    const uint32_t aux_bytes = 8 * 256 * 4 + 256 * 4 + 16;
+    mbar_expect_tx(bar_w, aux_bytes);
+    bulk_g2s(smem + S2_OFF_BIAS, p.blob + p.off_aux, aux_bytes, bar_w);
+  }
+  mbar_wait(bar_w, 0);
+
+  if (warp == 1) {
+    // ============================================================ TMA producer (own half)
+    if (lane == 0) {
+      const uint8_t* img = p.blob + p.off_img;
+      uint32_t fill = 0;
+      for (int it = 0; it < ntile; ++it) {
+        uint32_t off = 0;
+        for (int l = 0; l < SG_DEPTH; ++l)
+          for (int h = 0; h < 2; ++h) {
+            const int np = l == 0 ? 1 : (l == SG_SKIP + 1 ? 3 : 2);
+            for (int pi = 0; pi < np; ++pi) {
+              const int part = l == 0 ? 2 : pi;
+              const uint32_t half = part_bytes(part) / 2;
+              const uint32_t slot = fill % S2_NSLOT;
+              if (fill >= S2_NSLOT) mbar_wait(bar_empty + slot, ((fill / S2_NSLOT) - 1) & 1);
+              mbar_expect_tx(bar_full + slot, half);
+              bulk_g2s(s_ring + (size_t)slot * S2_SLOT_BYTES, img + off + rank * half, half,
+                       bar_full + slot);
+              off += 2 * half;
+              ++fill;
+            }
+          }
+      }
+    }
+  } else if (warp == 0 && rank == 1) {
+    // ============================================== peer: forward "my half landed" to the leader
+    if (lane == 0) {
+      uint32_t fill = 0;
+      for (int it = 0; it < ntile; ++it)
+        for (int c = 0; c < 32; ++c) {
+          const uint32_t slot = fill % S2_NSLOT;
+          mbar_wait(bar_full + slot, (fill / S2_NSLOT) & 1);
+          mbar_arrive_remote(bar_peer + slot, 0);
+          ++fill;
+        }
+    }
+  } else if (warp == 0) {
+    // ============================================================== MMA issuer (leader CTA)
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_mn(BF16, 256, 128);
+      const uint32_t ring0 = smem_u32(s_ring), e0 = smem_u32(s_e);
+      uint32_t fill = 0, na[2] = {0u, 0u};
+      auto wait_a = [&](int h) { mbar_wait(bar_aready + h, na[h] & 1); ++na[h]; };
+      for (int it = 0; it < ntile; ++it) {
+        const int eb = it & 1;
+        mbar_wait(bar_eready + eb, (it >> 1) & 1);
+        for (int l = 0; l < SG_DEPTH; ++l) {
+          const uint32_t xin = tmem_base + ((l & 1) ? COL_P : COL_Q);
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t d_t = tmem_base + (h ? COL_D1 : COL_D0);
+            const int np = l == 0 ? 1 : (l == SG_SKIP + 1 ? 3 : 2);
+            for (int pi = 0; pi < np; ++pi) {
+              const int part = l == 0 ? 2 : pi;
+              if (l == 0) { if (it > 0) wait_a(h); }
+              else if (h == 0 && part < 2) wait_a(part);
+              const uint32_t slot = fill % S2_NSLOT;
+              mbar_wait(bar_full + slot, (fill / S2_NSLOT) & 1);
+              mbar_wait(bar_peer + slot, (fill / S2_NSLOT) & 1);
+              tc_fence_after();
+              const uint32_t b0 = ring0 + slot * S2_SLOT_BYTES;
+              if (part == 2) {
+                const uint32_t a0 = e0 + eb * SG_E_BYTES;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                  tc2_mma_ss(d_t, make_b_desc(a0 + ks * 2 * SG_LBO, SG_LBO, SG_SBO),
+                             make_b_desc(b0 + ks * 2 * S2_LBO, S2_LBO, S2_SBO), idesc,
+                             (l == 0 && ks == 0) ? 0u : 1u);
+              } else {
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)
+                  tc2_mma_ts(d_t, xin + part * 64 + ks * 8,
+                             make_b_desc(b0 + ks * 2 * S2_LBO, S2_LBO, S2_SBO), idesc,
+                             (part == 0 && ks == 0) ? 0u : 1u);
+              }
+              tc2_commit_mc(bar_empty + slot, 3);
+              ++fill;
+            }
+            tc2_commit_mc(bar_dfull + h, 3);
+          }
+          if (l == SG_SKIP + 1) tc2_commit_mc(bar_efree + eb, 3);
+        }
+      }
+    }
+  } else if (warp >= 2 && warp < 10) {
+    // ================================================================ epilogue (both CTAs)
+    const int wq = warp & 3;
+    const int ch = (warp - 2) >> 2;
+    const int t = wq * 32 + lane;
+    const uint32_t tb = tmem_base + ((uint32_t)(wq * 32) << 16);
+    uint32_t nd[2] = {0u, 0u};
+    for (int it = 0; it < ntile; ++it) {
+      const long long tile = (long long)it * gridDim.x + blockIdx.x;
+      const long long g = tile * 128 + t;
+      float acc = 0.f;
+      for (int l = 0; l < SG_DEPTH; ++l) {
+        const uint32_t xout = tb + ((l & 1) ? COL_Q : COL_P);
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(bar_dfull + h, nd[h] & 1);
+          ++nd[h];
+          tc_fence_after();
+          const float* bias = s_bias + l * 256 + h * 128 + ch * 64;
+          uint32_t r0[32], r1[32];
+          TC_LD32(r0, tb + (h ? COL_D1 : COL_D0) + ch * 64);
+          TC_LD32(r1, tb + (h ? COL_D1 : COL_D0) + ch * 64 + 32);
+          tc_wait_ld();
+          if (l < SG_DEPTH - 1) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float2 bb = *reinterpret_cast<const float2*>(bias + 2 * i);
+              pk[i] = pack2<BF16, 1>(__uint_as_float(r0[2 * i]) + bb.x,
+                                     __uint_as_float(r0[2 * i + 1]) + bb.y);
+            }
+            TC_ST16(xout + h * 64 + ch * 32, pk);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float2 bb = *reinterpret_cast<const float2*>(bias + 32 + 2 * i);
+              pk[i] = pack2<BF16, 1>(__uint_as_float(r1[2 * i]) + bb.x,
+                                     __uint_as_float(r1[2 * i + 1]) + bb.y);
+            }
+            TC_ST16(xout + h * 64 + ch * 32 + 16, pk);
+            tc_wait_st();
+          } else {
+            const float* wo = s_wout + h * 128 + ch * 64;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float hv = fmaxf(__uint_as_float(r0[i]) + bias[i], 0.f);
+              acc = fmaf(hv, wo[i], acc);
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float hv = fmaxf(__uint_as_float(r1[i]) + bias[32 + i], 0.f);
+              acc = fmaf(hv, wo[32 + i], acc);
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (rank == 0) mbar_arrive(bar_aready + h);
+            else mbar_arrive_remote(bar_aready + h, 0);
+          }
+        }
+      }
+      if (ch == 1) s_part[t] = acc;
+      named_bar(1, 256);
+      if (ch == 0 && g < p.total) {
+        float v = fmaxf(acc + s_part[t] + s_bout[0], 0.f);
+        if (p.use_bbox) {
+          const long long ray = g / p.S;
+          const float zz = p.z[g];
+          const float px = __fadd_rn(p.rayo[ray * 3 + 0], __fmul_rn(p.rayd[ray * 3 + 0], zz));
+          const float py = __fadd_rn(p.rayo[ray * 3 + 1], __fmul_rn(p.rayd[ray * 3 + 1], zz));
+          const float pz = __fadd_rn(p.rayo[ray * 3 + 2], __fmul_rn(p.rayd[ray * 3 + 2], zz));
+          const bool in = px >= p.bbox[0] && px <= p.bbox[1] && py >= p.bbox[2] &&
+                          py <= p.bbox[3] && pz >= p.bbox[4] && pz <= p.bbox[5];
+          if (!in) v = 0.f;
+        }
+        p.sigma[g] = v;
+      }
+      named_bar(1, 256);
+    }
+  } else if (warp >= 10) {
+    // ================================================================ prologue (both CTAs)
+    const int t = (warp - 10) * 32 + lane;
+    for (int it = 0; it < ntile; ++it) {
+      const int eb = it & 1;
+      const long long tile = (long long)it * gridDim.x + blockIdx.x;
+      const long long g = tile * 128 + t;
+      float v[64];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) v[i] = 0.f;
+      if (g < p.total) {
+        const long long ray = g / p.S;
+        const float zz = p.z[g];
+        float pc[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          pc[c] = __fadd_rn(p.rayo[ray * 3 + c], __fmul_rn(p.rayd[ray * 3 + c], zz));
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          v[c] = pc[c];
+#pragma unroll
+          for (int f0 = 0; f0 < 10; f0 += 3) {
+            float s, co;
+            sincosf(pc[c] * (float)(1 << f0), &s, &co);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              if (f0 + j < 10) {
+                v[3 + 6 * (f0 + j) + c] = s;
+                v[3 + 6 * (f0 + j) + 3 + c] = co;
+                const float ns = 2.f * s * co, nc = 1.f - 2.f * s * s;
+                s = ns; co = nc;
+              }
+            }
+          }
+        }
+      }
+      if (it >= 2) mbar_wait(bar_efree + eb, ((it >> 1) - 1) & 1);
+      uint8_t* e = s_e + eb * SG_E_BYTES;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint4 q;
+        q.x = pack2<BF16, 0>(v[8 * j + 0], v[8 * j + 1]);
+        q.y = pack2<BF16, 0>(v[8 * j + 2], v[8 * j + 3]);
+        q.z = pack2<BF16, 0>(v[8 * j + 4], v[8 * j + 5]);
+        q.w = pack2<BF16, 0>(v[8 * j + 6], v[8 * j + 7]);
+        *reinterpret_cast<uint4*>(e + ((size_t)j * 128 + t) * 16) = q;
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(bar_eready + eb);
+        else mbar_arrive_remote(bar_eready + eb, 0);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 0) { __syncwarp(); tc2_dealloc(tmem_base, 512); }
+}
+
+template <int BF16>
+int launch_sigma2(nf_ctx* ctx, const SigmaTcParams& p, int grid, cudaStream_t st) {
+  NF_CUDA(ctx, cudaFuncSetAttribute(sigma_tc2_kernel<BF16>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S2_SMEM));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(SG_THREADS);
+  cfg.dynamicSmemBytes = S2_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  NF_CUDA(ctx, cudaLaunchKernelEx(&cfg, sigma_tc2_kernel<BF16>, p));
+  return NF_OK;
+}
+
 uint16_t h_bits(float f) {
   __half h = __float2half_rn(f);
   uint16_t b;
@@ -407,6 +723,35 @@ int nf_sigma_tc_pack(nf_mlp* m) {
   for (int l = 0; l < 8; ++l) memcpy(aux + l * 256, d.b[l], 256 * sizeof(float));
   for (int c = 0; c < 256; ++c) aux[8 * 256 + c] = d.W[8][c];
   aux[8 * 256 + 256] = d.b[8][0];
+  // CTA-pair images: every chunk as [rank][kg][64 n][8] (rank r holds output rows 64 r .. 64 r + 63)
+  {
+    size_t base2 = (m->blob.size() + 255) / 256 * 256;
+    m->off_tc2_f16 = base2;
+    m->off_tc2_bf16 = base2 + (halves * 2 + 255) / 256 * 256;
+    m->blob.resize(m->off_tc2_bf16 + (halves * 2 + 255) / 256 * 256, 0);
+    uint16_t* j16 = reinterpret_cast<uint16_t*>(m->blob.data() + m->off_tc2_f16);
+    uint16_t* jbf = reinterpret_cast<uint16_t*>(m->blob.data() + m->off_tc2_bf16);
+    size_t pos2 = 0;
+    for (int l = 0; l < 8; ++l)
+      for (int h = 0; h < 2; ++h) {
+        const int np = l == 0 ? 1 : (l == 5 ? 3 : 2);
+        for (int pi = 0; pi < np; ++pi) {
+          const int part = l == 0 ? 2 : pi;
+          const int kk = part == 2 ? 64 : 128;
+          const int r0 = part == 2 ? (l == 0 ? 0 : 256) : part * 128;
+          const int kreal = part == 2 ? 63 : 128;
+          for (int rk = 0; rk < 2; ++rk)
+            for (int k = 0; k < kk; ++k)
+              for (int n = 0; n < 64; ++n) {
+                float v = k < kreal ? d.W[l][(size_t)(r0 + k) * 256 + h * 128 + rk * 64 + n] : 0.f;
+                size_t idx = pos2 + (size_t)rk * kk * 64 + ((size_t)(k / 8) * 64 + n) * 8 + (k % 8);
+                j16[idx] = h_bits(v);
+                jbf[idx] = bf_bits(v);
+              }
+          pos2 += (size_t)kk * 128;
+        }
+      }
+  }
   return NF_OK;
 }
 
@@ -428,17 +773,27 @@ int nf_tc_sigma_launch(nf_ctx* ctx, const nf_mlp* m, const float* rayo, const fl
   p.total = (long long)n_rays * S;
   if (bbox_host) { memcpy(p.bbox, bbox_host, sizeof(p.bbox)); p.use_bbox = 1; }
   const long long tiles = (p.total + 127) / 128;
-  static int cl_env = -1;
-  if (cl_env < 0) {
-    const char* e = getenv("NF_SIGMA_CLUSTER");
-    cl_env = e ? atoi(e) : 2;
+  // Variant selection (tuning knobs, read per call): NF_SIGMA_CLUSTER = 1 | 2 | 4 multicast
+  // cluster of the single-CTA kernel (default 2); NF_SIGMA_PAIR = 1 selects the cta_group::2
+  // kernel (correct, but ~20 % slower on B200: see DESIGN.md section 6).
+  int cl_env = 2, pair_env = 0;
+  if (const char* e = getenv("NF_SIGMA_CLUSTER")) {
+    cl_env = atoi(e);
     if (cl_env != 1 && cl_env != 2 && cl_env != 4) cl_env = 2;
+  }
+  if (const char* e = getenv("NF_SIGMA_PAIR")) pair_env = atoi(e);
+  const bool bf = precision == NF_PREC_BF16;
+  if (pair_env) {
+    int grid2 = ctx->sm_count / 2 * 2;
+    if (tiles < grid2) grid2 = (int)((tiles + 1) / 2 * 2);
+    p.tiles_per_cta = (int)((tiles + grid2 - 1) / grid2);
+    p.off_img = bf ? m->off_tc2_bf16 : m->off_tc2_f16;
+    return bf ? launch_sigma2<1>(ctx, p, grid2, st) : launch_sigma2<0>(ctx, p, grid2, st);
   }
   int cl = cl_env;
   int grid = ctx->sm_count / cl * cl;
   if (tiles < grid) grid = (int)((tiles + cl - 1) / cl * cl);
   p.tiles_per_cta = (int)((tiles + grid - 1) / grid);
-  const bool bf = precision == NF_PREC_BF16;
   if (cl == 1) return bf ? launch_sigma<1, 1>(ctx, p, grid, st) : launch_sigma<0, 1>(ctx, p, grid, st);
   if (cl == 2) return bf ? launch_sigma<1, 2>(ctx, p, grid, st) : launch_sigma<0, 2>(ctx, p, grid, st);
   return bf ? launch_sigma<1, 4>(ctx, p, grid, st) : launch_sigma<0, 4>(ctx, p, grid, st);

@@ -65,8 +65,21 @@ def test_march_single_pass_fp32_vs_oracle_and_golden(ctx, golden_dir):
     assert rel_l2(out['surf'].cpu(), g['sp_surf']) < 1e-5
 
 
+@pytest.fixture(params=['cluster1', 'cluster2', 'pair'])
+def sigma_variant(request, monkeypatch):
+    """The streamed-weight sigma kernel has three variants (single CTA, 2-CTA multicast
+    cluster = default, cta_group::2 CTA pair); all must give the same results."""
+    monkeypatch.delenv('NF_SIGMA_PAIR', raising=False)
+    monkeypatch.delenv('NF_SIGMA_CLUSTER', raising=False)
+    if request.param == 'pair':
+        monkeypatch.setenv('NF_SIGMA_PAIR', '1')
+    else:
+        monkeypatch.setenv('NF_SIGMA_CLUSTER', request.param[-1])
+    return request.param
+
+
 @pytest.mark.parametrize('shape', [(8, 8, 32), (37, 5, 128), (50, 41, 77)])
-def test_sigma_tcgen05_vs_fp32_kernel_and_oracle(ctx, shape):
+def test_sigma_tcgen05_vs_fp32_kernel_and_oracle(ctx, shape, sigma_variant):
     """tcgen05 f16 sigma kernel (ragged tile counts, S not a tile divisor) against the
     FP32 kernel; the FP32 kernel against the oracle; bbox masking is exact."""
     from nerfactor_b200 import _lib
