@@ -91,3 +91,44 @@ def compute_light_visibility(model, surf, normal, config, lvis_near=.1, lvis_far
                                           want_surf=False)
         lvis.index_copy_(0, sel, 1. - occu)
     return lvis.reshape(m, L)
+
+
+def postprocess_view(occu, exp_depth, exp_normal, rayo, rayd, hw, occu_thres=0.):
+    """geometry_from_nerf.py:122-149 (spp = 1) on device tensors: alpha map (thresholded,
+    clipped), alpha-premultiplied xyz map, normal map blended towards (0, 1, 0) and
+    re-normalised.  Returns (alpha_map [H,W], xyz_map [H,W,3], normal_map [H,W,3], surf [N,3])."""
+    h, w = hw
+    occu = torch.where(occu < occu_thres, torch.zeros_like(occu), occu)
+    alpha_map = torch.clamp(occu.reshape(h, w), 0., 1.)
+    surf = rayo + rayd * exp_depth[:, None]
+    a = alpha_map[:, :, None]
+    xyz_map = surf.reshape(h, w, 3) * a
+    bg = torch.tensor((0., 1., 0.), device=occu.device)[None, None, :]
+    normal_map = exp_normal.reshape(h, w, 3) * a + bg * (1. - a)
+    sq = torch.sum(normal_map * normal_map, dim=2, keepdim=True)
+    normal_map = normal_map * torch.rsqrt(torch.clamp(sq, min=1e-12))
+    return alpha_map, xyz_map, torch.clamp(normal_map, -1., 1.), surf
+
+
+def process_view(model, rayo, rayd, hw, config, occu_thres=0., lvis_far=1., light_h=16,
+                 scene_bbox=None, precision=None, with_lvis=True):
+    """geometry_from_nerf.py:93-174 without the file I/O: the buffers the reference writes as
+    alpha.png / xyz.npy / normal.npy / lvis.npy, returned as device tensors."""
+    occu, depth, normal = compute_depth_and_normal(model, rayo, rayd, config, scene_bbox,
+                                                   precision)
+    alpha_map, xyz_map, normal_map, surf = postprocess_view(occu, depth, normal, rayo, rayd,
+                                                            hw, occu_thres)
+    out = {'alpha': alpha_map, 'xyz': xyz_map, 'normal': normal_map}
+    if with_lvis:
+        hit = alpha_map.reshape(-1) > 0.                                   # gfn.py:154
+        idx = torch.nonzero(hit, as_tuple=False)[:, 0]
+        lvis_hit = compute_light_visibility(
+            model, surf.index_select(0, idx).contiguous(), normal.index_select(0, idx).contiguous(),
+            config, lvis_far=lvis_far, light_h=light_h, scene_bbox=scene_bbox,
+            precision=precision)
+        lvis_hit = torch.clamp(lvis_hit, 0., 1.)                           # gfn.py:160
+        L = lvis_hit.shape[1]
+        lvis = torch.zeros((hw[0] * hw[1], L), device=surf.device)
+        lvis.index_copy_(0, idx, lvis_hit)
+        out['lvis'] = lvis.reshape(hw[0], hw[1], L) * alpha_map[:, :, None]   # gfn.py:170-171
+    return out

@@ -109,3 +109,27 @@ def test_default_configs_match_reference_ini_values():
     assert m.getfloat('DEFAULT', 'fresnel_f0') == 0.04
     n = nfconfig.default_config('nerf')
     assert n.getint('DEFAULT', 'enc_depth') == 8 and n.getint('DEFAULT', 'mlp_width') == 256
+
+
+def test_sample_rays_semantics():
+    """nerf_shape.py:84-121: train batches come only from alpha > 0.9 pixels, with
+    replacement; test batches are every ray in row-major order."""
+    import torch
+    from nerfactor_b200.datasets.nerf_shape import sample_rays
+    h, w, L = 6, 5, 4
+    g = torch.Generator().manual_seed(0)
+    idx = torch.arange(h * w, dtype=torch.float32)
+    maps = [idx.reshape(h, w, 1).expand(h, w, 3).clone() for _ in range(3)]
+    alpha = torch.zeros((h, w))
+    alpha[1, 2] = 1.0
+    alpha[4, 0] = 0.95
+    alpha[0, 0] = 0.9                       # not above the threshold
+    xyz, nrm = maps[0].clone(), maps[0].clone()
+    lvis = idx.reshape(h, w, 1).expand(h, w, L).clone()
+    out = sample_rays(maps[0], maps[1], maps[2], alpha, xyz, nrm, lvis, 'train', bs=64, generator=g)
+    picked = set(out[0][:, 0].long().tolist())
+    assert picked == {1 * w + 2, 4 * w + 0} and out[3].shape == (64, 1) and out[6].shape == (64, L)
+    allr = sample_rays(maps[0], maps[1], maps[2], alpha, xyz, nrm, lvis, 'test')
+    assert torch.equal(allr[0][:, 0], idx) and allr[6].shape == (h * w, L)
+    with pytest.raises(ValueError):
+        sample_rays(maps[0], maps[1], maps[2], torch.zeros((h, w)), xyz, nrm, lvis, 'train')

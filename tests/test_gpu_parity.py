@@ -152,6 +152,29 @@ def test_compute_depth_and_normal_vs_golden(ctx, golden_dir):
     assert np.median(dn) < 1e-3 and np.quantile(dn, 0.95) < 2e-2
 
 
+def test_process_view_buffers_vs_oracle(ctx):
+    """geometry_from_nerf.process_view (:93-174) without file I/O: alpha / xyz / normal / lvis
+    buffers of a 6x6 view against the oracle chain."""
+    from nerfactor_b200 import geometry_from_nerf as gfn
+    model = _nerf_model(ctx, 3)
+    h = w = 6
+    ro, rd = _rays(ctx, h, w)
+    cfg = nfconfig.default_config('nerf', n_samples_coarse=-32, n_samples_fine=-16)
+    out = gfn.process_view(model, ro, rd, (h, w), cfg, light_h=2, precision='fp32')
+    nerf = synth.make_nerf_params(3)
+    occu, depth, normal = stage_a.compute_depth_and_normal(
+        nerf, ro.cpu(), rd.cpu(), 2., 6., n_samples_coarse=-32, n_samples_fine=-16)
+    a_o, xyz_o, n_o, surf_o = stage_a.postprocess_view(occu, depth, normal, ro.cpu(), rd.cpu(), (h, w))
+    assert np.abs(out['alpha'].cpu().numpy() - a_o.numpy()).max() < 1e-3
+    d = np.abs(out['xyz'].cpu().numpy() - xyz_o.numpy()).max(axis=2)
+    assert np.median(d) < 1e-3
+    assert out['normal'].shape == (h, w, 3) and out['lvis'].shape == (h, w, 8)
+    nn = np.linalg.norm(out['normal'].cpu().numpy(), axis=2)
+    assert np.allclose(nn, 1., atol=1e-4)
+    lv = out['lvis'].cpu().numpy()
+    assert lv.min() >= 0. and lv.max() <= 1.
+
+
 def test_gen_z_and_gen_z_fine_vs_oracle(ctx):
     from nerfactor_b200 import _lib
     rng = np.random.default_rng(0)
