@@ -271,6 +271,4 @@ class Trainer:
         """trainvali.py:301-317: forward in 'vali' mode through the fused inference kernels."""
         self.sync_to_model()
         pred, gt, loss_kwargs, _ = self.model.call(batch, 'vali')
-        if 'mode' not in loss_kwargs:
-            return self.model.compute_loss(pred, gt, **loss_kwargs)
         return self.model.compute_loss(pred, gt, **loss_kwargs)
