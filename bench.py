@@ -46,6 +46,8 @@ def parse():
     ap.add_argument('--sigma-precision', default=os.environ.get('NF_SIGMA_PREC', 'auto'))
     ap.add_argument('--cpu-sample-rays', type=int, default=8192)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-secondary', action='store_true',
+                    help='skip the bounded secondary measurements (other BASELINE configs)')
     return ap.parse_args()
 
 
@@ -182,6 +184,58 @@ def workload_config(args, sigma_prec):
                           'point_mlps': 'f32', 'render': 'f32'},
             'l2_policy': 'per-step working set (lvis 1.3 GB, sigma 0.33 GB) exceeds the 126 MB L2',
             'parallelism': 'one view per GPU + all_gather of images'}
+
+
+def secondary_rows(ctx, nerf, kt):
+    """Bounded measurements of the other BASELINE configs (parity-tested in tests/; these are
+    context rows, not the headline): reference-exact hierarchical Stage A, the surface->light
+    visibility march, learned-BRDF relighting at L = 1024, and one train step."""
+    from nerfactor_b200 import _lib, synth, config as nfconfig
+    from nerfactor_b200 import geometry_from_nerf as gfn
+    from nerfactor_b200.models.nerfactor import Model as LearnedModel
+    from nerfactor_b200.trainvali import Trainer
+    from nerfactor_b200.brdf.renderer import gen_light_xyz
+    out = {}
+    cfg = nfconfig.default_config('nerf')
+    # (1) compute_depth_and_normal: 128 coarse + 320 fine samples with d sigma/dx normals
+    h = w = 96
+    ro, rd = _lib.gen_rays(ctx, synth.look_at_c2w(), synth.CAM_ANGLE_X, h, w, normalize=True)
+    t = kt(lambda: gfn.compute_depth_and_normal(nerf, ro, rd, cfg), 2)
+    out['stage_a_hierarchical'] = {
+        'what': 'geometry_from_nerf.compute_depth_and_normal, 128 coarse + 320 fine, fp32 gradient',
+        'rays': h * w, 'ms': t, 'rays_per_s': h * w / (t * 1e-3)}
+    # (2) compute_light_visibility: every front-lit (point, light) pair marched 128 + 320 samples
+    npts = 256
+    surf = (ro[:npts] + rd[:npts] * 3.0).contiguous()
+    nrm = (-rd[:npts]).contiguous()
+    t = kt(lambda: gfn.compute_light_visibility(nerf, surf, nrm, cfg, light_h=16), 2)
+    out['stage_a_light_visibility'] = {
+        'what': 'geometry_from_nerf.compute_light_visibility, 512 lights, 128 + 320 samples/pair, f16',
+        'points': npts, 'ms': t, 'pairs_per_s': npts * 512 / (t * 1e-3)}
+    # (3) configs[2]: learned-MERL BRDF, 1024 light dirs on a 16x32 env-map, one 200x200 view
+    lm = LearnedModel(nfconfig.default_config('nerfactor'),
+                      params=synth.make_stage_b_params(0, 'learned'), ctx=ctx, precision='f16')
+    lxyz, lareas = gen_light_xyz(16, 64)
+    lm.set_lights(lxyz.reshape(-1, 3), lareas.reshape(-1),
+                  light_idx=synth.light_index_map((16, 32), (16, 64)))
+    n = 40000
+    b = list(synth.make_stage_b_batch(1, n, 1, fg_frac=1.0))
+    b[8] = None
+    bt = tuple(torch.as_tensor(x).to(ctx.device) if isinstance(x, np.ndarray) and
+               x.dtype != np.dtype('S9') and x.dtype.kind == 'f' else x for x in b)
+    t = kt(lambda: lm.call(bt, 'test'), 2)
+    out['stage_b_learned_L1024'] = {
+        'what': 'nerfactor Model.call (learned BRDF), 1024 light dirs, 16x32 env-map',
+        'rays': n, 'ms': t, 'rays_per_s': n / (t * 1e-3)}
+    # (4) configs[3] semantics: one optimizer step, 1024 rays x 512 lights, fp32 training kernels
+    lm2 = LearnedModel(nfconfig.default_config('nerfactor'),
+                       params=synth.make_stage_b_params(0, 'learned'), ctx=ctx, precision='fp32')
+    tr = Trainer(lm2)
+    tb = synth.make_stage_b_batch(2, 1024, 512, fg_frac=1.0)
+    t = kt(lambda: tr.train_step(tb), 3)
+    out['train_step'] = {'what': 'Trainer.train_step, 1024 rays x 512 lights, jitter on, fp32',
+                         'ms': t, 'rays_per_s': 1024 / (t * 1e-3)}
+    return out
 
 
 # ------------------------------------------------------------------------ our arm
@@ -349,6 +403,10 @@ def main():
     dominant = dict(dominant, peak_source=pk['source'] + ', sustained bf16 cuBLAS' if
                     dominant['bound'] == 'tensor' else pk['source'])
 
+    secondary = None
+    if not args.no_secondary:
+        secondary = secondary_rows(ctx, nerf, kt)
+
     cpu = None
     if not args.no_cpu_baseline:
         rps, dt = cpu_reference_rays_per_s(args, args.cpu_sample_rays, 1, 1)
@@ -370,6 +428,7 @@ def main():
         'rooflines': [rf_sigma, rf_lvis, rf_int, rf_point],
         'foreground_rays': n_fg,
         'cpu_baseline': cpu,
+        'secondary': secondary,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -211,17 +211,21 @@ __global__ void __launch_bounds__(SG_THREADS, 1) sigma_tc_kernel(const SigmaTcPa
           if (l < SG_DEPTH - 1) {
             uint32_t pk[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float2 bb = *reinterpret_cast<const float2*>(bias + 2 * i);
-              pk[i] = pack2<BF16, 1>(__uint_as_float(r0[2 * i]) + bb.x,
-                                     __uint_as_float(r0[2 * i + 1]) + bb.y);
+            for (int i = 0; i < 8; ++i) {
+              float4 bb = *reinterpret_cast<const float4*>(bias + 4 * i);
+              pk[2 * i] = pack2<BF16, 1>(__uint_as_float(r0[4 * i]) + bb.x,
+                                             __uint_as_float(r0[4 * i + 1]) + bb.y);
+              pk[2 * i + 1] = pack2<BF16, 1>(__uint_as_float(r0[4 * i + 2]) + bb.z,
+                                                 __uint_as_float(r0[4 * i + 3]) + bb.w);
             }
             TC_ST16(xout + h * 64 + ch * 32, pk);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float2 bb = *reinterpret_cast<const float2*>(bias + 32 + 2 * i);
-              pk[i] = pack2<BF16, 1>(__uint_as_float(r1[2 * i]) + bb.x,
-                                     __uint_as_float(r1[2 * i + 1]) + bb.y);
+            for (int i = 0; i < 8; ++i) {
+              float4 bb = *reinterpret_cast<const float4*>(bias + 32 + 4 * i);
+              pk[2 * i] = pack2<BF16, 1>(__uint_as_float(r1[4 * i]) + bb.x,
+                                             __uint_as_float(r1[4 * i + 1]) + bb.y);
+              pk[2 * i + 1] = pack2<BF16, 1>(__uint_as_float(r1[4 * i + 2]) + bb.z,
+                                                 __uint_as_float(r1[4 * i + 3]) + bb.w);
             }
             TC_ST16(xout + h * 64 + ch * 32 + 16, pk);
             tc_wait_st();
@@ -505,17 +509,21 @@ __global__ void __launch_bounds__(SG_THREADS, 1) sigma_tc2_kernel(const SigmaTcP
           if (l < SG_DEPTH - 1) {
             uint32_t pk[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float2 bb = *reinterpret_cast<const float2*>(bias + 2 * i);
-              pk[i] = pack2<BF16, 1>(__uint_as_float(r0[2 * i]) + bb.x,
-                                     __uint_as_float(r0[2 * i + 1]) + bb.y);
+            for (int i = 0; i < 8; ++i) {
+              float4 bb = *reinterpret_cast<const float4*>(bias + 4 * i);
+              pk[2 * i] = pack2<BF16, 1>(__uint_as_float(r0[4 * i]) + bb.x,
+                                             __uint_as_float(r0[4 * i + 1]) + bb.y);
+              pk[2 * i + 1] = pack2<BF16, 1>(__uint_as_float(r0[4 * i + 2]) + bb.z,
+                                                 __uint_as_float(r0[4 * i + 3]) + bb.w);
             }
             TC_ST16(xout + h * 64 + ch * 32, pk);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float2 bb = *reinterpret_cast<const float2*>(bias + 32 + 2 * i);
-              pk[i] = pack2<BF16, 1>(__uint_as_float(r1[2 * i]) + bb.x,
-                                     __uint_as_float(r1[2 * i + 1]) + bb.y);
+            for (int i = 0; i < 8; ++i) {
+              float4 bb = *reinterpret_cast<const float4*>(bias + 32 + 4 * i);
+              pk[2 * i] = pack2<BF16, 1>(__uint_as_float(r1[4 * i]) + bb.x,
+                                             __uint_as_float(r1[4 * i + 1]) + bb.y);
+              pk[2 * i + 1] = pack2<BF16, 1>(__uint_as_float(r1[4 * i + 2]) + bb.z,
+                                                 __uint_as_float(r1[4 * i + 3]) + bb.w);
             }
             TC_ST16(xout + h * 64 + ch * 32 + 16, pk);
             tc_wait_st();
