@@ -325,6 +325,35 @@ def test_config5_relight_sweep_eight_envmaps(ctx):
     assert rel_l2(p2['albedo'].cpu(), o2['albedo']) < 1e-6
 
 
+def test_ragged_light_count_xyz_scale_and_ambient_olat(ctx):
+    """L = 200 (10 x 20 grid: two tiles per point, the second one ragged), xyz_scale != 1
+    (shape.py:47-48), and OLAT relighting with ambient light (nerfactor.py:68-84)."""
+    from nerfactor_b200.models.nerfactor import Model
+    lh, lw = 10, 20
+    params = synth.make_stage_b_params(61, 'learned', light_hw=(lh, lw))
+    lxyz, lareas = obrdf.gen_light_xyz(lh, lw)
+    cfg = nfconfig.default_config('nerfactor', light_h=lh, xyz_scale=0.37, ambient_inten=0.25)
+    m = Model(cfg, params=params, ctx=ctx, precision='f16')
+    m.set_lights(lxyz.reshape(-1, 3), lareas.reshape(-1))
+    m.light_res = (lh, lw)
+    om = stage_b.StageB(params, {'brdf': 'learned', 'xyz_scale': 0.37, 'ambient_inten': 0.25},
+                        lxyz=lxyz, lareas=lareas)
+    batch = synth.make_stage_b_batch(62, 45, lh * lw)
+    pred, _, _, _ = m.call(batch, 'test', relight_olat=True)
+    olats = om.novel_olat((lh, lw))
+    opred, _, _ = om.call(batch, 'test', relight_lights=olats[:25] + olats[-5:])
+    assert pred['lvis'].shape == (45, 200)
+    assert rel_l2(pred['lvis'].cpu(), opred['lvis']) < 3e-3
+    assert rel_l2(pred['rgb'].cpu(), opred['rgb']) < 1e-4
+    got = pred['rgb_olat'].cpu().numpy()
+    sel = np.concatenate((got[:, :25], got[:, -5:]), axis=1)
+    assert rel_l2(sel, opred['rgb_relit']) < 1e-4
+    for prec, tol in (('fp32', 1e-5), ('bf16', 2e-3)):
+        m.precision = prec
+        p2, _, _, _ = m.call(batch, 'test')
+        assert rel_l2(p2['rgb'].cpu(), opred['rgb']) < tol, prec
+
+
 def test_lvis_and_brdf_kernels_fp32_vs_f16_vs_oracle(ctx):
     from nerfactor_b200 import _lib
     m, om, params = _stage_b(ctx, 'learned', 16, 32, seed=5, precision='f16')
