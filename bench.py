@@ -181,7 +181,8 @@ def workload_config(args, sigma_prec):
             'rays_per_view': args.imh * args.imw, 'samples_per_ray': args.spp,
             'light_dirs': 2 * args.light_h ** 2, 'brdf': 'microfacet',
             'precision': {'sigma_mlp': sigma_prec, 'lvis_mlp': 'f16 operands / f32 accum',
-                          'point_mlps': 'f32', 'render': 'f32'},
+                          'point_mlps': 'f16 hi/lo split x3 (fp32-accurate) / f32 accum',
+                          'render': 'f32'},
             'l2_policy': 'per-step working set (lvis 1.3 GB, sigma 0.33 GB) exceeds the 126 MB L2',
             'parallelism': 'one view per GPU + all_gather of images'}
 
@@ -382,7 +383,7 @@ def main():
               'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'ms': t_int, 'traffic': None,
               'algorithmic_bytes': alg_int,
               'note': 'ALU-bound with the analytic GGX lobe (SURVEY 7 hard parts)'}
-    rf_point = {'kernel': 'nf_point_mlp_fwd (fp32 FFMA)', 'bound': 'fp32-alu',
+    rf_point = {'kernel': 'nf_point_mlp_fwd (tcgen05 f16x3 split, per net; x3 per step)', 'bound': 'latency',
                 'achieved': n_fg * FLOP_POINT / (t_point * 1e-3) / 1e12, 'peak': None,
                 'unit': 'TFLOP/s', 'ms': t_point, 'traffic': None}
     for r in (rf_sigma, rf_lvis, rf_int):

@@ -49,6 +49,7 @@ extern "C" {
 #define NF_PREC_FP32 0 /* CUDA-core FFMA, fp32 throughout (parity / small nets)   */
 #define NF_PREC_F16 1  /* tcgen05 kind::f16, fp16 operands, fp32 accumulate in TMEM */
 #define NF_PREC_BF16 2 /* tcgen05 kind::f16, bf16 operands, fp32 accumulate in TMEM */
+#define NF_PREC_F16X3 3 /* tcgen05, fp16 hi/lo split of both operands, 3 MMA chains: ~fp32 */
 
 typedef struct nf_ctx nf_ctx;
 typedef struct nf_mlp nf_mlp;

@@ -5,6 +5,9 @@
 int nf_simt_launch(nf_ctx* ctx, const nf_mlp* m, long long n_rows, int per, float xyz_scale,
                    const float* xyz, const float* a0, const float* a1, const float* a2,
                    const float* a3, const float* bbox_host, float* out, cudaStream_t st);
+// nf_point_tc.cu
+int nf_tc_point_launch(nf_ctx* ctx, const nf_mlp* m, const float* xyz, int n, float xyz_scale,
+                       float* out, cudaStream_t st);
 // nf_mlp_tc.cu
 int nf_tc_lvis_launch(nf_ctx* ctx, const nf_mlp* m, const float* xyz, int n, float xyz_scale,
                       const float* lxyz, int L, float* lvis, int precision, cudaStream_t st);
@@ -23,9 +26,12 @@ int nf_point_mlp_fwd(nf_ctx* ctx, const nf_mlp* mlp, const float* xyz_d, int n, 
   NF_CHECK_ARG(ctx, mlp->d.kind == NF_MLP_POINT, "network is not NF_MLP_POINT");
   if (n == 0) return NF_OK;
   NF_CHECK_ARG(ctx, xyz_d && out_d, "null buffer");
+  if (precision == NF_PREC_F16X3)
+    return nf_tc_point_launch(ctx, mlp, xyz_d, n, xyz_scale, out_d, (cudaStream_t)stream);
   if (precision != NF_PREC_FP32)
     return nf_set_error(ctx, NF_ERR_UNSUPPORTED,
-                        "nf_point_mlp_fwd: the per-point networks run in NF_PREC_FP32 only");
+                        "nf_point_mlp_fwd: the per-point networks need NF_PREC_FP32 or "
+                        "NF_PREC_F16X3 (plain 16-bit operands are not accurate enough)");
   return nf_simt_launch(ctx, mlp, n, 1, xyz_scale, xyz_d, nullptr, nullptr, nullptr, nullptr,
                         nullptr, out_d, (cudaStream_t)stream);
 }

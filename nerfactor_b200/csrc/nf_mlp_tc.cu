@@ -537,10 +537,12 @@ int launch_tc(nf_ctx* ctx, const nf_mlp* m, const TcParams& p, cudaStream_t st) 
 //   aux (fp32): b0..b3 [4][128], w_out [128], b_out [4], Wx0 [NR_PAD][128],
 //     Wx3 [NR_PAD][128] = the rows of W0 / W3 that multiply the per-point columns.
 int nf_sigma_tc_pack(nf_mlp* m);  // nf_sigma_tc.cu
+int nf_point_tc_pack(nf_mlp* m);  // nf_point_tc.cu
 
 int nf_tc_pack(nf_mlp* m) {
   const nf_mlp_desc& d = m->d;
   if (d.kind == NF_MLP_SIGMA) return nf_sigma_tc_pack(m);
+  if (d.kind == NF_MLP_POINT) return nf_point_tc_pack(m);
   const bool pair_kind = d.kind == NF_MLP_LVIS || d.kind == NF_MLP_BRDF;
   if (!pair_kind || d.width != 128 || d.depth != 4 || d.skip_at != 2 || d.out_dim != 1) return NF_OK;
   const int KE = d.kind == NF_MLP_LVIS ? 32 : 16;

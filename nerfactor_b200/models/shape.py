@@ -29,6 +29,7 @@ class Model(BaseModel):
         self.ctx = ctx or _lib.default_context()
         self.device = self.ctx.device
         self.precision = precision          # arithmetic of the per-(point,light) nets
+        self.point_precision = 'f16x3'      # per-point nets (see _pred_point)
         self.white_bg = self.config.getboolean('DEFAULT', 'white_bg')
         self.mlp_chunk = self.config.getint('DEFAULT', 'mlp_chunk')   # unused: fused kernels
         self.normal_smooth_weight = self.config.getfloat(
@@ -133,8 +134,17 @@ class Model(BaseModel):
 
     # ------------------------------------------------------------ network evals
     def _pred_point(self, name, pts):
+        """Per-point nets: fp32-accurate always -- FP32 CUDA cores when the model runs in
+        'fp32', otherwise tensor cores with the 3-term fp16 split ('f16x3')."""
         m = self._packed_mlp(name, 'point', n_freqs_a=self.embedder['xyz'].n_freqs)
-        return _lib.point_mlp_fwd(self.ctx, m, pts, self.xyz_scale, 'fp32')
+        prec = 'fp32' if self.precision == 'fp32' else self.point_precision
+        try:
+            return _lib.point_mlp_fwd(self.ctx, m, pts, self.xyz_scale, prec)
+        except _lib.NfError as e:
+            if prec != 'fp32' and 'NF_ERR_UNSUPPORTED' in str(e):
+                # network shape without a tcgen05 kernel: the FP32 CUDA kernel (still the GPU)
+                return _lib.point_mlp_fwd(self.ctx, m, pts, self.xyz_scale, 'fp32')
+            raise
 
     def _pred_normal_at(self, pts, eps=1e-6):
         """shape.py:196-211."""

@@ -354,6 +354,23 @@ def test_ragged_light_count_xyz_scale_and_ambient_olat(ctx):
         assert rel_l2(p2['rgb'].cpu(), opred['rgb']) < tol, prec
 
 
+@pytest.mark.parametrize('n', [1, 127, 128, 1000])
+def test_point_networks_f16x3_tcgen05_vs_fp32_and_oracle(ctx, n):
+    """Per-point nets on tensor cores with the 3-term fp16 split: fp32-level accuracy."""
+    from nerfactor_b200 import _lib
+    m, om, _ = _stage_b(ctx, 'learned', 2, 8, seed=5)
+    xyz = np.random.default_rng(n).uniform(-1.5, 1.5, (n, 3)).astype(np.float32)
+    xt = dev(xyz, ctx)
+    for name in ('normal', 'albedo', 'brdf_z'):
+        pm = m._packed_mlp(name, 'point', n_freqs_a=10)
+        a32 = _lib.point_mlp_fwd(ctx, pm, xt, 1.0, 'fp32').cpu().numpy()
+        a3 = _lib.point_mlp_fwd(ctx, pm, xt, 1.0, 'f16x3').cpu().numpy()
+        o = om._point_mlp(name, torch.tensor(xyz)).numpy()
+        assert rel_l2(a32, o) < 2e-6 and rel_l2(a3, o) < 1e-5, name
+    with pytest.raises(_lib.NfError):
+        _lib.point_mlp_fwd(ctx, pm, xt, 1.0, 'f16')       # plain fp16 is refused for these nets
+
+
 def test_lvis_and_brdf_kernels_fp32_vs_f16_vs_oracle(ctx):
     from nerfactor_b200 import _lib
     m, om, params = _stage_b(ctx, 'learned', 16, 32, seed=5, precision='f16')
