@@ -29,6 +29,21 @@ def dev(x, ctx, dtype=torch.float32):
     return torch.as_tensor(np.ascontiguousarray(x), dtype=dtype).to(ctx.device)
 
 
+# ------------------------------------------------------------- tcgen05 bring-up
+@pytest.mark.parametrize('K', [16, 32, 64, 128])
+def test_tcgen05_single_tile_exact(ctx, K):
+    """One 128x128xK tile through the TMEM-A / K-major no-swizzle smem-B layouts the fused
+    kernels use, and one 256x128xK CTA-pair (cta_group::2) tile: exact on small integers."""
+    from nerfactor_b200 import _lib
+    rng = np.random.default_rng(K)
+    a = rng.integers(-4, 5, (256, K)).astype(np.float32)
+    b = rng.integers(-4, 5, (128, K)).astype(np.float32)
+    one = _lib.selftest_umma(ctx, dev(a[:128], ctx), dev(b, ctx)).cpu().numpy()
+    assert np.array_equal(one, a[:128] @ b.T)
+    pair = _lib.selftest_umma2(ctx, dev(a, ctx), dev(b, ctx)).cpu().numpy()
+    assert np.array_equal(pair, a @ b.T)
+
+
 # ------------------------------------------------------------------- Stage A
 @pytest.mark.parametrize('hw', [(64, 64), (800, 800), (37, 53)])
 def test_gen_rays_bit_exact(ctx, hw):

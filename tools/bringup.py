@@ -24,7 +24,7 @@ for K in (16, 32, 128):
     ref = a @ b.T
     for swap in (0,):
         try:
-            got = _lib.selftest_umma(ctx, torch.tensor(a).cuda(), torch.tensor(b).cuda(), bool(swap))
+            got = _lib.selftest_umma(ctx, torch.tensor(a).cuda(), torch.tensor(b).cuda(), False)
             torch.cuda.synchronize()
             got = got.cpu().numpy()
             err = float(np.abs(got - ref).max())

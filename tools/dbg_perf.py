@@ -1,4 +1,5 @@
-"""Times the two tcgen05 kernels at full size (env NF_DBG_SIGMA / NF_DBG_LVIS experiments)."""
+"""Times the two big tcgen05 kernels at the full bench size (800x800, S=128, L=512).
+Variant knobs: NF_SIGMA_CLUSTER = 1|2|4, NF_SIGMA_PAIR = 1."""
 import sys, os, json
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -20,7 +21,7 @@ def t(fn, reps=3):
     for _ in range(reps): fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
-out = {'dbg_sigma': os.environ.get('NF_DBG_SIGMA'), 'dbg_lvis': os.environ.get('NF_DBG_LVIS'), 'cl': os.environ.get('NF_SIGMA_CLUSTER')}
+out = {'cluster': os.environ.get('NF_SIGMA_CLUSTER'), 'pair': os.environ.get('NF_SIGMA_PAIR')}
 which = sys.argv[1] if len(sys.argv) > 1 else 'both'
 if which in ('both', 'sigma'):
     out['sigma_ms'] = t(lambda: _lib.sigma_fwd(ctx, nerf.packed_sigma(True), ro, rd, z, None, 'f16'))
