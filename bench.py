@@ -199,11 +199,18 @@ def secondary_rows(ctx, nerf, kt):
     out = {}
     cfg = nfconfig.default_config('nerf')
     # (1) compute_depth_and_normal: 128 coarse + 320 fine samples with d sigma/dx normals
+    h = w = 200
+    ro, rd = _lib.gen_rays(ctx, synth.look_at_c2w(), synth.CAM_ANGLE_X, h, w, normalize=True)
+    t = kt(lambda: gfn.compute_depth_and_normal(nerf, ro, rd, cfg, precision='f16'), 2)
+    out['stage_a_hierarchical'] = {
+        'what': 'geometry_from_nerf.compute_depth_and_normal, 128 coarse + 320 fine, '
+                'tcgen05 forward + input-gradient kernel (f16 operands)',
+        'rays': h * w, 'ms': t, 'rays_per_s': h * w / (t * 1e-3)}
     h = w = 96
     ro, rd = _lib.gen_rays(ctx, synth.look_at_c2w(), synth.CAM_ANGLE_X, h, w, normalize=True)
-    t = kt(lambda: gfn.compute_depth_and_normal(nerf, ro, rd, cfg), 2)
-    out['stage_a_hierarchical'] = {
-        'what': 'geometry_from_nerf.compute_depth_and_normal, 128 coarse + 320 fine, fp32 gradient',
+    t = kt(lambda: gfn.compute_depth_and_normal(nerf, ro, rd, cfg, precision='fp32'), 2)
+    out['stage_a_hierarchical_fp32'] = {
+        'what': 'same, FP32 CUDA-core kernels throughout (the bit-level parity path)',
         'rays': h * w, 'ms': t, 'rays_per_s': h * w / (t * 1e-3)}
     # (2) compute_light_visibility: every front-lit (point, light) pair marched 128 + 320 samples
     npts = 256

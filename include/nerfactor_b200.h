@@ -184,11 +184,13 @@ int nf_sigma_fwd(nf_ctx* ctx, const nf_mlp* mlp, const float* rayo_d,
                  const float* bbox_host, float* sigma_d, int precision, void* stream);
 
 /* Same as nf_sigma_fwd plus normal[n,S,3] = -l2_normalize(d sigma / d xyz)
- * replaces the GradientTape.batch_jacobian block geometry_from_nerf.py:285-305     */
+ * replaces the GradientTape.batch_jacobian block geometry_from_nerf.py:285-305.
+ * precision: NF_PREC_FP32 (CUDA cores) or NF_PREC_F16 / NF_PREC_BF16 (tcgen05 forward +
+ * backward, fp32 accumulation; NF_ERR_UNSUPPORTED unless the net is 8 x 256, skip 4, F=10) */
 int nf_sigma_normal_fwd(nf_ctx* ctx, const nf_mlp* mlp, const float* rayo_d,
                         const float* rayd_d, const float* z_d, int n_rays,
                         int n_samples, const float* bbox_host, float* sigma_d,
-                        float* normal_d, void* stream);
+                        float* normal_d, int precision, void* stream);
 
 /* weights[n,S] (optional), occu[n], depth[n], surf[n,3] (optional),
  * exp_normal[n,3] (optional, needs normal_d [n,S,3])

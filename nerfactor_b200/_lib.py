@@ -87,7 +87,7 @@ def load_library():
     lib.nf_gen_rays.argtypes = [vp, C.POINTER(d), d, i, i, i, vp, vp, vp]
     lib.nf_gen_z.argtypes = [vp, f, f, i, i, i, vp, vp, vp]
     lib.nf_sigma_fwd.argtypes = [vp, vp, vp, vp, vp, i, i, C.POINTER(f), vp, i, vp]
-    lib.nf_sigma_normal_fwd.argtypes = [vp, vp, vp, vp, vp, i, i, C.POINTER(f), vp, vp, vp]
+    lib.nf_sigma_normal_fwd.argtypes = [vp, vp, vp, vp, vp, i, i, C.POINTER(f), vp, vp, i, vp]
     lib.nf_composite.argtypes = [vp, vp, vp, vp, vp, vp, i, i, vp, vp, vp, vp, vp, vp]
     lib.nf_gen_z_fine.argtypes = [vp, vp, vp, i, i, i, vp, vp]
     lib.nf_lvis_rays.argtypes = [vp, vp, vp, i, vp, i, vp, vp, vp, vp]
@@ -323,13 +323,14 @@ def sigma_fwd(ctx, mlp, rayo, rayd, z, bbox=None, precision='f16'):
     return sigma
 
 
-def sigma_normal_fwd(ctx, mlp, rayo, rayd, z, bbox=None):
+def sigma_normal_fwd(ctx, mlp, rayo, rayd, z, bbox=None, precision='fp32'):
     n, S = z.shape
     sigma = torch.empty((n, S), dtype=torch.float32, device=z.device)
     normal = torch.empty((n, S, 3), dtype=torch.float32, device=z.device)
     bb = _bbox(bbox)
     ctx.launch(ctx.lib.nf_sigma_normal_fwd(ctx.h, mlp.h, _f32(rayo), _f32(rayd), _f32(z), n,
-                                          S, bb, _f32(sigma), _f32(normal), _stream()))
+                                          S, bb, _f32(sigma), _f32(normal), PREC[precision],
+                                          _stream()))
     return sigma, normal
 
 

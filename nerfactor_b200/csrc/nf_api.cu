@@ -5,6 +5,7 @@
 
 int nf_tc_pack(nf_mlp* m);  // nf_mlp_tc.cu: appends the tcgen05 operand images
 int nf_sigma_grad_pack(nf_mlp* m);  // nf_sigma_grad.cu: appends W^T for the input gradient
+int nf_sigma_grad_tc_pack(nf_mlp* m);  // nf_sigma_grad_tc.cu: backward tcgen05 operand images
 
 int nf_set_error(nf_ctx* ctx, int code, const char* fmt, ...) {
   char buf[512];
@@ -108,6 +109,7 @@ int nf_mlp_create(nf_ctx* ctx, const nf_mlp_desc* desc, nf_mlp** out) {
   }
   int rc = nf_tc_pack(m);
   if (rc == NF_OK) rc = nf_sigma_grad_pack(m);
+  if (rc == NF_OK) rc = nf_sigma_grad_tc_pack(m);
   if (rc != NF_OK) {
     delete m;
     return nf_set_error(ctx, rc, "nf_mlp_create: tensor-core packing failed");

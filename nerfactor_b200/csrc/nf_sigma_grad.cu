@@ -312,16 +312,25 @@ int nf_sigma_grad_pack(nf_mlp* m) {
   return NF_OK;
 }
 
+int nf_tc_sigma_grad_launch(nf_ctx* ctx, const nf_mlp* m, const float* rayo, const float* rayd,
+                            const float* z, int n_rays, int S, const float* bbox_host,
+                            float* sigma, float* normal, int precision, cudaStream_t st);
+
 extern "C" int nf_sigma_normal_fwd(nf_ctx* ctx, const nf_mlp* m, const float* rayo_d,
                                    const float* rayd_d, const float* z_d, int n_rays,
                                    int n_samples, const float* bbox_host, float* sigma_d,
-                                   float* normal_d, void* stream) {
+                                   float* normal_d, int precision, void* stream) {
   NF_CHECK_ARG(ctx, m, "null network");
   NF_CHECK_ARG(ctx, m->d.kind == NF_MLP_SIGMA && m->d.out_dim == 1, "network is not NF_MLP_SIGMA");
   NF_CHECK_ARG(ctx, n_rays >= 0 && n_samples > 0, "bad sizes");
   if (n_rays == 0) return NF_OK;
   NF_CHECK_ARG(ctx, rayo_d && rayd_d && z_d && sigma_d && normal_d, "null buffer");
   NF_CHECK_ARG(ctx, m->dev, "network not uploaded (call nf_mlp_upload first)");
+  NF_CHECK_ARG(ctx, precision == NF_PREC_FP32 || precision == NF_PREC_F16 || precision == NF_PREC_BF16,
+               "precision must be NF_PREC_FP32, NF_PREC_F16 or NF_PREC_BF16");
+  if (precision != NF_PREC_FP32)
+    return nf_tc_sigma_grad_launch(ctx, m, rayo_d, rayd_d, z_d, n_rays, n_samples, bbox_host,
+                                   sigma_d, normal_d, precision, (cudaStream_t)stream);
   if (m->off_wt.empty())
     return nf_set_error(ctx, NF_ERR_UNSUPPORTED,
                         "nf_sigma_normal_fwd needs a width-256 sigma network (depth <= 8)");

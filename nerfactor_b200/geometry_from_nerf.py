@@ -54,8 +54,10 @@ def compute_depth_and_normal(model, rayo, rayd, config, scene_bbox=None, precisi
     sigma = eval_sigma_mlp(model, rayo, rayd, z, False, scene_bbox, precision)
     w, _, _, _, _ = _lib.composite(ctx, sigma, z, rayo, rayd, want_surf=False)
     z = _lib.gen_z_fine(ctx, z, w, n_f)
+    prec = precision or model.precision
     sigma, normal = _lib.sigma_normal_fwd(ctx, model.packed_sigma(True), rayo, rayd, z,
-                                          parse_bbox(scene_bbox))
+                                          parse_bbox(scene_bbox),
+                                          prec if prec in ('fp32', 'f16', 'bf16') else 'fp32')
     _, occu, depth, _, exp_normal = _lib.composite(
         ctx, sigma, z, rayo, rayd, normal=normal, want_weights=False, want_surf=False)
     return occu, depth, exp_normal

@@ -152,6 +152,100 @@ def test_sigma_normal_kernel_vs_oracle_autograd(ctx):
     assert rel_l2(sig.cpu(), s32.cpu()) < 1e-6
 
 
+def _emulate_sigma_normal_mixed(params, pts, dt):
+    """The tcgen05 gradient kernel's arithmetic restated with torch ops on the device:
+    operands rounded to `dt` (fp16 / bf16), products accumulated in fp32, ReLU patterns
+    taken from the fp32 pre-activations, the backward seed scaled by a power of two.
+    Independent of the kernel's tiling / TMEM / barrier structure."""
+    q = lambda x: x.to(dt).float()
+    dev = pts.device
+    Ws = [torch.as_tensor(w, device=dev) for w, _ in params['fine_enc']['layers']]
+    bs = [torch.as_tensor(b, device=dev) for _, b in params['fine_enc']['layers']]
+    w_out = torch.as_tensor(params['fine_sigma_out']['layers'][0][0], device=dev)[:, 0]
+    b_out = float(params['fine_sigma_out']['layers'][0][1][0])
+    cols = [pts]
+    for f0 in range(0, 10, 3):                    # octaves 0,3,6,9 + double-angle steps
+        s, c = torch.sin(pts * float(2 ** f0)), torch.cos(pts * float(2 ** f0))
+        for j in range(3):
+            if f0 + j < 10:
+                cols += [s, c]
+                s, c = 2. * s * c, 1. - 2. * s * s
+    E = q(torch.cat(cols, 1))                     # [N, 63]
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        h, masks, hf = E, [], None
+        for l in range(8):
+            if l == 0:
+                pre = E @ q(Ws[0]) + bs[0]
+            elif l == 5:
+                pre = h @ q(Ws[5][:256]) + E @ q(Ws[5][256:]) + bs[5]
+            else:
+                pre = h @ q(Ws[l]) + bs[l]
+            masks.append(pre > 0)
+            hf = torch.relu(pre)
+            h = q(hf)
+        raw = hf @ w_out + b_out
+        gs = 2. ** (1 - int(np.frexp(float(w_out.abs().max()))[1]))
+        g = q(gs * w_out[None, :] * masks[7])
+        GE = torch.zeros_like(E)
+        for l in range(7, 0, -1):
+            if l == 5:
+                GE = GE + g @ q(Ws[5][256:]).t()
+            g = q((g @ q(Ws[l][:256]).t()) * masks[l - 1])
+        GE = GE + g @ q(Ws[0]).t()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    grad = GE[:, :3].clone()
+    for f in range(10):
+        sn, cs = E[:, 3 + 6 * f:6 + 6 * f], E[:, 6 + 6 * f:9 + 6 * f]
+        grad = grad + float(2 ** f) * (cs * GE[:, 3 + 6 * f:6 + 6 * f] - sn * GE[:, 6 + 6 * f:9 + 6 * f])
+    grad = grad * (raw > 0).float()[:, None] / gs
+    nrm = -grad * torch.rsqrt(torch.clamp((grad * grad).sum(1, keepdim=True), min=1e-12))
+    return torch.relu(raw), nrm
+
+
+@pytest.mark.parametrize('prec', ['f16', 'bf16'])
+def test_sigma_normal_tcgen05(ctx, prec):
+    """nf_sigma_normal_fwd on the tensor cores (forward + input gradient, fp16 / bf16 operands):
+    sigma bit-identical to the forward-only kernel; normals (a) agree with a torch restatement
+    of the same mixed-precision arithmetic, (b) are independent of which tile / CTA iteration
+    a sample lands in, (c) track the FP32 kernel within the operand precision."""
+    from nerfactor_b200 import _lib
+    model = _nerf_model(ctx, 3)
+    mlp = model.packed_sigma(True)
+    ro, rd = _rays(ctx, 64, 64)
+    S = 19                                              # 77824 samples: 608 tiles, ragged tail
+    z = _lib.gen_z(ctx, 2., 6., S, ro.shape[0])
+    sig, nrm = _lib.sigma_normal_fwd(ctx, mlp, ro, rd, z, None, prec)
+    assert torch.equal(sig, _lib.sigma_fwd(ctx, mlp, ro, rd, z, None, prec))
+    assert not torch.isnan(nrm).any()
+    # (b) first 147 tiles on their own (one tile per CTA) == the same samples in the long run
+    k = 990
+    sig_k, nrm_k = _lib.sigma_normal_fwd(ctx, mlp, ro[:k].contiguous(), rd[:k].contiguous(),
+                                         z[:k].contiguous(), None, prec)
+    assert torch.equal(nrm_k, nrm[:k]) and torch.equal(sig_k, sig[:k])
+    # (a) same arithmetic, different machinery
+    pts = (ro[:, None, :] + rd[:, None, :] * z[:, :, None]).reshape(-1, 3)
+    se, ne = _emulate_sigma_normal_mixed(synth.make_nerf_params(3), pts,
+                                         torch.float16 if prec == 'f16' else torch.bfloat16)
+    live = (ne.norm(dim=1) > 0.5) & (nrm.reshape(-1, 3).norm(dim=1) > 0.5)
+    assert float(live.float().mean()) > 0.1
+    d = (nrm.reshape(-1, 3) - ne).abs().max(dim=1).values[live]
+    print(prec, 'vs emulation: median', float(d.median()), 'q99', float(torch.quantile(d, .99)),
+          'max', float(d.max()))
+    assert float(d.median()) < 2e-4 and float(torch.quantile(d, .99)) < 2e-2
+    # (c) against the FP32 CUDA-core kernel
+    s32, n32 = _lib.sigma_normal_fwd(ctx, mlp, ro, rd, z)
+    both = (n32.norm(dim=2) > 0.5) & (nrm.norm(dim=2) > 0.5)
+    d32 = (n32 - nrm).abs().max(dim=2).values[both]
+    print(prec, 'vs fp32: median', float(d32.median()), 'q90', float(torch.quantile(d32, .9)))
+    assert float(d32.median()) < (2e-3 if prec == 'f16' else 6e-2)
+    # zero gradient where relu(raw) is off
+    off = sig.reshape(-1) == 0
+    assert float(nrm.reshape(-1, 3)[off].abs().max()) < 1e-6
+
+
 def test_compute_depth_and_normal_vs_golden(ctx, golden_dir):
     """Hierarchical camera->surface march (geometry_from_nerf.py:249-319), 32 + 48 samples."""
     from nerfactor_b200 import geometry_from_nerf as gfn
