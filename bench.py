@@ -238,11 +238,16 @@ def secondary_rows(ctx, nerf, kt):
     # (4) configs[3] semantics: one optimizer step, 1024 rays x 512 lights, fp32 training kernels
     lm2 = LearnedModel(nfconfig.default_config('nerfactor'),
                        params=synth.make_stage_b_params(0, 'learned'), ctx=ctx, precision='fp32')
-    tr = Trainer(lm2)
     tb = synth.make_stage_b_batch(2, 1024, 512, fg_frac=1.0)
+    tr = Trainer(lm2, precision='bf16')
     t = kt(lambda: tr.train_step(tb), 3)
-    out['train_step'] = {'what': 'Trainer.train_step, 1024 rays x 512 lights, jitter on, fp32',
+    out['train_step'] = {'what': 'Trainer.train_step, 1024 rays x 512 lights, jitter on, '
+                                 'tcgen05 Dense kernels (bf16 operands, fp32 accumulate / master)',
                          'ms': t, 'rays_per_s': 1024 / (t * 1e-3)}
+    tr = Trainer(lm2, precision='fp32')
+    t = kt(lambda: tr.train_step(tb), 3)
+    out['train_step_fp32'] = {'what': 'same, FP32 CUDA-core Dense kernels',
+                              'ms': t, 'rays_per_s': 1024 / (t * 1e-3)}
     return out
 
 

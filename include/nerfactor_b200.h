@@ -217,20 +217,25 @@ int nf_lvis_rays(nf_ctx* ctx, const float* surf_d, const float* normal_d, int n_
 /* ---- training (config 4): Dense layers on materialised activations + optimizer ----
  * One Keras Dense of mlp.Network (nerfactor/networks/mlp.py:34, 39-50) at a time:
  *   y[m, n] = act([x1[m,k1] | x2[m,k2]] w[(k1+k2), n] + b[n])      (x2 = skip concat, k2 may be 0)
- * n, k1, k2 must be multiples of 4 (pad heads / embeddings with zero rows / columns).      */
+ * n, k1, k2 must be multiples of 4 (pad heads / embeddings with zero rows / columns).
+ * precision: NF_PREC_FP32 (CUDA cores) or NF_PREC_F16 / NF_PREC_BF16 (tcgen05: operands rounded
+ * to 16 bit, fp32 accumulation, fp32 inputs / outputs; shapes the tensor-core kernels do not
+ * cover -- more than 256 input or output features -- silently use the FP32 kernels).
+ * work_d: caller scratch of nf_dense_fwd_workspace_bytes() bytes (may be NULL when that is 0). */
+size_t nf_dense_fwd_workspace_bytes(int n, int k1, int k2, int precision);
 int nf_dense_fwd(nf_ctx* ctx, const float* x1_d, int k1, const float* x2_d, int k2,
                  const float* w_d, const float* b_d, long long m, int n, int act, float* y_d,
-                 void* stream);
+                 void* work_d, int precision, void* stream);
 /* Backward of nf_dense_fwd (what tape.gradient computes for one Dense,
  * nerfactor/trainvali.py:278-285): with dz = dy * act'(y),
  *   dx1 | dx2 = dz w^T (either may be NULL), dw += [x1 | x2]^T dz, db += colsum(dz)
  * (dw_d / db_d are ACCUMULATED into and may be NULL).  work_d: caller scratch of
- * nf_dense_bwd_workspace_bytes(m, n, k1, k2) bytes.                                   */
-size_t nf_dense_bwd_workspace_bytes(long long m, int n, int k1, int k2);
+ * nf_dense_bwd_workspace_bytes(m, n, k1, k2, precision) bytes.                         */
+size_t nf_dense_bwd_workspace_bytes(long long m, int n, int k1, int k2, int precision);
 int nf_dense_bwd(nf_ctx* ctx, const float* x1_d, int k1, const float* x2_d, int k2,
                  const float* w_d, const float* y_d, const float* dy_d, long long m, int n,
                  int act, float* dx1_d, float* dx2_d, float* dw_d, float* db_d, void* work_d,
-                 void* stream);
+                 int precision, void* stream);
 /* One AMSGrad-Adam update of a flat parameter buffer: tf.keras.optimizers.Adam(lr, amsgrad=True)
  * as configured at nerfactor/trainvali.py:110-127 (beta1 .9, beta2 .999, epsilon 1e-7);
  * `step` is the 1-based iteration count, `lr` the already-decayed learning rate.          */

@@ -27,7 +27,8 @@ EXPORTS = [
     'nf_mlp_upload', 'nf_point_mlp_fwd', 'nf_lvis_fwd', 'nf_brdf_learned_fwd',
     'nf_integrate_fwd', 'nf_integrate_olat_fwd', 'nf_gen_rays', 'nf_gen_z',
     'nf_sigma_fwd', 'nf_sigma_normal_fwd', 'nf_composite', 'nf_gen_z_fine',
-    'nf_lvis_rays', 'nf_selftest_umma', 'nf_selftest_umma2', 'nf_dense_fwd', 'nf_dense_bwd_workspace_bytes',
+    'nf_lvis_rays', 'nf_selftest_umma', 'nf_selftest_umma2', 'nf_dense_fwd',
+    'nf_dense_fwd_workspace_bytes', 'nf_dense_bwd_workspace_bytes',
     'nf_dense_bwd', 'nf_adam_amsgrad_step']
 
 
@@ -94,14 +95,16 @@ def load_library():
     lib.nf_selftest_umma.argtypes = [vp, vp, vp, i, i, vp, vp]
     lib.nf_selftest_umma2.argtypes = [vp, vp, vp, i, vp, vp]
     ll = C.c_longlong
-    lib.nf_dense_fwd.argtypes = [vp, vp, i, vp, i, vp, vp, ll, i, i, vp, vp]
-    lib.nf_dense_bwd_workspace_bytes.argtypes = [ll, i, i, i]
+    lib.nf_dense_fwd.argtypes = [vp, vp, i, vp, i, vp, vp, ll, i, i, vp, vp, i, vp]
+    lib.nf_dense_fwd_workspace_bytes.argtypes = [i, i, i, i]
+    lib.nf_dense_fwd_workspace_bytes.restype = C.c_size_t
+    lib.nf_dense_bwd_workspace_bytes.argtypes = [ll, i, i, i, i]
     lib.nf_dense_bwd_workspace_bytes.restype = C.c_size_t
-    lib.nf_dense_bwd.argtypes = [vp, vp, i, vp, i, vp, vp, vp, ll, i, i, vp, vp, vp, vp, vp, vp]
+    lib.nf_dense_bwd.argtypes = [vp, vp, i, vp, i, vp, vp, vp, ll, i, i, vp, vp, vp, vp, vp, i, vp]
     lib.nf_adam_amsgrad_step.argtypes = [vp, vp, vp, vp, vp, vp, ll, f, f, f, f, ll, vp]
     for name in EXPORTS:
         if name not in ('nf_last_error_string', 'nf_mlp_device_bytes',
-                        'nf_dense_bwd_workspace_bytes'):
+                        'nf_dense_bwd_workspace_bytes', 'nf_dense_fwd_workspace_bytes'):
             getattr(lib, name).restype = i
     _lib = lib
     return lib
@@ -381,19 +384,23 @@ def selftest_umma(ctx, a, b, swap_lbo_sbo=False):
 
 # ------------------------------------------------------------------ training ops
 
-def dense_fwd(ctx, x1, x2, w, b, act):
+def dense_fwd(ctx, x1, x2, w, b, act, precision='fp32'):
     """y = act([x1 | x2] @ w + b); x2 may be None.  All dims multiples of 4."""
     m, k1 = x1.shape
     k2 = 0 if x2 is None else x2.shape[1]
     n = w.shape[1]
     assert w.shape[0] == k1 + k2
     y = torch.empty((m, n), dtype=torch.float32, device=x1.device)
+    nbytes = ctx.lib.nf_dense_fwd_workspace_bytes(n, k1, k2, PREC[precision])
+    work = torch.empty((nbytes,), dtype=torch.uint8, device=x1.device) if nbytes else None
     ctx.launch(ctx.lib.nf_dense_fwd(ctx.h, _f32(x1), k1, _f32(x2) if x2 is not None else None,
-                                    k2, _f32(w), _f32(b), m, n, ACT[act], _f32(y), _stream()))
+                                    k2, _f32(w), _f32(b), m, n, ACT[act], _f32(y),
+                                    _ptr(work) if work is not None else None, PREC[precision],
+                                    _stream()))
     return y
 
 
-def dense_bwd(ctx, x1, x2, w, y, dy, act, need_dx1, need_dx2):
+def dense_bwd(ctx, x1, x2, w, y, dy, act, need_dx1, need_dx2, precision='fp32'):
     """-> (dx1 | None, dx2 | None, dw, db) for one Dense layer."""
     m, k1 = x1.shape
     k2 = 0 if x2 is None else x2.shape[1]
@@ -403,12 +410,13 @@ def dense_bwd(ctx, x1, x2, w, y, dy, act, need_dx1, need_dx2):
     dx2 = torch.empty((m, k2), dtype=torch.float32, device=dev) if (need_dx2 and k2) else None
     dw = torch.zeros((k1 + k2, n), dtype=torch.float32, device=dev)
     db = torch.zeros((n,), dtype=torch.float32, device=dev)
-    nbytes = ctx.lib.nf_dense_bwd_workspace_bytes(m, n, k1, k2)
+    nbytes = ctx.lib.nf_dense_bwd_workspace_bytes(m, n, k1, k2, PREC[precision])
     work = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
     ctx.launch(ctx.lib.nf_dense_bwd(
         ctx.h, _f32(x1), k1, _f32(x2) if x2 is not None else None, k2, _f32(w), _f32(y),
         _f32(dy), m, n, ACT[act], _f32(dx1) if dx1 is not None else None,
-        _f32(dx2) if dx2 is not None else None, _f32(dw), _f32(db), _ptr(work), _stream()))
+        _f32(dx2) if dx2 is not None else None, _f32(dw), _f32(db), _ptr(work), PREC[precision],
+        _stream()))
     return dx1, dx2, dw, db
 
 

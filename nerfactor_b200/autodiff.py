@@ -19,19 +19,20 @@ from . import _lib
 # ------------------------------------------------------------------ Dense layers
 
 class DenseFn(torch.autograd.Function):
-    """act([x1 | x2] @ w + b) through nf_dense_fwd / nf_dense_bwd."""
+    """act([x1 | x2] @ w + b) through nf_dense_fwd / nf_dense_bwd.  `prec`: 'fp32' (CUDA
+    cores) or 'bf16' / 'f16' (tcgen05, operands rounded to 16 bit, fp32 accumulation)."""
 
     @staticmethod
-    def forward(ctx, x1, x2, w, b, act):
+    def forward(ctx, x1, x2, w, b, act, prec='fp32'):
         c = _lib.default_context()
         x1 = x1.contiguous()
         x2c = None if x2 is None else x2.contiguous()
         w, b = w.contiguous(), b.contiguous()
         if w.data_ptr() % 16:            # cp.async needs 16-byte aligned weight rows
             w = w.clone()
-        y = _lib.dense_fwd(c, x1, x2c, w, b, act)
+        y = _lib.dense_fwd(c, x1, x2c, w, b, act, prec)
         ctx.save_for_backward(x1, x2c if x2c is not None else x1.new_empty(0), w, y)
-        ctx.has_x2, ctx.act = x2c is not None, act
+        ctx.has_x2, ctx.act, ctx.prec = x2c is not None, act, prec
         return y
 
     @staticmethod
@@ -40,15 +41,16 @@ class DenseFn(torch.autograd.Function):
         x2 = x2 if ctx.has_x2 else None
         c = _lib.default_context()
         n1, n2 = ctx.needs_input_grad[0], ctx.has_x2 and ctx.needs_input_grad[1]
-        dx1, dx2, dw, db = _lib.dense_bwd(c, x1, x2, w, y, dy.contiguous(), ctx.act, n1, n2)
-        return dx1, dx2, dw, db, None
+        dx1, dx2, dw, db = _lib.dense_bwd(c, x1, x2, w, y, dy.contiguous(), ctx.act, n1, n2,
+                                          ctx.prec)
+        return dx1, dx2, dw, db, None, None
 
 
 def _pad_to4(n):
     return (n + 3) // 4 * 4
 
 
-def mlp_apply(x, layers, acts, skip_at):
+def mlp_apply(x, layers, acts, skip_at, prec='fp32'):
     """mlp.Network.__call__ (nerfactor/networks/mlp.py:39-50) + seq.Network for the head.
     layers: [(W[in,out], b[out]), ...] torch tensors (Keras layout).  Inputs / outputs
     whose width is not a multiple of 4 are zero-padded for the kernels (and sliced back)."""
@@ -72,7 +74,7 @@ def mlp_apply(x, layers, acts, skip_at):
             bfull = F.pad(b, (0, n_pad - n))
         else:
             bfull = b
-        y = DenseFn.apply(x1, x2, wfull, bfull, act)
+        y = DenseFn.apply(x1, x2, wfull, bfull, act, prec)
         h = y[:, :n] if n_pad != n else y
         h_skip = xp if (skip_at is not None and i in skip_at) else None
     return h

@@ -257,16 +257,41 @@ __global__ void adam_amsgrad_kernel(float* __restrict__ p, const float* __restri
 
 }  // namespace
 
+// nf_train_tc.cu: tcgen05 versions (16-bit operands)
+bool nf_dense_tc_supported(int k1, int k2, int n);
+size_t nf_dense_tc_fwd_workspace(int k1, int k2, int n);
+size_t nf_dense_tc_bwd_workspace(long long m, int k1, int k2, int n, int sm_count);
+int nf_dense_tc_fwd(nf_ctx* ctx, const float* x1, int k1, const float* x2, int k2, const float* w,
+                    const float* b, long long m, int n, int act, float* y, void* work,
+                    int precision, cudaStream_t st);
+int nf_dense_tc_bwd(nf_ctx* ctx, const float* x1, int k1, const float* x2, int k2, const float* w,
+                    const float* y, const float* dy, long long m, int n, int act, float* dx1,
+                    float* dx2, float* dw, float* db, void* work, int precision, cudaStream_t st);
+
+static bool use_tc(int precision, int k1, int k2, int n) {
+  return (precision == NF_PREC_F16 || precision == NF_PREC_BF16) && nf_dense_tc_supported(k1, k2, n);
+}
+
 extern "C" {
+
+size_t nf_dense_fwd_workspace_bytes(int n, int k1, int k2, int precision) {
+  return use_tc(precision, k1, k2, n) ? nf_dense_tc_fwd_workspace(k1, k2, n) : 0;
+}
 
 int nf_dense_fwd(nf_ctx* ctx, const float* x1_d, int k1, const float* x2_d, int k2,
                  const float* w_d, const float* b_d, long long m, int n, int act, float* y_d,
-                 void* stream) {
+                 void* work_d, int precision, void* stream) {
   NF_CHECK_ARG(ctx, m >= 0 && n >= 1 && k1 >= 1 && k2 >= 0, "bad sizes");
   if (m == 0) return NF_OK;
   NF_CHECK_ARG(ctx, x1_d && w_d && b_d && y_d && (k2 == 0 || x2_d), "null buffer");
   NF_CHECK_ARG(ctx, n % 4 == 0 || n < 4, "n must be a multiple of 4 (or < 4)");
+  NF_CHECK_ARG(ctx, precision == NF_PREC_FP32 || precision == NF_PREC_F16 || precision == NF_PREC_BF16,
+               "precision must be NF_PREC_FP32, NF_PREC_F16 or NF_PREC_BF16");
   cudaStream_t st = (cudaStream_t)stream;
+  if (use_tc(precision, k1, k2, n)) {
+    NF_CHECK_ARG(ctx, work_d, "null workspace (nf_dense_fwd_workspace_bytes)");
+    return nf_dense_tc_fwd(ctx, x1_d, k1, x2_d, k2, w_d, b_d, m, n, act, y_d, work_d, precision, st);
+  }
   if (n < 4) {
     // tiny heads: pad the weight rows on the fly is not worth a kernel; use W = 128-wide path
     // through a padded copy is the caller's job -> not supported here
@@ -287,7 +312,8 @@ int nf_dense_fwd(nf_ctx* ctx, const float* x1_d, int k1, const float* x2_d, int 
   return NF_OK;
 }
 
-size_t nf_dense_bwd_workspace_bytes(long long m, int n, int k1, int k2) {
+size_t nf_dense_bwd_workspace_bytes(long long m, int n, int k1, int k2, int precision) {
+  if (use_tc(precision, k1, k2, n)) return nf_dense_tc_bwd_workspace(m, k1, k2, n, 160);
   size_t dz = (size_t)m * n * sizeof(float);
   size_t wt = (size_t)n * (k1 + k2) * sizeof(float);
   return (dz + 255) / 256 * 256 + (wt + 255) / 256 * 256;
@@ -296,12 +322,19 @@ size_t nf_dense_bwd_workspace_bytes(long long m, int n, int k1, int k2) {
 int nf_dense_bwd(nf_ctx* ctx, const float* x1_d, int k1, const float* x2_d, int k2,
                  const float* w_d, const float* y_d, const float* dy_d, long long m, int n,
                  int act, float* dx1_d, float* dx2_d, float* dw_d, float* db_d, void* work_d,
-                 void* stream) {
+                 int precision, void* stream) {
   NF_CHECK_ARG(ctx, m >= 0 && n >= 4 && n % 4 == 0 && k1 >= 1 && k2 >= 0, "bad sizes");
   if (m == 0) return NF_OK;
   NF_CHECK_ARG(ctx, x1_d && w_d && y_d && dy_d && work_d && (k2 == 0 || x2_d), "null buffer");
   NF_CHECK_ARG(ctx, k1 % 4 == 0 && k2 % 4 == 0, "k1, k2 must be multiples of 4");
+  NF_CHECK_ARG(ctx, precision == NF_PREC_FP32 || precision == NF_PREC_F16 || precision == NF_PREC_BF16,
+               "precision must be NF_PREC_FP32, NF_PREC_F16 or NF_PREC_BF16");
   cudaStream_t st = (cudaStream_t)stream;
+  if (use_tc(precision, k1, k2, n)) {
+    NF_CHECK_ARG(ctx, ctx->sm_count <= 160, "unexpected SM count");
+    return nf_dense_tc_bwd(ctx, x1_d, k1, x2_d, k2, w_d, y_d, dy_d, m, n, act, dx1_d, dx2_d, dw_d,
+                           db_d, work_d, precision, st);
+  }
   const int ktot = k1 + k2;
   float* dz = reinterpret_cast<float*>(work_d);
   float* wt = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(work_d) +

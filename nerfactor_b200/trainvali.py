@@ -21,7 +21,11 @@ from .models.shape import to_device
 
 
 class Trainer:
-    def __init__(self, model, config=None, world_size=1, rank=0):
+    def __init__(self, model, config=None, world_size=1, rank=0, precision=None):
+        """precision: arithmetic of the Dense layers -- 'fp32' (CUDA cores), 'bf16' or 'f16'
+        (tcgen05: 16-bit operands, fp32 accumulation, fp32 master weights / optimizer state).
+        Default: 'fp32' for an fp32 model, else 'bf16' (BASELINE configs[3])."""
+        self.precision = precision or ('fp32' if model.precision == 'fp32' else 'bf16')
         self.model = model
         self.ctx = model.ctx
         self.device = model.device
@@ -116,7 +120,7 @@ class Trainer:
     def _point(self, views, name, pts):
         layers, acts, skip = self.net_layers(views, name)
         e = ad.embed(self.model.xyz_scale * pts, self.model.embedder['xyz'].n_freqs)
-        return ad.mlp_apply(e, layers, acts, skip)
+        return ad.mlp_apply(e, layers, acts, skip, self.precision)
 
     def _lvis(self, views, pts, surf2l):
         layers, acts, skip = self.net_layers(views, 'lvis')
@@ -125,7 +129,7 @@ class Trainer:
         e_x = ad.embed(m.xyz_scale * pts, m.embedder['xyz'].n_freqs)
         e_l = ad.embed(surf2l.reshape(-1, 3), m.embedder['ldir'].n_freqs)
         e = torch.cat((e_x[:, None, :].expand(n, L, e_x.shape[1]).reshape(n * L, -1), e_l), -1)
-        return ad.mlp_apply(e, layers, acts, skip).reshape(n, L)
+        return ad.mlp_apply(e, layers, acts, skip, self.precision).reshape(n, L)
 
     def _brdf_learned(self, surf2l, surf2c, normal, albedo, z):
         """nerfactor.py:413-461 (all pairs evaluated; back-lit ones are zeroed, :454-455)."""
@@ -142,7 +146,7 @@ class Trainer:
         e = torch.cat((z_flat, ad.embed(rusink, m.embedder['rusink'].n_freqs)), 1)
         trunk = m.brdf_model.net['brdf_mlp']
         acts = [l.activation for l in trunk.layers] + ['softplus']
-        spec = ad.mlp_apply(e, self.brdf_layers, acts, trunk.skip_at)[:, 0] * front
+        spec = ad.mlp_apply(e, self.brdf_layers, acts, trunk.skip_at, self.precision)[:, 0] * front
         scale = m.config.getfloat('DEFAULT', 'learned_brdf_scale')
         return albedo[:, None, :] / math.pi + (spec.reshape(n, L, 1) * scale).expand(n, L, 3)
 

@@ -55,6 +55,46 @@ def test_dense_fwd_bwd_vs_torch(ctx, shape):
         assert rel_l2(a.cpu(), r.cpu()) < 2e-5
 
 
+@pytest.mark.parametrize('prec', ['bf16', 'f16'])
+@pytest.mark.parametrize('shape', [(1000, 92, 0, 128, 'relu'), (777, 128, 92, 128, 'relu'),
+                                   (513, 128, 0, 4, 'sigmoid'), (40000, 128, 0, 128, 'relu'),
+                                   (130, 20, 0, 128, 'softplus'), (64, 128, 0, 4, None),
+                                   (20000, 128, 20, 128, 'relu'), (300, 64, 0, 16, None)])
+def test_dense_tcgen05_fwd_bwd(ctx, shape, prec):
+    """The tensor-core Dense kernels against fp64 matmuls of the SAME 16-bit-rounded operands
+    (products of 16-bit values are exact in fp32, so only the accumulation order differs)."""
+    from nerfactor_b200 import autodiff as ad
+    m, k1, k2, n, act = shape
+    dt = torch.bfloat16 if prec == 'bf16' else torch.float16
+    q = lambda t: t.detach().to(dt).double()
+    g = torch.Generator(device='cpu').manual_seed(m + 1)
+    x1 = torch.randn((m, k1), generator=g).cuda().requires_grad_(True)
+    x2 = torch.randn((m, k2), generator=g).cuda().requires_grad_(True) if k2 else None
+    w = (torch.randn((k1 + k2, n), generator=g) * 0.1).cuda().requires_grad_(True)
+    b = (torch.randn((n,), generator=g) * 0.1).cuda().requires_grad_(True)
+    dy = torch.randn((m, n), generator=g).cuda()
+    y = ad.DenseFn.apply(x1, x2, w, b, act, prec)
+    ins = [x1, w, b] + ([x2] if k2 else [])
+    grads = torch.autograd.grad(y, ins, dy)
+    xcat = x1 if x2 is None else torch.cat((x1, x2), 1)
+    pre = q(xcat) @ q(w) + b.detach().double()
+    f = {'relu': torch.relu, 'sigmoid': torch.sigmoid, 'softplus': torch.nn.functional.softplus,
+         None: lambda t: t}[act]
+    assert rel_l2(y.detach().cpu(), f(pre).cpu()) < 1e-5
+    yk = y.detach().double()
+    dact = {'relu': (yk > 0).double(), 'sigmoid': yk * (1 - yk), 'softplus': 1 - torch.exp(-yk),
+            None: torch.ones_like(yk)}[act]
+    dz = dy.double() * dact                                  # fp32 product in the kernel
+    dzq = q(dz.float())
+    dx = dzq @ q(w).t()
+    ref = [dx[:, :k1], q(xcat).t() @ dzq, dz.sum(0)] + ([dx[:, k1:]] if k2 else [])
+    for a, r, name in zip(grads, ref, ('dx1', 'dw', 'db', 'dx2')):
+        assert rel_l2(a.cpu(), r.cpu()) < 2e-5, name
+    # and against the exact fp32 layer: operand rounding only
+    y32 = ad.DenseFn.apply(x1, x2, w, b, act, 'fp32')
+    assert rel_l2(y.detach().cpu(), y32.detach().cpu()) < (2e-2 if prec == 'bf16' else 3e-3)
+
+
 def test_amsgrad_kernel_vs_numpy(ctx):
     from nerfactor_b200 import _lib
     rng = np.random.default_rng(0)
@@ -139,11 +179,42 @@ def test_train_step_gradient_vs_oracle_autograd(ctx, brdf):
     assert checked >= 17
 
 
-def test_training_reduces_loss_and_syncs_back(ctx):
+@pytest.mark.parametrize('brdf', ['microfacet', 'learned'])
+def test_train_step_gradient_bf16_tensor_cores(ctx, brdf):
+    """configs[3]: the same step with every Dense on the tcgen05 kernels (bf16 operands, fp32
+    accumulation / master weights).  The gradient must stay aligned with the fp32 oracle's:
+    per-tensor cosine > 0.99 and norm within 10 % (bf16 operand rounding is ~4e-3 per value)."""
+    from nerfactor_b200.trainvali import Trainer
+    m, params, lights = _models(ctx, brdf)
+    batch = synth.make_stage_b_batch(11, 48, 16)
+    nfg = int((batch[5][:, 0] > 0).sum())
+    noise = (0.01 * np.random.default_rng(2).standard_normal((nfg, 3))).astype(np.float32)
+    tr = Trainer(m, precision='bf16')
+    loss, grad = tr.loss_and_grad(batch, xyz_noise=noise)
+    oloss, leaves = _oracle_grads(params, brdf, lights, batch, noise)
+    assert np.allclose(loss.cpu().numpy(), oloss.numpy(), atol=3e-3, rtol=5e-2)
+    gv = tr.views(grad)
+    cos_all = []
+    for key, t in leaves.items():
+        if key not in gv:
+            continue
+        ref = t.grad.numpy().reshape(-1).astype(np.float64)
+        got = gv[key].cpu().numpy().reshape(-1).astype(np.float64)
+        if np.linalg.norm(ref) < 1e-7:
+            continue
+        cos = float(ref @ got / (np.linalg.norm(ref) * np.linalg.norm(got)))
+        cos_all.append(cos)
+        assert cos > 0.99, (key, cos)
+        assert 0.9 < np.linalg.norm(got) / np.linalg.norm(ref) < 1.1, key
+    assert len(cos_all) >= 17
+
+
+@pytest.mark.parametrize('prec', ['fp32', 'bf16'])
+def test_training_reduces_loss_and_syncs_back(ctx, prec):
     from nerfactor_b200.trainvali import Trainer
     m, params, lights = _models(ctx, 'microfacet')
     batch = synth.make_stage_b_batch(5, 64, 16, fg_frac=1.0)
-    tr = Trainer(m)
+    tr = Trainer(m, precision=prec)
     tr.lr0 = 1e-3
     noise = np.zeros((64, 3), np.float32)
     losses = [float(tr.train_step(batch, xyz_noise=noise)) for _ in range(25)]
