@@ -90,6 +90,18 @@ def embed(x, n_freqs):
 
 # ------------------------------------------------------- TF semantics with custom grads
 
+_CONSTS = {}
+
+
+def _const(vals, device):
+    """Small constant vectors, uploaded once per device (a host->device copy of a Python tuple
+    cannot be captured into a CUDA graph)."""
+    key = (tuple(vals), str(device))
+    if key not in _CONSTS:
+        _CONSTS[key] = torch.tensor(vals, dtype=torch.float32, device=device)
+    return _CONSTS[key]
+
+
 def safe_l2_normalize(x, axis, eps=1e-6):
     """nerfactor/util/math.py:63-64 (tf.linalg.l2_normalize)."""
     sq = torch.sum(x * x, dim=axis, keepdim=True)
@@ -136,7 +148,7 @@ def divide_no_nan(a, b):
 def gen_world2local(normal, eps=1e-6):
     """nerfactor/util/geom.py:119-149."""
     normal = safe_l2_normalize(normal, 1)
-    z = (torch.tensor((0., 0., 1.), device=normal.device) + eps)[None, :].expand_as(normal)
+    z = (_const((0., 0., 1.), normal.device) + eps)[None, :].expand_as(normal)
     t = safe_l2_normalize(torch.linalg.cross(normal, z), 1)
     b = safe_l2_normalize(torch.linalg.cross(normal, t), 1)
     return torch.stack((t, b, normal), dim=1)
@@ -149,8 +161,8 @@ def dir2rusink(a, b):
     h = safe_l2_normalize((a + b) / 2, 1)
     theta_h = SafeAcos.apply(h[:, 2])
     phi_h = SafeAtan2.apply(h[:, 1], h[:, 0])
-    binormal = torch.tensor((0., 1., 0.), device=a.device)
-    normal = torch.tensor((0., 0., 1.), device=a.device)
+    binormal = _const((0., 1., 0.), a.device)
+    normal = _const((0., 0., 1.), a.device)
 
     def rot_vec(vector, axis, angle):
         cos_ang, sin_ang = torch.cos(angle).reshape(-1), torch.sin(angle).reshape(-1)

@@ -63,7 +63,14 @@ class Trainer:
         self.m = torch.zeros_like(self.flat)
         self.v = torch.zeros_like(self.flat)
         self.vhat = torch.zeros_like(self.flat)
-        # frozen BRDF prior (nerfactor.py:58-60), device copies
+        # frozen layers (trainable = False) and the frozen BRDF prior (nerfactor.py:58-60): device copies
+        self._frozen = {}
+        for net_name, net in model.net.items():
+            for li, layer in enumerate(net.layers):
+                if not layer.trainable:
+                    self._frozen[(net_name, li)] = (to_device(layer.kernel, self.device),
+                                                    to_device(layer.bias, self.device))
+        self._graphs = {}
         self.brdf_layers = None
         if getattr(model, 'brdf_model', None) is not None:
             bm = model.brdf_model
@@ -90,8 +97,7 @@ class Trainer:
                 if key in views:
                     layers.append((views[key], views[(name + part, li, 'bias')]))
                 else:      # frozen layer
-                    layers.append((to_device(layer.kernel, self.device),
-                                   to_device(layer.bias, self.device)))
+                    layers.append(self._frozen[(name + part, li)])
         trunk = self.model.net[name + '_mlp']
         head = self.model.net[name + '_out']
         acts = [l.activation for l in trunk.layers] + [l.activation for l in head.layers]
@@ -150,8 +156,11 @@ class Trainer:
         scale = m.config.getfloat('DEFAULT', 'learned_brdf_scale')
         return albedo[:, None, :] / math.pi + (spec.reshape(n, L, 1) * scale).expand(n, L, 3)
 
-    def forward(self, flat, batch, mode, xyz_noise=None):
-        """Differentiable `Model.call` (shape.py:146-182 / nerfactor.py:181-313) + loss."""
+    def forward(self, flat, batch, mode, xyz_noise=None, all_fg=False):
+        """Differentiable `Model.call` (shape.py:146-182 / nerfactor.py:181-313) + loss.
+        all_fg: the caller guarantees alpha > 0 for every ray (what the train-mode sampler
+        produces, nerf_shape.py:84-121), so the foreground compaction is the identity and the
+        step has static shapes (CUDA-graph capturable)."""
         m = self.model
         views = self.views(flat)
         dev = self.device
@@ -160,7 +169,7 @@ class Trainer:
                                                (rayo, rgb, alpha, xyz, normal, lvis)]
         is_shape = not hasattr(m, 'shape_mode')
         jitter_std = m.config.getfloat('DEFAULT', 'xyz_jitter_std')
-        if is_shape:
+        if is_shape or all_fg:
             sel = lambda x: x
             ind = None
         else:
@@ -245,18 +254,60 @@ class Trainer:
         return loss, pred
 
     # ------------------------------------------------------------------ steps
-    def loss_and_grad(self, batch, xyz_noise=None, global_batch=None):
+    def loss_and_grad(self, batch, xyz_noise=None, global_batch=None, all_fg=False):
         """-> (per-ray loss [N], flat gradient of sum(loss) / global_batch)."""
         flat = self.flat.detach().requires_grad_(True)
-        loss, _ = self.forward(flat, batch, 'train', xyz_noise)
+        loss, _ = self.forward(flat, batch, 'train', xyz_noise, all_fg)
         gb = global_batch or (loss.shape[0] * self.world_size)
         total = torch.sum(loss) / gb                      # tf.nn.compute_average_loss
         (grad,) = torch.autograd.grad(total, flat)
         return loss.detach(), grad
 
-    def train_step(self, batch, xyz_noise=None):
-        """trainvali.py:273-295: one optimizer iteration; returns the summed loss / global bs."""
-        loss, grad = self.loss_and_grad(batch, xyz_noise)
+    # ---- CUDA-graph replay of forward + backward (the ~2000 small launches of one step)
+    def _all_foreground(self, alpha):
+        a = alpha[:, 0] if getattr(alpha, 'ndim', 2) == 2 else alpha
+        return bool((a > 0).all())
+
+    def _graphed_loss_and_grad(self, batch, xyz_noise):
+        """Captures loss_and_grad once per input-shape signature and replays it; inputs are copied
+        into static device buffers.  Returns None when the batch is not graphable."""
+        is_shape = not hasattr(self.model, 'shape_mode')
+        if not is_shape and not self._all_foreground(batch[5]):
+            return None
+        fields = (2, 4, 5, 6, 7, 8)                      # rayo, rgb, alpha, xyz, normal, lvis
+        key = tuple(tuple(batch[i].shape) for i in fields) + (xyz_noise is not None,)
+        st = self._graphs.get(key)
+        if st is None:
+            bufs = {i: torch.empty(tuple(batch[i].shape), dtype=torch.float32, device=self.device)
+                    for i in fields}
+            nbuf = None if xyz_noise is None else torch.empty(
+                tuple(xyz_noise.shape), dtype=torch.float32, device=self.device)
+            static = tuple(bufs.get(i, batch[i] if i < 2 else None) for i in range(9))
+            st = {'bufs': bufs, 'noise': nbuf, 'batch': static, 'graph': None}
+            self._graphs[key] = st
+        for i, bt in st['bufs'].items():
+            bt.copy_(torch.as_tensor(batch[i]), non_blocking=True)
+        if st['noise'] is not None:
+            st['noise'].copy_(torch.as_tensor(xyz_noise), non_blocking=True)
+        if st['graph'] is None:
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):                # warm-up off the capture stream
+                self.loss_and_grad(st['batch'], st['noise'], all_fg=True)
+            cur.wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                st['loss'], st['grad'] = self.loss_and_grad(st['batch'], st['noise'], all_fg=True)
+            st['graph'] = g
+        st['graph'].replay()
+        return st['loss'], st['grad']
+
+    def train_step(self, batch, xyz_noise=None, graph=True):
+        """trainvali.py:273-295: one optimizer iteration; returns the summed loss / global bs.
+        graph=True replays forward + backward as one CUDA graph when the batch allows it."""
+        out = self._graphed_loss_and_grad(batch, xyz_noise) if graph else None
+        loss, grad = out if out is not None else self.loss_and_grad(batch, xyz_noise)
         if self.world_size > 1:
             import torch.distributed as dist
             dist.all_reduce(grad, op=dist.ReduceOp.SUM)   # gradient all-reduce (one flat buffer)

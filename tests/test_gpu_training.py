@@ -227,6 +227,30 @@ def test_training_reduces_loss_and_syncs_back(ctx, prec):
     assert torch.isfinite(pred['rgb']).all()
 
 
+@pytest.mark.parametrize('brdf', ['microfacet', 'learned'])
+def test_graph_replay_equals_eager_step(ctx, brdf):
+    """train_step(graph=True) replays forward + backward as one CUDA graph; parameters after
+    three steps must equal the eager path's bit for bit (same kernels, same order)."""
+    from nerfactor_b200.trainvali import Trainer
+    batch = synth.make_stage_b_batch(5, 64, 16, fg_frac=1.0)
+    noise = (0.01 * np.random.default_rng(4).standard_normal((64, 3))).astype(np.float32)
+    flats = []
+    for graph in (False, True):
+        m, _, _ = _models(ctx, brdf)
+        tr = Trainer(m, precision='bf16')
+        for _ in range(3):
+            tr.train_step(batch, xyz_noise=noise, graph=graph)
+        if graph:
+            assert len(tr._graphs) == 1 and next(iter(tr._graphs.values()))['graph'] is not None
+        flats.append(tr.flat.clone())
+    assert torch.equal(flats[0], flats[1])
+    # a batch with background rays falls back to the eager path
+    m, _, _ = _models(ctx, brdf)
+    tr = Trainer(m, precision='bf16')
+    tr.train_step(synth.make_stage_b_batch(5, 64, 16, fg_frac=0.5))
+    assert not tr._graphs
+
+
 def test_shape_model_train_step(ctx):
     """shape.py pre-training (normal + visibility MLPs, shape.py:239-277)."""
     from nerfactor_b200.models.shape import Model
