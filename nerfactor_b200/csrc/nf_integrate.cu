@@ -92,56 +92,213 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// smem: lx4[L] (lxyz, area) ++ light4[ec][L] (texel of light idx(l), padded)
-__global__ void __launch_bounds__(WARPS * 32) integrate_kernel(const nf_integrate_args a) {
+// ---- packed-FP32 (FFMA2 / FMUL2 / FADD2, sm_100) version of the pair evaluation ------------
+// Two consecutive lights per lane, every vector quantity as a float2 (light 2j, light 2j+1).
+// Same formulas as eval_pair with three identities applied (each exact up to 1 ulp):
+//   h.v = l.h            (h is the normalised half vector of two unit vectors)
+//   l.n2 = l.n1 = cos    (n2 = l2n(n1) is n1)
+//   spec * cos / |l.n| = spec' for cos > 0: the division by |l.n| cancels against the cosine of
+//   the rendering equation, so   brdf * w = (lambert * cos + F K / u^2) * [cos>0] lvis area,
+//   K = g_view a2 / (4 pi |v.n|)  (0 when v.n = 0: tf.math.divide_no_nan, microfacet.py:58-61).
+__device__ __forceinline__ float2 bc2(float s) { return make_float2(s, s); }
+__device__ __forceinline__ float rsq_fast(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_fast(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float2 dot3_2(float2 ax, float2 ay, float2 az, float2 bx, float2 by, float2 bz) {
+  return __ffma2_rn(az, bz, __ffma2_rn(ay, by, __fmul2_rn(ax, bx)));
+}
+
+struct PointCtx2 {
+  float2 npx, npy, npz;        // -point
+  float2 nx, ny, nz;           // unit normal
+  float2 vx, vy, vz;           // unit view direction
+  float2 a2m1;                 // alpha^2 - 1   (u = 1 + (a2 - 1) cm^2)
+  float2 k;                    // g_view a2 / (4 pi |v.n|)
+  float2 f0, omf0;
+  float2 lr, lg, lb;           // albedo / pi
+  float cos_v;
+};
+
+// sw = specular * [cos>0] lvis area (already multiplied by the cosine, see above), dw = diffuse
+// weight [cos>0] lvis area cos
+template <int KIND>
+__device__ __forceinline__ void eval_pair2(const nf_integrate_args& a, const PointCtx2& c,
+                                           float2 lx, float2 ly, float2 lz, float2 la,
+                                           float2 lvis, float2 spec_in, float2& sw, float2& dw) {
+  const float2 dx = __fadd2_rn(lx, c.npx), dy = __fadd2_rn(ly, c.npy), dz = __fadd2_rn(lz, c.npz);
+  float2 dd = dot3_2(dx, dy, dz, dx, dy, dz);
+  const float2 inv = make_float2(rsq_fast(fmaxf(dd.x, 1e-6f)), rsq_fast(fmaxf(dd.y, 1e-6f)));
+  const float2 l1x = __fmul2_rn(dx, inv), l1y = __fmul2_rn(dy, inv), l1z = __fmul2_rn(dz, inv);
+  const float2 cosv = dot3_2(l1x, l1y, l1z, c.nx, c.ny, c.nz);          // nerfactor.py:325
+  const float2 wl = __fmul2_rn(lvis, la);                               // lvis * area
+  dw = __fmul2_rn(wl, make_float2(fmaxf(cosv.x, 0.f), fmaxf(cosv.y, 0.f)));   // :329-335
+  if (KIND == 0) {
+    const float2 hx = __fadd2_rn(l1x, c.vx), hy = __fadd2_rn(l1y, c.vy), hz = __fadd2_rn(l1z, c.vz);
+    const float2 hh = dot3_2(hx, hy, hz, hx, hy, hz);
+    const float2 invh = make_float2(rsq_fast(fmaxf(hh.x, 1e-6f)), rsq_fast(fmaxf(hh.y, 1e-6f)));
+    const float2 cm = __fmul2_rn(dot3_2(hx, hy, hz, c.nx, c.ny, c.nz), invh);      // :96
+    const float2 ldh = __fmul2_rn(dot3_2(hx, hy, hz, l1x, l1y, l1z), invh);        // = h.v, :78
+    const float2 om = __ffma2_rn(ldh, bc2(-1.f), bc2(1.f));
+    const float2 om2 = __fmul2_rn(om, om);
+    const float2 om5 = __fmul2_rn(__fmul2_rn(om2, om2), om);
+    const float2 f = __ffma2_rn(om5, c.omf0, c.f0);                                 // :106-111
+    const float2 u = __ffma2_rn(c.a2m1, __fmul2_rn(cm, cm), bc2(1.f));
+    const float2 uu = __fmul2_rn(u, u);
+    const float2 r = make_float2(rcp_fast(uu.x), rcp_fast(uu.y));
+    const float2 sp = __fmul2_rn(__fmul2_rn(f, c.k), __fmul2_rn(wl, r));
+    // chi_d (m.n > 0), chi_g ((h.v)(n.v) > 0), front-lit, non-degenerate lobe
+    const float2 hv = __fmul2_rn(ldh, bc2(c.cos_v));
+    const float gx = fminf(fminf(cosv.x, cm.x), fminf(hv.x, u.x));
+    const float gy = fminf(fminf(cosv.y, cm.y), fminf(hv.y, u.y));
+    sw = make_float2(gx > 0.f ? sp.x : 0.f, gy > 0.f ? sp.y : 0.f);
+  } else {
+    // learned BRDF: spec * learned_brdf_scale (nerfactor.py:460), times the diffuse weight
+    sw = __fmul2_rn(__fmul2_rn(spec_in, bc2(a.spec_scale)), dw);
+  }
+}
+
+__device__ __forceinline__ PointCtx2 load_point2(const nf_integrate_args& a, int i) {
+  const PointCtx s = load_point(a, i);
+  PointCtx2 c;
+  c.npx = bc2(-s.pt.x); c.npy = bc2(-s.pt.y); c.npz = bc2(-s.pt.z);
+  c.nx = bc2(s.n1.x); c.ny = bc2(s.n1.y); c.nz = bc2(s.n1.z);
+  c.vx = bc2(s.v2.x); c.vy = bc2(s.v2.y); c.vz = bc2(s.v2.z);
+  c.a2m1 = bc2(s.alpha2_sq - 1.f);
+  c.k = bc2(s.abs_vn != 0.f ? s.g_view * s.alpha2_sq / (4.f * NF_PI_F * s.abs_vn) : 0.f);
+  c.f0 = bc2(a.f0); c.omf0 = bc2(1.f - a.f0);
+  c.lr = bc2(s.lambert.x); c.lg = bc2(s.lambert.y); c.lb = bc2(s.lambert.z);
+  c.cos_v = s.cos_v;
+  return c;
+}
+
+// smem (floats, Lp = L rounded up to 2): X[Lp] Y[Lp] Z[Lp] AREA[Lp], then per env-map of the
+// chunk R[Lp] G[Lp] B[Lp] (texel of light idx(l)); pad entries have area 0.
+// EC = env-maps per pass (compile time: the accumulation loop has no branches).  The lvis /
+// spec row of a point is fetched in one burst of up to 8 float2 per lane (512 lights) BEFORE the
+// arithmetic, so each warp pays the DRAM latency once per point instead of once per 64 lights.
+template <int EC, int KIND>
+__global__ void __launch_bounds__(WARPS * 32, KIND == 0 && EC == 1 ? 3 : 1) integrate_kernel(const nf_integrate_args a) {
   extern __shared__ float4 sm4[];
-  float4* lx4 = sm4;
-  float4* lt4 = sm4 + a.n_lights;
-  const int L = a.n_lights;
-  for (int l = threadIdx.x; l < L; l += blockDim.x)
-    lx4[l] = make_float4(a.lxyz_d[l * 3], a.lxyz_d[l * 3 + 1], a.lxyz_d[l * 3 + 2], a.lareas_d[l]);
+  float* smf = reinterpret_cast<float*>(sm4);
+  const int L = a.n_lights, Lp = (L + 1) & ~1;
+  float* sx = smf; float* sy = sx + Lp; float* sz = sy + Lp; float* sa = sz + Lp;
+  float* st = sa + Lp;
+  for (int l = threadIdx.x; l < Lp; l += blockDim.x) {
+    const bool in = l < L;
+    sx[l] = in ? a.lxyz_d[l * 3] : 0.f;
+    sy[l] = in ? a.lxyz_d[l * 3 + 1] : 0.f;
+    sz[l] = in ? a.lxyz_d[l * 3 + 2] : 1.f;
+    sa[l] = in ? a.lareas_d[l] : 0.f;
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int e0 = 0; e0 < a.n_envmaps; e0 += E_CHUNK) {
-    const int ec = min(E_CHUNK, a.n_envmaps - e0);
+  const bool vec = (L & 1) == 0;                 // rows of lvis / spec are 8-byte aligned
+  for (int e0 = 0; e0 < a.n_envmaps; e0 += EC) {
+    const int ec = min(EC, a.n_envmaps - e0);    // < EC only in a tail pass: extra maps read as 0
     __syncthreads();
-    for (int i = threadIdx.x; i < ec * L; i += blockDim.x) {
-      int e = i / L, l = i % L;
-      int px = a.light_idx_d ? a.light_idx_d[l] : l;
-      const float* t = a.light_d + ((size_t)(e0 + e) * a.envmap_pixels + px) * 3;
-      lt4[e * L + l] = make_float4(t[0], t[1], t[2], 0.f);
+    for (int i = threadIdx.x; i < EC * Lp; i += blockDim.x) {
+      const int e = i / Lp, l = i % Lp;
+      float r = 0.f, g = 0.f, b = 0.f;
+      if (l < L && e < ec) {
+        const int px = a.light_idx_d ? a.light_idx_d[l] : l;
+        const float* t = a.light_d + ((size_t)(e0 + e) * a.envmap_pixels + px) * 3;
+        r = t[0]; g = t[1]; b = t[2];
+      }
+      st[(e * 3 + 0) * Lp + l] = r;
+      st[(e * 3 + 1) * Lp + l] = g;
+      st[(e * 3 + 2) * Lp + l] = b;
     }
     __syncthreads();
-    for (int i = blockIdx.x * WARPS + warp; i < a.n; i += gridDim.x * WARPS) {
-      PointCtx c = load_point(a, i);
-      float acc[E_CHUNK][3];
+    // A warp takes 32 consecutive points at a time: the per-point set-up (normalisations, the
+    // view-side shadowing term) and the tone-mapping epilogue run lane-parallel, one point per
+    // lane; inside, the points are visited one by one with all lanes striding the lights, the
+    // point's constants arriving by shuffle from its lane.
+    for (int base = (blockIdx.x * WARPS + warp) * 32; base < a.n; base += gridDim.x * WARPS * 32) {
+      const int pi = base + lane;
+      const bool pv = pi < a.n;
+      const PointCtx s = load_point(a, pv ? pi : a.n - 1);
+      const float my_k = s.abs_vn != 0.f ? s.g_view * s.alpha2_sq / (4.f * NF_PI_F * s.abs_vn) : 0.f;
+      float outv[EC][3];
 #pragma unroll
-      for (int e = 0; e < E_CHUNK; ++e) acc[e][0] = acc[e][1] = acc[e][2] = 0.f;
-      const float* lv = a.lvis_d + (size_t)i * L;
-      const float* sp = a.brdf_kind == 1 ? a.spec_d + (size_t)i * L : nullptr;
-      for (int l = lane; l < L; l += 32) {
-        float spec, w;
-        eval_pair(a, c, lx4[l], __ldg(lv + l), sp ? __ldg(sp + l) : 0.f, spec, w);
-        float b0 = spec + c.lambert.x, b1 = spec + c.lambert.y, b2 = spec + c.lambert.z;
+      for (int e = 0; e < EC; ++e) outv[e][0] = outv[e][1] = outv[e][2] = 0.f;
+      const int cnt = min(32, a.n - base);
+      for (int j = 0; j < cnt; ++j) {
+        const int i = base + j;
+        const float* lv = a.lvis_d + (size_t)i * L;
+        const float* sp = KIND == 1 ? a.spec_d + (size_t)i * L : nullptr;
+        float2 acc[EC][3];
 #pragma unroll
-        for (int e = 0; e < E_CHUNK; ++e) {
-          if (e < ec) {
-            float4 t = lt4[e * L + l];
-            // brdf * (lvis * light) * cos * area, nerfactor.py:334-336
-            acc[e][0] += b0 * (w * t.x);
-            acc[e][1] += b1 * (w * t.y);
-            acc[e][2] += b2 * (w * t.z);
+        for (int e = 0; e < EC; ++e) acc[e][0] = acc[e][1] = acc[e][2] = bc2(0.f);
+        PointCtx2 c;
+#define NF_BC(x) __shfl_sync(0xffffffffu, (x), j)
+        c.npx = bc2(-NF_BC(s.pt.x)); c.npy = bc2(-NF_BC(s.pt.y)); c.npz = bc2(-NF_BC(s.pt.z));
+        c.nx = bc2(NF_BC(s.n1.x)); c.ny = bc2(NF_BC(s.n1.y)); c.nz = bc2(NF_BC(s.n1.z));
+        c.vx = bc2(NF_BC(s.v2.x)); c.vy = bc2(NF_BC(s.v2.y)); c.vz = bc2(NF_BC(s.v2.z));
+        c.a2m1 = bc2(NF_BC(s.alpha2_sq) - 1.f);
+        c.k = bc2(NF_BC(my_k));
+        c.f0 = bc2(a.f0); c.omf0 = bc2(1.f - a.f0);
+        c.lr = bc2(NF_BC(s.lambert.x)); c.lg = bc2(NF_BC(s.lambert.y)); c.lb = bc2(NF_BC(s.lambert.z));
+        c.cos_v = NF_BC(s.cos_v);
+#undef NF_BC
+        for (int l0 = 0; l0 < L; l0 += 512) {
+          float2 lvr[8], spr[KIND == 1 ? 8 : 1];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int l = l0 + 64 * q + 2 * lane;
+            lvr[q] = bc2(0.f);
+            if (KIND == 1) spr[q] = bc2(0.f);
+            if (l < L) {
+              if (vec) {
+                lvr[q] = __ldg(reinterpret_cast<const float2*>(lv + l));
+                if (KIND == 1) spr[q] = __ldg(reinterpret_cast<const float2*>(sp + l));
+              } else {
+                lvr[q] = make_float2(__ldg(lv + l), l + 1 < L ? __ldg(lv + l + 1) : 0.f);
+                if (KIND == 1) spr[q] = make_float2(__ldg(sp + l), l + 1 < L ? __ldg(sp + l + 1) : 0.f);
+              }
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int l = l0 + 64 * q + 2 * lane;
+            if (l < L) {
+              float2 sw, dw;
+              eval_pair2<KIND>(a, c, *reinterpret_cast<const float2*>(sx + l),
+                         *reinterpret_cast<const float2*>(sy + l), *reinterpret_cast<const float2*>(sz + l),
+                         *reinterpret_cast<const float2*>(sa + l), lvr[q], spr[KIND == 1 ? q : 0], sw, dw);
+              // brdf * (lvis * light) * cos * area (nerfactor.py:334-336) = (lambert dw + sw) * texel
+              const float2 b0 = __ffma2_rn(c.lr, dw, sw), b1 = __ffma2_rn(c.lg, dw, sw),
+                           b2 = __ffma2_rn(c.lb, dw, sw);
+#pragma unroll
+              for (int e = 0; e < EC; ++e) {
+                const float* te = st + (size_t)e * 3 * Lp + l;
+                acc[e][0] = __ffma2_rn(b0, *reinterpret_cast<const float2*>(te), acc[e][0]);
+                acc[e][1] = __ffma2_rn(b1, *reinterpret_cast<const float2*>(te + Lp), acc[e][1]);
+                acc[e][2] = __ffma2_rn(b2, *reinterpret_cast<const float2*>(te + 2 * Lp), acc[e][2]);
+              }
+            }
           }
         }
-      }
 #pragma unroll
-      for (int e = 0; e < E_CHUNK; ++e) {
-        if (e < ec) {
-          float r = warp_sum(acc[e][0]), g = warp_sum(acc[e][1]), b = warp_sum(acc[e][2]);
-          if (lane == 0) {
-            float* o = a.rgb_d + ((size_t)i * a.n_envmaps + e0 + e) * 3;
-            o[0] = tonemap(r, a.linear2srgb);
-            o[1] = tonemap(g, a.linear2srgb);
-            o[2] = tonemap(b, a.linear2srgb);
+        for (int e = 0; e < EC; ++e) {
+          const float r = warp_sum(acc[e][0].x + acc[e][0].y), g = warp_sum(acc[e][1].x + acc[e][1].y),
+                      b = warp_sum(acc[e][2].x + acc[e][2].y);
+          if (lane == j) { outv[e][0] = r; outv[e][1] = g; outv[e][2] = b; }
+        }
+      }
+      if (pv) {
+#pragma unroll
+        for (int e = 0; e < EC; ++e) {
+          if (e < ec) {
+            float* o = a.rgb_d + ((size_t)pi * a.n_envmaps + e0 + e) * 3;
+            o[0] = tonemap(outv[e][0], a.linear2srgb);
+            o[1] = tonemap(outv[e][1], a.linear2srgb);
+            o[2] = tonemap(outv[e][2], a.linear2srgb);
           }
         }
       }
@@ -208,13 +365,37 @@ int nf_integrate_fwd(nf_ctx* ctx, const nf_integrate_args* a, void* stream) {
   NF_CHECK_ARG(ctx, a->n_envmaps >= 1 && a->light_d && a->rgb_d, "missing env-maps / output");
   NF_CHECK_ARG(ctx, a->envmap_pixels >= 1, "bad envmap_pixels");
   int ec = a->n_envmaps < E_CHUNK ? a->n_envmaps : E_CHUNK;
-  size_t sm = sizeof(float4) * (size_t)a->n_lights * (1 + ec);
+  const size_t lp = ((size_t)a->n_lights + 1) & ~(size_t)1;
+  size_t sm = sizeof(float) * lp * (4 + 3 * ec);
   NF_CHECK_ARG(ctx, sm <= ctx->smem_optin, "n_lights too large for shared memory");
-  NF_CUDA(ctx, cudaFuncSetAttribute(integrate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  int blocks_needed = (a->n + WARPS - 1) / WARPS;
-  int grid = ctx->sm_count * 8;
-  if (grid > blocks_needed) grid = blocks_needed;
-  integrate_kernel<<<grid, WARPS * 32, sm, (cudaStream_t)stream>>>(*a);
+  // resident grid (blocks per SM from the occupancy calculator): every warp then walks ~8 batches
+  // of 32 points at the full 800 x 800 size, keeping the tail imbalance small
+  const int blocks_needed = (a->n + WARPS * 32 - 1) / (WARPS * 32);
+  cudaStream_t st = (cudaStream_t)stream;
+#define NF_LAUNCH_INTEGRATE_K(EC, KIND)                                                           \
+  do {                                                                                            \
+    NF_CUDA(ctx, cudaFuncSetAttribute(integrate_kernel<EC, KIND>,                                 \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));    \
+    int per_sm = 1;                                                                               \
+    NF_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(                                   \
+                     &per_sm, integrate_kernel<EC, KIND>, WARPS * 32, sm));                       \
+    int grid = ctx->sm_count * (per_sm > 0 ? per_sm : 1);                                         \
+    if (grid > blocks_needed) grid = blocks_needed;                                               \
+    integrate_kernel<EC, KIND><<<grid, WARPS * 32, sm, st>>>(*a);                                 \
+  } while (0)
+#define NF_LAUNCH_INTEGRATE(EC)                                                                   \
+  do {                                                                                            \
+    if (a->brdf_kind == 0) NF_LAUNCH_INTEGRATE_K(EC, 0);                                          \
+    else NF_LAUNCH_INTEGRATE_K(EC, 1);                                                            \
+  } while (0)
+  switch (ec) {
+    case 1: NF_LAUNCH_INTEGRATE(1); break;
+    case 2: NF_LAUNCH_INTEGRATE(2); break;
+    case 3: NF_LAUNCH_INTEGRATE(3); break;
+    default: NF_LAUNCH_INTEGRATE(4); break;
+  }
+#undef NF_LAUNCH_INTEGRATE
+#undef NF_LAUNCH_INTEGRATE_K
   NF_LAUNCH_CHECK(ctx);
   return NF_OK;
 }
