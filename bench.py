@@ -184,7 +184,7 @@ def workload_config(args, sigma_prec):
                           'point_mlps': 'f16 hi/lo split x3 (fp32-accurate) / f32 accum',
                           'render': 'f32'},
             'l2_policy': 'per-step working set (lvis 1.3 GB, sigma 0.33 GB) exceeds the 126 MB L2',
-            'parallelism': 'one view per GPU + all_gather of images'}
+            'parallelism': 'one view per GPU (same synthetic camera on every rank) + all_gather of images'}
 
 
 def secondary_rows(ctx, nerf, kt):
@@ -293,7 +293,10 @@ def main():
                   params=synth.make_stage_b_params(0, 'microfacet', light_hw=(lh, 2 * lh)),
                   ctx=ctx, precision='f16')
     vr = ViewRenderer(nerf, model, n_samples=args.spp, use_fine=True)
-    c2w = synth.look_at_c2w(4.0, 30.0 + 45.0 * rank, 30.0)      # one view per rank
+    # one view per rank; weak scaling = identical per-GPU work, so every rank renders the same
+    # synthetic camera (a different azimuth changes the foreground fraction and with it the
+    # Stage-B work, which would measure the scene, not the system)
+    c2w = synth.look_at_c2w(4.0, 30.0, 30.0)
     light_host = torch.rand((lh, 2 * lh, 3)).pin_memory()
     rgb_host = torch.empty((n_rays, 3)).pin_memory()
     alpha_host = torch.empty((n_rays, 1)).pin_memory()
