@@ -321,6 +321,60 @@ class Trainer:
             dist.all_reduce(total, op=dist.ReduceOp.SUM)
         return total
 
+    # ------------------------------------------------------------ checkpoint / resume
+    def _var_path(self, key):
+        net_name, li, kind = key
+        return 'net/_light' if kind == 'light' else 'net/net_%s_layer%d/%s' % (net_name, li, kind)
+
+    def save_checkpoint(self, ckpt_dir, step):
+        """trainvali.py:134-141, 197-200: writes `ckpt_dir/ckpt-<step>` in TensorFlow's tensor-
+        bundle format under the reference's variable names (weights, light, `step`, AMSGrad
+        `iter` / `m` / `v` / `vhat` slots) and updates the `checkpoint` state file."""
+        import os
+        from .util import tfckpt
+        sfx = '/.ATTRIBUTES/VARIABLE_VALUE'
+        tensors = {'step' + sfx: np.asarray(step, np.int32),
+                   'optimizer/iter' + sfx: np.asarray(self.iterations, np.int64)}
+        host = {n: t.detach().cpu().numpy() for n, t in
+                (('p', self.flat), ('m', self.m), ('v', self.v), ('vhat', self.vhat))}
+        for key, off, shp in zip(self.names, self.offsets[:-1], self.shapes):
+            n = int(np.prod(shp))
+            path = self._var_path(key)
+            tensors[path + sfx] = host['p'][off:off + n].reshape(shp)
+            for slot in ('m', 'v', 'vhat'):
+                tensors['%s/.OPTIMIZER_SLOT/optimizer/%s%s' % (path, slot, sfx)] = \
+                    host[slot][off:off + n].reshape(shp)
+        prefix = os.path.join(ckpt_dir, 'ckpt-%d' % step)
+        tfckpt.write_checkpoint(prefix, tensors)
+        with open(os.path.join(ckpt_dir, 'checkpoint'), 'w') as f:
+            f.write('model_checkpoint_path: "ckpt-%d"\nall_model_checkpoint_paths: "ckpt-%d"\n'
+                    % (step, step))
+        return prefix
+
+    def restore_checkpoint(self, prefix):
+        """Resumes weights, light, optimizer slots and iteration count from `prefix` (a file
+        written by save_checkpoint or by the reference's CheckpointManager); variables the
+        checkpoint lacks keep their values.  Returns the stored `step` (0 if absent)."""
+        from .util import tfckpt
+        sfx = '/.ATTRIBUTES/VARIABLE_VALUE'
+        t = tfckpt.read_checkpoint(prefix)
+        bufs = {'p': self.flat, 'm': self.m, 'v': self.v, 'vhat': self.vhat}
+        for key, off, shp in zip(self.names, self.offsets[:-1], self.shapes):
+            n = int(np.prod(shp))
+            path = self._var_path(key)
+            for slot, buf in bufs.items():
+                name = path + sfx if slot == 'p' else \
+                    '%s/.OPTIMIZER_SLOT/optimizer/%s%s' % (path, slot, sfx)
+                if name in t:
+                    if tuple(t[name].shape) != tuple(shp):
+                        raise ValueError("%s: shape %s, expected %s" % (name, t[name].shape, shp))
+                    buf[off:off + n] = torch.as_tensor(
+                        np.ascontiguousarray(t[name], np.float32).reshape(-1)).to(self.device)
+        if 'optimizer/iter' + sfx in t:
+            self.iterations = int(t['optimizer/iter' + sfx])
+        self.sync_to_model()
+        return int(t['step' + sfx]) if 'step' + sfx in t else 0
+
     @torch.no_grad()
     def vali_step(self, batch):
         """trainvali.py:301-317: forward in 'vali' mode through the fused inference kernels."""

@@ -264,3 +264,40 @@ def test_shape_model_train_step(ctx):
     for _ in range(15):
         l1 = float(tr.train_step(batch, xyz_noise=noise))
     assert np.isfinite(l0) and l1 < l0
+
+
+def test_checkpoint_save_resume_and_restore_model(ctx, tmp_path):
+    """trainvali.py:134-141 / util/io.py:36-45 without TensorFlow: a trainer checkpoints in the
+    tensor-bundle format under the reference's variable names, a fresh trainer resumes from it
+    and continues bit-identically, and `restore_model` loads the weights into a fresh model."""
+    from nerfactor_b200.trainvali import Trainer
+    from nerfactor_b200.util import io as ioutil, tfckpt
+    batch = synth.make_stage_b_batch(5, 64, 16, fg_frac=1.0)
+    noise = (0.01 * np.random.default_rng(4).standard_normal((64, 3))).astype(np.float32)
+    m0, _, _ = _models(ctx, 'microfacet')
+    tr0 = Trainer(m0, precision='bf16')
+    for _ in range(3):
+        tr0.train_step(batch, xyz_noise=noise)
+    prefix = tr0.save_checkpoint(str(tmp_path / 'checkpoints'), step=3)
+    assert ioutil.latest_checkpoint(str(tmp_path / 'checkpoints')) == prefix
+    names = tfckpt.read_checkpoint(prefix)
+    assert 'net/net_albedo_mlp_layer0/kernel/.ATTRIBUTES/VARIABLE_VALUE' in names
+    assert 'net/net_albedo_mlp_layer0/kernel/.OPTIMIZER_SLOT/optimizer/vhat/.ATTRIBUTES/VARIABLE_VALUE' in names
+    assert 'net/_light/.ATTRIBUTES/VARIABLE_VALUE' in names
+    for _ in range(2):
+        tr0.train_step(batch, xyz_noise=noise)
+    # resume in a fresh trainer (different initial weights) and replay the same two steps
+    m1, _, _ = _models(ctx, 'microfacet', seed=99)
+    tr1 = Trainer(m1, precision='bf16')
+    assert tr1.restore_checkpoint(prefix) == 3 and tr1.iterations == 3
+    for _ in range(2):
+        tr1.train_step(batch, xyz_noise=noise)
+    assert torch.equal(tr0.flat, tr1.flat) and torch.equal(tr0.vhat, tr1.vhat)
+    # inference model restored from the checkpoint == the trainer's synced model
+    tr1.restore_checkpoint(prefix)
+    m2, _, _ = _models(ctx, 'microfacet', seed=5)
+    found = ioutil.restore_model(m2, prefix)
+    assert {'albedo_mlp', 'lvis_out', 'light'} <= found
+    p1, _, _, _ = m1.call(batch, 'test')
+    p2, _, _, _ = m2.call(batch, 'test')
+    assert torch.equal(p1['rgb'], p2['rgb'])
