@@ -27,7 +27,9 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-FLOP_SIGMA = 982528       # per sample  
+FLOP_SIGMA = 982528
+FLOP_NERF = 982528 - 512 + 2 * (256 * 256 + 283 * 128 + 128 * 3) + 512   # + bottleneck + colour
+       # per sample  
 FLOP_LVIS = 144640        # per (ray, light)
 FLOP_POINT = 131328       # per ray, normal / albedo nets (rough: 130816)
 FALLBACK_PEAKS = {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}
@@ -212,6 +214,16 @@ def secondary_rows(ctx, nerf, kt):
     out['stage_a_hierarchical_fp32'] = {
         'what': 'same, FP32 CUDA-core kernels throughout (the bit-level parity path)',
         'rays': h * w, 'ms': t, 'rays_per_s': h * w / (t * 1e-3)}
+    # (1b) the step before Stage A: NeRF colour rendering (nerf.py:149-252), 64 coarse + 192 fine
+    h = w = 400
+    ro, rd = _lib.gen_rays(ctx, synth.look_at_c2w(), synth.CAM_ANGLE_X, h, w, normalize=False)
+    nb = ('bench', (h, w), ro, rd, None)
+    t = kt(lambda: nerf.call(nb, 'test', precision='f16'), 2)
+    out['nerf_render_rgb'] = {
+        'what': 'nerf Model.call (coarse 64 + fine 192 samples, view-dependent colour), fused '
+                'tcgen05 trunk + bottleneck + colour kernel (f16)',
+        'rays': h * w, 'ms': t, 'rays_per_s': h * w / (t * 1e-3),
+        'tflops': h * w * (64 + 192) * FLOP_NERF / (t * 1e-3) / 1e12}
     # (2) compute_light_visibility: every front-lit (point, light) pair marched 128 + 320 samples
     npts = 256
     surf = (ro[:npts] + rd[:npts] * 3.0).contiguous()

@@ -192,6 +192,31 @@ int nf_sigma_normal_fwd(nf_ctx* ctx, const nf_mlp* mlp, const float* rayo_d,
                         int n_samples, const float* bbox_host, float* sigma_d,
                         float* normal_d, int precision, void* stream);
 
+/* ---- full NeRF network with viewing directions (the step before Stage A) ----
+ * Colour branch of nerfactor/models/nerf.py:53-71 on top of an NF_MLP_SIGMA network:
+ * bottleneck Dense(256, linear), rgb_out = Dense(128, relu) -> Dense(3, linear) on
+ * concat(bottleneck, embed(view)) (Keras layouts [in, out]; n_freqs_view = 4 => 27 columns). */
+typedef struct nf_nerf_rgb_desc {
+  int n_freqs_view;            /* nerf.ini n_freqs_view                          */
+  int hidden;                  /* mlp_width // 2                                 */
+  const float* w_bottleneck;   /* [256, 256]                                     */
+  const float* b_bottleneck;   /* [256]                                          */
+  const float* w_rgb0;         /* [256 + 3 (1 + 2 n_freqs_view), hidden]         */
+  const float* b_rgb0;         /* [hidden]                                       */
+  const float* w_rgb1;         /* [hidden, 3]                                    */
+  const float* b_rgb1;         /* [3]                                            */
+} nf_nerf_rgb_desc;
+/* Appends the colour-branch operand images to a packed sigma network; call between
+ * nf_mlp_create and nf_mlp_device_bytes / nf_mlp_upload.                                  */
+int nf_mlp_attach_rgb(nf_ctx* ctx, nf_mlp* sigma_mlp, const nf_nerf_rgb_desc* rgb);
+/* rgbs[n, S, 4] = (raw r, g, b, raw sigma) at the samples o + z d, views = d:
+ * replaces Model._eval_nerf_at nerfactor/models/nerf.py:254-290 (use_views = True); the
+ * caller composites with nf_composite (sigmoid / ReLU applied there, nerf.py:214-252).
+ * tcgen05 only (NF_PREC_F16 / NF_PREC_BF16).                                              */
+int nf_nerf_fwd(nf_ctx* ctx, const nf_mlp* mlp, const float* rayo_d, const float* rayd_d,
+                const float* z_d, int n_rays, int n_samples, float* rgbs_d, int precision,
+                void* stream);
+
 /* weights[n,S] (optional), occu[n], depth[n], surf[n,3] (optional),
  * exp_normal[n,3] (optional, needs normal_d [n,S,3])
  * replaces nerf.Model.accumulate_sigma nerfactor/models/nerf.py:184-212 (noise 0) and

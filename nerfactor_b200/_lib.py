@@ -26,7 +26,7 @@ EXPORTS = [
     'nf_ctx_sm_count', 'nf_mlp_create', 'nf_mlp_destroy', 'nf_mlp_device_bytes',
     'nf_mlp_upload', 'nf_point_mlp_fwd', 'nf_lvis_fwd', 'nf_brdf_learned_fwd',
     'nf_integrate_fwd', 'nf_integrate_olat_fwd', 'nf_gen_rays', 'nf_gen_z',
-    'nf_sigma_fwd', 'nf_sigma_normal_fwd', 'nf_composite', 'nf_gen_z_fine',
+    'nf_sigma_fwd', 'nf_sigma_normal_fwd', 'nf_mlp_attach_rgb', 'nf_nerf_fwd', 'nf_composite', 'nf_gen_z_fine',
     'nf_lvis_rays', 'nf_selftest_umma', 'nf_selftest_umma2', 'nf_dense_fwd',
     'nf_dense_fwd_workspace_bytes', 'nf_dense_bwd_workspace_bytes',
     'nf_dense_bwd', 'nf_adam_amsgrad_step']
@@ -42,6 +42,13 @@ class MlpDesc(C.Structure):
                 ('out_act', C.c_int), ('n_freqs_a', C.c_int), ('n_freqs_b', C.c_int),
                 ('z_dim', C.c_int), ('W', C.POINTER(C.c_void_p)),
                 ('b', C.POINTER(C.c_void_p))]
+
+
+class NerfRgbDesc(C.Structure):
+    _fields_ = [('n_freqs_view', C.c_int), ('hidden', C.c_int),
+                ('w_bottleneck', C.c_void_p), ('b_bottleneck', C.c_void_p),
+                ('w_rgb0', C.c_void_p), ('b_rgb0', C.c_void_p),
+                ('w_rgb1', C.c_void_p), ('b_rgb1', C.c_void_p)]
 
 
 class IntegrateArgs(C.Structure):
@@ -88,6 +95,8 @@ def load_library():
     lib.nf_gen_rays.argtypes = [vp, C.POINTER(d), d, i, i, i, vp, vp, vp]
     lib.nf_gen_z.argtypes = [vp, f, f, i, i, i, vp, vp, vp]
     lib.nf_sigma_fwd.argtypes = [vp, vp, vp, vp, vp, i, i, C.POINTER(f), vp, i, vp]
+    lib.nf_mlp_attach_rgb.argtypes = [vp, vp, C.POINTER(NerfRgbDesc)]
+    lib.nf_nerf_fwd.argtypes = [vp, vp, vp, vp, vp, i, i, vp, i, vp]
     lib.nf_sigma_normal_fwd.argtypes = [vp, vp, vp, vp, vp, i, i, C.POINTER(f), vp, vp, i, vp]
     lib.nf_composite.argtypes = [vp, vp, vp, vp, vp, vp, i, i, vp, vp, vp, vp, vp, vp]
     lib.nf_gen_z_fine.argtypes = [vp, vp, vp, i, i, i, vp, vp]
@@ -182,8 +191,10 @@ class PackedMlp:
     torch-owned device buffer."""
 
     def __init__(self, ctx, kind, layers, skip_at, out_act, n_freqs_a=0, n_freqs_b=0,
-                 z_dim=0):
-        """layers: [(W[in,out], b[out]) ...] fp32 NumPy, trunk layers then head."""
+                 z_dim=0, rgb=None):
+        """layers: [(W[in,out], b[out]) ...] fp32 NumPy, trunk layers then head.
+        rgb (sigma nets): {'bottleneck': (W, b), 'rgb_out': [(W0, b0), (W1, b1)],
+        'n_freqs_view': F} -- the NeRF colour branch (nf_mlp_attach_rgb)."""
         self.ctx = ctx
         depth = len(layers) - 1
         Ws = [np.ascontiguousarray(w, dtype=np.float32) for w, _ in layers]
@@ -201,6 +212,18 @@ class PackedMlp:
         h = C.c_void_p()
         ctx.check(ctx.lib.nf_mlp_create(ctx.h, C.byref(d), C.byref(h)))
         self.h = h
+        self.has_rgb = rgb is not None
+        if rgb is not None:
+            c32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+            arrs = [c32(rgb['bottleneck'][0]), c32(rgb['bottleneck'][1]),
+                    c32(rgb['rgb_out'][0][0]), c32(rgb['rgb_out'][0][1]),
+                    c32(rgb['rgb_out'][1][0]), c32(rgb['rgb_out'][1][1])]
+            self._keep_rgb = arrs
+            rd = NerfRgbDesc(int(rgb['n_freqs_view']), int(arrs[2].shape[1]),
+                             *[a.ctypes.data for a in arrs])
+            assert arrs[0].shape == (256, 256) and arrs[4].shape == (arrs[2].shape[1], 3)
+            assert arrs[2].shape[0] == 256 + 3 * (1 + 2 * int(rgb['n_freqs_view']))
+            ctx.check(ctx.lib.nf_mlp_attach_rgb(ctx.h, h, C.byref(rd)))
         nbytes = ctx.lib.nf_mlp_device_bytes(h)
         self.buf = torch.empty(nbytes + 256, dtype=torch.uint8, device=ctx.device)
         off = (-self.buf.data_ptr()) % 256
@@ -324,6 +347,15 @@ def sigma_fwd(ctx, mlp, rayo, rayd, z, bbox=None, precision='f16'):
     ctx.launch(ctx.lib.nf_sigma_fwd(ctx.h, mlp.h, _f32(rayo), _f32(rayd), _f32(z), n, S,
                                    bb, _f32(sigma), PREC[precision], _stream()))
     return sigma
+
+
+def nerf_fwd(ctx, mlp, rayo, rayd, z, precision='f16'):
+    """-> rgbs [n, S, 4] = (raw r, g, b, raw sigma), nerf.py:254-290 (use_views)."""
+    n, S = z.shape
+    out = torch.empty((n, S, 4), dtype=torch.float32, device=z.device)
+    ctx.launch(ctx.lib.nf_nerf_fwd(ctx.h, mlp.h, _f32(rayo), _f32(rayd), _f32(z), n, S,
+                                  _f32(out), PREC[precision], _stream()))
+    return out
 
 
 def sigma_normal_fwd(ctx, mlp, rayo, rayd, z, bbox=None, precision='fp32'):

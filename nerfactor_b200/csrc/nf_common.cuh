@@ -33,6 +33,7 @@ struct nf_mlp {
   size_t off_tc_aux = 0, tc_aux_bytes = 0;               // fp32 side blocks
   size_t off_tc2_f16 = 0, off_tc2_bf16 = 0;              // CTA-pair (cta_group::2) images
   size_t off_tcb_f16 = 0, off_tcb_bf16 = 0;              // sigma nets: backward (d sigma / d x) images
+  size_t off_rgb_f16 = 0, off_rgb_bf16 = 0, off_rgb_aux = 0;   // NeRF colour branch (nf_mlp_attach_rgb)
   std::vector<size_t> off_wt;   // sigma nets: transposed trunk weights for d sigma / d xyz
   std::vector<int> ldk;
   void* dev = nullptr;        // caller-owned device buffer (after nf_mlp_upload)

@@ -1,8 +1,9 @@
-"""Mirror of the parts of nerfactor/models/nerf.py Stage A uses: the coarse / fine
-sigma networks (`net['coarse_enc']`, `net['coarse_sigma_out']`, ... nerf.py:53-71),
-the `xyz` embedder and the static samplers `gen_z`, `gen_z_fine`,
-`accumulate_sigma` (nerf.py:120-147, 184-212).  NeRF's RGB branch and its own
-training are a "next" row."""
+"""Mirror of nerfactor/models/nerf.py (forward): the coarse / fine networks
+(`net['coarse_enc']`, `net['coarse_sigma_out']`, `net['coarse_bottleneck']`,
+`net['coarse_rgb_out']`, ... nerf.py:53-71), the `xyz` / `view` embedders, the static
+samplers `gen_z`, `gen_z_fine`, `accumulate_sigma` (nerf.py:120-147, 184-212) and the colour
+rendering `_render_rays` / `_accumulate` / `_eval_nerf_at` / `call` (nerf.py:100-118, 149-290,
+SURVEY.md 8f.2).  NeRF's own training is out of scope."""
 import numpy as np
 import torch
 
@@ -36,19 +37,27 @@ class Model(BaseModel):
             if pref + 'enc' in self.net:
                 self.net[pref + 'enc'].build(self.embedder['xyz'].out_dims, rng)
                 self.net[pref + 'sigma_out'].build(width, rng)
+                if self.use_views:
+                    self.net[pref + 'bottleneck'].build(width, rng)
+                    self.net[pref + 'rgb_out'].build(width + self.embedder['view'].out_dims, rng)
         self._packed = {}
         if params is not None:
             self.load_params(params)
 
     def _init_net(self):
-        """nerf.py:53-71 (sigma branch; bottleneck / rgb_out belong to the RGB branch)."""
+        """nerf.py:53-71."""
         w = self.config.getint('DEFAULT', 'mlp_width')
         d = self.config.getint('DEFAULT', 'enc_depth')
         act = self.config.get('DEFAULT', 'act', fallback='relu')
         if act != 'relu':
             raise NotImplementedError(act)
-        return {'enc': mlp.Network([w] * d, act=[act] * d, skip_at=[d // 2]),
-                'sigma_out': mlp.Network([1], act=[None])}
+        net = {'enc': mlp.Network([w] * d, act=[act] * d, skip_at=[d // 2])}
+        if not self.use_views:
+            raise NotImplementedError("use_views = False (rgbs_out head, nerf.py:61-65)")
+        net['sigma_out'] = mlp.Network([1], act=[None])                 # ReLU later
+        net['bottleneck'] = mlp.Network([w], act=[None])
+        net['rgb_out'] = mlp.Network([w // 2, 3], act=[act, None])      # sigmoid later
+        return net
 
     def _init_embedder(self):
         """nerf.py:73-98."""
@@ -72,6 +81,95 @@ class Model(BaseModel):
                 self.ctx, 'sigma', trunk.weights() + head.weights(), trunk.skip_at[0], None,
                 n_freqs_a=self.embedder['xyz'].n_freqs)
         return self._packed[pref]
+
+    def packed_nerf(self, use_fine):
+        """Sigma network + colour branch packed together (nf_mlp_attach_rgb)."""
+        pref = 'fine_' if use_fine else 'coarse_'
+        key = pref + 'rgb'
+        if key not in self._packed:
+            trunk, head = self.net[pref + 'enc'], self.net[pref + 'sigma_out']
+            rgb = {'bottleneck': self.net[pref + 'bottleneck'].weights()[0],
+                   'rgb_out': self.net[pref + 'rgb_out'].weights(),
+                   'n_freqs_view': self.embedder['view'].n_freqs}
+            self._packed[key] = _lib.PackedMlp(
+                self.ctx, 'sigma', trunk.weights() + head.weights(), trunk.skip_at[0], None,
+                n_freqs_a=self.embedder['xyz'].n_freqs, rgb=rgb)
+        return self._packed[key]
+
+    # ---- colour rendering (nerf.py:100-118, 149-290) -------------------------------
+    def _eval_nerf_at(self, rayo, rayd, z, use_fine=False, precision=None):
+        """nerf.py:254-290 at the samples pts = rayo + rayd z, views = rayd (never
+        materialised; nerf.py:162-165): rgbs [n, S, 4] = (raw r, g, b, raw sigma).
+        precision 'fp32': layer-by-layer FP32 Dense kernels on materialised activations (the
+        tight-parity path); 'f16' / 'bf16': one fused tcgen05 kernel."""
+        prec = precision or self.precision
+        if prec != 'fp32':
+            return _lib.nerf_fwd(self.ctx, self.packed_nerf(use_fine), rayo, rayd, z, prec)
+        from .. import autodiff as ad
+        pref = 'fine_' if use_fine else 'coarse_'
+        n, S = z.shape
+        dev = self.device
+        lay = lambda name: [(torch.as_tensor(w).to(dev), torch.as_tensor(b).to(dev))
+                            for w, b in self.net[pref + name].weights()]
+        pts = (rayo[:, None, :] + rayd[:, None, :] * z[:, :, None]).reshape(-1, 3)
+        views = rayd[:, None, :].expand(n, S, 3).reshape(-1, 3)
+        with torch.no_grad():
+            enc = self.net[pref + 'enc']
+            feat = ad.mlp_apply(ad.embed(pts, self.embedder['xyz'].n_freqs), lay('enc'),
+                                ['relu'] * len(enc.layers), enc.skip_at)
+            sigma = ad.mlp_apply(feat, lay('sigma_out'), [None], None)
+            bott = ad.mlp_apply(feat, lay('bottleneck'), [None], None)
+            fv = torch.cat((bott, ad.embed(views, self.embedder['view'].n_freqs)), -1)
+            rgb = ad.mlp_apply(fv, lay('rgb_out'), ['relu', None], None)
+        return torch.cat((rgb, sigma), -1).reshape(n, S, 4)
+
+    def _accumulate(self, rgbs, z, rayd, eps=1e-10):
+        """nerf.py:214-252 -> (rgb, occu, depth, disp, weights)."""
+        sigma = rgbs[:, :, 3].contiguous()
+        rgb_s = torch.sigmoid(rgbs[:, :, :3]).contiguous()
+        weights, occu, depth, _, rgb = _lib.composite(self.ctx, sigma, z, rayd, rayd,
+                                                      normal=rgb_s, want_surf=False)
+        disp = 1. / torch.clamp(depth, min=eps)
+        bg = torch.ones_like(rgb) if self.white_bg else torch.zeros_like(rgb)
+        rgb = rgb * occu[:, None] + bg * (1. - occu[:, None])          # imgutil.alpha_blend
+        return rgb, occu, depth, disp, weights
+
+    def _render_rays(self, rayo, rayd, mode='train', precision=None, perturb_u=None):
+        """nerf.py:149-182.  Stratified perturbation only with explicit uniforms (`perturb_u`
+        [n, n_samples_coarse]); the fine pass is deterministic (gen_z_fine)."""
+        n_c = self.config.getint('DEFAULT', 'n_samples_coarse')
+        lin = self.config.getboolean('DEFAULT', 'lin_in_disp')
+        rayo = rayo.to(self.device, torch.float32).contiguous()
+        rayd = rayd.to(self.device, torch.float32)
+        rayd = (rayd * torch.rsqrt(torch.clamp((rayd * rayd).sum(1, keepdim=True), min=1e-12))
+                ).contiguous()                                         # tf.linalg.l2_normalize
+        n = rayo.shape[0]
+        z = _lib.gen_z(self.ctx, self.near, self.far, n_c, n, lin,
+                       perturb_u if mode == 'train' else None)
+        rgbs = self._eval_nerf_at(rayo, rayd, z, False, precision)
+        rgb, occu, depth, disp, weights = self._accumulate(rgbs, z, rayd)
+        pred_coarse = {'rgb': rgb, 'occu': occu, 'depth': depth, 'disp': disp}
+        if self.n_samples_fine <= 0:
+            return pred_coarse, {}
+        z = _lib.gen_z_fine(self.ctx, z, weights, self.n_samples_fine)
+        rgbs = self._eval_nerf_at(rayo, rayd, z, True, precision)
+        rgb, occu, depth, disp, _ = self._accumulate(rgbs, z, rayd)
+        return pred_coarse, {'rgb': rgb, 'occu': occu, 'depth': depth, 'disp': disp}
+
+    def call(self, batch, mode='train', precision=None):
+        """nerf.py:100-118: batch = (id_, hw, rayo, rayd, rgb), all flattened."""
+        self._validate_mode(mode)
+        id_, hw, rayo, rayd, rgb = batch
+        to_t = lambda x: x if torch.is_tensor(x) else torch.as_tensor(np.asarray(x, np.float32))
+        pred_coarse, pred_fine = self._render_rays(to_t(rayo), to_t(rayd), mode, precision)
+        pred = {'coarse': pred_coarse['rgb'], 'fine': pred_fine.get('rgb', None)}
+        gt = rgb
+        to_vis = {'id': id_, 'hw': hw, 'gt_rgb': gt}
+        for k, v in pred_coarse.items():
+            to_vis['coarse_' + k] = v
+        for k, v in pred_fine.items():
+            to_vis['fine_' + k] = v
+        return pred, gt, {}, to_vis
 
     # ---- static samplers, same signatures as the reference ------------------
     @staticmethod

@@ -81,7 +81,7 @@ def make_stage_b_params(seed=0, brdf='microfacet', light_hw=(16, 32), width=128,
 
 
 def make_nerf_params(seed=0, width=256, enc_depth=8, n_freqs_xyz=10,
-                     bias_std=0.05, sigma_gain=40.0, sigma_bias=8.0):
+                     bias_std=0.05, sigma_gain=40.0, sigma_bias=8.0, n_freqs_view=4):
     """Random-init NeRF sigma networks (models/nerf.py:53-71: enc = 8x256 ReLU
     with the input re-concatenated after layer enc_depth//2, sigma_out =
     Dense(1)); coarse and fine copies (nerf.py:42-47).  A glorot-init field is a
@@ -99,6 +99,14 @@ def make_nerf_params(seed=0, width=256, enc_depth=8, n_freqs_xyz=10,
         so['layers'][0] = ((so['layers'][0][0] * sigma_gain).astype(np.float32),
                            np.full((1,), sigma_bias, np.float32))
         p[pref + 'sigma_out'] = so
+    # colour branch (nerf.py:66-70); its own generator so the sigma networks above -- and every
+    # golden fixture made from them -- do not depend on it
+    rng2 = np.random.default_rng(100003 + seed)
+    dv = embed_dims(n_freqs_view)
+    for pref in ('coarse_', 'fine_'):
+        p[pref + 'bottleneck'] = init_mlp(rng2, width, [width], [None], None, bias_std)
+        p[pref + 'rgb_out'] = init_mlp(rng2, width + dv, [width // 2, 3], ['relu', None], None,
+                                       bias_std)
     return p
 
 

@@ -99,6 +99,53 @@ def _sigma_raw(nerf, pts, use_fine, n_freqs_xyz=10):
         nerf[pref + 'sigma_out'], nets.mlp_forward(nerf[pref + 'enc'], e))
 
 
+def eval_nerf_at(nerf, pts, views, use_fine=False, n_freqs_xyz=10, n_freqs_view=4):
+    """nerfactor/models/nerf.py:254-290 (use_views = True): [P, 4] = (raw rgb, raw sigma);
+    pts, views: [P, 3]."""
+    pref = 'fine_' if use_fine else 'coarse_'
+    feat = nets.mlp_forward(nerf[pref + 'enc'], nets.embed(pts, n_freqs_xyz))
+    sigma = nets.mlp_forward(nerf[pref + 'sigma_out'], feat)
+    feat = nets.mlp_forward(nerf[pref + 'bottleneck'], feat)
+    feat_views = torch.cat((feat, nets.embed(views, n_freqs_view)), -1)
+    rgb = nets.mlp_forward(nerf[pref + 'rgb_out'], feat_views)
+    return torch.cat((rgb, sigma), -1)
+
+
+def nerf_accumulate(rgbs, z, rayd, white_bg=True, eps=1e-10):
+    """nerf.py:214-252: weights from sigma (accumulate_sigma), sigmoid colours, weighted sums,
+    disparity, composite onto the background."""
+    weights = accumulate_sigma(rgbs[:, :, 3], z, rayd)
+    rgb = torch.sigmoid(rgbs[:, :, :3])
+    occu = torch.sum(weights, dim=-1)
+    rgb = torch.sum(weights[:, :, None] * rgb, dim=-2)
+    depth = torch.sum(weights * z, dim=-1)
+    disp = 1. / torch.clamp(depth, min=eps)
+    bg = torch.ones_like(rgb) if white_bg else torch.zeros_like(rgb)
+    rgb = rgb * occu[:, None] + bg * (1. - occu[:, None])          # imgutil.alpha_blend
+    return rgb, occu, depth, disp, weights
+
+
+def nerf_render_rays(nerf, rayo, rayd, near, far, n_samples_coarse=64, n_samples_fine=128,
+                     lin_in_disp=False, white_bg=True):
+    """nerf.py:149-182 at test time (perturb = False)."""
+    rayd = l2_normalize(rayd, 1, 1e-12)
+    n = rayo.shape[0]
+    z = gen_z(near, far, n_samples_coarse, n, lin_in_disp, dtype=rayo.dtype)
+    pts = rayo[:, None, :] + rayd[:, None, :] * z[:, :, None]
+    views = rayd[:, None, :].expand_as(pts)
+    rgbs = eval_nerf_at(nerf, pts.reshape(-1, 3), views.reshape(-1, 3), False).reshape(n, -1, 4)
+    rgb, occu, depth, disp, weights = nerf_accumulate(rgbs, z, rayd, white_bg)
+    coarse = {'rgb': rgb, 'occu': occu, 'depth': depth, 'disp': disp}
+    if n_samples_fine <= 0:
+        return coarse, {}
+    z = gen_z_fine(z, weights, n_samples_fine)
+    pts = rayo[:, None, :] + rayd[:, None, :] * z[:, :, None]
+    views = rayd[:, None, :].expand_as(pts)
+    rgbs = eval_nerf_at(nerf, pts.reshape(-1, 3), views.reshape(-1, 3), True).reshape(n, -1, 4)
+    rgb, occu, depth, disp, _ = nerf_accumulate(rgbs, z, rayd, white_bg)
+    return coarse, {'rgb': rgb, 'occu': occu, 'depth': depth, 'disp': disp}
+
+
 def check_bounds(pts, scene_bbox=None):
     """geometry_from_nerf.py:365-378. scene_bbox = (x0,x1,y0,y1,z0,z1) or None."""
     if scene_bbox is None:

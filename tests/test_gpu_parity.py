@@ -547,3 +547,66 @@ def test_full_size_properties(ctx):
     white = _lib.integrate_fwd(ctx, xyz, nrm, cam, albedo, lvis,
                                light=torch.full((1, 512, 3), 1e-3, device=ctx.device), **args)
     assert rel_l2(olat.sum(1).cpu(), white[:, 0].cpu()) < 1e-4
+
+
+# ------------------------------------------------------------------ NeRF colour branch (8f.2)
+def test_nerf_eval_fp32_layered_vs_oracle(ctx):
+    """Model._eval_nerf_at (nerf.py:254-290) on the FP32 Dense kernels vs the oracle."""
+    from nerfactor_b200 import _lib
+    model = _nerf_model(ctx, 3)
+    ro, rd = _rays(ctx, 6, 7)
+    z = _lib.gen_z(ctx, 2., 6., 11, ro.shape[0])
+    rgbs = model._eval_nerf_at(ro, rd, z, use_fine=True, precision='fp32')
+    pts = (ro[:, None, :] + rd[:, None, :] * z[:, :, None]).reshape(-1, 3).cpu()
+    views = rd[:, None, :].expand(-1, 11, 3).reshape(-1, 3).cpu()
+    ref = stage_a.eval_nerf_at(synth.make_nerf_params(3), pts, views, True)
+    assert rel_l2(rgbs.cpu().reshape(-1, 4)[:, :3], ref[:, :3]) < 2e-5
+    assert rel_l2(rgbs.cpu().reshape(-1, 4)[:, 3], ref[:, 3]) < 2e-5
+
+
+@pytest.mark.parametrize('prec', ['f16', 'bf16'])
+def test_nerf_tcgen05_kernel(ctx, prec):
+    """nf_nerf_fwd: sigma column bit-identical to the sigma-only kernel (same trunk, same head
+    order), colours within operand precision of the FP32 path, results independent of the tile
+    a sample lands in (ragged sizes, several tiles per CTA)."""
+    from nerfactor_b200 import _lib
+    model = _nerf_model(ctx, 3)
+    ro, rd = _rays(ctx, 64, 64)
+    S = 19
+    z = _lib.gen_z(ctx, 2., 6., S, ro.shape[0])
+    rgbs = model._eval_nerf_at(ro, rd, z, use_fine=True, precision=prec)
+    assert rgbs.shape == (4096, S, 4) and not torch.isnan(rgbs).any()
+    sig = _lib.sigma_fwd(ctx, model.packed_sigma(True), ro, rd, z, None, prec)
+    assert torch.equal(torch.relu(rgbs[:, :, 3]), sig)
+    k = 990                                              # 147 tiles: one per CTA
+    sub = model._eval_nerf_at(ro[:k].contiguous(), rd[:k].contiguous(), z[:k].contiguous(),
+                              use_fine=True, precision=prec)
+    assert torch.equal(sub, rgbs[:k])
+    kk = 300
+    ref = model._eval_nerf_at(ro[:kk].contiguous(), rd[:kk].contiguous(), z[:kk].contiguous(),
+                              use_fine=True, precision='fp32')
+    tol = 3e-3 if prec == 'f16' else 3e-2
+    assert rel_l2(rgbs[:kk, :, :3].cpu(), ref[:, :, :3].cpu()) < tol
+    assert rel_l2(rgbs[:kk, :, 3].cpu(), ref[:, :, 3].cpu()) < tol
+
+
+def test_nerf_render_rays_vs_oracle(ctx):
+    """Model.call / _render_rays (nerf.py:100-118, 149-252): coarse 16 + fine 24 samples, white
+    background, against the oracle chain; then the tensor-core path against the FP32 one."""
+    model = _nerf_model(ctx, 3)
+    model.config.set('DEFAULT', 'n_samples_coarse', '16')
+    model.n_samples_fine = 24
+    ro, rd = _rays(ctx, 8, 8)
+    batch = ('view', (8, 8), ro * 1.0, rd * 3.0, torch.zeros_like(ro))   # un-normalised rayd
+    pred, gt, lk, vis = model.call(batch, 'test', precision='fp32')
+    oc, of = stage_a.nerf_render_rays(synth.make_nerf_params(3), ro.cpu(), (rd * 3.0).cpu(),
+                                      2., 6., 16, 24, False, True)
+    assert pred['coarse'].shape == (64, 3) and lk == {}
+    assert np.abs(pred['coarse'].cpu().numpy() - oc['rgb'].numpy()).max() < 2e-4
+    d = np.abs(pred['fine'].cpu().numpy() - of['rgb'].numpy())
+    assert np.median(d) < 1e-4 and np.quantile(d, 0.95) < 5e-3      # gen_z_fine discontinuities
+    assert np.abs(vis['coarse_occu'].cpu().numpy() - oc['occu'].numpy()).max() < 1e-4
+    assert np.abs(vis['coarse_disp'].cpu().numpy() - oc['disp'].numpy()).max() < 1e-3
+    p16, _, _, _ = model.call(batch, 'test', precision='f16')
+    d16 = (p16['coarse'] - pred['coarse']).abs()
+    assert float(d16.mean()) < 2e-3 and float(d16.max()) < 3e-2
