@@ -28,7 +28,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOP_SIGMA = 982528
-FLOP_NERF = 982528 - 512 + 2 * (256 * 256 + 283 * 128 + 128 * 3) + 512   # + bottleneck + colour
+FLOP_NERF = 982528 + 2 * (256 * 256 + 283 * 128 + 128 * 3)   # + bottleneck + colour branch
        # per sample  
 FLOP_LVIS = 144640        # per (ray, light)
 FLOP_POINT = 131328       # per ray, normal / albedo nets (rough: 130816)
