@@ -410,6 +410,23 @@ def main():
               'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'ms': t_int, 'traffic': None,
               'algorithmic_bytes': alg_int,
               'note': 'ALU-bound with the analytic GGX lobe (SURVEY 7 hard parts)'}
+    # the other integrate variant (nf_integrate_fwd brdf_kind = 1: pre-computed learned-BRDF lobe,
+    # SURVEY 8b "pre-computed-BRDF variant"): reads the lvis AND spec rows (8L + 76 B / ray) and has
+    # no GGX arithmetic, i.e. the memory-heavier of the two.  Context row; never the headline.
+    rf_int_spec = None
+    try:
+        spec = torch.rand_like(lvis)
+        t_int1 = kt(lambda: _lib.integrate_fwd(ctx, xyz_m, nrm, cam, alb, lvis, model.lxyz,
+                                               model.lareas, light, spec=spec, spec_scale=1.0))
+        alg_int1 = n_fg * (8 * L + 64 + 12)
+        rf_int_spec = {'kernel': 'nf_integrate_fwd (pre-computed BRDF lobe)', 'bound': 'hbm',
+                       'achieved': alg_int1 / (t_int1 * 1e-3) / 1e9, 'peak': pk['hbm_gbs'],
+                       'unit': 'GB/s', 'ms': t_int1, 'traffic': None,
+                       'algorithmic_bytes': alg_int1}
+        rf_int_spec['frac'] = rf_int_spec['achieved'] / rf_int_spec['peak']
+        del spec
+    except Exception as e:                                  # context row only
+        rf_int_spec = {'kernel': 'nf_integrate_fwd (pre-computed BRDF lobe)', 'error': repr(e)}
     rf_point = {'kernel': 'nf_point_mlp_fwd (tcgen05 f16x3 split, per net; x3 per step)', 'bound': 'latency',
                 'achieved': n_fg * FLOP_POINT / (t_point * 1e-3) / 1e12, 'peak': None,
                 'unit': 'TFLOP/s', 'ms': t_point, 'traffic': None}
@@ -453,7 +470,7 @@ def main():
                 'd2h_bytes_per_step': int(rgb_host.numel() * 4 + alpha_host.numel() * 4)},
         'gpu_launches': launches, 'clocks': clocks,
         'roofline': dominant,
-        'rooflines': [rf_sigma, rf_lvis, rf_int, rf_point],
+        'rooflines': [rf_sigma, rf_lvis, rf_int, rf_point] + ([rf_int_spec] if rf_int_spec else []),
         'foreground_rays': n_fg,
         'cpu_baseline': cpu,
         'secondary': secondary,

@@ -1,3 +1,10 @@
-"""Mirror of the hot-path parts of nerfactor/datasets (ray generation lives in the CUDA
-library: nf_gen_rays; file I/O is out of scope)."""
+"""Mirror of nerfactor/datasets/__init__.py:18-20 (name -> class registry).  `nerf` and
+`nerf_shape` are the data formats either side of the hot path; `mvs_shape` and
+`brdf_merl` are out of scope."""
+from importlib import import_module
+
 from . import nerf_shape  # noqa: F401
+
+
+def get_dataset_class(name):
+    return import_module('nerfactor_b200.datasets.' + name).Dataset

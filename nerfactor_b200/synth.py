@@ -149,3 +149,67 @@ def light_index_map(envmap_hw, light_hw):
     ii = (np.arange(lh) * eh) // lh
     jj = (np.arange(lw) * ew) // lw
     return (ii[:, None] * ew + jj[None, :]).reshape(-1).astype(np.int32)
+
+
+def write_scene(root, imh=16, imw=16, n_train=2, n_val=1, n_test=2, seed=0, nerf_root=None,
+                n_lights=None, envmap_dir=None, n_probes=2, light_hw=(16, 32)):
+    """Writes a tiny synthetic scene in the reference's on-disk layout (data_gen output,
+    datasets/nerf.py:64-90): `<root>/{train,val,test}_NNN/metadata.json` (+ `rgba.png` for
+    train / val: a shaded sphere on a transparent background), optionally the Stage-A buffers
+    `<nerf_root>/<view>/{alpha.png,xyz.npy,normal.npy,lvis.npy}` (analytic sphere of radius 1)
+    and `n_probes` Radiance .hdr light probes in `envmap_dir`.  Returns the list of view ids."""
+    import json
+    import os
+    from PIL import Image
+    rng = np.random.default_rng(seed)
+    ids = []
+    k = 0
+    for mode, n in (('train', n_train), ('val', n_val), ('test', n_test)):
+        for i in range(n):
+            id_ = '%s_%03d' % (mode, i)
+            ids.append(id_)
+            c2w = look_at_c2w(4.0, 30.0 + 40.0 * k, 20.0 + 5.0 * k)
+            k += 1
+            d = os.path.join(root, id_)
+            os.makedirs(d, exist_ok=True)
+            meta = {'id': id_, 'imh': imh, 'imw': imw, 'cam_angle_x': CAM_ANGLE_X,
+                    'cam_transform_mat': ','.join('%.17g' % v for v in c2w.reshape(-1))}
+            with open(os.path.join(d, 'metadata.json'), 'w') as f:
+                json.dump(meta, f)
+            # analytic unit sphere seen from this camera
+            fl = .5 * imw / np.tan(.5 * CAM_ANGLE_X)
+            xs, ys = np.meshgrid(np.arange(imw, dtype=float), np.arange(imh, dtype=float))
+            dl = np.stack(((xs - .5 * imw) / fl, -(ys - .5 * imh) / fl, -np.ones_like(xs)), -1)
+            dw = np.sum(dl[:, :, None, :] * c2w[:3, :3], -1)
+            dn = dw / np.linalg.norm(dw, axis=-1, keepdims=True)
+            o = c2w[:3, 3]
+            b = dn @ o
+            disc = b * b - (o @ o - 1.0)
+            hit = disc > 0
+            t = -b - np.sqrt(np.where(hit, disc, 0.))
+            p = o[None, None, :] + dn * t[..., None]
+            nrm = np.where(hit[..., None], p, np.array([0., 1., 0.]))
+            alpha = hit.astype(np.float32)
+            if mode != 'test':
+                shade = np.clip(nrm @ np.array([0.3, 0.5, 0.8]), 0.05, 1.)[..., None]
+                rgb = shade * np.array([0.8, 0.6, 0.4])
+                rgba = np.concatenate([rgb * alpha[..., None], alpha[..., None]], -1)
+                Image.fromarray((np.clip(rgba, 0, 1) * 255).astype(np.uint8), 'RGBA').save(
+                    os.path.join(d, 'rgba.png'))
+            if nerf_root is not None:
+                bd = os.path.join(nerf_root, id_)
+                os.makedirs(bd, exist_ok=True)
+                L = n_lights or light_hw[0] * light_hw[1]
+                Image.fromarray((alpha * 255).astype(np.uint8)).save(os.path.join(bd, 'alpha.png'))
+                np.save(os.path.join(bd, 'xyz.npy'), (p * alpha[..., None]).astype(np.float32))
+                np.save(os.path.join(bd, 'normal.npy'), nrm.astype(np.float32))
+                np.save(os.path.join(bd, 'lvis.npy'),
+                        (rng.uniform(size=(imh, imw, L)) * alpha[..., None]).astype(np.float32))
+    if envmap_dir is not None:
+        import cv2
+        os.makedirs(envmap_dir, exist_ok=True)
+        probes = make_probes(seed + 1, n_probes, (4 * light_hw[0], 4 * light_hw[1]))
+        for i, pr in enumerate(probes):
+            cv2.imwrite(os.path.join(envmap_dir, 'probe%d.hdr' % i),
+                        np.ascontiguousarray(pr[:, :, ::-1]))
+    return ids

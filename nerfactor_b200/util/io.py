@@ -31,3 +31,85 @@ def restore_model(model, ckpt_path, submodel=''):
 
 
 latest_checkpoint = tfckpt.latest_checkpoint
+
+
+# ---------------------------------------------------------------- nerfactor/util/io.py:29-120
+def all_exist(path_dict):
+    """util/io.py:29-33."""
+    import os
+    return all(os.path.exists(v) for v in path_dict.values())
+
+
+def read_config(path):
+    """util/io.py:48-52: the flat `[DEFAULT]` .ini files of nerfactor/config/."""
+    from configparser import ConfigParser
+    config = ConfigParser()
+    with open(path, 'r') as h:
+        config.read_file(h)
+    return config
+
+
+def write_config(config, path):
+    """util/io.py:55-57."""
+    import os
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    with open(path, 'w') as h:
+        config.write(h)
+
+
+def prepare_outdir(outdir, overwrite=False, quiet=True):
+    """util/io.py:60-74: wipe when `overwrite`, otherwise keep what is there."""
+    import os
+    from shutil import rmtree
+    if os.path.isdir(outdir):
+        if not overwrite:
+            return
+        rmtree(outdir)
+    os.makedirs(outdir)
+
+
+def read_json(path):
+    """util/io.py:96-99."""
+    import json
+    with open(path, 'r') as h:
+        return json.load(h)
+
+
+def write_json(data, path):
+    """util/io.py:102-108."""
+    import json
+    import os
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    with open(path, 'w') as h:
+        json.dump(data, h, indent=4, sort_keys=True)
+
+
+def load_np(np_f):
+    """util/io.py:111-120."""
+    import numpy as np
+    if np_f.endswith('.npy'):
+        with open(np_f, 'rb') as h:
+            return np.load(h)
+    with open(np_f, 'rb') as h:
+        return dict(np.load(h, allow_pickle=True))
+
+
+def sortglob(directory, filename='*', ext=None):
+    """xiuminglib os.sortglob (local paths): sorted glob of `filename` + each extension."""
+    import os
+    from glob import glob
+    if ext is None:
+        ext = ()
+    elif isinstance(ext, str):
+        ext = (ext,)
+    if isinstance(filename, str):
+        filename = (filename,)
+    exts = [x if x.startswith('.') else '.' + x for x in ext]
+    files = []
+    for f in filename:
+        if exts:
+            for e in exts:
+                files += glob(os.path.join(directory, f + e))
+        else:
+            files += glob(os.path.join(directory, f))
+    return sorted(files)
