@@ -134,3 +134,95 @@ def process_view(model, rayo, rayd, hw, config, occu_thres=0., lvis_far=1., ligh
         lvis.index_copy_(0, idx, lvis_hit)
         out['lvis'] = lvis.reshape(hw[0], hw[1], L) * alpha_map[:, :, None]   # gfn.py:170-171
     return out
+
+
+# =============================================================================== script
+def _parse_args(argv=None):
+    """geometry_from_nerf.py:30-58 (same flag names; `mlp_chunk` / `lpix_chunk` are accepted and
+    ignored: the fused kernels are persistent over tiles and march all lights together)."""
+    import argparse
+    ap = argparse.ArgumentParser(description="Stage A: surface, normals and light visibility "
+                                             "from a trained NeRF")
+    ap.add_argument('--trained_nerf', default='',
+                    help="path to trained NeRF up to (and including) learning rate folder")
+    ap.add_argument('--data_root', default='', help="input data root")
+    ap.add_argument('--out_root', default='', help="output root")
+    ap.add_argument('--imh', type=int, default=None,
+                    help="image height (defaults to what was used for NeRF training)")
+    ap.add_argument('--scene_bbox', default=None,
+                    help="x_min,x_max,y_min,y_max,z_min,z_max")
+    ap.add_argument('--lvis_far', type=float, default=1.)
+    ap.add_argument('--occu_thres', type=float, default=0.)
+    ap.add_argument('--light_h', type=int, default=16)
+    ap.add_argument('--mlp_chunk', type=int, default=1_500_000)
+    ap.add_argument('--lpix_chunk', type=int, default=1)
+    ap.add_argument('--spp', type=int, default=1)
+    ap.add_argument('--fps', type=int, default=12)
+    ap.add_argument('--debug', action='store_true')
+    ap.add_argument('--precision', default='f16', choices=['f16', 'bf16', 'fp32'],
+                    help="'fp32' = CUDA-core kernels throughout (tight parity), else tcgen05")
+    return ap.parse_args(argv)
+
+
+def main(argv=None):
+    """geometry_from_nerf.py:63-90: latest NeRF checkpoint -> for every train / vali / test view
+    the four geometry buffers under `<out_root>/<view>/` (views already done are skipped,
+    :106-115).  Under torchrun the views are split round-robin over the ranks."""
+    import os
+    from os.path import basename, join
+    from . import datasets, models
+    from .util import config as configutil, geom_io, io as ioutil
+
+    FLAGS = _parse_args(argv)
+    if FLAGS.spp != 1:
+        # the reference's visibility step masks un-averaged points with an [H*W] mask
+        # (gfn.py:154-156): only spp = 1 is self-consistent there (SURVEY.md appendix A)
+        raise NotImplementedError("spp != 1")
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
+    ckpts = ioutil.sortglob(join(FLAGS.trained_nerf, 'checkpoints'), 'ckpt-*', ext='index')
+    assert ckpts, "no checkpoint under %s/checkpoints" % FLAGS.trained_nerf
+    ckpt_ind = [int(basename(x)[len('ckpt-'):-len('.index')]) for x in ckpts]
+    latest_ckpt = ckpts[int(np.argmax(ckpt_ind))][:-len('.index')]
+    config = ioutil.read_config(configutil.get_config_ini(latest_ckpt))
+    if FLAGS.imh is not None:
+        config.set('DEFAULT', 'imh', str(FLAGS.imh))
+    if FLAGS.data_root:
+        config.set('DEFAULT', 'data_root', FLAGS.data_root)
+    Model = models.get_model_class(config.get('DEFAULT', 'model', fallback='nerf'))
+    model = Model(config, precision=FLAGS.precision)
+    ioutil.restore_model(model, latest_ckpt)
+    Dataset = datasets.get_dataset_class(config.get('DEFAULT', 'dataset', fallback='nerf'))
+    done = []
+    k = 0
+    for mode in ('train', 'vali', 'test'):
+        try:
+            dataset = Dataset(config, mode, always_all_rays=True, spp=FLAGS.spp)
+        except AssertionError:            # no view of this mode
+            continue
+        for batch in dataset.build_pipeline(no_batch=True, no_shuffle=True):
+            k += 1
+            if (k - 1) % world != rank:
+                continue
+            id_, hw, rayo, rayd, _ = batch
+            out_dir = join(FLAGS.out_root, id_)
+            if geom_io.view_done(out_dir):
+                continue
+            rayo = rayo.to(model.device, non_blocking=True)
+            rayd = rayd.to(model.device, non_blocking=True)
+            rayd = rayd * torch.rsqrt(torch.clamp((rayd * rayd).sum(1, keepdim=True), min=1e-12))
+            with torch.no_grad():
+                buffers = process_view(
+                    model, rayo.contiguous(), rayd.contiguous(), hw, config,
+                    occu_thres=FLAGS.occu_thres, lvis_far=FLAGS.lvis_far, light_h=FLAGS.light_h,
+                    scene_bbox=FLAGS.scene_bbox, precision=FLAGS.precision)
+            geom_io.write_view_buffers(buffers, out_dir)
+            done.append(id_)
+            if FLAGS.debug:
+                break
+    return done
+
+
+if __name__ == '__main__':
+    main()

@@ -11,9 +11,10 @@ from .. import _lib
 from ..networks import mlp
 from ..networks.embedder import Embedder
 from .base import Model as BaseModel
+from ._visualize import NerfVis
 
 
-class Model(BaseModel):
+class Model(NerfVis, BaseModel):
     def __init__(self, config, debug=False, params=None, ctx=None, precision='f16'):
         super().__init__(config, debug=debug)
         self.ctx = ctx or _lib.default_context()

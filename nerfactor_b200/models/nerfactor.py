@@ -6,6 +6,7 @@ reference's 9-tuple batch (nerfactor/datasets/nerf_shape.py:72-95).  Everything
 per-(point, light) runs in the fused kernels of libnerfactor_b200.so; torch ops
 here only compact / scatter the foreground rays and do [N,3]-sized glue.
 """
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -15,15 +16,24 @@ from .. import _lib
 from ..config import default_config
 from ..networks import mlp
 from ..networks.embedder import Embedder
-from ..util import math as mathutil, img as imgutil
+from ..util import math as mathutil, img as imgutil, io as ioutil, config as configutil, \
+    light as lightutil
+from ..util.io import restore_model
 from .shape import Model as ShapeModel, to_device
 from .brdf import Model as BRDFModel
+from ._visualize import NeRFactorVis
 
 
-class Model(ShapeModel):
+class Model(NeRFactorVis, ShapeModel):
     def __init__(self, config, debug=False, params=None, ctx=None, precision='f16',
                  config_brdf=None, test_time_jitter=False):
-        # BRDF (nerfactor.py:36-42): the prior's config normally sits next to its ckpt
+        # BRDF (nerfactor.py:36-42): the prior's config sits next to its checkpoint
+        # (`brdf_model_ckpt` -> `<outroot>/<xname>.ini`); without one, brdf.ini's defaults
+        self.brdf_model_ckpt = config.get('DEFAULT', 'brdf_model_ckpt', fallback='')
+        if config_brdf is None and self.brdf_model_ckpt:
+            ini = configutil.get_config_ini(self.brdf_model_ckpt)
+            if os.path.exists(ini):
+                config_brdf = ioutil.read_config(ini)
         self.config_brdf = config_brdf or default_config('brdf')
         self.pred_brdf = config.getboolean('DEFAULT', 'pred_brdf')
         if not self.pred_brdf:
@@ -52,7 +62,13 @@ class Model(ShapeModel):
         ambi = self.config.getfloat('DEFAULT', 'ambient_inten', fallback=0)
         self.ambient_inten = ambi if self.white_bg else 0.
         self.novel_olat = _LazyOlat(self)
-        self.novel_probes = OrderedDict()      # name -> [h, 2h, 3] tensor (set by caller)
+        # (2) light probes: every .hdr of `test_envmap_dir` resampled to the light resolution
+        # (nerfactor.py:85-92, 169-179); name -> [h, 2h, 3].  Callers may also fill it directly.
+        self.novel_probes = OrderedDict()
+        envmap_dir = self.config.get('DEFAULT', 'test_envmap_dir', fallback='')
+        for name, envmap in lightutil.load_probes(envmap_dir, light_h).items():
+            self.novel_probes[name] = to_device(envmap, self.device)
+        self._restore_submodels()
         if params is not None:
             self.load_params(params)
 
@@ -64,6 +80,27 @@ class Model(ShapeModel):
     def _init_brdf_model(self, params):
         self.brdf_model = BRDFModel(self.config_brdf, params=params if params and
                                     'brdf_mlp' in params else None)
+
+    def _load_light(self, path):
+        """nerfactor.py:169-179."""
+        return to_device(lightutil.load_light(path, self.light_res[0]), self.device)
+
+    def _restore_submodels(self):
+        """What the reference restores while constructing the model, when the checkpoints named in
+        the config exist: the frozen BRDF prior (nerfactor.py:57-60) and, for shape_mode
+        'frozen' / 'finetune', the pre-trained normal / visibility MLPs (nerfactor.py:156-163)."""
+        from ..util import tfckpt
+        if self.brdf_model is not None and self.brdf_model_ckpt and \
+                os.path.exists(self.brdf_model_ckpt + '.index'):
+            restore_model(self.brdf_model, self.brdf_model_ckpt)
+            n_z = np.asarray(self.brdf_model.latent_code.z).shape[0]
+            if len(self.brdf_model.brdf_names) != n_z:
+                self.brdf_model.brdf_names = ['brdf_%03d' % i for i in range(n_z)]
+        ckpt = self.config.get('DEFAULT', 'shape_model_ckpt', fallback='')
+        if self.shape_mode in ('frozen', 'finetune') and ckpt and os.path.exists(ckpt + '.index'):
+            params = tfckpt.params_from_checkpoint(ckpt)
+            ShapeModel.load_params(self, {k: params[k] for k in (
+                'normal_mlp', 'normal_out', 'lvis_mlp', 'lvis_out')})
 
     def _init_embedder(self):
         """nerfactor.py:107-126."""

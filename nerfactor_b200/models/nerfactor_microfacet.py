@@ -29,5 +29,10 @@ class Model(NeRFactorModel):
         fresnel_f0 = self.config.getfloat('DEFAULT', 'fresnel_f0')
         return {'microfacet': Microfacet(f0=fresnel_f0), 'rough': brdf_prop.contiguous()}
 
+    def _brdf_prop_as_img(self, brdf_prop):
+        """nerfactor_microfacet.py:126-132: roughness as a grey image."""
+        import numpy as np
+        return np.concatenate([brdf_prop] * 3, axis=2)
+
     def _brdf_kernel_args(self, brdf):
         return {'rough': brdf['rough'], 'f0': brdf['microfacet'].f0}

@@ -13,6 +13,7 @@ from ..networks import mlp
 from ..networks.embedder import Embedder
 from ..util import math as mathutil, img as imgutil
 from .base import Model as BaseModel
+from ._visualize import ShapeVis
 
 
 def to_device(x, device, dtype=torch.float32):
@@ -23,7 +24,7 @@ def to_device(x, device, dtype=torch.float32):
         device, non_blocking=True)
 
 
-class Model(BaseModel):
+class Model(ShapeVis, BaseModel):
     def __init__(self, config, debug=False, params=None, ctx=None, precision='f16'):
         super().__init__(config, debug=debug)
         self.ctx = ctx or _lib.default_context()

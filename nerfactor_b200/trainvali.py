@@ -381,3 +381,163 @@ class Trainer:
         self.sync_to_model()
         pred, gt, loss_kwargs, _ = self.model.call(batch, 'vali')
         return self.model.compute_loss(pred, gt, **loss_kwargs)
+
+
+# =============================================================================== script
+def _parse_args(argv=None):
+    import argparse
+    ap = argparse.ArgumentParser(
+        description="Mirror of nerfactor/trainvali.py's command line (trainvali.py:33-39)")
+    ap.add_argument('--config', default='nerfactor.ini',
+                    help="base .ini file in config/ or a full path")
+    ap.add_argument('--config_override', default='', help="e.g., 'key1=value1,key2=value2'")
+    ap.add_argument('--debug', action='store_true')
+    ap.add_argument('--device', default='gpu', choices=['gpu'],
+                    help="the reference's 'cpu' strategy does not exist here: no CPU fallback")
+    ap.add_argument('--precision', default=None, choices=[None, 'bf16', 'f16', 'fp32'],
+                    help="arithmetic of the training Dense kernels (default bf16)")
+    return ap.parse_args(argv)
+
+
+def load_config(path, override=''):
+    """trainvali.py:53-62: a full path, or a name resolved against the built-in defaults
+    (`nerfactor.ini`, `nerfactor_microfacet.ini`, `shape.ini`; the reference ships these under
+    nerfactor/config/ with site-specific paths), then `key=value,...` overrides."""
+    import os
+    from .config import default_config
+    from .util import io as ioutil
+    if os.path.exists(path):
+        config = ioutil.read_config(path)
+    else:
+        config = default_config(os.path.basename(path)[:-len('.ini')]
+                                if path.endswith('.ini') else path)
+    if override:
+        for kv in override.split(','):
+            k, v = kv.split('=', 1)
+            config.set('DEFAULT', k, v)
+    return config
+
+
+def _prune(ckptdir, keep):
+    """tf.train.CheckpointManager(max_to_keep=keep): drop all but the newest `keep` checkpoints."""
+    import glob
+    import os
+    if not keep or keep <= 0:
+        return
+    steps = sorted(int(os.path.basename(p)[len('ckpt-'):-len('.index')])
+                   for p in glob.glob(os.path.join(ckptdir, 'ckpt-*.index')))
+    for s in steps[:-keep]:
+        for p in glob.glob(os.path.join(ckptdir, 'ckpt-%d.*' % s)):
+            os.remove(p)
+
+
+def main(argv=None):
+    """trainvali.py:45-256: config -> output directory -> datasets -> model + AMSGrad ->
+    resume -> epochs of (one gradient step per training view) with periodic checkpoints and
+    validation visualisations.  One process per GPU under torchrun: every rank draws its share
+    of `n_rays_per_step` rays of the same view, gradients meet in one all-reduce."""
+    import json
+    import os
+    import time
+    from os.path import join
+    from . import datasets, models
+    from .util import io as ioutil, config as configutil
+
+    FLAGS = _parse_args(argv)
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
+    if world > 1:
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            dist.init_process_group('nccl')
+    config = load_config(FLAGS.config, FLAGS.config_override)
+    config_dict = configutil.config2dict(config)
+    xname = config.get('DEFAULT', 'xname', fallback='lr{lr}').format(**config_dict)
+    outdir = join(config.get('DEFAULT', 'outroot'), xname)
+    if rank == 0:
+        ioutil.prepare_outdir(outdir, overwrite=config.getboolean('DEFAULT', 'overwrite',
+                                                                  fallback=False))
+        ioutil.write_config(config, outdir.rstrip('/') + '.ini')
+    if world > 1:
+        dist.barrier()
+    # ---- data (trainvali.py:76-100)
+    Dataset = datasets.get_dataset_class(config.get('DEFAULT', 'dataset', fallback='nerf_shape'))
+    dataset_train = Dataset(config, 'train', debug=FLAGS.debug, seed=1000 + rank)
+    global_bs_train = dataset_train.bs
+    dataset_train.bs = max(1, global_bs_train // world)       # this rank's share of the rays
+    datapipe_train = dataset_train.build_pipeline(no_batch=True, seed=0)   # same view order
+    vali_batches = None
+    try:
+        dataset_vali = Dataset(config, 'vali', debug=FLAGS.debug)
+        vali_batches = dataset_vali.build_pipeline(no_batch=True).take(
+            config.getint('DEFAULT', 'vali_batches', fallback=4))
+    except (FileNotFoundError, AssertionError):
+        pass
+    # ---- model + optimizer (trainvali.py:102-127)
+    Model = models.get_model_class(config.get('DEFAULT', 'model'))
+    model = Model(config, debug=FLAGS.debug, precision='fp32' if FLAGS.precision == 'fp32'
+                  else 'f16')
+    model.register_trainable()
+    for k in ('clipnorm', 'clipvalue'):
+        if config.getfloat('DEFAULT', k, fallback=-1) > 0:
+            raise NotImplementedError("%s > 0 (the reference's configs all use -1)" % k)
+    trainer = Trainer(model, config, world_size=world, rank=rank, precision=FLAGS.precision)
+    # ---- resume (trainvali.py:129-146)
+    ckptdir = join(outdir, 'checkpoints')
+    keep = config.getint('DEFAULT', 'keep_recent_epochs', fallback=-1)
+    latest = ioutil.latest_checkpoint(ckptdir) if os.path.isdir(ckptdir) else None
+    step = trainer.restore_checkpoint(latest) if latest else 0
+    print("Resumed from step:\n\t%s" % latest if latest else "Started from scratch")
+    epochs = config.getint('DEFAULT', 'epochs')
+    ckpt_period = config.getint('DEFAULT', 'ckpt_period')
+    vali_period = config.getint('DEFAULT', 'vali_period')
+    vali_vis_epoch_dir = join(outdir, 'vis_vali', 'epoch{e:09d}')
+
+    def log(name, rec):
+        if rank == 0:
+            with open(join(outdir, name + '.jsonl'), 'a') as f:
+                f.write(json.dumps(rec) + '\n')
+
+    # ---- training loop (trainvali.py:168-256); an "epoch" = one step per training view
+    while step < epochs:
+        batch_loss, batch_time = [], []
+        for batch in datapipe_train:
+            t0 = time.time()
+            loss = trainer.train_step(batch)
+            batch_loss.append(float(loss))
+            batch_time.append(time.time() - t0)
+            if FLAGS.debug:
+                break
+        assert batch_time, "Dataset is empty"
+        step += 1
+        if step % ckpt_period == 0:
+            if rank == 0:
+                saved = trainer.save_checkpoint(ckptdir, step)
+                _prune(ckptdir, keep)
+                print("Checkpointed step %s:\n\t%s" % (step, saved))
+            log('summary_train', {'step': step, 'loss_train': float(np.mean(batch_loss)),
+                                  'batch_time_train': float(np.mean(batch_time))})
+        if vali_batches is not None and vali_period > 0 and step % vali_period == 0 and rank == 0:
+            trainer.sync_to_model()
+            losses, vis_dirs = [], []
+            for batch_i, batch in enumerate(vali_batches):
+                with torch.no_grad():
+                    pred, gt, loss_kwargs, to_vis = model.call(batch, 'vali')
+                    loss_kwargs['keep_batch'] = True
+                    per_ray = model.compute_loss(pred, gt, **loss_kwargs)
+                losses.append(float(per_ray.sum() / per_ray.shape[0]))
+                vis_dir = join(vali_vis_epoch_dir.format(e=step), 'batch{b:09d}'.format(b=batch_i))
+                model.vis_batch(to_vis, vis_dir, mode='vali')
+                vis_dirs.append(vis_dir)
+            view_at = model.compile_batch_vis(
+                vis_dirs, join(vali_vis_epoch_dir.format(e=step), 'all'), mode='vali')
+            log('summary_vali', {'step': step, 'loss_vali': float(np.mean(losses)),
+                                 'vis_vali': view_at})
+        if world > 1:
+            dist.barrier()
+    return outdir
+
+
+if __name__ == '__main__':
+    main()
