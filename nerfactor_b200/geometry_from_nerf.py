@@ -180,7 +180,8 @@ def main(argv=None):
         raise NotImplementedError("spp != 1")
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
-    torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
+    if torch.cuda.is_available():          # without a GPU the model constructor raises (no CPU path)
+        torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
     ckpts = ioutil.sortglob(join(FLAGS.trained_nerf, 'checkpoints'), 'ckpt-*', ext='index')
     assert ckpts, "no checkpoint under %s/checkpoints" % FLAGS.trained_nerf
     ckpt_ind = [int(basename(x)[len('ckpt-'):-len('.index')]) for x in ckpts]

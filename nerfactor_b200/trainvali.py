@@ -306,7 +306,8 @@ class Trainer:
     def train_step(self, batch, xyz_noise=None, graph=True):
         """trainvali.py:273-295: one optimizer iteration; returns the summed loss / global bs.
         graph=True replays forward + backward as one CUDA graph when the batch allows it."""
-        out = self._graphed_loss_and_grad(batch, xyz_noise) if graph else None
+        out = self._graphed_loss_and_grad(batch, xyz_noise) if (
+            graph and self.device.type == 'cuda') else None
         loss, grad = out if out is not None else self.loss_and_grad(batch, xyz_noise)
         if self.world_size > 1:
             import torch.distributed as dist
@@ -446,7 +447,8 @@ def main(argv=None):
     FLAGS = _parse_args(argv)
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
-    torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
+    if torch.cuda.is_available():          # without a GPU the model constructor raises (no CPU path)
+        torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
     if world > 1:
         import torch.distributed as dist
         if not dist.is_initialized():
