@@ -10,7 +10,7 @@
 namespace {
 
 constexpr int WARPS = 8;
-constexpr int E_CHUNK = 4;
+constexpr int E_CHUNK = 8;   // env-maps per pass over the lvis rows (instantiated: 1 2 3 4 6 8)
 
 struct PointCtx {  // per-point quantities (nerfactor.py:195-196, 212; microfacet.py:46-49)
   f3 pt, n1, v1, n2, v2, lambert;
@@ -94,12 +94,20 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // ---- packed-FP32 (FFMA2 / FMUL2 / FADD2, sm_100) version of the pair evaluation ------------
 // Two consecutive lights per lane, every vector quantity as a float2 (light 2j, light 2j+1).
-// Same formulas as eval_pair with three identities applied (each exact up to 1 ulp):
-//   h.v = l.h            (h is the normalised half vector of two unit vectors)
-//   l.n2 = l.n1 = cos    (n2 = l2n(n1) is n1)
+// Same formulas as eval_pair with these identities applied (each exact up to 1 ulp; l, v, n unit):
+//   h . v = l . h = |l + v| / 2  (>= 0)                so chi_g = [(h.v)(n.v) > 0] = [n.v > 0]: per
+//                                                      point, folded into K
+//   h . n = (l.n + v.n) / |l + v|                      > 0 whenever l.n > 0 and n.v > 0: chi_d is
+//                                                      implied by the front-lit test
+//   l . n2 = l . n1 = cos                              (n2 = l2n(n1) is n1)
 //   spec * cos / |l.n| = spec' for cos > 0: the division by |l.n| cancels against the cosine of
 //   the rendering equation, so   brdf * w = (lambert * cos + F K / u^2) * [cos>0] lvis area,
-//   K = g_view a2 / (4 pi |v.n|)  (0 when v.n = 0: tf.math.divide_no_nan, microfacet.py:58-61).
+//   K = [n.v > 0] g_view a2 / (4 pi |v.n|)  (0 when v.n = 0: tf.math.divide_no_nan,
+//   microfacet.py:58-61),  u = 1 + (a2 - 1) (h.n)^2.
+// NOT applied: |l + v|^2 = 2 + 2 l.v.  At grazing mirror configurations (|l + v| = 2 n.v -> 0) it
+// cancels catastrophically -- measured 8e-5 (rough 0.4) / 1.6e-2 (rough 0.2) rel-L2 against an
+// fp64 evaluation, vs 1e-6 / 2e-4 with the half vector formed component-wise as below
+// (tools/diag_integrate.py).
 __device__ __forceinline__ float2 bc2(float s) { return make_float2(s, s); }
 __device__ __forceinline__ float rsq_fast(float x) {
   float y;
@@ -120,10 +128,10 @@ struct PointCtx2 {
   float2 nx, ny, nz;           // unit normal
   float2 vx, vy, vz;           // unit view direction
   float2 a2m1;                 // alpha^2 - 1   (u = 1 + (a2 - 1) cm^2)
-  float2 k;                    // g_view a2 / (4 pi |v.n|)
+  float2 k;                    // [n.v > 0] g_view a2 / (4 pi |v.n|)
   float2 f0, omf0;
   float2 lr, lg, lb;           // albedo / pi
-  float cos_v;
+  float2 cos_v;                // n . v
 };
 
 // sw = specular * [cos>0] lvis area (already multiplied by the cosine, see above), dw = diffuse
@@ -133,49 +141,31 @@ __device__ __forceinline__ void eval_pair2(const nf_integrate_args& a, const Poi
                                            float2 lx, float2 ly, float2 lz, float2 la,
                                            float2 lvis, float2 spec_in, float2& sw, float2& dw) {
   const float2 dx = __fadd2_rn(lx, c.npx), dy = __fadd2_rn(ly, c.npy), dz = __fadd2_rn(lz, c.npz);
-  float2 dd = dot3_2(dx, dy, dz, dx, dy, dz);
-  const float2 inv = make_float2(rsq_fast(fmaxf(dd.x, 1e-6f)), rsq_fast(fmaxf(dd.y, 1e-6f)));
+  const float2 dd = dot3_2(dx, dy, dz, dx, dy, dz);
+  const float2 inv = make_float2(rsq_fast(fmaxf(dd.x, 1e-6f)), rsq_fast(fmaxf(dd.y, 1e-6f)));   // shape.py:128-135
   const float2 l1x = __fmul2_rn(dx, inv), l1y = __fmul2_rn(dy, inv), l1z = __fmul2_rn(dz, inv);
   const float2 cosv = dot3_2(l1x, l1y, l1z, c.nx, c.ny, c.nz);          // nerfactor.py:325
   const float2 wl = __fmul2_rn(lvis, la);                               // lvis * area
   dw = __fmul2_rn(wl, make_float2(fmaxf(cosv.x, 0.f), fmaxf(cosv.y, 0.f)));   // :329-335
   if (KIND == 0) {
     const float2 hx = __fadd2_rn(l1x, c.vx), hy = __fadd2_rn(l1y, c.vy), hz = __fadd2_rn(l1z, c.vz);
-    const float2 hh = dot3_2(hx, hy, hz, hx, hy, hz);
-    const float2 invh = make_float2(rsq_fast(fmaxf(hh.x, 1e-6f)), rsq_fast(fmaxf(hh.y, 1e-6f)));
-    const float2 cm = __fmul2_rn(dot3_2(hx, hy, hz, c.nx, c.ny, c.nz), invh);      // :96
-    const float2 ldh = __fmul2_rn(dot3_2(hx, hy, hz, l1x, l1y, l1z), invh);        // = h.v, :78
-    const float2 om = __ffma2_rn(ldh, bc2(-1.f), bc2(1.f));
+    const float2 hh = dot3_2(hx, hy, hz, hx, hy, hz);                           // |l + v|^2
+    const float2 invh = make_float2(rsq_fast(fmaxf(hh.x, 1e-6f)), rsq_fast(fmaxf(hh.y, 1e-6f)));   // microfacet.py:51-52
+    const float2 om = __ffma2_rn(__fmul2_rn(hh, invh), bc2(-0.5f), bc2(1.f));   // 1 - l.h
     const float2 om2 = __fmul2_rn(om, om);
     const float2 om5 = __fmul2_rn(__fmul2_rn(om2, om2), om);
-    const float2 f = __ffma2_rn(om5, c.omf0, c.f0);                                 // :106-111
+    const float2 f = __ffma2_rn(om5, c.omf0, c.f0);                             // :106-111
+    const float2 cm = __fmul2_rn(__fadd2_rn(cosv, c.cos_v), invh);              // h . n, :96
     const float2 u = __ffma2_rn(c.a2m1, __fmul2_rn(cm, cm), bc2(1.f));
     const float2 uu = __fmul2_rn(u, u);
     const float2 r = make_float2(rcp_fast(uu.x), rcp_fast(uu.y));
     const float2 sp = __fmul2_rn(__fmul2_rn(f, c.k), __fmul2_rn(wl, r));
-    // chi_d (m.n > 0), chi_g ((h.v)(n.v) > 0), front-lit, non-degenerate lobe
-    const float2 hv = __fmul2_rn(ldh, bc2(c.cos_v));
-    const float gx = fminf(fminf(cosv.x, cm.x), fminf(hv.x, u.x));
-    const float gy = fminf(fminf(cosv.y, cm.y), fminf(hv.y, u.y));
-    sw = make_float2(gx > 0.f ? sp.x : 0.f, gy > 0.f ? sp.y : 0.f);
+    // front-lit (which implies chi_d once n.v > 0, folded into K) and a non-degenerate lobe
+    sw = make_float2(fminf(cosv.x, u.x) > 0.f ? sp.x : 0.f, fminf(cosv.y, u.y) > 0.f ? sp.y : 0.f);
   } else {
     // learned BRDF: spec * learned_brdf_scale (nerfactor.py:460), times the diffuse weight
     sw = __fmul2_rn(__fmul2_rn(spec_in, bc2(a.spec_scale)), dw);
   }
-}
-
-__device__ __forceinline__ PointCtx2 load_point2(const nf_integrate_args& a, int i) {
-  const PointCtx s = load_point(a, i);
-  PointCtx2 c;
-  c.npx = bc2(-s.pt.x); c.npy = bc2(-s.pt.y); c.npz = bc2(-s.pt.z);
-  c.nx = bc2(s.n1.x); c.ny = bc2(s.n1.y); c.nz = bc2(s.n1.z);
-  c.vx = bc2(s.v2.x); c.vy = bc2(s.v2.y); c.vz = bc2(s.v2.z);
-  c.a2m1 = bc2(s.alpha2_sq - 1.f);
-  c.k = bc2(s.abs_vn != 0.f ? s.g_view * s.alpha2_sq / (4.f * NF_PI_F * s.abs_vn) : 0.f);
-  c.f0 = bc2(a.f0); c.omf0 = bc2(1.f - a.f0);
-  c.lr = bc2(s.lambert.x); c.lg = bc2(s.lambert.y); c.lb = bc2(s.lambert.z);
-  c.cos_v = s.cos_v;
-  return c;
 }
 
 // smem (floats, Lp = L rounded up to 2): X[Lp] Y[Lp] Z[Lp] AREA[Lp], then per env-map of the
@@ -223,7 +213,9 @@ __global__ void __launch_bounds__(WARPS * 32, KIND == 0 && EC == 1 ? 3 : 1) inte
       const int pi = base + lane;
       const bool pv = pi < a.n;
       const PointCtx s = load_point(a, pv ? pi : a.n - 1);
-      const float my_k = s.abs_vn != 0.f ? s.g_view * s.alpha2_sq / (4.f * NF_PI_F * s.abs_vn) : 0.f;
+      // chi_g = [(h.v)(n.v) > 0] with h.v >= 0: a per-point gate on n.v (h.v = 0 needs l = -v,
+      // where the pair is back-lit or the view is)
+      const float my_k = s.cos_v > 0.f ? s.g_view * s.alpha2_sq / (4.f * NF_PI_F * s.abs_vn) : 0.f;
       float outv[EC][3];
 #pragma unroll
       for (int e = 0; e < EC; ++e) outv[e][0] = outv[e][1] = outv[e][2] = 0.f;
@@ -244,7 +236,7 @@ __global__ void __launch_bounds__(WARPS * 32, KIND == 0 && EC == 1 ? 3 : 1) inte
         c.k = bc2(NF_BC(my_k));
         c.f0 = bc2(a.f0); c.omf0 = bc2(1.f - a.f0);
         c.lr = bc2(NF_BC(s.lambert.x)); c.lg = bc2(NF_BC(s.lambert.y)); c.lb = bc2(NF_BC(s.lambert.z));
-        c.cos_v = NF_BC(s.cos_v);
+        c.cos_v = bc2(NF_BC(s.cos_v));
 #undef NF_BC
         for (int l0 = 0; l0 < L; l0 += 512) {
           float2 lvr[8], spr[KIND == 1 ? 8 : 1];
@@ -364,7 +356,12 @@ int nf_integrate_fwd(nf_ctx* ctx, const nf_integrate_args* a, void* stream) {
   if (a->n == 0) return NF_OK;
   NF_CHECK_ARG(ctx, a->n_envmaps >= 1 && a->light_d && a->rgb_d, "missing env-maps / output");
   NF_CHECK_ARG(ctx, a->envmap_pixels >= 1, "bad envmap_pixels");
-  int ec = a->n_envmaps < E_CHUNK ? a->n_envmaps : E_CHUNK;
+  // env-maps per pass: as few passes over the lvis rows as E_CHUNK allows, split evenly
+  // (E = 9 -> 2 passes of 5, run by the EC = 6 instantiation)
+  const int n_pass = (a->n_envmaps + E_CHUNK - 1) / E_CHUNK;
+  int ec = (a->n_envmaps + n_pass - 1) / n_pass;
+  if (ec == 5) ec = 6;
+  if (ec == 7) ec = 8;
   const size_t lp = ((size_t)a->n_lights + 1) & ~(size_t)1;
   size_t sm = sizeof(float) * lp * (4 + 3 * ec);
   NF_CHECK_ARG(ctx, sm <= ctx->smem_optin, "n_lights too large for shared memory");
@@ -392,7 +389,9 @@ int nf_integrate_fwd(nf_ctx* ctx, const nf_integrate_args* a, void* stream) {
     case 1: NF_LAUNCH_INTEGRATE(1); break;
     case 2: NF_LAUNCH_INTEGRATE(2); break;
     case 3: NF_LAUNCH_INTEGRATE(3); break;
-    default: NF_LAUNCH_INTEGRATE(4); break;
+    case 4: NF_LAUNCH_INTEGRATE(4); break;
+    case 6: NF_LAUNCH_INTEGRATE(6); break;
+    default: NF_LAUNCH_INTEGRATE(8); break;
   }
 #undef NF_LAUNCH_INTEGRATE
 #undef NF_LAUNCH_INTEGRATE_K
