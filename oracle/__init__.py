@@ -30,4 +30,6 @@ generates the fixtures, tests/test_oracle_pinning.py checks them):
   third_party.xiuminglib ... sph2cart              -> oracle.brdf.sph2cart
   third_party.xiuminglib ... img.linear2srgb       -> oracle.stage_b.linear2srgb
   third_party.xiuminglib ... normal.gen_world2local (no-eps twin)
+  brdf.renderer.SphereRenderer (NumPy light-stage estimator) -> oracle.stage_b.StageB.calc_ldir
+                                                   + render (tests/golden/ref_sphere_renderer.npz)
 """

@@ -10,6 +10,11 @@ Two kinds of fixture:
 * ref_pinned.npz   outputs of the pieces of the reference that import without
                    TensorFlow, run here on seeded inputs.  These
                    pin the oracle (tests/test_oracle_pinning.py).
+* ref_sphere_renderer.npz   the reference's NumPy light-stage renderer
+                   (brdf/renderer.py SphereRenderer: gen_light_xyz, light directions,
+                   cosines, front-lit visibility, `calc_light_contrib`, `render`) run here on
+                   its own sphere scene with a seeded env-map and a Lambertian BRDF: pins the
+                   rendering-equation estimator (oracle AND, on the GPU, nf_integrate_fwd).
 * oracle_*.npz     outputs of the oracle itself on seeded synthetic inputs
                    (the reference ships no golden vectors), so
                    the CUDA parity tests have frozen vectors that do not drift
@@ -60,6 +65,28 @@ def make_ref_pinned():
     print('ref_pinned.npz:', sorted(out))
 
 
+def make_ref_sphere_renderer():
+    """brdf/renderer.py:23-183 as it is (NumPy, fp64)."""
+    sys.path.insert(0, '/root/reference')
+    from brdf.renderer import SphereRenderer                     # noqa
+    rng = np.random.default_rng(4321)
+    h, ims = 8, 24
+    r = SphereRenderer('point', '/tmp/nf_sphere_renderer', envmap_h=h, ims=ims, spp=1)
+    envmap = rng.uniform(0., 0.4, size=(h, 2 * h, 3))           # render stays below the clip
+    envmap[2, 5] = 3.0                                          # one bright texel
+    lcontrib = r.calc_light_contrib(envmap)                     # H x W x L x 3
+    albedo = rng.uniform(0.1, 0.9, size=(ims, ims, 3))
+    brdf = np.tile((albedo / np.pi)[:, :, None, :], (1, 1, lcontrib.shape[2], 1))
+    r.lcontrib = lcontrib
+    render = r.render(brdf, white_bg=True)
+    out = dict(xyz=r.xyz, normal=r.normal, is_fg=r.is_fg, lvis=r.lvis.astype(np.uint8),
+               lcos=r.lcos, lxyz=r.lxyz, lareas=r.lareas, envmap=envmap, albedo=albedo,
+               render=render, cam_loc=np.asarray(r.cam.loc, float))
+    np.savez_compressed(os.path.join(HERE, 'ref_sphere_renderer.npz'), **out)
+    print('ref_sphere_renderer.npz: fg pixels', int(r.is_fg.sum()), 'render max',
+          float(render[r.is_fg].max()))
+
+
 def make_oracle_goldens():
     from oracle import stage_a, stage_b, brdf as obrdf
     from nerfactor_b200 import synth
@@ -100,5 +127,9 @@ def make_oracle_goldens():
 
 
 if __name__ == '__main__':
+    if 'sphere' in sys.argv[1:]:
+        make_ref_sphere_renderer()
+        sys.exit(0)
     make_ref_pinned()
+    make_ref_sphere_renderer()
     make_oracle_goldens()

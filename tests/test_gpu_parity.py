@@ -549,6 +549,44 @@ def test_full_size_properties(ctx):
     assert rel_l2(olat.sum(1).cpu(), white[:, 0].cpu()) < 1e-4
 
 
+def test_integrate_kernel_vs_reference_sphere_renderer(ctx, golden_dir):
+    """nf_integrate_fwd / nf_integrate_olat_fwd against numbers produced by the REFERENCE ITSELF:
+    its NumPy light-stage renderer (brdf/renderer.py SphereRenderer, run in the build container by
+    tests/golden/make_golden.py) on its sphere scene, Lambertian BRDF, seeded env-map with one
+    bright texel.  Pins light directions, cosine, area weights, front-lit mask, env-map lookup and
+    the hemisphere sum of the kernels without going through the oracle."""
+    from nerfactor_b200 import _lib
+    g = np.load(os.path.join(golden_dir, 'ref_sphere_renderer.npz'))
+    fg = g['is_fg']
+    n = int(fg.sum())
+    L = g['lxyz'].shape[0] * g['lxyz'].shape[1]
+    xyz, nrm, alb = [dev(g[k][fg].astype(np.float32), ctx) for k in ('xyz', 'normal', 'albedo')]
+    cam = dev(np.tile(g['cam_loc'].astype(np.float32)[None], (n, 1)), ctx)
+    lvis = torch.ones((n, L), device=ctx.device)
+    zeros = torch.zeros((n, L), device=ctx.device)
+    lxyz = dev(g['lxyz'].reshape(-1, 3).astype(np.float32), ctx)
+    lareas = dev(g['lareas'].reshape(-1).astype(np.float32), ctx)
+    light = dev(g['envmap'].reshape(1, L, 3).astype(np.float32), ctx)
+    want = g['render'][fg]
+    # pre-computed-lobe variant with a zero lobe = pure Lambert albedo / pi
+    rgb = _lib.integrate_fwd(ctx, xyz, nrm, cam, alb, lvis, lxyz, lareas, light, spec=zeros,
+                             spec_scale=1.0, linear2srgb=False)[:, 0]
+    assert rel_l2(rgb.cpu(), want) < 5e-6
+    # eight copies of the env-map in one call (EC = 8 path), each scaled differently
+    scales = torch.arange(1, 9, device=ctx.device, dtype=torch.float32)[:, None, None] / 8
+    rgb8 = _lib.integrate_fwd(ctx, xyz, nrm, cam, alb, lvis, lxyz, lareas,
+                              (light * scales).contiguous(), spec=zeros, spec_scale=1.0,
+                              linear2srgb=False)
+    for e in range(8):
+        assert rel_l2(rgb8[:, e].cpu(), want * (e + 1) / 8) < 5e-6, e
+    # OLAT kernel: env-map = inten * onehot(l); summing the one-light renders weighted by the
+    # texel values reproduces the env-map render (per channel)
+    olat = _lib.integrate_olat_fwd(ctx, xyz, nrm, cam, alb, lvis, lxyz, lareas, olat_inten=1.0,
+                                   ambient=0., spec=zeros, spec_scale=1.0, linear2srgb=False)
+    recon = torch.einsum('nlc,lc->nc', olat, light[0])
+    assert rel_l2(recon.cpu(), want) < 5e-6
+
+
 def test_integrate_kernels_vs_fp64_incl_grazing_views(ctx):
     """Both rendering-equation kernels (packed-FP32 nf_integrate_fwd, scalar nf_integrate_olat_fwd)
     against an fp64 evaluation of the reference formulas, LINEAR output (no clip / tone curve to

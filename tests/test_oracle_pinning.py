@@ -58,6 +58,36 @@ def test_gen_world2local_matches_reference_numpy_twin(golden_dir):
     assert np.allclose(out[:, 2, :], ref['w2l_normal'], atol=1e-6)
 
 
+def test_rendering_equation_matches_reference_sphere_renderer(golden_dir):
+    """oracle StageB.calc_ldir + render (nerfactor.py:315-365) vs the reference's own NumPy
+    estimator run in the build container (brdf/renderer.py SphereRenderer: light directions,
+    cosines, front-lit visibility, light contribution, hemisphere sum) on its sphere scene with a
+    Lambertian BRDF."""
+    g = np.load(os.path.join(golden_dir, 'ref_sphere_renderer.npz'))
+    fg = g['is_fg']
+    xyz, normal = torch.tensor(g['xyz'][fg]), torch.tensor(g['normal'][fg])
+    albedo = torch.tensor(g['albedo'][fg])
+    lvis_fg = torch.ones((int(fg.sum()), g['lxyz'].shape[0] * g['lxyz'].shape[1]),
+                         dtype=torch.float64)          # the reference's lvis = fg & front-lit
+    for dtype, tol in ((torch.float64, 1e-12), (torch.float32, 2e-6)):
+        om = stage_b.StageB({'light': g['envmap']}, {'brdf': 'microfacet', 'linear2srgb': False},
+                            lxyz=g['lxyz'], lareas=g['lareas'], dtype=dtype)
+        if dtype == torch.float64:        # StageB casts the lights to fp32 first (shape.py:75-76)
+            om.lxyz = torch.tensor(g['lxyz'].reshape(-1, 3))
+            om.lareas = torch.tensor(g['lareas'].reshape(-1))
+        x, n, a = xyz.to(dtype), normal.to(dtype), albedo.to(dtype)
+        l = om.calc_ldir(x)
+        cos = torch.einsum('ijk,ik->ij', l, n)
+        assert np.abs(cos.double().numpy() - g['lcos'][fg]).max() < (1e-12 if tol < 1e-9 else 1e-6)
+        assert np.array_equal((cos > 0).numpy(), g['lvis'][fg].astype(bool)) or tol > 1e-9
+        brdf = (a / np.pi)[:, None, :].expand(-1, l.shape[1], -1)
+        rgb, _ = om.render(lvis_fg.to(dtype), brdf, l, n)
+        want = g['render'][fg]
+        err = np.linalg.norm(rgb.double().numpy() - want) / np.linalg.norm(want)
+        assert err < tol, (dtype, err)
+    assert np.all(g['render'][~fg] == 1.)              # white background of the reference render
+
+
 def test_oracle_stage_b_goldens_frozen(golden_dir):
     for brdf in ('microfacet', 'learned'):
         g = np.load(os.path.join(golden_dir, 'oracle_stage_b_%s.npz' % brdf))
