@@ -19,11 +19,24 @@ legs may import it; the product package `nerfactor_b200` never does.
 PARITY PINNING.  The reference ships no tests, golden vectors or checkpoints
  and its arithmetic lives in TensorFlow 2.2
 (environment.yml:19, an un-vendored pip dependency that cannot be installed in
-this image), so the TF-dependent parts of this oracle are **parity unpinned**:
-they are a line-by-line restatement reviewed against the cited ranges.  The
-pieces of the reference that ARE importable without TensorFlow are pinned
-against the reference run in the build container (tests/golden/make_golden.py
-generates the fixtures, tests/test_oracle_pinning.py checks them):
+this image).  The oracle is pinned in two ways, both by running the reference
+itself in the build container (generators committed under tests/golden/):
+
+(1) THE REFERENCE'S OWN MODEL CODE, unmodified, executed op by op through a
+    small eager TensorFlow look-alike (tests/golden/tfshim: each function is
+    the documented semantics of the one TF op of that name, on PyTorch-CPU):
+    nerfactor/models/{shape,nerfactor,nerfactor_microfacet,brdf,nerf}.py
+    Model.call / compute_loss, networks/*, brdf/microfacet/microfacet.py,
+    util/{math,geom,img,tensor,light}.py and geometry_from_nerf.py
+    compute_depth_and_normal / compute_light_visibility / eval_sigma_mlp
+    -> tests/golden/ref_tfshim_*.npz (make_golden_tfshim.py).  The oracle
+    reproduces them bit-for-bit (Stage B: forward, jitter, losses, edits, OLAT,
+    probes; Stage A coarse pass, sigma) or to <= 2e-6 (Stage A fine pass).
+    What this leaves to trust is the per-op semantics of the shim (l2_normalize,
+    divide_no_nan, exclusive cumprod, searchsorted side, floormod, Dense,
+    LinSpace, antialiased resize, scatter / gather), not the algorithm.
+(2) The pieces of the reference that import without TensorFlow, run as they are
+    (tests/golden/make_golden.py, tests/test_oracle_pinning.py):
 
   brdf.renderer.gen_light_xyz                      -> oracle.brdf.gen_light_xyz
   third_party.nielsen2015on DirectionsToRusink     -> oracle.brdf.dir2rusink

@@ -1,0 +1,187 @@
+"""Runs the UNMODIFIED reference model code (/root/reference) through the TensorFlow shim
+(tests/golden/tfshim) on seeded inputs and writes its outputs to tests/golden/ref_tfshim_*.npz.
+
+Build container only (needs /root/reference):
+
+    python tests/golden/make_golden_tfshim.py
+
+The reference decides WHAT is computed -- Model.call / compute_loss of
+nerfactor/models/{shape,nerfactor,nerfactor_microfacet}.py, brdf/microfacet/microfacet.py,
+geometry_from_nerf.compute_depth_and_normal / compute_light_visibility with models/nerf.py; the
+shim only supplies each individual TF op.  The fixtures pin the oracle
+(tests/test_oracle_pinning.py) and the CUDA kernels (tests/test_gpu_parity.py) against numbers the
+reference's own code produced.
+"""
+import os
+import sys
+import tempfile
+import warnings
+from collections import OrderedDict
+from configparser import ConfigParser
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = '/root/reference'
+sys.path[:0] = [os.path.join(HERE, 'tfshim'), REF, os.path.join(REF, 'nerfactor'), ROOT]
+warnings.filterwarnings('ignore')
+
+import tensorflow as tf  # noqa: E402  (the shim)
+import torch  # noqa: E402
+
+assert tf.__version__.endswith('shim')
+from nerfactor_b200 import synth  # noqa: E402
+
+
+def read_ini(name, **override):
+    """The reference's own hyper-parameter file, site paths replaced."""
+    cfg = ConfigParser()
+    with open(os.path.join(REF, 'nerfactor', 'config', name)) as h:
+        cfg.read_file(h)
+    for k, v in override.items():
+        cfg.set('DEFAULT', k, str(v))
+    return cfg
+
+
+def write_ini(cfg, path):
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    with open(path, 'w') as h:
+        cfg.write(h)
+
+
+def set_weights(net_dict, params):
+    for name, net in net_dict.items():
+        if name not in params:
+            continue
+        layers = params[name]['layers']
+        assert len(layers) == len(net.layers), name
+        for layer, (w, b) in zip(net.layers, layers):
+            layer.set_weights([w, b])
+
+
+def t32(x):
+    return tf.convert_to_tensor(np.asarray(x, np.float32))
+
+
+def to_np(d):
+    return {k: (v.detach().numpy() if isinstance(v, torch.Tensor) else v)
+            for k, v in d.items() if v is not None and not isinstance(v, (str, bytes))}
+
+
+def build_stage_b(kind, light_h, tmp, seed_params):
+    """The reference Model constructed the reference's way: config next to (stub) checkpoints."""
+    envdir = os.path.join(tmp, 'envmaps')
+    os.makedirs(envdir, exist_ok=True)
+    shape_ckpt = os.path.join(tmp, 'shape', 'lr1e-2', 'checkpoints', 'ckpt-2')
+    write_ini(read_ini('shape.ini', light_h=light_h), os.path.join(tmp, 'shape', 'lr1e-2.ini'))
+    brdf_ckpt = os.path.join(tmp, 'merl', 'lr1e-2', 'checkpoints', 'ckpt-50')
+    write_ini(read_ini('brdf.ini', data_root=os.path.join(tmp, 'merl_data')),
+              os.path.join(tmp, 'merl', 'lr1e-2.ini'))
+    ini = 'nerfactor_microfacet.ini' if kind == 'microfacet' else 'nerfactor.ini'
+    cfg = read_ini(ini, light_h=light_h, shape_model_ckpt=shape_ckpt, brdf_model_ckpt=brdf_ckpt,
+                   test_envmap_dir=envdir, data_root=tmp, data_nerf_root=tmp, outroot=tmp)
+    from nerfactor.models import get_model_class
+    Model = get_model_class(cfg.get('DEFAULT', 'model'))
+    model = Model(cfg)
+    params = synth.make_stage_b_params(seed_params, 'microfacet' if kind == 'microfacet' else
+                                       'learned', light_hw=(light_h, 2 * light_h))
+    set_weights(model.net, params)
+    if kind != 'microfacet':
+        set_weights(model.brdf_model.net, params)
+    model._light = tf.Variable(t32(params['light']))
+    return model, cfg, params
+
+
+def run_stage_b(kind, light_h, n_rays, seed_params, seed_batch, out_name):
+    with tempfile.TemporaryDirectory() as tmp:
+        model, cfg, params = build_stage_b(kind, light_h, tmp, seed_params)
+        L = 2 * light_h * light_h
+        batch_np = synth.make_stage_b_batch(seed_batch, n_rays, L)
+        probes = synth.make_probes(seed_batch + 1, 2, (light_h, 2 * light_h))
+        model.novel_probes = OrderedDict(('p%d' % i, t32(p)) for i, p in enumerate(probes))
+        batch = tuple(x if i < 2 else t32(x) for i, x in enumerate(batch_np))
+        out = {'kind': kind, 'light_h': light_h, 'n_rays': n_rays, 'seed_params': seed_params,
+               'seed_batch': seed_batch, 'probes': probes}
+        # ---- test mode (jitter drawn by the reference, irrelevant to pred)
+        pred, gt, lk, _ = model.call(batch, mode='test', relight_olat=True, relight_probes=True)
+        for k, v in to_np(pred).items():
+            out['test_' + k] = v
+        # ---- train mode with the jitter noise recorded (nerfactor.py:198-201) + compute_loss
+        tf.random.set_seed(777)
+        pred, gt, lk, _ = model.call(batch, mode='train')
+        tf.random.set_seed(777)
+        n_fg = int((batch_np[5][:, 0] > 0).sum())
+        out['xyz_noise'] = tf.random.normal(
+            (n_fg, 3), stddev=cfg.getfloat('DEFAULT', 'xyz_jitter_std')).numpy()
+        for k, v in to_np(pred).items():
+            out['train_' + k] = v
+        for k, v in to_np(lk).items():
+            out['train_' + k] = v
+        lk['keep_batch'] = True
+        out['train_loss'] = model.compute_loss(pred, gt, **lk).numpy()
+        pred_v, gt_v, lk_v, _ = model.call(batch, mode='vali')
+        out['vali_loss'] = model.compute_loss(pred_v, gt_v, **lk_v).numpy()
+        # ---- edits (test.py:91-132, 168-186)
+        alb_o = np.array([0.3, 0.5, 0.7], np.float32)
+        kw = {'albedo_override': t32(alb_o), 'albedo_scales': None}
+        if kind != 'microfacet':
+            kw['brdf_z_override'] = t32([0.01, -0.02, 0.005])
+        pred_e, _, _, _ = model.call(batch, mode='test', **kw)
+        out['edit_rgb'] = pred_e['rgb'].numpy()
+        pred_s, _, _, _ = model.call(batch, mode='test', albedo_scales=t32([0.5, 1., 2.]))
+        out['scaled_rgb'] = pred_s['rgb'].numpy()
+    np.savez_compressed(os.path.join(HERE, out_name), **out)
+    print(out_name, {k: getattr(v, 'shape', v) for k, v in out.items() if k.startswith('test_')})
+    return out
+
+
+def run_stage_a(seed_nerf, hw, light_h, out_name):
+    """geometry_from_nerf.compute_depth_and_normal / compute_light_visibility / eval_sigma_mlp and
+    the NeRF colour rendering (models/nerf.py call) of the reference, on a random-init NeRF."""
+    from nerfactor import geometry_from_nerf as gfn
+    from nerfactor.models.nerf import Model as NerfModel
+    from oracle import stage_a                       # only for its NumPy ray generator
+    if not gfn.FLAGS.is_parsed():
+        gfn.FLAGS(['make_golden_tfshim', '--light_h=%d' % light_h])
+    cfg = read_ini('nerf.ini', n_samples_coarse=-48, n_samples_fine=8, data_root='/tmp',
+                   outroot='/tmp')                   # geometry_from_nerf adds 64 to both
+    model = NerfModel(cfg)
+    params = synth.make_nerf_params(seed_nerf)
+    set_weights(model.net, params)
+    h, w = hw
+    rayo, rayd = stage_a.gen_rays(synth.look_at_c2w(), synth.CAM_ANGLE_X, h, w)
+    rayo, rayd = rayo.reshape(-1, 3), rayd.reshape(-1, 3)
+    rayd_n = tf.linalg.l2_normalize(t32(rayd), axis=1)                  # gfn.py:100
+    out = {'seed_nerf': seed_nerf, 'h': h, 'w': w, 'light_h': light_h, 'rayo': rayo,
+           'rayd': rayd, 'rayd_n': rayd_n.numpy(), 'n_samples_coarse': 16, 'n_samples_fine': 72}
+    occu, depth, normal = [x.detach() for x in gfn.compute_depth_and_normal(
+        model, t32(rayo), rayd_n, cfg)]       # values only (the tape's graph is torch autograd here)
+    out.update(occu=occu.numpy(), depth=depth.numpy(), normal=normal.numpy())
+    surf = t32(rayo) + rayd_n * depth[:, None]                          # gfn.py:134
+    out['lvis_hit'] = gfn.compute_light_visibility(model, surf, normal, cfg)
+    pts = t32(np.random.default_rng(5).uniform(-1.5, 1.5, size=(257, 3)))
+    out['sigma_pts'] = pts.numpy()
+    out['sigma_coarse'] = gfn.eval_sigma_mlp(model, pts, use_fine=False).numpy()
+    out['sigma_fine'] = gfn.eval_sigma_mlp(model, pts, use_fine=True).numpy()
+    # NeRF colour rendering with the config's own sample counts (16 + 24 here)
+    cfg2 = read_ini('nerf.ini', n_samples_coarse=16, n_samples_fine=24, data_root='/tmp',
+                    outroot='/tmp')
+    model2 = NerfModel(cfg2)
+    set_weights(model2.net, params)
+    batch = (np.array([b'v'] * (h * w)), np.tile(np.array([[h, w]], np.int32), (h * w, 1)),
+             t32(rayo), t32(rayd), t32(np.zeros((h * w, 3))))
+    pred, _, _, to_vis = model2.call(batch, mode='test')
+    for k in ('coarse_rgb', 'coarse_occu', 'coarse_depth', 'fine_rgb', 'fine_occu', 'fine_depth',
+              'fine_disp'):
+        out['nerf_' + k] = to_vis[k].numpy()
+    np.savez_compressed(os.path.join(HERE, out_name), **out)
+    print(out_name, 'occu range', float(out['occu'].min()), float(out['occu'].max()),
+          'front-lit pairs', int((out['lvis_hit'] != 0).sum()))
+    return out
+
+
+if __name__ == '__main__':
+    run_stage_a(3, (6, 6), 2, 'ref_tfshim_stage_a.npz')
+    run_stage_b('microfacet', 4, 80, 7, 11, 'ref_tfshim_stage_b_microfacet.npz')
+    run_stage_b('learned', 4, 80, 7, 11, 'ref_tfshim_stage_b_learned.npz')

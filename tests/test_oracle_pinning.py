@@ -4,10 +4,17 @@ TensorFlow (fixtures: tests/golden/ref_pinned.npz, made by make_golden.py from
 import os
 
 import numpy as np
+import pytest
 import torch
 
 from oracle import brdf as obrdf, stage_b, stage_a
 from nerfactor_b200 import synth
+
+
+def _rel(a, b):
+    a = a.detach().numpy() if hasattr(a, 'detach') else np.asarray(a)
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
 
 
 def _ref(golden_dir):
@@ -86,6 +93,68 @@ def test_rendering_equation_matches_reference_sphere_renderer(golden_dir):
         err = np.linalg.norm(rgb.double().numpy() - want) / np.linalg.norm(want)
         assert err < tol, (dtype, err)
     assert np.all(g['render'][~fg] == 1.)              # white background of the reference render
+
+
+# ---- the reference's own model code, run op by op through the TensorFlow shim
+# (tests/golden/tfshim + make_golden_tfshim.py, build container) -> ref_tfshim_*.npz
+@pytest.mark.parametrize('kind', ['microfacet', 'learned'])
+def test_stage_b_oracle_equals_reference_code_via_shim(golden_dir, kind):
+    """nerfactor/models/{nerfactor,nerfactor_microfacet,shape,brdf}.py Model.call (test / train /
+    vali), compute_loss, the albedo / BRDF edits, OLAT and probe relighting -- the reference's
+    files unmodified, TF ops supplied by the shim -- against the oracle on the same inputs."""
+    g = np.load(os.path.join(golden_dir, 'ref_tfshim_stage_b_%s.npz' % kind))
+    lh, n = int(g['light_h']), int(g['n_rays'])
+    params = synth.make_stage_b_params(int(g['seed_params']), kind, light_hw=(lh, 2 * lh))
+    batch = synth.make_stage_b_batch(int(g['seed_batch']), n, 2 * lh * lh)
+    om = stage_b.StageB(params, {'brdf': kind}, light_h=lh)
+    tol = 1e-6
+    op, _, _ = om.call(batch, 'test', relight_lights=list(g['probes']) + om.novel_olat((lh, 2 * lh)))
+    for k in ('rgb', 'normal', 'lvis', 'albedo', 'brdf'):
+        assert _rel(op[k], g['test_' + k]) < tol, k
+    assert _rel(op['rgb_relit'][:, :2], g['test_rgb_probes']) < tol
+    assert _rel(op['rgb_relit'][:, 2:], g['test_rgb_olat']) < tol
+    op, ogt, olk = om.call(batch, 'train', xyz_noise=g['xyz_noise'])
+    for k in ('normal_jitter', 'lvis_jitter', 'albedo_jitter', 'brdf_prop_jitter'):
+        assert _rel(olk[k], g['train_' + k]) < tol, k
+    wts = {'brdf_smooth_weight': 0.} if kind == 'microfacet' else None   # the two .ini files
+    assert _rel(om.compute_loss(op, ogt, weights=wts, **olk), g['train_loss']) < tol
+    op, ogt, olk = om.call(batch, 'vali')
+    assert _rel(om.compute_loss(op, ogt, weights=wts, **olk), g['vali_loss']) < tol
+    kw = {'albedo_override': np.array([0.3, 0.5, 0.7], np.float32)}
+    if kind != 'microfacet':
+        kw['brdf_z_override'] = np.array([0.01, -0.02, 0.005], np.float32)
+    assert _rel(om.call(batch, 'test', **kw)[0]['rgb'], g['edit_rgb']) < tol
+    assert _rel(om.call(batch, 'test', albedo_scales=np.array([0.5, 1., 2.], np.float32))[0][
+        'rgb'], g['scaled_rgb']) < tol
+
+
+def test_stage_a_oracle_equals_reference_code_via_shim(golden_dir):
+    """geometry_from_nerf.{compute_depth_and_normal, compute_light_visibility, eval_sigma_mlp}
+    and models/nerf.py call (colour rendering), reference files unmodified via the shim."""
+    g = np.load(os.path.join(golden_dir, 'ref_tfshim_stage_a.npz'))
+    nerf = synth.make_nerf_params(int(g['seed_nerf']))
+    ro, rdn = torch.tensor(g['rayo']), torch.tensor(g['rayd_n'])
+    occu, depth, normal = stage_a.compute_depth_and_normal(
+        nerf, ro, rdn, 2., 6., n_samples_coarse=-48, n_samples_fine=8)
+    assert _rel(occu, g['occu']) < 1e-6 and _rel(depth, g['depth']) < 2e-6
+    assert np.abs(normal.numpy() - g['normal']).max() < 5e-5
+    surf = ro + rdn * torch.tensor(g['depth'])[:, None]
+    lh = int(g['light_h'])
+    lxyz, _ = obrdf.gen_light_xyz(lh, 2 * lh)
+    lv = stage_a.compute_light_visibility(nerf, surf, torch.tensor(g['normal']),
+                                          lxyz.reshape(-1, 3), n_samples_coarse=-48,
+                                          n_samples_fine=8)
+    assert np.array_equal(np.asarray(lv) != 0, g['lvis_hit'] != 0)       # same front-lit pairs
+    assert np.abs(np.asarray(lv) - g['lvis_hit']).max() < 3e-5
+    p = torch.tensor(g['sigma_pts'])
+    assert _rel(stage_a.eval_sigma_mlp(nerf, p, False), g['sigma_coarse']) < 1e-6
+    assert _rel(stage_a.eval_sigma_mlp(nerf, p, True), g['sigma_fine']) < 1e-6
+    c, f = stage_a.nerf_render_rays(nerf, ro, torch.tensor(g['rayd']), 2., 6.,
+                                    n_samples_coarse=16, n_samples_fine=24)
+    for k in ('rgb', 'occu', 'depth'):
+        assert _rel(c[k], g['nerf_coarse_' + k]) < 1e-6, k
+        assert _rel(f[k], g['nerf_fine_' + k]) < 5e-6, k
+    assert _rel(f['disp'], g['nerf_fine_disp']) < 5e-6
 
 
 def test_oracle_stage_b_goldens_frozen(golden_dir):

@@ -1,0 +1,76 @@
+"""CUDA kernels against outputs of the REFERENCE'S OWN CODE: the unmodified model files of
+/root/reference run op by op through the TensorFlow shim (tests/golden/tfshim) in the build
+container by tests/golden/make_golden_tfshim.py -> tests/golden/ref_tfshim_*.npz.  Same
+tolerances as the oracle-golden tests of test_gpu_parity.py (the oracle reproduces these fixtures
+to <= 1e-6, tests/test_oracle_pinning.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from nerfactor_b200 import config as nfconfig, synth
+from test_gpu_parity import rel_l2, dev, _stage_b, _nerf_model, ctx  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('brdf', ['microfacet', 'learned'])
+@pytest.mark.parametrize('precision', ['fp32', 'f16'])
+def test_model_call_vs_reference_code_via_shim(ctx, golden_dir, brdf, precision):
+    """Model.call on the GPU against outputs of the REFERENCE'S OWN model code (unmodified files of
+    /root/reference run op by op through tests/golden/tfshim by make_golden_tfshim.py): the
+    reference's native light grid light_h = 4 (32 lights), 80 rays with background rows, probe and
+    OLAT relighting, the test.py edits."""
+    g = np.load(os.path.join(golden_dir, 'ref_tfshim_stage_b_%s.npz' % brdf))
+    lh = int(g['light_h'])
+    m, _, _ = _stage_b(ctx, brdf, lh, 2 * lh, int(g['seed_params']), precision)
+    batch = synth.make_stage_b_batch(int(g['seed_batch']), int(g['n_rays']), 2 * lh * lh)
+    for i, p in enumerate(g['probes']):
+        m.novel_probes['p%d' % i] = p
+    pred, _, _, _ = m.call(batch, 'test', relight_probes=True, relight_olat=True)
+    tol_net = 1e-5 if precision == 'fp32' else 3e-3
+    tol_rgb = 1e-5 if precision == 'fp32' else 1e-4      # north-star bar on RGB
+    for k in ('normal', 'albedo', 'brdf'):
+        assert rel_l2(pred[k].cpu(), g['test_' + k]) < 1e-5, k
+    assert rel_l2(pred['lvis'].cpu(), g['test_lvis']) < tol_net
+    assert rel_l2(pred['rgb'].cpu(), g['test_rgb']) < tol_rgb
+    assert rel_l2(pred['rgb_probes'].cpu(), g['test_rgb_probes']) < tol_rgb
+    assert rel_l2(pred['rgb_olat'].cpu(), g['test_rgb_olat']) < tol_rgb
+    kw = {'albedo_override': np.array([0.3, 0.5, 0.7], np.float32)}
+    if brdf != 'microfacet':
+        kw['brdf_z_override'] = np.array([0.01, -0.02, 0.005], np.float32)
+    assert rel_l2(m.call(batch, 'test', **kw)[0]['rgb'].cpu(), g['edit_rgb']) < tol_rgb
+    p2 = m.call(batch, 'test', albedo_scales=np.array([0.5, 1., 2.], np.float32))[0]
+    assert rel_l2(p2['rgb'].cpu(), g['scaled_rgb']) < tol_rgb
+    if precision == 'fp32':      # per-ray training loss with the reference's recorded jitter
+        pr, gt, lk, _ = m.call(batch, 'train', xyz_noise=g['xyz_noise'])
+        loss = m.compute_loss(pr, gt, **lk)
+        assert np.allclose(loss.cpu().numpy(), g['train_loss'], atol=2e-6, rtol=1e-4)
+
+
+def test_stage_a_vs_reference_code_via_shim(ctx, golden_dir):
+    """compute_depth_and_normal / compute_light_visibility / eval_sigma_mlp (FP32 kernels) against
+    the reference's geometry_from_nerf.py run through the shim (16 coarse + 88 fine samples)."""
+    from nerfactor_b200 import geometry_from_nerf as gfn, _lib
+    g = np.load(os.path.join(golden_dir, 'ref_tfshim_stage_a.npz'))
+    model = _nerf_model(ctx, int(g['seed_nerf']))
+    ro, rdn = dev(g['rayo'], ctx), dev(g['rayd_n'], ctx)
+    cfg = nfconfig.default_config('nerf', n_samples_coarse=-48, n_samples_fine=8)
+    occu, depth, normal = gfn.compute_depth_and_normal(model, ro, rdn, cfg, precision='fp32')
+    d = np.abs(depth.cpu().numpy() - g['depth'])
+    assert np.median(d) < 1e-4 and np.quantile(d, 0.95) < 5e-3
+    assert np.abs(occu.cpu().numpy() - g['occu']).max() < 1e-3
+    dn = np.abs(normal.cpu().numpy() - g['normal']).max(axis=1)
+    assert np.median(dn) < 1e-3 and np.quantile(dn, 0.95) < 2e-2
+    surf = ro + rdn * dev(g['depth'], ctx)[:, None]
+    model.precision = 'fp32'
+    lv = gfn.compute_light_visibility(model, surf.contiguous(), dev(g['normal'], ctx), cfg,
+                                      light_h=int(g['light_h']))
+    assert np.allclose(lv.cpu().numpy(), g['lvis_hit'], atol=3e-4)
+    pts = dev(g['sigma_pts'], ctx)
+    z1 = torch.ones((pts.shape[0], 1), device=ctx.device)
+    zero = torch.zeros_like(pts)                         # samples o + z d with d = 0: the points
+    for fine, key in ((False, 'sigma_coarse'), (True, 'sigma_fine')):
+        sg = _lib.sigma_fwd(ctx, model.packed_sigma(fine), pts, zero, z1, None, 'fp32')
+        assert rel_l2(sg.cpu(), g[key]) < 2e-5
