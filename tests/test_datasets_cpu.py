@@ -183,3 +183,92 @@ def test_against_importable_reference_helpers(tmp_path):
     open(str(tmp_path / 'a.txt'), 'w').close()
     assert ioutil.sortglob(str(tmp_path), '*', ext='txt') == xm.os.sortglob(
         str(tmp_path), '*', ext='txt')
+
+
+# ---- the reference's own loaders / writers, imported through the TensorFlow shim ------------
+def _reference_via_shim():
+    """sys.path set-up for importing /root/reference modules that `import tensorflow` at the
+    top (their loaders / writers are NumPy underneath)."""
+    import warnings
+    warnings.filterwarnings('ignore')
+    paths = [os.path.join(HERE, 'golden', 'tfshim'), REF, os.path.join(REF, 'nerfactor')]
+    for p in reversed(paths):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import tensorflow as tf
+    assert tf.__version__.endswith('shim')
+    return paths
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason='reference tree only in the build container')
+def test_dataset_loaders_equal_reference_loaders(tmp_path):
+    """nerfactor/datasets/{nerf,nerf_shape}.py `_glob` + `_load_data` (the reference's files,
+    unmodified) vs the loaders here, on a synthetic scene in the reference's layout, incl. the
+    resize-on-load path (imh != stored height)."""
+    paths = _reference_via_shim()
+    try:
+        from nerfactor.datasets.nerf import Dataset as RefNerf
+        from nerfactor.datasets.nerf_shape import Dataset as RefShape
+        root, nroot = tmp_path / 'scene', tmp_path / 'surf'
+        synth.write_scene(str(root), imh=16, imw=16, n_train=2, n_val=1, n_test=1,
+                          nerf_root=str(nroot), n_lights=8)
+        for imh in (16, 8):
+            cfg = _cfg(root, nroot, use_nerf_alpha=False, no_batch=True)
+            cfg.set('DEFAULT', 'imh', str(imh))
+            for mode in ('train', 'vali', 'test'):
+                ref = RefShape.__new__(RefShape)            # skip tf.data-related __init__ parts
+                ref.config, ref.mode, ref.debug = cfg, mode, False
+                ref.meta2buf, ref.meta2img, ref.sps = {}, {}, 1
+                ref.files = ref._glob()
+                mine = get_dataset_class('nerf_shape')(cfg, mode)
+                assert mine.files == ref.files
+                for path in ref.files:
+                    r, m = ref._load_data(path), mine._load_data(path)
+                    assert r[0] == m[0]
+                    for a, b in zip(r[1:], m[1:]):
+                        assert a.shape == b.shape and np.array_equal(
+                            np.asarray(a, np.float32), b), (mode, imh)
+            refn = RefNerf.__new__(RefNerf)
+            refn.config, refn.mode, refn.debug, refn.meta2img, refn.sps = cfg, 'train', False, {}, 1
+            refn.files = refn._glob()
+            minen = get_dataset_class('nerf')(cfg, 'train')
+            assert minen.files == refn.files
+            for path in refn.files:
+                r, m = refn._load_data(path), minen._load_data(path)
+                assert r[0] == m[0] and all(np.array_equal(a, b) for a, b in zip(r[1:], m[1:]))
+    finally:
+        for p in paths:
+            sys.path.remove(p)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason='reference tree only in the build container')
+def test_geometry_buffer_writers_equal_reference_writers(tmp_path):
+    """nerfactor/util/geom.py write_alpha / write_xyz / write_normal (and the raw + averaged part
+    of write_lvis) vs util/geom_io.py: same .npy bytes, same PNG pixels."""
+    paths = _reference_via_shim()
+    try:
+        from nerfactor.util import geom as refgeom
+        from nerfactor_b200.util import geom_io
+        rng = np.random.default_rng(0)
+        alpha = rng.random((9, 7)).astype(np.float32)
+        xyz = (rng.standard_normal((9, 7, 3)) * alpha[..., None]).astype(np.float32)
+        nrm = rng.standard_normal((9, 7, 3)).astype(np.float32)
+        nrm /= np.linalg.norm(nrm, axis=2, keepdims=True)
+        lvis = rng.random((9, 7, 8)).astype(np.float32)
+        rd, md = str(tmp_path / 'ref'), str(tmp_path / 'mine')
+        os.makedirs(rd)
+        refgeom.write_alpha(alpha, rd)
+        refgeom.write_xyz(xyz, rd)
+        refgeom.write_normal(nrm, rd)
+        np.save(os.path.join(rd, 'lvis.npy'), lvis)             # geom.py:30-32
+        from third_party.xiuminglib import xiuminglib as xm
+        xm.io.img.write_arr(np.mean(lvis, axis=2), os.path.join(rd, 'lvis.png'))   # geom.py:34-36
+        geom_io.write_view_buffers({'alpha': alpha, 'xyz': xyz, 'normal': nrm, 'lvis': lvis}, md)
+        for f in ('xyz.npy', 'normal.npy', 'lvis.npy'):
+            assert open(os.path.join(rd, f), 'rb').read() == open(os.path.join(md, f), 'rb').read()
+        for f in ('alpha.png', 'xyz.png', 'normal.png', 'lvis.png'):
+            a, b = imgutil.read(os.path.join(rd, f)), imgutil.read(os.path.join(md, f))
+            assert a.shape == b.shape and np.array_equal(a, b), f
+    finally:
+        for p in paths:
+            sys.path.remove(p)
