@@ -136,6 +136,51 @@ def run_stage_b(kind, light_h, n_rays, seed_params, seed_batch, out_name):
     return out
 
 
+def run_train_gradients(kind, light_h, n_rays, seed_params, seed_batch, out_name):
+    """One `train_step` of nerfactor/trainvali.py:276-285 up to the gradients: forward in train
+    mode, per-ray loss, tf.nn.compute_average_loss, tape.gradient over model.trainable_variables
+    (shape_mode finetune: all four shape MLPs, albedo, BRDF-z / roughness MLPs and the light)."""
+    tf.shim_set_training(True)
+    try:
+        with tempfile.TemporaryDirectory() as tmp:
+            model, cfg, params = build_stage_b(kind, light_h, tmp, seed_params)
+            model.register_trainable()
+            L = 2 * light_h * light_h
+            batch_np = synth.make_stage_b_batch(seed_batch, n_rays, L, fg_frac=1.0)
+            batch = tuple(x if i < 2 else t32(x) for i, x in enumerate(batch_np))
+            tf.random.set_seed(4242)
+            with tf.GradientTape() as tape:                       # trainvali.py:277-283
+                pred, gt, loss_kwargs, _ = model(batch, mode='train')
+                loss_kwargs['keep_batch'] = True
+                per_example_loss = model.compute_loss(pred, gt, **loss_kwargs)
+                weighted_loss = tf.nn.compute_average_loss(
+                    per_example_loss, global_batch_size=n_rays)
+            variables = model.trainable_variables
+            grads = tape.gradient(weighted_loss, variables)       # trainvali.py:284
+            tf.random.set_seed(4242)
+            noise = tf.random.normal((n_rays, 3), stddev=cfg.getfloat('DEFAULT', 'xyz_jitter_std'))
+            out = {'kind': kind, 'light_h': light_h, 'n_rays': n_rays, 'seed_params': seed_params,
+                   'seed_batch': seed_batch, 'xyz_noise': noise.numpy(),
+                   'per_example_loss': per_example_loss.detach().numpy(),
+                   'weighted_loss': float(weighted_loss)}
+            # name every gradient by the owner of its variable
+            owner = {}
+            for net_name, net in model.net.items():
+                for li, layer in enumerate(net.layers):
+                    owner[id(layer.kernel)] = 'grad/%s/%d/kernel' % (net_name, li)
+                    owner[id(layer.bias)] = 'grad/%s/%d/bias' % (net_name, li)
+            owner[id(model._light)] = 'grad/light'
+            for v, g_ in zip(variables, grads):
+                assert g_ is not None, owner[id(v)]
+                out[owner[id(v)]] = g_.numpy()
+    finally:
+        tf.shim_set_training(False)
+    np.savez_compressed(os.path.join(HERE, out_name), **out)
+    print(out_name, len([k for k in out if k.startswith('grad/')]), 'gradient tensors, loss',
+          out['weighted_loss'])
+    return out
+
+
 def run_stage_a(seed_nerf, hw, light_h, out_name):
     """geometry_from_nerf.compute_depth_and_normal / compute_light_visibility / eval_sigma_mlp and
     the NeRF colour rendering (models/nerf.py call) of the reference, on a random-init NeRF."""
@@ -182,6 +227,12 @@ def run_stage_a(seed_nerf, hw, light_h, out_name):
 
 
 if __name__ == '__main__':
+    if 'grad' in sys.argv[1:]:
+        run_train_gradients('microfacet', 2, 48, 7, 11, 'ref_tfshim_train_grad_microfacet.npz')
+        run_train_gradients('learned', 2, 48, 7, 11, 'ref_tfshim_train_grad_learned.npz')
+        sys.exit(0)
     run_stage_a(3, (6, 6), 2, 'ref_tfshim_stage_a.npz')
     run_stage_b('microfacet', 4, 80, 7, 11, 'ref_tfshim_stage_b_microfacet.npz')
     run_stage_b('learned', 4, 80, 7, 11, 'ref_tfshim_stage_b_learned.npz')
+    run_train_gradients('microfacet', 2, 48, 7, 11, 'ref_tfshim_train_grad_microfacet.npz')
+    run_train_gradients('learned', 2, 48, 7, 11, 'ref_tfshim_train_grad_learned.npz')

@@ -72,8 +72,22 @@ def constant(value, dtype=None, **_):
     return _t(value, dtype)
 
 
+_TRAINING = [False]
+
+
+def shim_set_training(flag):
+    """Shim control (not a TF symbol): when on, Variables / Dense weights created or set from now
+    on are autograd leaves, so GradientTape.gradient works like TF's automatic variable watching.
+    Off by default so that forward-only runs keep plain tensors (`.numpy()` works everywhere)."""
+    _TRAINING[0] = builtins.bool(flag)
+
+
 def Variable(initial_value=None, trainable=True, dtype=None, **_):
-    return _t(initial_value, dtype).clone()
+    v = _t(initial_value, dtype).detach().clone()
+    v._shim_variable = True
+    if trainable and _TRAINING[0] and v.is_floating_point():
+        v.requires_grad_(True)
+    return v
 
 
 def identity(x):
@@ -306,12 +320,27 @@ def ensure_shape(x, shape_):
     return x
 
 
-def custom_gradient(f):
-    """Forward value of the wrapped function (the golden vectors are forward passes; where the
-    reference differentiates, it does so through plain ops or the analytic `grad` is irrelevant)."""
-    def wrapped(*args, **kwargs):
-        y, _grad = f(*args, **kwargs)
+class _CustomGradient(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, f, n_args, *args):
+        with torch.no_grad():
+            y, grad_fn = f(*[a.detach() if isinstance(a, torch.Tensor) else a for a in args])
+        ctx.grad_fn_, ctx.n = grad_fn, n_args
         return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        g = ctx.grad_fn_(dy)
+        g = g if isinstance(g, (tuple, list)) else (g,)
+        return (None, None) + tuple(g) + (None,) * (ctx.n - len(g))
+
+
+def custom_gradient(f):
+    """y, grad = f(*args): forward value y, backward through the function's own `grad`."""
+    def wrapped(*args, **kwargs):
+        assert not kwargs
+        args = [a if isinstance(a, torch.Tensor) else _t(a) for a in args]
+        return _CustomGradient.apply(f, len(args), *args)
     return wrapped
 
 

@@ -47,12 +47,16 @@ class Dense(Layer):
         self.built = True
 
     def set_weights(self, weights):
-        self.kernel = torch.as_tensor(np.asarray(weights[0], np.float32))
-        self.bias = torch.as_tensor(np.asarray(weights[1], np.float32))
+        from . import _TRAINING
+        self.kernel = torch.as_tensor(np.asarray(weights[0], np.float32)).clone()
+        self.bias = torch.as_tensor(np.asarray(weights[1], np.float32)).clone()
+        if _TRAINING[0] and self.trainable:
+            self.kernel.requires_grad_(True)
+            self.bias.requires_grad_(True)
         self.built = True
 
     def get_weights(self):
-        return [self.kernel.numpy(), self.bias.numpy()]
+        return [self.kernel.detach().numpy(), self.bias.detach().numpy()]
 
     def call(self, x):
         if not self.built:
@@ -86,10 +90,15 @@ class Model(Layer):
 
     @property
     def trainable_variables(self):
+        """Dense layers and Variables directly under `self` (what Keras tracks once
+        models/base.py register_trainable has aliased the layers), in attribute order."""
         out = []
         for v in vars(self).values():
             if isinstance(v, Dense) and v.built and v.trainable:
                 out += [v.kernel, v.bias]
+            elif isinstance(v, torch.Tensor) and getattr(v, '_shim_variable', False) \
+                    and v.requires_grad:
+                out.append(v)
         return out
 
 

@@ -128,6 +128,42 @@ def test_stage_b_oracle_equals_reference_code_via_shim(golden_dir, kind):
         'rgb'], g['scaled_rgb']) < tol
 
 
+@pytest.mark.parametrize('kind', ['microfacet', 'learned'])
+def test_train_step_gradients_equal_reference_tape_via_shim(golden_dir, kind):
+    """trainvali.py:276-285 (forward in train mode, per-ray loss, compute_average_loss,
+    tape.gradient over model.trainable_variables) run by the reference's code through the shim
+    (GradientTape = torch autograd, tf.custom_gradient honoured: util/math.py safe_acos /
+    safe_atan2) vs the oracle's autograd: all 20 Dense layers and the light."""
+    g = np.load(os.path.join(golden_dir, 'ref_tfshim_train_grad_%s.npz' % kind))
+    lh, n = int(g['light_h']), int(g['n_rays'])
+    params = synth.make_stage_b_params(int(g['seed_params']), kind, light_hw=(lh, 2 * lh))
+    batch = synth.make_stage_b_batch(int(g['seed_batch']), n, 2 * lh * lh, fg_frac=1.0)
+    tp, leaves = {}, {}
+    for k, v in params.items():
+        if k == 'light':
+            tp[k] = leaves['grad/light'] = torch.tensor(v, requires_grad=True)
+            continue
+        layers = []
+        for li, (w, b) in enumerate(v['layers']):
+            wt, bt = torch.tensor(w, requires_grad=True), torch.tensor(b, requires_grad=True)
+            layers.append((wt, bt))
+            leaves['grad/%s/%d/kernel' % (k, li)], leaves['grad/%s/%d/bias' % (k, li)] = wt, bt
+        tp[k] = dict(v, layers=layers)
+    om = stage_b.StageB(tp, {'brdf': kind, 'shape_mode': 'finetune'}, light_h=lh)
+    pred, gt, lk = om.call(batch, 'train', xyz_noise=g['xyz_noise'])
+    wts = {'brdf_smooth_weight': 0.} if kind == 'microfacet' else None
+    loss = om.compute_loss(pred, gt, weights=wts, **lk)
+    assert np.abs(loss.detach().numpy() - g['per_example_loss']).max() < 1e-6
+    (loss.sum() / n).backward()
+    keys = [k for k in g.files if k.startswith('grad/')]
+    assert len(keys) == 41
+    for k in keys:
+        got, want = leaves[k].grad.numpy(), g[k]
+        assert np.abs(got - want).max() <= 1e-6 * max(np.abs(want).max(), 1e-6) + 1e-9, k
+    # the frozen BRDF prior gets no gradient in the reference (nerfactor.py:58-60)
+    assert not any(k.startswith(('grad/brdf_mlp', 'grad/brdf_out')) for k in keys)
+
+
 def test_stage_a_oracle_equals_reference_code_via_shim(golden_dir):
     """geometry_from_nerf.{compute_depth_and_normal, compute_light_visibility, eval_sigma_mlp}
     and models/nerf.py call (colour rendering), reference files unmodified via the shim."""
