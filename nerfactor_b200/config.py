@@ -39,7 +39,7 @@ _SHAPE = dict(_COMMON_MLP, **_PIPELINE, **{                # nerfactor/config/sh
     'ndc': 'False', 'n_rays_per_step': '1024',
     'model': 'shape', 'loss': 'l2', 'light_h': '16', 'white_bg': 'True',
     'xyz_jitter_std': '0.01', 'smooth_use_l1': 'True', 'normal_loss_weight': '1',
-    'lvis_loss_weight': '1', 'normal_smooth_weight': '0.01', 'lvis_smooth_weight': '0.5'})
+    'lvis_loss_weight': '1'})     # no smoothness weights in shape.ini: shape.py:37-40 falls back to 0
 
 _BRDF = {                                     # nerfactor/config/brdf.ini
     'model': 'brdf', 'loss': 'l2', 'pos_enc': 'True', 'n_freqs': '2', 'z_dim': '3',

@@ -153,7 +153,10 @@ class Model(ShapeVis, BaseModel):
 
     def _pred_lvis_at(self, pts, surf2l=None):
         """shape.py:213-237.  `surf2l` is accepted for signature parity and ignored:
-        the kernel derives l2n(lxyz - pts) itself (shape.py:128-135)."""
+        the kernel derives l2n(lxyz - pts) itself (shape.py:128-135).  Known deviation: for the
+        JITTERED evaluation the reference passes the un-jittered point's directions
+        (shape.py:170, nerfactor.py:225); here they follow the jittered point (<= 1e-4 in the
+        jittered visibility, smoothness term of the reported loss only)."""
         m = self._packed_mlp('lvis', 'lvis', n_freqs_a=self.embedder['xyz'].n_freqs,
                              n_freqs_b=self.embedder['ldir'].n_freqs)
         return _lib.lvis_fwd(self.ctx, m, pts, self.lxyz.reshape(-1, 3), self.xyz_scale,
@@ -169,6 +172,8 @@ class Model(ShapeVis, BaseModel):
             to_device(x, self.device) for x in (alpha, xyz, normal, lvis)]
         if xyz_noise is None and xyz_jitter_std > 0:
             xyz_noise = torch.randn_like(xyz) * xyz_jitter_std
+        elif xyz_noise is not None:
+            xyz_noise = to_device(xyz_noise, self.device)
         normal_pred = self._pred_normal_at(xyz)
         if xyz_noise is not None and self.normal_smooth_weight > 0:
             normal_jitter = self._pred_normal_at(xyz + xyz_noise)

@@ -181,6 +181,35 @@ def run_train_gradients(kind, light_h, n_rays, seed_params, seed_batch, out_name
     return out
 
 
+def run_shape(light_h, n_rays, seed_params, seed_batch, out_name):
+    """nerfactor/models/shape.py Model.call (train, recorded jitter) + compute_loss."""
+    from nerfactor.models.shape import Model
+    # shape.ini ships without smoothness weights (fallback 0, shape.py:37-40); set them so the
+    # jittered branch is exercised too
+    cfg = read_ini('shape.ini', light_h=light_h, data_root='/tmp', data_nerf_root='/tmp',
+                   outroot='/tmp', normal_smooth_weight=0.01, lvis_smooth_weight=0.5)
+    model = Model(cfg)
+    params = synth.make_stage_b_params(seed_params, 'learned', light_hw=(light_h, 2 * light_h))
+    set_weights(model.net, params)
+    L = 2 * light_h * light_h
+    batch_np = synth.make_stage_b_batch(seed_batch, n_rays, L)
+    batch = tuple(x if i < 2 else t32(x) for i, x in enumerate(batch_np))
+    tf.random.set_seed(99)
+    pred, gt, lk, _ = model.call(batch, mode='train')
+    tf.random.set_seed(99)
+    noise = tf.random.normal((n_rays, 3), stddev=cfg.getfloat('DEFAULT', 'xyz_jitter_std'))
+    out = {'light_h': light_h, 'n_rays': n_rays, 'seed_params': seed_params,
+           'seed_batch': seed_batch, 'xyz_noise': noise.numpy()}
+    for k, v in to_np(pred).items():
+        out['pred_' + k] = v
+    for k, v in to_np(lk).items():
+        out[k] = v
+    out['loss'] = model.compute_loss(pred, gt, **lk).numpy()
+    np.savez_compressed(os.path.join(HERE, out_name), **out)
+    print(out_name, sorted(out))
+    return out
+
+
 def run_stage_a(seed_nerf, hw, light_h, out_name):
     """geometry_from_nerf.compute_depth_and_normal / compute_light_visibility / eval_sigma_mlp and
     the NeRF colour rendering (models/nerf.py call) of the reference, on a random-init NeRF."""
@@ -227,11 +256,15 @@ def run_stage_a(seed_nerf, hw, light_h, out_name):
 
 
 if __name__ == '__main__':
+    if 'shape' in sys.argv[1:]:
+        run_shape(2, 40, 3, 9, 'ref_tfshim_shape.npz')
+        sys.exit(0)
     if 'grad' in sys.argv[1:]:
         run_train_gradients('microfacet', 2, 48, 7, 11, 'ref_tfshim_train_grad_microfacet.npz')
         run_train_gradients('learned', 2, 48, 7, 11, 'ref_tfshim_train_grad_learned.npz')
         sys.exit(0)
     run_stage_a(3, (6, 6), 2, 'ref_tfshim_stage_a.npz')
+    run_shape(2, 40, 3, 9, 'ref_tfshim_shape.npz')
     run_stage_b('microfacet', 4, 80, 7, 11, 'ref_tfshim_stage_b_microfacet.npz')
     run_stage_b('learned', 4, 80, 7, 11, 'ref_tfshim_stage_b_learned.npz')
     run_train_gradients('microfacet', 2, 48, 7, 11, 'ref_tfshim_train_grad_microfacet.npz')

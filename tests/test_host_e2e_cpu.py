@@ -51,3 +51,61 @@ def test_model_call_glue_matches_oracle_on_test_double(monkeypatch):
         'mode', 'normal_jitter', 'lvis_jitter', 'brdf_prop_jitter', 'albedo_jitter'}
     with pytest.raises(ValueError):
         m.call(batch, 'predict')
+
+
+def test_shape_model_call_and_loss_equal_reference_code(monkeypatch):
+    """nerfactor_b200.models.shape.Model (host code; kernels replaced by the test double) against
+    the REFERENCE'S shape.py Model.call + compute_loss run through the TensorFlow shim
+    (tests/golden/ref_tfshim_shape.npz): predictions, jittered predictions, per-ray loss."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden',
+                             'ref_tfshim_shape.npz'))
+    ctx = cpu_backend.install(monkeypatch)
+    from nerfactor_b200.models.shape import Model
+    lh, n = int(g['light_h']), int(g['n_rays'])
+    params = synth.make_stage_b_params(int(g['seed_params']), 'learned', light_hw=(lh, 2 * lh))
+    cfg = nfconfig.default_config('shape', light_h=lh, normal_smooth_weight=0.01,
+                                  lvis_smooth_weight=0.5)      # as in the generator
+    m = Model(cfg, params=params, ctx=ctx, precision='fp32')
+    batch = synth.make_stage_b_batch(int(g['seed_batch']), n, 2 * lh * lh)
+    pred, gt, lk, _ = m.call(batch, 'train', xyz_noise=g['xyz_noise'])
+    for k in ('normal', 'lvis'):
+        assert np.abs(pred[k].numpy() - g['pred_' + k]).max() < 2e-6, k
+    assert np.abs(lk['normal_jitter'].numpy() - g['normal_jitter']).max() < 2e-6
+    # KNOWN DEVIATION (DESIGN.md section 9): the reference evaluates the jittered visibility at
+    # xyz + noise but with the light directions of the UN-jittered point (shape.py:151, 170);
+    # nf_lvis_fwd derives the directions from the point it is given.  With the lights at radius
+    # 100 and a jitter of 0.01 the directions differ by ~1e-4; the effect stays below 1e-4 in
+    # lvis_jitter and only enters the smoothness term of the loss Model.call reports (training
+    # goes through Trainer.forward, which reuses the un-jittered directions like the reference).
+    d = np.abs(lk['lvis_jitter'].numpy() - g['lvis_jitter']).max()
+    assert 0 < d < 1e-4
+    loss = m.compute_loss(pred, gt, **lk)
+    assert loss.shape == (n,) and np.abs(loss.numpy() - g['loss']).max() < 2e-5
+
+
+@pytest.mark.parametrize('kind', ['microfacet'])
+def test_nerfactor_model_call_equals_reference_code(monkeypatch, kind):
+    """Same for the NeRFactor model's host glue (mask / compaction / scatter, overrides, probe and
+    OLAT relighting, loss) against tests/golden/ref_tfshim_stage_b_microfacet.npz."""
+    import os
+    from importlib import import_module
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden',
+                             'ref_tfshim_stage_b_%s.npz' % kind))
+    ctx = cpu_backend.install(monkeypatch)
+    Model = import_module('nerfactor_b200.models.nerfactor_microfacet').Model
+    lh = int(g['light_h'])
+    params = synth.make_stage_b_params(int(g['seed_params']), kind, light_hw=(lh, 2 * lh))
+    m = Model(nfconfig.default_config('nerfactor_microfacet', light_h=lh), params=params, ctx=ctx,
+              precision='fp32')
+    batch = synth.make_stage_b_batch(int(g['seed_batch']), int(g['n_rays']), 2 * lh * lh)
+    for i, p in enumerate(g['probes']):
+        m.novel_probes['p%d' % i] = p
+    pred, _, _, _ = m.call(batch, 'test', relight_probes=True, relight_olat=True)
+    for k in ('rgb', 'normal', 'lvis', 'albedo', 'brdf', 'rgb_probes', 'rgb_olat'):
+        assert np.abs(pred[k].numpy() - g['test_' + k]).max() < 5e-6, k
+    pr, gt, lk, _ = m.call(batch, 'train', xyz_noise=g['xyz_noise'])
+    loss = m.compute_loss(pr, gt, **lk)
+    assert np.abs(loss.numpy() - g['train_loss']).max() < 2e-6
+    pv, gtv, lkv, _ = m.call(batch, 'vali')
+    assert np.abs(m.compute_loss(pv, gtv, **lkv).numpy() - g['vali_loss']).max() < 2e-6
