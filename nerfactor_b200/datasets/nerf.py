@@ -100,29 +100,31 @@ class Dataset(BaseDataset):
     def _gen_rays(self, to_world, angle_x, imh, imw):
         """nerf.py:172-214 in fp64 like the reference (the device version, nf_gen_rays, is
         bit-identical for spp = 1: tests/test_gpu_parity.py).  Pixel corners, no half-pixel
-        offset; un-normalised directions."""
-        near = self.config.getfloat('DEFAULT', 'near')
-        ndc = self.config.getboolean('DEFAULT', 'ndc')
-        cam_loc = to_world[:3, 3]
-        rayo = np.tile(cam_loc[None, None, :], (imh * self.sps, imw * self.sps, 1))
-        xs = np.linspace(0, imw, imw * self.sps, endpoint=False)
-        ys = np.linspace(0, imh, imh * self.sps, endpoint=False)
-        xs, ys = np.meshgrid(xs, ys)
-        fl = .5 * imw / np.tan(.5 * angle_x)
-        rayd = np.stack(((xs - .5 * imw) / fl, -(ys - .5 * imh) / fl, -np.ones_like(xs)), axis=-1)
-        rayd = np.sum(rayd[:, :, np.newaxis, :] * to_world[:3, :3], axis=-1)
-        if ndc:                                   # nerf.py:194-213 ("not in use" upstream)
-            cv2gl_rot = np.diag((1.0, -1.0, -1.0))
-            rayo, rayd = rayo.dot(cv2gl_rot), rayd.dot(cv2gl_rot)
-            t = -(near + rayo[..., 2]) / rayd[..., 2]
-            rayo = rayo + t[..., None] * rayd
-            o1 = -1. / (imw / (2. * fl)) * rayo[..., 0] / rayo[..., 2]
-            o2 = -1. / (imh / (2. * fl)) * rayo[..., 1] / rayo[..., 2]
-            o3 = 1. + 2. * near / rayo[..., 2]
-            d1 = -1. / (imw / (2. * fl)) * (
-                rayd[..., 0] / rayd[..., 2] - rayo[..., 0] / rayo[..., 2])
-            d2 = -1. / (imh / (2. * fl)) * (
-                rayd[..., 1] / rayd[..., 2] - rayo[..., 1] / rayo[..., 2])
-            d3 = -2. * near / rayo[..., 2]
-            rayo, rayd = np.dstack((o1, o2, o3)), np.dstack((d1, d2, d3))
+        offset; un-normalised directions; `sps` sub-samples per pixel side."""
+        n_y, n_x = imh * self.sps, imw * self.sps
+        px, py = np.meshgrid(np.linspace(0, imw, n_x, endpoint=False),
+                             np.linspace(0, imh, n_y, endpoint=False))
+        focal = .5 * imw / np.tan(.5 * angle_x)
+        local = np.stack(((px - .5 * imw) / focal, -(py - .5 * imh) / focal, -np.ones_like(px)),
+                         axis=-1)
+        rayd = np.sum(local[:, :, np.newaxis, :] * to_world[:3, :3], axis=-1)     # R . d_local
+        rayo = np.tile(to_world[:3, 3][None, None, :], (n_y, n_x, 1))
+        if self.config.getboolean('DEFAULT', 'ndc'):
+            rayo, rayd = _to_ndc(rayo, rayd, self.config.getfloat('DEFAULT', 'near'), focal,
+                                 imh, imw)
         return rayo, rayd
+
+
+def _to_ndc(rayo, rayd, near, focal, imh, imw):
+    """NeRF's normalised-device-coordinate rays (nerf.py:194-213; marked "not in use" upstream,
+    ndc = False in every shipped config).  OpenGL convention: flip y / z of SfM cameras, move the
+    origins onto the near plane, then project origins and directions."""
+    flip = np.diag((1.0, -1.0, -1.0))
+    o, d = rayo.dot(flip), rayd.dot(flip)
+    o = o + (-(near + o[..., 2]) / d[..., 2])[..., None] * d
+    sx, sy = -1. / (imw / (2. * focal)), -1. / (imh / (2. * focal))
+    ox_z, oy_z = o[..., 0] / o[..., 2], o[..., 1] / o[..., 2]
+    o_ndc = np.dstack((sx * ox_z, sy * oy_z, 1. + 2. * near / o[..., 2]))
+    d_ndc = np.dstack((sx * (d[..., 0] / d[..., 2] - ox_z), sy * (d[..., 1] / d[..., 2] - oy_z),
+                       -2. * near / o[..., 2]))
+    return o_ndc, d_ndc

@@ -228,6 +228,18 @@ def test_dataset_loaders_equal_reference_loaders(tmp_path):
                     for a, b in zip(r[1:], m[1:]):
                         assert a.shape == b.shape and np.array_equal(
                             np.asarray(a, np.float32), b), (mode, imh)
+            # ray generation incl. the NDC branch and 2 x 2 sub-pixel samples (nerf.py:172-214)
+            for ndc in ('False', 'True'):
+                cfg.set('DEFAULT', 'ndc', ndc)
+                for sps in (1, 2):
+                    rr, mm = RefNerf.__new__(RefNerf), get_dataset_class('nerf').__new__(
+                        get_dataset_class('nerf'))
+                    rr.config = mm.config = cfg
+                    rr.sps = mm.sps = sps
+                    c2w = synth.look_at_c2w(3.0, 40.0, 25.0)
+                    for a, b in zip(rr._gen_rays(c2w, 0.7, 6, 9), mm._gen_rays(c2w, 0.7, 6, 9)):
+                        assert a.shape == b.shape and np.allclose(a, b, rtol=1e-13, atol=1e-13)
+            cfg.set('DEFAULT', 'ndc', 'False')
             refn = RefNerf.__new__(RefNerf)
             refn.config, refn.mode, refn.debug, refn.meta2img, refn.sps = cfg, 'train', False, {}, 1
             refn.files = refn._glob()
