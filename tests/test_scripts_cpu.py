@@ -226,3 +226,71 @@ def test_nerf_vis_batch(tmp_path):
     assert np.array_equal(occ, ((1 - tv['fine_occu'].reshape(6, 6)) * 255).astype(np.uint8))
     assert m.compile_batch_vis([vdir], str(tmp_path / 'e' / 'all'), 'vali').endswith('.html')
     assert m.compile_batch_vis([vdir], str(tmp_path / 'e' / 'vid'), 'test').endswith('.mp4')
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason='reference tree only in the build container')
+def test_vis_batch_equals_reference_vis_batch(tmp_path, monkeypatch):
+    """The reference's NeRFactor `vis_batch` (nerfactor.py:562-739, its own file, run through the
+    TensorFlow shim on the reference model's own outputs) vs `vis_batch` here on the same
+    `to_vis`: same files, same pixels (text-free images), incl. OLAT / probe renders composited
+    on the average light and the per-light visibility maps."""
+    import warnings
+    warnings.filterwarnings('ignore')
+    here = os.path.dirname(os.path.abspath(__file__))
+    paths = [os.path.join(here, 'golden', 'tfshim'), REF, os.path.join(REF, 'nerfactor'),
+             os.path.join(here, 'golden')]
+    for p in reversed(paths):
+        sys.path.insert(0, p)
+    try:
+        import tensorflow as tf
+        assert tf.__version__.endswith('shim')
+        import make_golden_tfshim as gen
+        import torch
+        from nerfactor_b200 import synth
+        lh, h, w = 2, 6, 5
+        model, cfg, params = gen.build_stage_b('microfacet', lh, str(tmp_path / 'cfg'), 7)
+        L = 2 * lh * lh
+        batch_np = list(synth.make_stage_b_batch(11, h * w, L))
+        batch_np[1] = np.tile(np.array([[h, w]], np.int32), (h * w, 1))
+
+        class _Id:                                   # an eager string tensor: x[0].numpy() -> bytes
+            def __getitem__(self, i):
+                return self
+
+            def numpy(self):
+                return b'test_007'
+        batch = tuple(_Id() if i == 0 else gen.t32(x) if i > 1 else torch.as_tensor(x)
+                      for i, x in enumerate(batch_np))
+        probes = synth.make_probes(5, 2, (lh, 2 * lh))
+        from collections import OrderedDict
+        model.novel_probes = OrderedDict(('p%d' % i, gen.t32(p)) for i, p in enumerate(probes))
+        from nerfactor.util import light as reflight
+        model.novel_probes_uint = {k: reflight.vis_light(v, h=model.embed_light_h)
+                                   for k, v in model.novel_probes.items()}
+        _, _, _, to_vis = model.call(batch, mode='test', relight_olat=True, relight_probes=True)
+        mine_in = {k: (v.detach().numpy().copy() if isinstance(v, torch.Tensor) else v)
+                   for k, v in to_vis.items()}
+        mine_in['id'], mine_in['hw'] = 'test_007', (h, w)
+        rdir, mdir = str(tmp_path / 'ref'), str(tmp_path / 'mine')
+        model.vis_batch(to_vis, rdir, mode='test', olat_vis=True)
+        # ---- the model here (host code only: vis_batch never touches the kernels)
+        import cpu_backend
+        ctx = cpu_backend.install(monkeypatch)
+        from nerfactor_b200.models.nerfactor_microfacet import Model
+        m = Model(nfconfig.default_config('nerfactor_microfacet', light_h=lh), params=params,
+                  ctx=ctx, precision='fp32')
+        for i, p in enumerate(probes):
+            m.novel_probes['p%d' % i] = torch.as_tensor(p)
+        m.vis_batch(mine_in, mdir, mode='test', olat_vis=True)
+        rf, mf = sorted(os.listdir(rdir)), sorted(os.listdir(mdir))
+        assert rf == mf and len(rf) > 20
+        assert ioutil.read_json(os.path.join(rdir, 'metadata.json')) == ioutil.read_json(
+            os.path.join(mdir, 'metadata.json'))
+        for f in rf:
+            if f.endswith('.png'):
+                a = imgutil.read(os.path.join(rdir, f)).astype(int)
+                b = imgutil.read(os.path.join(mdir, f)).astype(int)
+                assert a.shape == b.shape and np.abs(a - b).max() <= 1, f
+    finally:
+        for p in paths:
+            sys.path.remove(p)
