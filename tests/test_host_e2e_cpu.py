@@ -109,3 +109,35 @@ def test_nerfactor_model_call_equals_reference_code(monkeypatch, kind):
     assert np.abs(loss.numpy() - g['train_loss']).max() < 2e-6
     pv, gtv, lkv, _ = m.call(batch, 'vali')
     assert np.abs(m.compute_loss(pv, gtv, **lkv).numpy() - g['vali_loss']).max() < 2e-6
+
+
+@pytest.mark.parametrize('kind', ['microfacet', 'learned'])
+def test_trainer_gradients_equal_reference_tape(monkeypatch, kind):
+    """`Trainer.loss_and_grad` (trainvali.forward + autodiff.py: the differentiable host path of
+    the train step, Dense kernels replaced by the test double) against the gradients the
+    REFERENCE's train_step produced through the shim (tests/golden/ref_tfshim_train_grad_*.npz):
+    per-ray loss and all 41 gradient tensors, frozen BRDF prior excluded."""
+    import os
+    from importlib import import_module
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden',
+                             'ref_tfshim_train_grad_%s.npz' % kind))
+    ctx = cpu_backend.install(monkeypatch)
+    name = 'nerfactor_microfacet' if kind == 'microfacet' else 'nerfactor'
+    Model = import_module('nerfactor_b200.models.' + name).Model
+    from nerfactor_b200.trainvali import Trainer
+    lh, n = int(g['light_h']), int(g['n_rays'])
+    params = synth.make_stage_b_params(int(g['seed_params']), kind, light_hw=(lh, 2 * lh))
+    m = Model(nfconfig.default_config(name, light_h=lh), params=params, ctx=ctx, precision='fp32')
+    batch = synth.make_stage_b_batch(int(g['seed_batch']), n, 2 * lh * lh, fg_frac=1.0)
+    tr = Trainer(m, precision='fp32')
+    loss, grad = tr.loss_and_grad(batch, xyz_noise=g['xyz_noise'])
+    assert np.allclose(loss.numpy(), g['per_example_loss'], atol=2e-6, rtol=1e-5)
+    gv = tr.views(grad)
+    keys = [k for k in g.files if k.startswith('grad/')]
+    assert len(keys) == len(gv) == 41
+    for k in keys:
+        parts = k.split('/')
+        key = ('light', 0, 'light') if parts[1] == 'light' else (parts[1], int(parts[2]), parts[3])
+        want = g[k]
+        got = gv[key].numpy().reshape(want.shape)
+        assert np.abs(got - want).max() <= 2e-5 * max(np.abs(want).max(), 1e-8), k
