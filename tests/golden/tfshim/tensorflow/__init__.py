@@ -20,6 +20,23 @@ import torch
 from . import keras, math, linalg, debugging, random, image, nn, train  # noqa: F401
 
 __version__ = '2.2.0-shim'
+
+# Eager TF tensors are plain values: `.numpy()` works on anything, also on results computed under
+# a GradientTape.  torch refuses that for tensors with autograd history, so while the shim is
+# loaded (golden generator / build-container-only tests) `.numpy()` and `np.asarray` detach first.
+if not getattr(torch.Tensor, '_shim_numpy', False):
+    _orig_numpy = torch.Tensor.numpy
+
+    def _numpy(self, *a, **k):
+        return _orig_numpy(self.detach(), *a, **k)
+
+    def _array(self, dtype=None, *a, **k):
+        arr = _orig_numpy(self.detach())
+        return arr if dtype is None else arr.astype(dtype, copy=False)
+
+    torch.Tensor.numpy = _numpy
+    torch.Tensor.__array__ = _array
+    torch.Tensor._shim_numpy = True
 Tensor = torch.Tensor
 float16, float32, float64 = torch.float16, torch.float32, torch.float64
 int32, int64, uint8 = torch.int32, torch.int64, torch.uint8

@@ -294,3 +294,78 @@ def test_vis_batch_equals_reference_vis_batch(tmp_path, monkeypatch):
     finally:
         for p in paths:
             sys.path.remove(p)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason='reference tree only in the build container')
+def test_stage_a_files_equal_reference_process_view(tmp_path, monkeypatch):
+    """geometry_from_nerf.process_view of the reference (its own file through the shim: march,
+    occupancy threshold, alpha / xyz / normal maps, hit mask, light visibility, alpha masking,
+    file writers) vs `process_view` + `write_view_buffers` here on the CPU test double: the four
+    buffers a Stage-B dataset reads."""
+    import warnings
+    warnings.filterwarnings('ignore')
+    here = os.path.dirname(os.path.abspath(__file__))
+    paths = [os.path.join(here, 'golden', 'tfshim'), REF, os.path.join(REF, 'nerfactor'),
+             os.path.join(here, 'golden')]
+    for p in reversed(paths):
+        sys.path.insert(0, p)
+    try:
+        import tensorflow as tf
+        import torch
+        import make_golden_tfshim as gen
+        from nerfactor import geometry_from_nerf as refgfn
+        from nerfactor.models.nerf import Model as RefNerf
+        from third_party.xiuminglib import xiuminglib as xm
+        from nerfactor_b200 import synth
+        from oracle import stage_a
+        monkeypatch.setattr(xm.vis.video, 'make_video', lambda *a, **k: None)   # lvis.mp4: vis only
+        lh, h, w = 2, 5, 6
+        rdir, mdir = str(tmp_path / 'ref'), str(tmp_path / 'mine')
+        if not refgfn.FLAGS.is_parsed():
+            refgfn.FLAGS(['t'])
+        refgfn.FLAGS.light_h, refgfn.FLAGS.out_root = lh, rdir
+        refgfn.FLAGS.occu_thres, refgfn.FLAGS.spp = 0.9, 1
+        cfg = gen.read_ini('nerf.ini', n_samples_coarse=-48, n_samples_fine=8, data_root='/tmp',
+                           outroot='/tmp')
+        ref_model = RefNerf(cfg)
+        params = synth.make_nerf_params(3)
+        gen.set_weights(ref_model.net, params)
+        rayo, rayd = stage_a.gen_rays(synth.look_at_c2w(), synth.CAM_ANGLE_X, h, w)
+        rayo, rayd = rayo.reshape(-1, 3), rayd.reshape(-1, 3)
+
+        class _Id:
+            def __getitem__(self, i):
+                return self
+
+            def numpy(self):
+                return b'train_003'
+        batch = (_Id(), torch.tensor([[h, w]] * (h * w), dtype=torch.int32), gen.t32(rayo),
+                 gen.t32(rayd), None)
+        refgfn.process_view(cfg, ref_model, batch)
+        # ---- here, kernels replaced by the test double
+        import cpu_backend
+        ctx = cpu_backend.install(monkeypatch)
+        from nerfactor_b200 import geometry_from_nerf as gfn
+        from nerfactor_b200.models.nerf import Model
+        from nerfactor_b200.util import geom_io
+        model = Model(nfconfig.default_config('nerf', n_samples_coarse=-48, n_samples_fine=8),
+                      params=params, ctx=ctx, precision='fp32')
+        ro = torch.as_tensor(rayo)
+        rd = torch.as_tensor(rayd)
+        rd = rd * torch.rsqrt(torch.clamp((rd * rd).sum(1, keepdim=True), min=1e-12))
+        buffers = gfn.process_view(model, ro, rd, (h, w), model.config, occu_thres=0.9,
+                                   lvis_far=1., light_h=lh, precision='fp32')
+        geom_io.write_view_buffers(buffers, os.path.join(mdir, 'train_003'))
+        rd_, md_ = os.path.join(rdir, 'train_003'), os.path.join(mdir, 'train_003')
+        assert geom_io.view_done(rd_) and geom_io.view_done(md_)
+        a_r = imgutil.read(os.path.join(rd_, 'alpha.png')).astype(int)
+        a_m = imgutil.read(os.path.join(md_, 'alpha.png')).astype(int)
+        assert a_r.shape == a_m.shape and np.abs(a_r - a_m).max() <= 1
+        assert 0 < (a_r > 0).mean() < 1                   # the threshold removed some pixels
+        for f, tol in (('xyz.npy', 2e-5), ('normal.npy', 2e-4), ('lvis.npy', 5e-5)):
+            r, m_ = np.load(os.path.join(rd_, f)), np.load(os.path.join(md_, f))
+            assert r.shape == m_.shape and r.dtype == m_.dtype == np.float32
+            assert np.abs(r - m_).max() < tol, (f, np.abs(r - m_).max())
+    finally:
+        for p in paths:
+            sys.path.remove(p)
