@@ -49,11 +49,19 @@ class Model(ShapeVis, BaseModel):
 
     # ------------------------------------------------------------ construction
     def _gen_lights(self):
-        """shape.py:59-77 (mvs_root lights.npz variant: pass lxyz via set_lights)."""
-        light_h = self.config.getint('DEFAULT', 'light_h')
-        lxyz, lareas = gen_light_xyz(light_h, int(2 * light_h))
-        return (torch.as_tensor(lxyz.astype(np.float32)).to(self.device),
-                torch.as_tensor(lareas.astype(np.float32)).to(self.device))
+        """shape.py:59-77: the lat-long grid of brdf/renderer.py, or -- MVS geometry, whose scale
+        and scene centre differ -- the light positions stored in `<mvs_root>/lights.npz`."""
+        mvs_root = self.config.get('DEFAULT', 'mvs_root', fallback=None)
+        if mvs_root is None:
+            light_h = self.config.getint('DEFAULT', 'light_h')
+            lxyz, lareas = gen_light_xyz(light_h, int(2 * light_h))
+        else:
+            import os
+            with open(os.path.join(mvs_root, 'lights.npz'), 'rb') as h:
+                data = dict(np.load(h))
+            lxyz, lareas = data['lxyzs'], data['lareas']
+        return (torch.as_tensor(np.asarray(lxyz, np.float32)).to(self.device),
+                torch.as_tensor(np.asarray(lareas, np.float32)).to(self.device))
 
     def set_lights(self, lxyz, lareas):
         """Arbitrary light sets (the reference's mvs_root/lights.npz path,

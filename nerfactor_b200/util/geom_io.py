@@ -125,17 +125,25 @@ def gen_rays_host(cam_to_world, cam_angle_x, imh, imw):
 
 
 def load_view(metadata_path, buffer_dir, imh, mode='test', rgba_path=None, use_nerf_alpha=False,
-              debug=False, n_lights_debug=512):
+              debug=False, n_lights_debug=512, rays_from_cam_loc=False):
     """nerf_shape.py:133-190.  Returns (id_, rayo, rayd, rgb, alpha, xyz, normal, lvis), arrays
     [H, W, ...] float32 (alpha [H, W]).  `mode` 'test': NeRF-traced alpha, zero RGB;
     'train' / 'vali': RGBA image at `rgba_path` (ground-truth alpha unless use_nerf_alpha)."""
     id_ = os.path.basename(os.path.dirname(metadata_path))
     with open(metadata_path) as f:
         metadata = json.load(f)
-    imw = int(imh / metadata['imh'] * metadata['imw'])
-    cam_to_world = np.array([float(x) for x in metadata['cam_transform_mat'].split(',')]).reshape(4, 4)
-    rayo, rayd = gen_rays_host(cam_to_world, metadata['cam_angle_x'], imh, imw)
-    rayo, rayd = rayo.astype(np.float32), rayd.astype(np.float32)
+    if rays_from_cam_loc:
+        # MVS geometry (datasets/mvs_shape.py:72-78): only the camera location is known; rays keep
+        # the metadata's own size and the directions are dummies (Stage B never reads them)
+        rayo = np.tile(np.array(metadata['cam_loc'])[None, None, :],
+                       (metadata['imh'], metadata['imw'], 1)).astype(np.float32)
+        rayd = np.zeros_like(rayo)
+    else:
+        imw = int(imh / metadata['imh'] * metadata['imw'])
+        cam_to_world = np.array(
+            [float(x) for x in metadata['cam_transform_mat'].split(',')]).reshape(4, 4)
+        rayo, rayd = gen_rays_host(cam_to_world, metadata['cam_angle_x'], imh, imw)
+        rayo, rayd = rayo.astype(np.float32), rayd.astype(np.float32)
     xyz = np.load(os.path.join(buffer_dir, 'xyz.npy'))
     normal = np.load(os.path.join(buffer_dir, 'normal.npy'))
     if debug:

@@ -284,3 +284,62 @@ def test_geometry_buffer_writers_equal_reference_writers(tmp_path):
     finally:
         for p in paths:
             sys.path.remove(p)
+
+
+def _write_mvs_scene(root, imh=8):
+    """The MVS layout (datasets/mvs_shape.py): everything of a view in <mvs_root>/<view>/, the
+    metadata carries `cam_loc`, the lights sit in <mvs_root>/lights.npz."""
+    import json
+    import shutil
+    from nerfactor_b200.brdf.renderer import gen_light_xyz
+    tmp = str(root) + '_src'
+    synth.write_scene(tmp, imh=imh, imw=imh, n_train=2, n_val=1, n_test=1,
+                      nerf_root=tmp + '_buf', n_lights=8)
+    for id_ in sorted(os.listdir(tmp)):
+        d = os.path.join(str(root), id_)
+        shutil.copytree(os.path.join(tmp, id_), d)
+        for f in os.listdir(os.path.join(tmp + '_buf', id_)):
+            shutil.copy(os.path.join(tmp + '_buf', id_, f), d)
+        meta = json.load(open(os.path.join(d, 'metadata.json')))
+        c2w = np.array([float(x) for x in meta['cam_transform_mat'].split(',')]).reshape(4, 4)
+        meta['cam_loc'] = [float(x) for x in c2w[:3, 3]]
+        json.dump(meta, open(os.path.join(d, 'metadata.json'), 'w'))
+    lxyz, lareas = gen_light_xyz(2, 4)
+    np.savez(os.path.join(str(root), 'lights.npz'), lxyzs=lxyz * 0.5, lareas=lareas)
+
+
+def test_mvs_shape_dataset(tmp_path):
+    root = tmp_path / 'mvs'
+    _write_mvs_scene(root)
+    cfg = _cfg(tmp_path / 'unused', None, mvs_root=str(root), use_nerf_alpha=True)
+    ds = get_dataset_class('mvs_shape')(cfg, 'train', seed=0)
+    assert ds.get_n_views() == 2
+    id_, hw, rayo, rayd, rgb, alpha, xyz, normal, lvis = next(iter(ds.build_pipeline()))
+    assert hw == (8, 8) and tuple(lvis.shape) == (32, 8)
+    assert float(rayd.abs().max()) == 0.                      # dummy directions
+    assert np.allclose(np.linalg.norm(rayo.numpy(), axis=1), 4., atol=1e-5)   # the camera location
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason='reference tree only in the build container')
+def test_mvs_shape_loader_equals_reference_loader(tmp_path):
+    paths = _reference_via_shim()
+    try:
+        from nerfactor.datasets.mvs_shape import Dataset as RefMvs
+        root = tmp_path / 'mvs'
+        _write_mvs_scene(root)
+        cfg = _cfg(tmp_path / 'unused', None, mvs_root=str(root), use_nerf_alpha=False)
+        for mode in ('train', 'vali', 'test'):
+            ref = RefMvs.__new__(RefMvs)
+            ref.config, ref.mode, ref.debug, ref.meta2buf, ref.meta2img, ref.sps = \
+                cfg, mode, False, {}, {}, 1
+            ref.files = ref._glob()
+            mine = get_dataset_class('mvs_shape')(cfg, mode)
+            assert mine.files == ref.files and ref.files
+            for path in ref.files:
+                r, m = ref._load_data(path), mine._load_data(path)
+                assert r[0] == m[0]
+                for a, b in zip(r[1:], m[1:]):
+                    assert a.shape == b.shape and np.array_equal(np.asarray(a, np.float32), b)
+    finally:
+        for p in paths:
+            sys.path.remove(p)

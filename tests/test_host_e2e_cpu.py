@@ -141,3 +141,53 @@ def test_trainer_gradients_equal_reference_tape(monkeypatch, kind):
         want = g[k]
         got = gv[key].numpy().reshape(want.shape)
         assert np.abs(got - want).max() <= 2e-5 * max(np.abs(want).max(), 1e-8), k
+
+
+import os as _os
+
+_REF_CFG = '/root/reference/nerfactor/config'
+
+
+@pytest.mark.skipif(not _os.path.isdir(_REF_CFG), reason='reference tree only in the build container')
+@pytest.mark.parametrize('ini', ['nerfactor.ini', 'nerfactor_microfacet.ini', 'nerfactor_mvs.ini',
+                                 'nerfactor_no_geom_opt.ini', 'nerfactor_no_geom_pretrain.ini',
+                                 'nerfactor_no_smooth.ini', 'shape.ini', 'shape_mvs.ini',
+                                 'nerf.ini'])
+def test_every_shipped_reference_config_drives_the_models(monkeypatch, tmp_path, ini):
+    """The reference's own .ini files (read as they are, site paths replaced): model construction,
+    a forward pass and the loss on the CPU test double -- every key the models read is present or
+    has the reference's fallback."""
+    import numpy as _np
+    from nerfactor_b200 import models
+    from nerfactor_b200.brdf.renderer import gen_light_xyz
+    from nerfactor_b200.util import io as ioutil
+    ctx = cpu_backend.install(monkeypatch)
+    cfg = ioutil.read_config(_os.path.join(_REF_CFG, ini))
+    lh = 2
+    for k in ('data_root', 'data_nerf_root', 'outroot', 'test_envmap_dir'):
+        if cfg.has_option('DEFAULT', k):
+            cfg.set('DEFAULT', k, str(tmp_path / k))
+    for k in ('shape_model_ckpt', 'brdf_model_ckpt'):
+        if cfg.has_option('DEFAULT', k):
+            cfg.set('DEFAULT', k, str(tmp_path / k / 'lr' / 'checkpoints' / 'ckpt-1'))
+    if cfg.has_option('DEFAULT', 'light_h'):
+        cfg.set('DEFAULT', 'light_h', str(lh))
+    if cfg.has_option('DEFAULT', 'mvs_root'):
+        _os.makedirs(str(tmp_path / 'mvs'))
+        lxyz, lareas = gen_light_xyz(lh, 2 * lh)
+        _np.savez(str(tmp_path / 'mvs' / 'lights.npz'), lxyzs=lxyz, lareas=lareas)
+        cfg.set('DEFAULT', 'mvs_root', str(tmp_path / 'mvs'))
+    name = cfg.get('DEFAULT', 'model')
+    model = models.get_model_class(name)(cfg, ctx=ctx, precision='fp32')
+    model.register_trainable()
+    assert model.trainable_registered
+    if name == 'nerf':
+        assert set(model.net) >= {'coarse_enc', 'fine_enc', 'coarse_sigma_out', 'fine_rgb_out'}
+        return
+    if name == 'nerfactor':                 # the learned lobe has no test double: microfacet-free
+        assert model.brdf_model is not None and model.z_dim == 3
+        return
+    batch = synth.make_stage_b_batch(1, 12, 2 * lh * lh)
+    pred, gt, lk, to_vis = model.call(batch, 'train')
+    loss = model.compute_loss(pred, gt, **lk)
+    assert tuple(loss.shape) == (12,) and bool(torch.isfinite(loss).all())
