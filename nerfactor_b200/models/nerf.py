@@ -3,7 +3,7 @@
 `net['coarse_rgb_out']`, ... nerf.py:53-71), the `xyz` / `view` embedders, the static
 samplers `gen_z`, `gen_z_fine`, `accumulate_sigma` (nerf.py:120-147, 184-212) and the colour
 rendering `_render_rays` / `_accumulate` / `_eval_nerf_at` / `call` (nerf.py:100-118, 149-290,
-SURVEY.md 8f.2).  NeRF's own training is out of scope."""
+SURVEY.md 8f.2).  NeRF's own training: trainvali.NerfTrainer."""
 import numpy as np
 import torch
 
@@ -171,6 +171,26 @@ class Model(NerfVis, BaseModel):
         for k, v in pred_fine.items():
             to_vis['fine_' + k] = v
         return pred, gt, {}, to_vis
+
+    def compute_loss(self, pred, gt, **kwargs):
+        """nerf.py:292-300 with `loss = l2` (losses.py:32-47): per-ray MSE of the coarse and the
+        fine rendering when `keep_batch` is set, their scalar means otherwise."""
+        if self.config.get('DEFAULT', 'loss', fallback='l2') != 'l2':
+            raise NotImplementedError("only the l2 loss of the shipped nerf.ini")
+        keep_batch = kwargs.get('keep_batch', False)
+        gt = gt if torch.is_tensor(gt) else torch.as_tensor(np.asarray(gt, np.float32))
+        gt = gt.to(self.device)
+        loss = 0
+        for p in (pred['coarse'], pred['fine']):
+            if p is None:
+                continue
+            per_ray = torch.mean((p - gt) ** 2, dim=-1)
+            loss = loss + (per_ray if keep_batch else per_ray.mean())
+        return loss
+
+    def weights_changed(self):
+        """Call after editing layer weights so they are re-packed for the GPU."""
+        self._packed.clear()
 
     # ---- static samplers, same signatures as the reference ------------------
     @staticmethod

@@ -384,6 +384,168 @@ class Trainer:
         return self.model.compute_loss(pred, gt, **loss_kwargs)
 
 
+class NerfTrainer(Trainer):
+    """Train step of the NeRF itself (the stage before Stage A; nerfactor/models/nerf.py:100-300
+    driven by trainvali.py:273-295): stratified + hierarchical sampling, both networks, L2 on the
+    coarse and the fine rendering.  The Dense contractions run in nf_dense_fwd / nf_dense_bwd
+    (8 x 256 trunk with the skip, sigma head, bottleneck, view-dependent colour head); sampling,
+    compositing and the loss are torch ops on the device, so autograd supplies their adjoint.
+    The hierarchical samples carry no gradient (tf.stop_gradient, nerf.py:143).
+
+    Random draws of the reference (tf.random.uniform for the stratified / importance samples,
+    nerf.py:133, util/math.py:81; tf.random.normal for the density noise, nerf.py:196) are explicit
+    optional inputs (`perturb_u`, `fine_u`, `sigma_noise`), drawn with torch when not given."""
+
+    def __init__(self, model, config=None, world_size=1, rank=0, precision=None):
+        super().__init__(model, config, world_size, rank, precision or 'fp32')
+        cfg = config or model.config
+        self.n_c = cfg.getint('DEFAULT', 'n_samples_coarse')
+        self.n_f = cfg.getint('DEFAULT', 'n_samples_fine')
+        self.lin_in_disp = cfg.getboolean('DEFAULT', 'lin_in_disp')
+        self.perturb = cfg.getboolean('DEFAULT', 'perturb')
+        self.noise_std = cfg.getfloat('DEFAULT', 'noise_std')
+
+    # ---- pieces -------------------------------------------------------------------
+    def _layers(self, views, name):
+        net = self.model.net[name]
+        out = []
+        for li in range(len(net.layers)):
+            key = (name, li, 'kernel')
+            out.append((views[key], views[(name, li, 'bias')]) if key in views
+                       else self._frozen[(name, li)])
+        return out
+
+    def _eval(self, views, pref, rayo, rayd, z):
+        """nerf.py:254-290 (use_views): rgbs [n, S, 4] = (raw rgb, raw sigma)."""
+        m = self.model
+        n, S = z.shape
+        pts = (rayo[:, None, :] + rayd[:, None, :] * z[:, :, None]).reshape(-1, 3)
+        vdir = rayd[:, None, :].expand(n, S, 3).reshape(-1, 3)
+        enc = m.net[pref + 'enc']
+        feat = ad.mlp_apply(ad.embed(pts, m.embedder['xyz'].n_freqs), self._layers(views, pref + 'enc'),
+                            ['relu'] * len(enc.layers), enc.skip_at, self.precision)
+        sigma = ad.mlp_apply(feat, self._layers(views, pref + 'sigma_out'), [None], None,
+                             self.precision)
+        bott = ad.mlp_apply(feat, self._layers(views, pref + 'bottleneck'), [None], None,
+                            self.precision)
+        fv = torch.cat((bott, ad.embed(vdir, m.embedder['view'].n_freqs)), -1)
+        rgb = ad.mlp_apply(fv, self._layers(views, pref + 'rgb_out'), ['relu', None], None,
+                           self.precision)
+        return torch.cat((rgb, sigma), -1).reshape(n, S, 4)
+
+    def _accumulate(self, rgbs, z, rayd, sigma_noise=None, inf=1e10, eps=1e-6):
+        """nerf.py:184-252: weights, colour composited onto the background, occupancy."""
+        dist = torch.cat((z[:, 1:] - z[:, :-1], torch.full_like(z[:, :1], inf)), -1)
+        dist = dist * torch.linalg.norm(rayd[:, None, :], dim=-1)
+        sigma = rgbs[:, :, 3]
+        if sigma_noise is not None:
+            sigma = sigma + sigma_noise
+        elif self.noise_std > 0:
+            sigma = sigma + torch.randn_like(sigma) * self.noise_std
+        density = 1. - torch.exp(-torch.relu(sigma) * dist)
+        t = 1. - density + eps                                   # util/math.py:67-68
+        trans = torch.cat((torch.ones_like(t[:, :1]), torch.cumprod(t, -1)[:, :-1]), -1)
+        weights = density * trans
+        occu = weights.sum(-1)
+        rgb = (weights[:, :, None] * torch.sigmoid(rgbs[:, :, :3])).sum(-2)
+        bg = 1. if self.model.white_bg else 0.
+        return rgb * occu[:, None] + bg * (1. - occu[:, None]), weights
+
+    @staticmethod
+    def _inv_transform_sample(val, weights, n_samples, u=None, eps=1e-5):
+        """util/math.py:71-94 (searchsorted side='right'); deterministic u = linspace(0, 1, n)
+        when `u` is None and perturbation is off."""
+        pdf = weights / (weights.sum(-1, keepdim=True) + eps)
+        cdf = torch.cat((torch.zeros_like(pdf[:, :1]), torch.cumsum(pdf, -1)), -1)
+        ind = torch.searchsorted(cdf.contiguous(), u.contiguous(), right=True)
+        below = torch.clamp(ind - 1, min=0)
+        above = torch.clamp(ind, max=cdf.shape[-1] - 1)
+        c0, c1 = torch.gather(cdf, 1, below), torch.gather(cdf, 1, above)
+        v0, v1 = torch.gather(val, 1, below), torch.gather(val, 1, above)
+        denom = c1 - c0
+        denom = torch.where(denom < eps, torch.ones_like(denom), denom)
+        return v0 + (u - c0) / denom * (v1 - v0)
+
+    # ---- step ---------------------------------------------------------------------
+    def forward(self, flat, batch, mode='train', perturb_u=None, fine_u=None, sigma_noise=None):
+        """-> (per-ray loss [N], {'coarse': rgb, 'fine': rgb})."""
+        m, dev = self.model, self.device
+        views = self.views(flat)
+        _, _, rayo, rayd, rgb_gt = batch
+        rayo, rayd, rgb_gt = [to_device(x, dev) for x in (rayo, rayd, rgb_gt)]
+        rayd = rayd * torch.rsqrt(torch.clamp((rayd * rayd).sum(1, keepdim=True), min=1e-12))
+        n = rayo.shape[0]
+        perturb = self.perturb and mode == 'train'
+        t = torch.linspace(0., 1., self.n_c, device=dev)
+        if self.lin_in_disp:
+            z = 1. / (1. / m.near * (1. - t) + 1. / m.far * t)
+        else:
+            z = m.near * (1. - t) + m.far * t
+        z = z[None, :].expand(n, self.n_c)
+        if perturb or perturb_u is not None:                       # nerf.py:129-135
+            mid = .5 * (z[:, 1:] + z[:, :-1])
+            upper, lower = torch.cat((mid, z[:, -1:]), -1), torch.cat((z[:, :1], mid), -1)
+            u = to_device(perturb_u, dev) if perturb_u is not None else torch.rand_like(lower)
+            z = lower + (upper - lower) * u
+        sn = (None, None) if sigma_noise is None else [to_device(x, dev) for x in sigma_noise]
+        rgb_c, w = self._accumulate(self._eval(views, 'coarse_', rayo, rayd, z), z, rayd, sn[0])
+        mse = lambda a: torch.mean((a - rgb_gt) ** 2, dim=-1)
+        loss, pred = mse(rgb_c), {'coarse': rgb_c, 'fine': None}
+        if self.n_f > 0:
+            with torch.no_grad():                                   # tf.stop_gradient, nerf.py:143
+                if fine_u is not None:
+                    u = to_device(fine_u, dev)
+                elif perturb:
+                    u = torch.rand((n, self.n_f), device=dev)
+                else:
+                    u = torch.linspace(0., 1., self.n_f, device=dev)[None, :].expand(n, self.n_f)
+                z_f = self._inv_transform_sample(.5 * (z[:, 1:] + z[:, :-1]), w[:, 1:-1].detach(),
+                                                 self.n_f, u.contiguous())
+                z_all = torch.sort(torch.cat((z, z_f), -1), -1).values
+            rgb_f, _ = self._accumulate(self._eval(views, 'fine_', rayo, rayd, z_all), z_all, rayd,
+                                        sn[1])
+            loss = loss + mse(rgb_f)
+            pred['fine'] = rgb_f
+        return loss, pred
+
+    def loss_and_grad(self, batch, global_batch=None, **draws):
+        flat = self.flat.detach().requires_grad_(True)
+        loss, _ = self.forward(flat, batch, 'train', **draws)
+        gb = global_batch or (loss.shape[0] * self.world_size)
+        (grad,) = torch.autograd.grad(torch.sum(loss) / gb, flat)
+        return loss.detach(), grad
+
+    def _graphed_loss_and_grad(self, batch, xyz_noise):
+        return None                  # data-dependent hierarchical sampling: eager
+
+    def train_step(self, batch, graph=False, **draws):
+        loss, grad = self.loss_and_grad(batch, **draws)
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(grad, op=dist.ReduceOp.SUM)
+        lr = self.learning_rate()
+        self.iterations += 1
+        _lib.adam_amsgrad_step(self.ctx, self.flat, grad.contiguous(), self.m, self.v, self.vhat,
+                               lr, self.iterations)
+        total = torch.sum(loss) / (loss.shape[0] * self.world_size)
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(total, op=dist.ReduceOp.SUM)
+        return total
+
+    @torch.no_grad()
+    def vali_step(self, batch):
+        self.sync_to_model()
+        pred, gt, loss_kwargs, _ = self.model.call(batch, 'vali')
+        return self.model.compute_loss(pred, gt, keep_batch=True, **loss_kwargs)
+
+
+def make_trainer(model, config=None, **kw):
+    """The trainer for a model: NeRF (models/nerf.py) or shape / NeRFactor."""
+    is_nerf = 'coarse_enc' in getattr(model, 'net', {})
+    return (NerfTrainer if is_nerf else Trainer)(model, config, **kw)
+
+
 # =============================================================================== script
 def _parse_args(argv=None):
     import argparse
@@ -484,7 +646,7 @@ def main(argv=None):
     for k in ('clipnorm', 'clipvalue'):
         if config.getfloat('DEFAULT', k, fallback=-1) > 0:
             raise NotImplementedError("%s > 0 (the reference's configs all use -1)" % k)
-    trainer = Trainer(model, config, world_size=world, rank=rank, precision=FLAGS.precision)
+    trainer = make_trainer(model, config, world_size=world, rank=rank, precision=FLAGS.precision)
     # ---- resume (trainvali.py:129-146)
     ckptdir = join(outdir, 'checkpoints')
     keep = config.getint('DEFAULT', 'keep_recent_epochs', fallback=-1)

@@ -181,6 +181,62 @@ def run_train_gradients(kind, light_h, n_rays, seed_params, seed_batch, out_name
     return out
 
 
+def run_nerf_train_gradients(seed_nerf, n_rays, out_name):
+    """The NeRF's own train step (models/nerf.py call + compute_loss under trainvali.py:276-285)
+    with stratified perturbation, importance sampling with random u and density noise ON; the
+    four random draws are recorded in call order (gen_z uniform, coarse density normal,
+    gen_z_fine uniform, fine density normal)."""
+    from nerfactor.models.nerf import Model as NerfModel
+    n_c, n_f, noise_std = 8, 6, 0.5
+    tf.shim_set_training(True)
+    try:
+        cfg = read_ini('nerf.ini', n_samples_coarse=n_c, n_samples_fine=n_f, perturb=True,
+                       noise_std=noise_std, data_root='/tmp', outroot='/tmp')
+        model = NerfModel(cfg)
+        params = synth.make_nerf_params(seed_nerf)
+        set_weights(model.net, params)
+        model.register_trainable()
+        rng = np.random.default_rng(21)
+        c2w = synth.look_at_c2w()
+        from oracle import stage_a
+        rayo, rayd = stage_a.gen_rays(c2w, synth.CAM_ANGLE_X, 8, 8)
+        sel = rng.choice(64, n_rays, replace=False)
+        rayo, rayd = rayo.reshape(-1, 3)[sel], rayd.reshape(-1, 3)[sel]
+        rgb = rng.uniform(0, 1, (n_rays, 3)).astype(np.float32)
+        batch = (None, None, t32(rayo), t32(rayd), t32(rgb))
+        tf.random.set_seed(31337)
+        with tf.GradientTape() as tape:
+            pred, gt, loss_kwargs, _ = model(batch, mode='train')
+            loss_kwargs['keep_batch'] = True
+            per_example_loss = model.compute_loss(pred, gt, **loss_kwargs)
+            weighted_loss = tf.nn.compute_average_loss(per_example_loss,
+                                                       global_batch_size=n_rays)
+        variables = model.trainable_variables
+        grads = tape.gradient(weighted_loss, variables)
+        tf.random.set_seed(31337)                       # replay the draws in call order
+        u1 = tf.random.uniform((n_rays, n_c))
+        g1 = tf.random.normal((n_rays, n_c)) * noise_std
+        u2 = tf.random.uniform((n_rays, n_f))
+        g2 = tf.random.normal((n_rays, n_c + n_f)) * noise_std
+        out = {'seed_nerf': seed_nerf, 'n_c': n_c, 'n_f': n_f, 'noise_std': noise_std,
+               'rayo': rayo, 'rayd': rayd, 'rgb': rgb, 'perturb_u': u1.numpy(),
+               'fine_u': u2.numpy(), 'noise_coarse': g1.numpy(), 'noise_fine': g2.numpy(),
+               'pred_coarse': pred['coarse'].numpy(), 'pred_fine': pred['fine'].numpy(),
+               'per_example_loss': per_example_loss.numpy()}
+        owner = {}
+        for net_name, net in model.net.items():
+            for li, layer in enumerate(net.layers):
+                owner[id(layer.kernel)] = 'grad/%s/%d/kernel' % (net_name, li)
+                owner[id(layer.bias)] = 'grad/%s/%d/bias' % (net_name, li)
+        for v, g_ in zip(variables, grads):
+            out[owner[id(v)]] = g_.numpy().astype(np.float16 if g_.numel() > 40000 else np.float32)
+    finally:
+        tf.shim_set_training(False)
+    np.savez_compressed(os.path.join(HERE, out_name), **out)
+    print(out_name, len([k for k in out if k.startswith('grad/')]), 'gradient tensors')
+    return out
+
+
 def run_shape(light_h, n_rays, seed_params, seed_batch, out_name):
     """nerfactor/models/shape.py Model.call (train, recorded jitter) + compute_loss."""
     from nerfactor.models.shape import Model
@@ -256,6 +312,9 @@ def run_stage_a(seed_nerf, hw, light_h, out_name):
 
 
 if __name__ == '__main__':
+    if 'nerfgrad' in sys.argv[1:]:
+        run_nerf_train_gradients(3, 12, 'ref_tfshim_nerf_train_grad.npz')
+        sys.exit(0)
     if 'shape' in sys.argv[1:]:
         run_shape(2, 40, 3, 9, 'ref_tfshim_shape.npz')
         sys.exit(0)
@@ -265,6 +324,7 @@ if __name__ == '__main__':
         sys.exit(0)
     run_stage_a(3, (6, 6), 2, 'ref_tfshim_stage_a.npz')
     run_shape(2, 40, 3, 9, 'ref_tfshim_shape.npz')
+    run_nerf_train_gradients(3, 12, 'ref_tfshim_nerf_train_grad.npz')
     run_stage_b('microfacet', 4, 80, 7, 11, 'ref_tfshim_stage_b_microfacet.npz')
     run_stage_b('learned', 4, 80, 7, 11, 'ref_tfshim_stage_b_learned.npz')
     run_train_gradients('microfacet', 2, 48, 7, 11, 'ref_tfshim_train_grad_microfacet.npz')

@@ -253,8 +253,15 @@ def tensor_scatter_nd_update(tensor, indices, updates):
     return tensor
 
 
+def _no_axes(axis):
+    """axis=() / []: TF reduces over NO dimension (torch would reduce over all of them)."""
+    return isinstance(axis, (tuple, list)) and len(axis) == 0
+
+
 def reduce_sum(x, axis=None, keepdims=False):
     x = _t(x)
+    if _no_axes(axis):
+        return x
     return x.sum() if axis is None else x.sum(dim=axis, keepdim=keepdims)
 
 
@@ -262,6 +269,8 @@ def reduce_mean(x, axis=None, keepdims=False):
     x = _t(x)
     if isinstance(x, torch.Tensor) and not x.is_floating_point():
         x = x.float()
+    if _no_axes(axis):
+        return x
     return x.mean() if axis is None else x.mean(dim=axis, keepdim=keepdims)
 
 

@@ -191,3 +191,81 @@ def test_every_shipped_reference_config_drives_the_models(monkeypatch, tmp_path,
     pred, gt, lk, to_vis = model.call(batch, 'train')
     loss = model.compute_loss(pred, gt, **lk)
     assert tuple(loss.shape) == (12,) and bool(torch.isfinite(loss).all())
+
+
+def test_nerf_trainer_equals_reference_train_step(monkeypatch):
+    """`NerfTrainer` (stratified + hierarchical sampling, both networks, density noise, L2 on both
+    renderings; Dense kernels replaced by the test double) against the REFERENCE's NeRF train
+    step run through the shim with all four random draws recorded
+    (tests/golden/ref_tfshim_nerf_train_grad.npz): renderings, per-ray loss, 48 gradient tensors
+    (big kernels are stored as fp16 in the fixture)."""
+    g = np.load(_os.path.join(_os.path.dirname(_os.path.abspath(__file__)), 'golden',
+                              'ref_tfshim_nerf_train_grad.npz'))
+    ctx = cpu_backend.install(monkeypatch)
+    from nerfactor_b200.models.nerf import Model
+    from nerfactor_b200.trainvali import make_trainer, NerfTrainer
+    cfg = nfconfig.default_config('nerf', n_samples_coarse=int(g['n_c']),
+                                  n_samples_fine=int(g['n_f']), perturb=True,
+                                  noise_std=float(g['noise_std']))
+    m = Model(cfg, params=synth.make_nerf_params(int(g['seed_nerf'])), ctx=ctx, precision='fp32')
+    tr = make_trainer(m, precision='fp32')
+    assert isinstance(tr, NerfTrainer)
+    batch = (None, None, g['rayo'], g['rayd'], g['rgb'])
+    draws = dict(perturb_u=g['perturb_u'], fine_u=g['fine_u'],
+                 sigma_noise=(g['noise_coarse'], g['noise_fine']))
+    with torch.no_grad():
+        loss_f, pred = tr.forward(tr.flat, batch, 'train', **draws)
+    assert np.abs(pred['coarse'].numpy() - g['pred_coarse']).max() < 2e-6
+    # the fine samples go through a discontinuous inverse-CDF lookup and a 2^9-frequency
+    # encoding: 1-ulp differences of the sample positions show up at the 1e-5 level on single rays
+    assert np.abs(pred['fine'].numpy() - g['pred_fine']).max() < 5e-5
+    assert np.median(np.abs(pred['fine'].numpy() - g['pred_fine'])) < 1e-6
+    loss, grad = tr.loss_and_grad(batch, **draws)
+    assert np.allclose(loss.numpy(), g['per_example_loss'], atol=2e-5, rtol=1e-4)
+    gv = tr.views(grad)
+    keys = [k for k in g.files if k.startswith('grad/')]
+    assert len(keys) == len(gv) == 48
+    for k in keys:
+        _, net, li, kind = k.split('/')
+        want = g[k].astype(np.float32)
+        got = gv[(net, int(li), kind)].numpy()
+        # fp16-stored big kernels: 2e-3; fine network: the 1e-5 forward sensitivity above
+        rel = 2e-3 if g[k].dtype == np.float16 else (5e-4 if net.startswith('fine_') else 5e-5)
+        tol = rel * max(np.abs(want).max(), 1e-8)
+        assert np.abs(got - want).max() <= tol, k
+    # one optimizer step moves the weights and a few more reduce the loss on this batch
+    l0 = float(tr.train_step(batch, **draws))
+    for _ in range(5):
+        l1 = float(tr.train_step(batch, **draws))
+    assert l1 < l0
+
+
+def test_nerf_training_script_then_stage_a(tmp_path, monkeypatch):
+    """The stage before Stage A through the scripts: `trainvali --config <nerf .ini>` trains the
+    NeRF (NerfTrainer), checkpoints under the reference's variable names and writes the validation
+    visualisation; `geometry_from_nerf --trained_nerf <that run>` then finds the latest checkpoint
+    and its .ini and produces the geometry buffers.  CPU test double, FP32 layered NeRF path."""
+    cpu_backend.install(monkeypatch)
+    from nerfactor_b200 import trainvali, geometry_from_nerf as gfn
+    from nerfactor_b200.util import io as ioutil, tfckpt
+    data = str(tmp_path / 'data')
+    ids = synth.write_scene(data, imh=8, imw=8, n_train=2, n_val=1, n_test=1)
+    cfg = nfconfig.default_config(
+        'nerf', data_root=data, imh=6, n_samples_coarse=6, n_samples_fine=6, n_rays_per_step=24,
+        epochs=2, ckpt_period=1, vali_period=2, vali_batches=1, outroot=str(tmp_path / 'out'))
+    ini = str(tmp_path / 'nerf.ini')
+    ioutil.write_config(cfg, ini)
+    outdir = trainvali.main(['--config', ini, '--precision', 'fp32'])
+    ckpt = ioutil.latest_checkpoint(_os.path.join(outdir, 'checkpoints'))
+    assert ckpt.endswith('ckpt-2')
+    names = tfckpt.read_checkpoint(ckpt)
+    assert 'net/net_coarse_enc_layer0/kernel/.ATTRIBUTES/VARIABLE_VALUE' in names
+    assert 'net/net_fine_rgb_out_layer1/bias/.OPTIMIZER_SLOT/optimizer/vhat/.ATTRIBUTES/VARIABLE_VALUE' in names
+    vdir = _os.path.join(outdir, 'vis_vali', 'epoch000000002')
+    assert _os.path.exists(_os.path.join(vdir, 'all.html'))
+    assert _os.path.exists(_os.path.join(vdir, 'batch000000000', 'fine-vs-gt_rgb.apng'))
+    surf = str(tmp_path / 'surf')
+    done = gfn.main(['--trained_nerf', outdir, '--out_root', surf, '--light_h', '2',
+                     '--precision', 'fp32'])
+    assert sorted(done) == sorted(ids)
+    assert np.load(_os.path.join(surf, 'test_000', 'lvis.npy')).shape == (6, 6, 8)
