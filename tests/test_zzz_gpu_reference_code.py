@@ -74,3 +74,39 @@ def test_stage_a_vs_reference_code_via_shim(ctx, golden_dir):
     for fine, key in ((False, 'sigma_coarse'), (True, 'sigma_fine')):
         sg = _lib.sigma_fwd(ctx, model.packed_sigma(fine), pts, zero, z1, None, 'fp32')
         assert rel_l2(sg.cpu(), g[key]) < 2e-5
+
+
+def test_nerf_trainer_vs_reference_train_step(ctx, golden_dir):
+    """NerfTrainer on the GPU (FP32 Dense kernels) against the reference's NeRF train step run
+    through the shim with its four random draws recorded (ref_tfshim_nerf_train_grad.npz):
+    renderings, per-ray loss, all 48 gradient tensors; then a few optimizer steps."""
+    from nerfactor_b200.models.nerf import Model
+    from nerfactor_b200.trainvali import make_trainer
+    g = np.load(os.path.join(golden_dir, 'ref_tfshim_nerf_train_grad.npz'))
+    cfg = nfconfig.default_config('nerf', n_samples_coarse=int(g['n_c']),
+                                  n_samples_fine=int(g['n_f']), perturb=True,
+                                  noise_std=float(g['noise_std']))
+    m = Model(cfg, params=synth.make_nerf_params(int(g['seed_nerf'])), ctx=ctx, precision='fp32')
+    tr = make_trainer(m, precision='fp32')
+    batch = (None, None, g['rayo'], g['rayd'], g['rgb'])
+    draws = dict(perturb_u=g['perturb_u'], fine_u=g['fine_u'],
+                 sigma_noise=(g['noise_coarse'], g['noise_fine']))
+    with torch.no_grad():
+        _, pred = tr.forward(tr.flat, batch, 'train', **draws)
+    assert np.abs(pred['coarse'].cpu().numpy() - g['pred_coarse']).max() < 1e-5
+    d = np.abs(pred['fine'].cpu().numpy() - g['pred_fine'])
+    assert d.max() < 5e-4 and np.median(d) < 1e-5      # importance sampling: see the CPU test
+    loss, grad = tr.loss_and_grad(batch, **draws)
+    assert np.allclose(loss.cpu().numpy(), g['per_example_loss'], atol=1e-4, rtol=2e-3)
+    gv = tr.views(grad)
+    keys = [k for k in g.files if k.startswith('grad/')]
+    assert len(keys) == len(gv) == 48
+    for k in keys:
+        _, net, li, kind = k.split('/')
+        want = g[k].astype(np.float32)
+        got = gv[(net, int(li), kind)].cpu().numpy()
+        assert np.abs(got - want).max() <= 5e-3 * max(np.abs(want).max(), 1e-8), k
+    l0 = float(tr.train_step(batch, **draws))
+    for _ in range(5):
+        l1 = float(tr.train_step(batch, **draws))
+    assert np.isfinite(l0) and l1 < l0
