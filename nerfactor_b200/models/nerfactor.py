@@ -246,7 +246,7 @@ class Model(NeRFactorVis, ShapeModel):
             lvis_pred, lvis_jitter = torch.clamp(lvis_m, 1e-8, 1.), None
         else:
             lvis_pred = self._pred_lvis_at(xyz_m)
-            lvis_jitter = None if xyz_j is None else self._pred_lvis_at(xyz_j)
+            lvis_jitter = None if xyz_j is None else self._pred_lvis_jitter_at(xyz_j, xyz_m)
         # Albedo (:228-242)
         albedo = self._pred_albedo_at(xyz_m)
         albedo_jitter = None if xyz_j is None else self._pred_albedo_at(xyz_j)

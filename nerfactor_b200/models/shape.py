@@ -161,14 +161,44 @@ class Model(ShapeVis, BaseModel):
 
     def _pred_lvis_at(self, pts, surf2l=None):
         """shape.py:213-237.  `surf2l` is accepted for signature parity and ignored:
-        the kernel derives l2n(lxyz - pts) itself (shape.py:128-135).  Known deviation: for the
-        JITTERED evaluation the reference passes the un-jittered point's directions
-        (shape.py:170, nerfactor.py:225); here they follow the jittered point (<= 1e-4 in the
-        jittered visibility, smoothness term of the reported loss only)."""
+        the kernel derives l2n(lxyz - pts) itself (shape.py:128-135).  The jittered evaluation,
+        where the reference passes the UN-jittered point's directions, is
+        `_pred_lvis_jitter_at`."""
         m = self._packed_mlp('lvis', 'lvis', n_freqs_a=self.embedder['xyz'].n_freqs,
                              n_freqs_b=self.embedder['ldir'].n_freqs)
         return _lib.lvis_fwd(self.ctx, m, pts, self.lxyz.reshape(-1, 3), self.xyz_scale,
                              self.precision)
+
+    JITTER_EXACT_MAX_PAIRS = 1 << 22      # (point, light) pairs materialised for the jittered net
+
+    def _pred_lvis_jitter_at(self, pts_jitter, pts):
+        """The smoothness-loss evaluation of shape.py:170 / nerfactor.py:225: the visibility net at
+        the JITTERED point but with the light directions of the un-jittered one (`surf2l` is
+        computed once from `pts` in the reference).  The fused kernel derives directions from the
+        point it is given, so this runs the net layer by layer on materialised
+        [embed(x + noise) | embed(surf2l)] rows through the FP32 Dense kernels (nf_dense_fwd) --
+        train batches are 1024 rays x 512 lights.  Above JITTER_EXACT_MAX_PAIRS pairs (full-view
+        validation batches, whose NeRFactor loss ignores the jitter terms) it falls back to the
+        fused kernel: directions then follow the jittered point (<= 1e-4 in the result)."""
+        lxyz = self.lxyz.reshape(-1, 3)
+        n, L = pts.shape[0], lxyz.shape[0]
+        if n == 0 or n * L > self.JITTER_EXACT_MAX_PAIRS:
+            return self._pred_lvis_at(pts_jitter)
+        from .. import autodiff as ad
+        trunk, head = self.net['lvis_mlp'], self.net['lvis_out']
+        if 'lvis_dev_layers' not in self._packed:
+            self._packed['lvis_dev_layers'] = [
+                (to_device(w, self.device), to_device(b, self.device))
+                for w, b in trunk.weights() + head.weights()]
+        acts = [l.activation for l in trunk.layers] + [l.activation for l in head.layers]
+        with torch.no_grad():
+            surf2l = mathutil.safe_l2_normalize(lxyz[None, :, :] - pts[:, None, :], axis=2)
+            e_xyz = ad.embed(self.xyz_scale * pts_jitter, self.embedder['xyz'].n_freqs)
+            e_dir = ad.embed(surf2l.reshape(-1, 3), self.embedder['ldir'].n_freqs)
+            x = torch.cat((e_xyz[:, None, :].expand(n, L, e_xyz.shape[1]).reshape(n * L, -1),
+                           e_dir), -1)
+            out = ad.mlp_apply(x, self._packed['lvis_dev_layers'], acts, trunk.skip_at, 'fp32')
+        return out.reshape(n, L)
 
     # ------------------------------------------------------------------- call
     def call(self, batch, mode='train', xyz_noise=None):
@@ -192,7 +222,7 @@ class Model(ShapeVis, BaseModel):
             normal_jitter = mathutil.safe_l2_normalize(normal_jitter, axis=1)
         lvis_pred = self._pred_lvis_at(xyz)
         if xyz_noise is not None and self.lvis_smooth_weight > 0:
-            lvis_jitter = self._pred_lvis_at(xyz + xyz_noise)
+            lvis_jitter = self._pred_lvis_jitter_at((xyz + xyz_noise).contiguous(), xyz)
         else:
             lvis_jitter = None
         pred = {'normal': normal_pred, 'lvis': lvis_pred}
