@@ -56,6 +56,8 @@ def lvis_fwd(ctx, mlp, xyz, lxyz, xyz_scale=1.0, precision='f16'):
     ctx.launches += 1
     lxyz = lxyz.reshape(-1, 3)
     n, L = xyz.shape[0], lxyz.shape[0]
+    if n == 0:
+        return torch.zeros((0, L))
     surf2l = tfops.safe_l2_normalize(lxyz[None] - xyz[:, None], 2)         # shape.py:128-135
     e_xyz = onets.embed(xyz * xyz_scale, mlp.n_freqs_a)[:, None, :].expand(n, L, -1)
     x = torch.cat((e_xyz, onets.embed(surf2l, mlp.n_freqs_b)), -1).reshape(n * L, -1)
