@@ -260,6 +260,15 @@ def secondary_rows(ctx, nerf, kt):
     t = kt(lambda: tr.train_step(tb), 3)
     out['train_step_fp32'] = {'what': 'same, FP32 CUDA-core Dense kernels',
                               'ms': t, 'rays_per_s': 1024 / (t * 1e-3)}
+    # (5) the stage before Stage A: one NeRF train step (trainvali.NerfTrainer), in a subprocess
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'bench_nerf_train.py')],
+                           capture_output=True, text=True, timeout=300)
+        line = [l for l in r.stdout.splitlines() if l.startswith('{')]
+        out['nerf_train_step'] = json.loads(line[-1]) if (r.returncode == 0 and line) else {
+            'error': (r.stderr or r.stdout)[-400:]}
+    except Exception as e:
+        out['nerf_train_step'] = {'error': repr(e)}
     return out
 
 
