@@ -42,7 +42,12 @@ _SHAPE = dict(_COMMON_MLP, **_PIPELINE, **{                # nerfactor/config/sh
     'lvis_loss_weight': '1'})     # no smoothness weights in shape.ini: shape.py:37-40 falls back to 0
 
 _BRDF = {                                     # nerfactor/config/brdf.ini
-    'model': 'brdf', 'loss': 'l2', 'pos_enc': 'True', 'n_freqs': '2', 'z_dim': '3',
+    'model': 'brdf', 'dataset': 'brdf_merl', 'loss': 'l2', 'loss_transform': 'log', 'lr': '1e-2',
+    'lr_decay_steps': '500_000', 'lr_decay_rate': '0.1', 'epochs': '50_000',
+    'ckpt_period': '1_000', 'vali_period': '1_000', 'vali_batches': '4', 'n_rays_per_step': '1024',
+    'clipnorm': '-1', 'clipvalue': '-1', 'keep_recent_epochs': '-1', 'overwrite': 'False',
+    'xname': 'lr{lr}', 'cache': 'True', 'no_batch': 'True', 'viewer_prefix': '',
+    'pos_enc': 'True', 'n_freqs': '2', 'z_dim': '3',
     'z_gauss_mean': '0.', 'z_gauss_std': '0.01', 'normalize_z': 'False',
     'mlp_chunk': '65536', 'mlp_width': '128', 'mlp_depth': '4', 'mlp_skip_at': '2'}
 

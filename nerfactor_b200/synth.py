@@ -213,3 +213,24 @@ def write_scene(root, imh=16, imw=16, n_train=2, n_val=1, n_test=2, seed=0, nerf
             cv2.imwrite(os.path.join(envmap_dir, 'probe%d.hdr' % i),
                         np.ascontiguousarray(pr[:, :, ::-1]))
     return ids
+
+
+def write_merl_npz(root, names=('alum-bronze', 'blue-rubber', 'gold-paint'), n_rows=400, seed=0):
+    """Synthetic stand-ins for the BRDF prior's training files (data_gen/merl/make_dataset.py
+    output, read by datasets/brdf_merl.py): `train_<name>.npz` / `vali_<name>.npz` with Rusinkiewicz
+    coordinates (phi_d, theta_h, theta_d) and positive reflectance, and one shared `test.npz`."""
+    import os
+    rng = np.random.default_rng(seed)
+    os.makedirs(root, exist_ok=True)
+
+    def coords(n):
+        return np.stack((rng.uniform(0, np.pi, n), rng.uniform(0, np.pi / 2, n),
+                         rng.uniform(0, np.pi / 2, n)), 1).astype(np.float32)
+    for i, name in enumerate(names):
+        for split in ('train', 'vali'):
+            r = coords(n_rows)
+            refl = np.exp(rng.normal(-1. + 0.3 * i, 0.8, (n_rows, 1))).astype(np.float32)
+            np.savez(os.path.join(root, '%s_%s.npz' % (split, name)), name=name, i=i, envmap_h=16,
+                     ims=128, spp=1, rusink=r, refl=refl)
+    np.savez(os.path.join(root, 'test.npz'), envmap_h=16, ims=128, spp=1, rusink=coords(n_rows))
+    return list(names)

@@ -42,10 +42,17 @@ class Trainer:
                 if layer.trainable:
                     self.names += [(net_name, li, 'kernel'), (net_name, li, 'bias')]
                     shapes += [layer.kernel.shape, layer.bias.shape]
+        # trainable tensors that are not Dense layers: the light probe (nerfactor.py:367-375), the
+        # latent codes of the BRDF prior (networks/layers.py:24-45)
         self.has_light = hasattr(model, '_light')
+        extras = {}
         if self.has_light:
-            self.names.append(('light', 0, 'light'))
-            shapes.append(tuple(model._light.shape))
+            extras['light'] = model._light
+        if hasattr(model, 'latent_code'):
+            extras['z'] = torch.as_tensor(np.asarray(model.latent_code._z, np.float32))
+        for kind, t in extras.items():
+            self.names.append((kind, 0, kind))
+            shapes.append(tuple(t.shape))
         sizes = [int(np.prod(s)) for s in shapes]
         # every view starts on a 16-byte boundary (the kernels stream weights with cp.async 16)
         padded = [(n + 3) // 4 * 4 for n in sizes]
@@ -53,8 +60,8 @@ class Trainer:
         total = int(self.offsets[-1])
         self.flat = torch.zeros(total, device=self.device)
         for (net_name, li, kind), off, shp in zip(self.names, self.offsets[:-1], shapes):
-            if kind == 'light':
-                src = model._light
+            if kind in extras:
+                src = extras[kind]
             else:
                 layer = model.net[net_name].layers[li]
                 src = torch.as_tensor(getattr(layer, kind))
@@ -109,6 +116,8 @@ class Trainer:
         for (net_name, li, kind), t in v.items():
             if kind == 'light':
                 self.model._light = t.detach().clone()
+            elif kind == 'z':
+                self.model.latent_code.z = t.detach().cpu().numpy().copy()
             else:
                 layer = self.model.net[net_name].layers[li]
                 arr = t.detach().cpu().numpy().copy()
@@ -325,7 +334,9 @@ class Trainer:
     # ------------------------------------------------------------ checkpoint / resume
     def _var_path(self, key):
         net_name, li, kind = key
-        return 'net/_light' if kind == 'light' else 'net/net_%s_layer%d/%s' % (net_name, li, kind)
+        if kind in ('light', 'z'):
+            return 'net/_light' if kind == 'light' else 'net/latent_code/_z'
+        return 'net/net_%s_layer%d/%s' % (net_name, li, kind)
 
     def save_checkpoint(self, ckpt_dir, step):
         """trainvali.py:134-141, 197-200: writes `ckpt_dir/ckpt-<step>` in TensorFlow's tensor-
@@ -540,10 +551,57 @@ class NerfTrainer(Trainer):
         return self.model.compute_loss(pred, gt, keep_batch=True, **loss_kwargs)
 
 
+class BrdfTrainer(Trainer):
+    """Training of the BRDF prior (nerfactor/models/brdf.py under trainvali.py:273-295): one
+    material per step, `n_rays_per_step` random entries of its MERL table; the softplus MLP on
+    [z | embed(rusink)] and on the reciprocal coordinates, log-space L2 against the measured
+    reflectance; the MLP AND the per-material latent codes are optimised (Generative Latent
+    Optimization), so only the row of the step's material receives a gradient."""
+
+    def __init__(self, model, config=None, world_size=1, rank=0, precision=None):
+        if not hasattr(model, 'ctx'):           # the prior's model is host-only until trained
+            model.ctx = _lib.default_context()
+            model.device, model.precision = model.ctx.device, 'fp32'
+        super().__init__(model, config, world_size, rank, precision or 'fp32')
+
+    def forward(self, flat, batch, mode='train'):
+        m, dev = self.model, self.device
+        views = self.views(flat)
+        _, i, _, _, _, rusink, refl = batch
+        rusink, refl = to_device(rusink, dev), to_device(refl, dev)
+        layers = [(views[(name, li, 'kernel')], views[(name, li, 'bias')])
+                  for name in ('brdf_mlp', 'brdf_out') for li in range(len(m.net[name].layers))]
+        z_all = views[('z', 0, 'z')]
+        if m.latent_code.normalize:
+            z_all = ad.safe_l2_normalize(z_all, 1)
+        i0 = int(np.asarray(i).reshape(-1)[0])
+        z = z_all[i0:i0 + 1].expand(rusink.shape[0], -1)
+        brdf, brdf_reci = m._eval_brdf_at(z, rusink, layers, self.precision)
+        pred = {'brdf': brdf, 'brdf_reci': brdf_reci}
+        return m.compute_loss(pred, {'brdf': refl}, keep_batch=True), pred
+
+    def loss_and_grad(self, batch, global_batch=None):
+        flat = self.flat.detach().requires_grad_(True)
+        loss, _ = self.forward(flat, batch, 'train')
+        gb = global_batch or (loss.shape[0] * self.world_size)
+        (grad,) = torch.autograd.grad(torch.sum(loss) / gb, flat)
+        return loss.detach(), grad
+
+    def _graphed_loss_and_grad(self, batch, xyz_noise):
+        return None
+
+    def train_step(self, batch, graph=False):
+        return NerfTrainer.train_step(self, batch)
+
+
 def make_trainer(model, config=None, **kw):
-    """The trainer for a model: NeRF (models/nerf.py) or shape / NeRFactor."""
-    is_nerf = 'coarse_enc' in getattr(model, 'net', {})
-    return (NerfTrainer if is_nerf else Trainer)(model, config, **kw)
+    """The trainer for a model: NeRF (models/nerf.py), the BRDF prior, or shape / NeRFactor."""
+    net = getattr(model, 'net', {})
+    if 'coarse_enc' in net:
+        return NerfTrainer(model, config, **kw)
+    if 'brdf_mlp' in net:
+        return BrdfTrainer(model, config, **kw)
+    return Trainer(model, config, **kw)
 
 
 # =============================================================================== script

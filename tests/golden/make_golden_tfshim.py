@@ -237,6 +237,52 @@ def run_nerf_train_gradients(seed_nerf, n_rays, out_name):
     return out
 
 
+def run_brdf_train_gradients(out_name):
+    """The BRDF prior's train step: nerfactor/models/brdf.py call + compute_loss (log-space L2,
+    reciprocity term) under trainvali.py:276-285; gradients of the MLP and of the latent codes."""
+    from nerfactor.models.brdf import Model as BrdfModel
+    tf.shim_set_training(True)
+    try:
+        with tempfile.TemporaryDirectory() as tmp:
+            names = synth.write_merl_npz(tmp, n_rows=64)
+            cfg = read_ini('brdf.ini', data_root=tmp, outroot=tmp)
+            model = BrdfModel(cfg)
+            assert model.brdf_names == sorted(names)
+            params = synth.make_stage_b_params(5, 'learned')
+            set_weights(model.net, params)
+            z0 = (0.01 * np.random.default_rng(8).standard_normal((len(names), 3))).astype(np.float32)
+            model.latent_code.z = t32(z0)
+            model.register_trainable()
+            d = dict(np.load(os.path.join(tmp, 'train_%s.npz' % model.brdf_names[1])))
+            n = d['rusink'].shape[0]
+            batch = (None, tf.convert_to_tensor(np.full((n,), int(d['i']), np.int32)), None, None,
+                     None, t32(d['rusink']), t32(d['refl']))
+            with tf.GradientTape() as tape:
+                pred, gt, loss_kwargs, _ = model(batch, mode='train')
+                loss_kwargs['keep_batch'] = True
+                per_example_loss = model.compute_loss(pred, gt, **loss_kwargs)
+                weighted_loss = tf.nn.compute_average_loss(per_example_loss, global_batch_size=n)
+            variables = model.trainable_variables
+            grads = tape.gradient(weighted_loss, variables)
+            out = {'names': np.array(model.brdf_names), 'i': int(d['i']), 'z0': z0,
+                   'rusink': d['rusink'], 'refl': d['refl'], 'pred_brdf': pred['brdf'].numpy(),
+                   'pred_brdf_reci': pred['brdf_reci'].numpy(),
+                   'per_example_loss': per_example_loss.numpy()}
+            owner = {id(model.latent_code._z): 'grad/z'}
+            for net_name, net in model.net.items():
+                for li, layer in enumerate(net.layers):
+                    owner[id(layer.kernel)] = 'grad/%s/%d/kernel' % (net_name, li)
+                    owner[id(layer.bias)] = 'grad/%s/%d/bias' % (net_name, li)
+            for v, g_ in zip(variables, grads):
+                out[owner[id(v)]] = g_.numpy()
+            assert 'grad/z' in out
+    finally:
+        tf.shim_set_training(False)
+    np.savez_compressed(os.path.join(HERE, out_name), **out)
+    print(out_name, len([k for k in out if k.startswith('grad/')]), 'gradient tensors')
+    return out
+
+
 def run_shape(light_h, n_rays, seed_params, seed_batch, out_name):
     """nerfactor/models/shape.py Model.call (train, recorded jitter) + compute_loss."""
     from nerfactor.models.shape import Model
@@ -312,6 +358,9 @@ def run_stage_a(seed_nerf, hw, light_h, out_name):
 
 
 if __name__ == '__main__':
+    if 'brdfgrad' in sys.argv[1:]:
+        run_brdf_train_gradients('ref_tfshim_brdf_train_grad.npz')
+        sys.exit(0)
     if 'nerfgrad' in sys.argv[1:]:
         run_nerf_train_gradients(3, 12, 'ref_tfshim_nerf_train_grad.npz')
         sys.exit(0)
@@ -325,6 +374,7 @@ if __name__ == '__main__':
     run_stage_a(3, (6, 6), 2, 'ref_tfshim_stage_a.npz')
     run_shape(2, 40, 3, 9, 'ref_tfshim_shape.npz')
     run_nerf_train_gradients(3, 12, 'ref_tfshim_nerf_train_grad.npz')
+    run_brdf_train_gradients('ref_tfshim_brdf_train_grad.npz')
     run_stage_b('microfacet', 4, 80, 7, 11, 'ref_tfshim_stage_b_microfacet.npz')
     run_stage_b('learned', 4, 80, 7, 11, 'ref_tfshim_stage_b_learned.npz')
     run_train_gradients('microfacet', 2, 48, 7, 11, 'ref_tfshim_train_grad_microfacet.npz')

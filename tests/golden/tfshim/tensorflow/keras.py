@@ -99,6 +99,11 @@ class Model(Layer):
             elif isinstance(v, torch.Tensor) and getattr(v, '_shim_variable', False) \
                     and v.requires_grad:
                 out.append(v)
+            elif isinstance(v, Layer) and not isinstance(v, (Dense, Model)):
+                for vv in vars(v).values():              # e.g. networks/layers.py LatentCode._z
+                    if isinstance(vv, torch.Tensor) and getattr(vv, '_shim_variable', False) \
+                            and vv.requires_grad:
+                        out.append(vv)
         return out
 
 

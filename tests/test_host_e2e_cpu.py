@@ -155,7 +155,7 @@ _REF_CFG = '/root/reference/nerfactor/config'
 @pytest.mark.parametrize('ini', ['nerfactor.ini', 'nerfactor_microfacet.ini', 'nerfactor_mvs.ini',
                                  'nerfactor_no_geom_opt.ini', 'nerfactor_no_geom_pretrain.ini',
                                  'nerfactor_no_smooth.ini', 'shape.ini', 'shape_mvs.ini',
-                                 'nerf.ini'])
+                                 'nerf.ini', 'brdf.ini'])
 def test_every_shipped_reference_config_drives_the_models(monkeypatch, tmp_path, ini):
     """The reference's own .ini files (read as they are, site paths replaced): model construction,
     a forward pass and the loss on the CPU test double -- every key the models read is present or
@@ -184,6 +184,9 @@ def test_every_shipped_reference_config_drives_the_models(monkeypatch, tmp_path,
     model = models.get_model_class(name)(cfg, ctx=ctx, precision='fp32')
     model.register_trainable()
     assert model.trainable_registered
+    if name == 'brdf':
+        assert model.latent_code.z.shape[1] == 3 and cfg.get('DEFAULT', 'loss_transform') == 'log'
+        return
     if name == 'nerf':
         assert set(model.net) >= {'coarse_enc', 'fine_enc', 'coarse_sigma_out', 'fine_rgb_out'}
         return
@@ -272,3 +275,91 @@ def test_nerf_training_script_then_stage_a(tmp_path, monkeypatch):
                      '--precision', 'fp32'])
     assert sorted(done) == sorted(ids)
     assert np.load(_os.path.join(surf, 'test_000', 'lvis.npy')).shape == (6, 6, 8)
+
+
+def test_brdf_prior_trainer_equals_reference_train_step(monkeypatch, tmp_path):
+    """`BrdfTrainer` + models/brdf.py `call` / `compute_loss` (BRDF prior: softplus MLP on
+    [z | embed(rusink)] and the reciprocal coordinates, log-space L2, latent codes optimised with
+    the network) against the reference's train step through the shim
+    (tests/golden/ref_tfshim_brdf_train_grad.npz): predictions, per-row loss, the 10 Dense
+    gradients and the latent-code gradient (non-zero only in the step's material row)."""
+    g = np.load(_os.path.join(_os.path.dirname(_os.path.abspath(__file__)), 'golden',
+                              'ref_tfshim_brdf_train_grad.npz'))
+    ctx = cpu_backend.install(monkeypatch)
+    from nerfactor_b200.models.brdf import Model
+    from nerfactor_b200.trainvali import make_trainer, BrdfTrainer
+    names = [str(x) for x in g['names']]
+    params = synth.make_stage_b_params(5, 'learned')
+    m = Model(nfconfig.default_config('brdf', lr=1e-3), params=params, brdf_names=names)
+    m.latent_code.z = g['z0']
+    i = int(g['i'])
+    batch = (names[i], i, 16, 128, 1, g['rusink'], g['refl'])
+    pred, gt, lk, to_vis = m.call(batch, 'vali')
+    assert np.abs(pred['brdf'].numpy() - g['pred_brdf']).max() < 1e-6
+    assert np.abs(pred['brdf_reci'].numpy() - g['pred_brdf_reci']).max() < 1e-6
+    loss = m.compute_loss(pred, gt, keep_batch=True, **lk)
+    assert np.allclose(loss.numpy(), g['per_example_loss'], atol=1e-6, rtol=1e-5)
+    tr = make_trainer(m)
+    assert isinstance(tr, BrdfTrainer)
+    loss, grad = tr.loss_and_grad(batch)
+    assert np.allclose(loss.numpy(), g['per_example_loss'], atol=1e-6, rtol=1e-5)
+    gv = tr.views(grad)
+    keys = [k for k in g.files if k.startswith('grad/')]
+    assert len(keys) == len(gv) == 11
+    for k in keys:
+        parts = k.split('/')
+        key = ('z', 0, 'z') if parts[1] == 'z' else (parts[1], int(parts[2]), parts[3])
+        want = g[k]
+        assert np.abs(gv[key].numpy() - want).max() <= 2e-5 * max(np.abs(want).max(), 1e-8), k
+    gz = gv[('z', 0, 'z')].numpy()
+    assert np.abs(gz[i]).max() > 0 and np.abs(np.delete(gz, i, axis=0)).max() == 0
+    l0 = float(tr.train_step(batch))
+    for _ in range(30):
+        l1 = float(tr.train_step(batch))
+    assert l1 < l0
+    tr.sync_to_model()
+    assert not np.array_equal(m.latent_code.z[i], g['z0'][i])       # the code moved ...
+    assert np.array_equal(np.delete(m.latent_code.z, i, 0), np.delete(g['z0'], i, 0))  # only it
+    # novel identity at test time: interpolated latent code (brdf.py:89-97)
+    pi, _, _, _ = m.call(('000000_0.250000_%s_0.750000_%s' % (names[0], names[2]), -1, 16, 128, 1,
+                          g['rusink'], np.zeros_like(g['refl'])), 'test')
+    z_mix = 0.25 * m.latent_code.z[0] + 0.75 * m.latent_code.z[2]
+    m2 = Model(nfconfig.default_config('brdf'), params=params, brdf_names=['mix'])
+    for k in ('brdf_mlp', 'brdf_out'):
+        m2.net[k].load({'layers': m.net[k].weights()})
+    m2.latent_code.z = z_mix[None]
+    p2, _, _, _ = m2.call(('mix', 0, 16, 128, 1, g['rusink'], g['refl']), 'vali')
+    assert np.abs(pi['brdf'].numpy() - p2['brdf'].numpy()).max() < 1e-6
+
+
+def test_brdf_prior_training_script_feeds_nerfactor(tmp_path, monkeypatch):
+    """`trainvali --config <brdf .ini>` on synthetic MERL-style tables: checkpoints carry the MLP
+    and the latent codes under the reference's names (`net/latent_code/_z`), and a NeRFactor model
+    whose config names that checkpoint restores the prior (network, codes, material names) the
+    way nerfactor.py:36-60 does."""
+    cpu_backend.install(monkeypatch)
+    from nerfactor_b200 import trainvali
+    from nerfactor_b200.util import io as ioutil, tfckpt
+    from nerfactor_b200.models.nerfactor import Model as NeRFactor
+    data = str(tmp_path / 'merl')
+    names = synth.write_merl_npz(data, n_rows=96)
+    cfg = nfconfig.default_config('brdf', data_root=data, n_rays_per_step=32, epochs=2,
+                                  ckpt_period=1, vali_period=2, vali_batches=1, lr=1e-3,
+                                  outroot=str(tmp_path / 'out'))
+    ini = str(tmp_path / 'brdf.ini')
+    ioutil.write_config(cfg, ini)
+    outdir = trainvali.main(['--config', ini])
+    ckpt = ioutil.latest_checkpoint(_os.path.join(outdir, 'checkpoints'))
+    t = tfckpt.read_checkpoint(ckpt)
+    z = t['net/latent_code/_z/.ATTRIBUTES/VARIABLE_VALUE']
+    assert z.shape == (3, 3) and 'net/net_brdf_mlp_layer0/kernel/.ATTRIBUTES/VARIABLE_VALUE' in t
+    assert int(t['optimizer/iter/.ATTRIBUTES/VARIABLE_VALUE']) == 2 * len(names)
+    assert _os.path.exists(_os.path.join(outdir, 'vis_vali', 'epoch000000002', 'batch000000000',
+                                         'log10_brdf.npy'))
+    ncfg = nfconfig.default_config('nerfactor', light_h=2, brdf_model_ckpt=ckpt,
+                                   shape_mode='scratch')
+    m = NeRFactor(ncfg)
+    assert m.brdf_model.brdf_names == sorted(names)
+    assert np.array_equal(np.asarray(m.brdf_model.latent_code.z), z)
+    w_ckpt = t['net/net_brdf_out_layer0/kernel/.ATTRIBUTES/VARIABLE_VALUE']
+    assert np.array_equal(m.brdf_model.net['brdf_out'].weights()[0][0], w_ckpt)
