@@ -110,3 +110,34 @@ def test_nerf_trainer_vs_reference_train_step(ctx, golden_dir):
     for _ in range(5):
         l1 = float(tr.train_step(batch, **draws))
     assert np.isfinite(l0) and l1 < l0
+
+
+def test_brdf_prior_trainer_vs_reference_train_step(ctx, golden_dir):
+    """BrdfTrainer on the GPU (FP32 Dense kernels) against the reference's BRDF-prior train step
+    through the shim (ref_tfshim_brdf_train_grad.npz): predictions, per-row loss, the 10 Dense
+    gradients and the latent-code gradient."""
+    from nerfactor_b200.models.brdf import Model
+    from nerfactor_b200.trainvali import make_trainer
+    g = np.load(os.path.join(golden_dir, 'ref_tfshim_brdf_train_grad.npz'))
+    names = [str(x) for x in g['names']]
+    m = Model(nfconfig.default_config('brdf', lr=1e-3), params=synth.make_stage_b_params(5, 'learned'),
+              brdf_names=names)
+    m.latent_code.z = g['z0']
+    i = int(g['i'])
+    batch = (names[i], i, 16, 128, 1, g['rusink'], g['refl'])
+    pred, gt, lk, _ = m.call(batch, 'vali')
+    assert np.abs(pred['brdf'].cpu().numpy() - g['pred_brdf']).max() < 1e-5
+    assert np.abs(pred['brdf_reci'].cpu().numpy() - g['pred_brdf_reci']).max() < 1e-5
+    tr = make_trainer(m)
+    loss, grad = tr.loss_and_grad(batch)
+    assert np.allclose(loss.cpu().numpy(), g['per_example_loss'], atol=1e-5, rtol=1e-4)
+    gv = tr.views(grad)
+    for k in [k for k in g.files if k.startswith('grad/')]:
+        parts = k.split('/')
+        key = ('z', 0, 'z') if parts[1] == 'z' else (parts[1], int(parts[2]), parts[3])
+        want = g[k]
+        assert np.abs(gv[key].cpu().numpy() - want).max() <= 2e-3 * max(np.abs(want).max(), 1e-8), k
+    l0 = float(tr.train_step(batch))
+    for _ in range(30):
+        l1 = float(tr.train_step(batch))
+    assert np.isfinite(l0) and l1 < l0
