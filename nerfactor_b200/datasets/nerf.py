@@ -2,7 +2,6 @@
 metadata.json` (+ `rgba.png`), rays from the camera in the metadata, RGBA composited onto the
 background colour.  Element: `(id_, hw, rayo, rayd, rgb)`; id_ / hw are per-view values (the
 reference tiles them per ray only to satisfy tf.distribute, nerf.py:112-115)."""
-import os
 from os.path import basename, dirname, exists, join
 
 import numpy as np

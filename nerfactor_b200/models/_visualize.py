@@ -9,7 +9,6 @@ the reference's per-view directory: `pred_*.png` / `gt_*.png`, `pred-vs-gt_*.apn
 `metadata.json` (view id, PSNR), and per run an HTML table (validation) or an .mp4 (test).
 Mixed into the model classes; nothing here touches the GPU beyond the device->host copy.
 """
-import os
 from os.path import basename, dirname, exists, join
 
 import numpy as np
