@@ -357,9 +357,15 @@ def main():
             ms = float(t.item())
         return ms, ctx.launches - l0
 
-    with ClockSampler(local) as cs:
+    # clocks / throttle reasons are sampled on rank 0 only (its line is the one printed): one
+    # nvidia-smi poller per rank would put 5 N queries per second on the box during the timed region
+    if rank == 0:
+        with ClockSampler(local) as cs:
+            ms, launches = timed(step_device, args.steps, max(3, args.warmup))
+        clocks = cs.summary()
+    else:
         ms, launches = timed(step_device, args.steps, max(3, args.warmup))
-    clocks = cs.summary()
+        clocks = None
     ms_step = ms / args.steps
     value = world * n_rays / (ms_step * 1e-3)
     ms_e2e, _ = timed(step_e2e, args.steps, 1)
