@@ -364,6 +364,12 @@ int nf_integrate_fwd(nf_ctx* ctx, const nf_integrate_args* a, void* stream) {
   if (ec == 7) ec = 8;
   const size_t lp = ((size_t)a->n_lights + 1) & ~(size_t)1;
   size_t sm = sizeof(float) * lp * (4 + 3 * ec);
+  // many lights AND many env-maps: fewer maps per pass until the texel arrays fit in shared memory
+  static const int kLower[9] = {0, 1, 1, 2, 3, 4, 4, 6, 6};
+  while (sm > ctx->smem_optin && ec > 1) {
+    ec = kLower[ec];
+    sm = sizeof(float) * lp * (4 + 3 * ec);
+  }
   NF_CHECK_ARG(ctx, sm <= ctx->smem_optin, "n_lights too large for shared memory");
   // resident grid (blocks per SM from the occupancy calculator): every warp then walks ~8 batches
   // of 32 points at the full 800 x 800 size, keeping the tail imbalance small
