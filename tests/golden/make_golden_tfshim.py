@@ -93,7 +93,7 @@ def build_stage_b(kind, light_h, tmp, seed_params):
     return model, cfg, params
 
 
-def run_stage_b(kind, light_h, n_rays, seed_params, seed_batch, out_name):
+def run_stage_b(kind, light_h, n_rays, seed_params, seed_batch, out_name, slim=False):
     with tempfile.TemporaryDirectory() as tmp:
         model, cfg, params = build_stage_b(kind, light_h, tmp, seed_params)
         L = 2 * light_h * light_h
@@ -107,6 +107,11 @@ def run_stage_b(kind, light_h, n_rays, seed_params, seed_batch, out_name):
         pred, gt, lk, _ = model.call(batch, mode='test', relight_olat=True, relight_probes=True)
         for k, v in to_np(pred).items():
             out['test_' + k] = v
+        if slim:            # the 512-light case: forward + relighting only (file size)
+            out['test_rgb_olat'] = out['test_rgb_olat'][:, ::16]        # every 16th OLAT
+            np.savez_compressed(os.path.join(HERE, out_name), **out)
+            print(out_name, 'slim', out['test_rgb_olat'].shape)
+            return out
         # ---- train mode with the jitter noise recorded (nerfactor.py:198-201) + compute_loss
         tf.random.set_seed(777)
         pred, gt, lk, _ = model.call(batch, mode='train')
@@ -358,6 +363,10 @@ def run_stage_a(seed_nerf, hw, light_h, out_name):
 
 
 if __name__ == '__main__':
+    if 'l512' in sys.argv[1:]:
+        run_stage_b('microfacet', 16, 40, 21, 22, 'ref_tfshim_stage_b_microfacet_L512.npz', slim=True)
+        run_stage_b('learned', 16, 40, 21, 22, 'ref_tfshim_stage_b_learned_L512.npz', slim=True)
+        sys.exit(0)
     if 'brdfgrad' in sys.argv[1:]:
         run_brdf_train_gradients('ref_tfshim_brdf_train_grad.npz')
         sys.exit(0)
@@ -377,5 +386,7 @@ if __name__ == '__main__':
     run_brdf_train_gradients('ref_tfshim_brdf_train_grad.npz')
     run_stage_b('microfacet', 4, 80, 7, 11, 'ref_tfshim_stage_b_microfacet.npz')
     run_stage_b('learned', 4, 80, 7, 11, 'ref_tfshim_stage_b_learned.npz')
+    run_stage_b('microfacet', 16, 40, 21, 22, 'ref_tfshim_stage_b_microfacet_L512.npz', slim=True)
+    run_stage_b('learned', 16, 40, 21, 22, 'ref_tfshim_stage_b_learned_L512.npz', slim=True)
     run_train_gradients('microfacet', 2, 48, 7, 11, 'ref_tfshim_train_grad_microfacet.npz')
     run_train_gradients('learned', 2, 48, 7, 11, 'ref_tfshim_train_grad_learned.npz')

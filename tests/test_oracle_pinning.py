@@ -129,6 +129,24 @@ def test_stage_b_oracle_equals_reference_code_via_shim(golden_dir, kind):
 
 
 @pytest.mark.parametrize('kind', ['microfacet', 'learned'])
+def test_stage_b_512_lights_oracle_equals_reference_code_via_shim(golden_dir, kind):
+    """The reference's native light grid (light_h = 16: 512 lights, nerfactor.ini:49) through the
+    shim: forward, two probes and every 16th OLAT render."""
+    g = np.load(os.path.join(golden_dir, 'ref_tfshim_stage_b_%s_L512.npz' % kind))
+    lh, n = int(g['light_h']), int(g['n_rays'])
+    assert lh == 16
+    params = synth.make_stage_b_params(int(g['seed_params']), kind, light_hw=(lh, 2 * lh))
+    batch = synth.make_stage_b_batch(int(g['seed_batch']), n, 2 * lh * lh)
+    om = stage_b.StageB(params, {'brdf': kind}, light_h=lh)
+    op, _, _ = om.call(batch, 'test', relight_lights=list(g['probes']) + om.novel_olat(
+        (lh, 2 * lh))[::16])
+    for k in ('rgb', 'normal', 'lvis', 'albedo', 'brdf'):
+        assert _rel(op[k], g['test_' + k]) < 1e-6, k
+    assert _rel(op['rgb_relit'][:, :2], g['test_rgb_probes']) < 1e-6
+    assert _rel(op['rgb_relit'][:, 2:], g['test_rgb_olat']) < 1e-6
+
+
+@pytest.mark.parametrize('kind', ['microfacet', 'learned'])
 def test_train_step_gradients_equal_reference_tape_via_shim(golden_dir, kind):
     """trainvali.py:276-285 (forward in train mode, per-ray loss, compute_average_loss,
     tape.gradient over model.trainable_variables) run by the reference's code through the shim

@@ -49,6 +49,25 @@ def test_model_call_vs_reference_code_via_shim(ctx, golden_dir, brdf, precision)
         assert np.allclose(loss.cpu().numpy(), g['train_loss'], atol=2e-6, rtol=1e-4)
 
 
+@pytest.mark.parametrize('brdf', ['microfacet', 'learned'])
+def test_model_call_512_lights_vs_reference_code_via_shim(ctx, golden_dir, brdf):
+    """The north-star light configuration (16 x 32 = 512 lights) in the tcgen05 f16 path against
+    the reference's own code through the shim: RGB, probe and OLAT relighting within 1e-4."""
+    g = np.load(os.path.join(golden_dir, 'ref_tfshim_stage_b_%s_L512.npz' % brdf))
+    lh = int(g['light_h'])
+    m, _, _ = _stage_b(ctx, brdf, lh, 2 * lh, int(g['seed_params']), 'f16')
+    batch = synth.make_stage_b_batch(int(g['seed_batch']), int(g['n_rays']), 2 * lh * lh)
+    for i, p in enumerate(g['probes']):
+        m.novel_probes['p%d' % i] = p
+    pred, _, _, _ = m.call(batch, 'test', relight_probes=True, relight_olat=True)
+    for k in ('normal', 'albedo', 'brdf'):
+        assert rel_l2(pred[k].cpu(), g['test_' + k]) < 1e-5, k
+    assert rel_l2(pred['lvis'].cpu(), g['test_lvis']) < 3e-3
+    assert rel_l2(pred['rgb'].cpu(), g['test_rgb']) < 1e-4
+    assert rel_l2(pred['rgb_probes'].cpu(), g['test_rgb_probes']) < 1e-4
+    assert rel_l2(pred['rgb_olat'].cpu().numpy()[:, ::16], g['test_rgb_olat']) < 1e-4
+
+
 def test_stage_a_vs_reference_code_via_shim(ctx, golden_dir):
     """compute_depth_and_normal / compute_light_visibility / eval_sigma_mlp (FP32 kernels) against
     the reference's geometry_from_nerf.py run through the shim (16 coarse + 88 fine samples)."""
