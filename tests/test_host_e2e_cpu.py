@@ -270,6 +270,13 @@ def test_nerf_training_script_then_stage_a(tmp_path, monkeypatch):
     vdir = _os.path.join(outdir, 'vis_vali', 'epoch000000002')
     assert _os.path.exists(_os.path.join(vdir, 'all.html'))
     assert _os.path.exists(_os.path.join(vdir, 'batch000000000', 'fine-vs-gt_rgb.apng'))
+    # nerf_test.py: the test cameras rendered with the trained NeRF, compiled into a video
+    from nerfactor_b200 import nerf_test
+    vroot, view_at = nerf_test.main(['--ckpt', ckpt, '--precision', 'fp32'])
+    assert _os.path.exists(_os.path.join(vroot, 'batch000000000', 'fine_rgb.png'))
+    assert ioutil.read_json(_os.path.join(vroot, 'batch000000000', 'metadata.json')) == {
+        'id': 'test_000'}
+    assert view_at.endswith('ckpt-2.mp4') and _os.path.getsize(view_at) > 0
     surf = str(tmp_path / 'surf')
     done = gfn.main(['--trained_nerf', outdir, '--out_root', surf, '--light_h', '2',
                      '--precision', 'fp32'])
