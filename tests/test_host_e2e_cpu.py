@@ -363,6 +363,15 @@ def test_brdf_prior_training_script_feeds_nerfactor(tmp_path, monkeypatch):
     assert int(t['optimizer/iter/.ATTRIBUTES/VARIABLE_VALUE']) == 2 * len(names)
     assert _os.path.exists(_os.path.join(outdir, 'vis_vali', 'epoch000000002', 'batch000000000',
                                          'log10_brdf.npy'))
+    # explore_brdf_space.py: every seen material + the interpolated identities on the test coords
+    from nerfactor_b200 import explore_brdf_space
+    vroot, n_done = explore_brdf_space.main(['--ckpt', ckpt])
+    assert n_done == 3 + 2 * 11                      # 3 materials, 2 pairs x 11 blends
+    assert ioutil.read_json(_os.path.join(vroot, 'batch000000000', 'metadata.json'))['id'] == \
+        sorted(names)[0]
+    lb = np.load(_os.path.join(vroot, 'batch000000004', 'log10_brdf.npy'))
+    assert lb.shape[1] == 2 and np.isfinite(lb).all()
+    assert explore_brdf_space.main(['--ckpt', ckpt])[1] == 0          # all done: skipped
     ncfg = nfconfig.default_config('nerfactor', light_h=2, brdf_model_ckpt=ckpt,
                                    shape_mode='scratch')
     m = NeRFactor(ncfg)
