@@ -133,3 +133,23 @@ def test_sample_rays_semantics():
     assert torch.equal(allr[0][:, 0], idx) and allr[6].shape == (h * w, L)
     with pytest.raises(ValueError):
         sample_rays(maps[0], maps[1], maps[2], torch.zeros((h, w)), xyz, nrm, lvis, 'train')
+
+
+def test_product_never_imports_test_infrastructure():
+    """The package has no CPU path: nothing under nerfactor_b200/ may import the oracle, the test
+    double or the TensorFlow shim (only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline
+    legs may)."""
+    import ast
+    import glob
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'nerfactor_b200')
+    banned = ('oracle', 'cpu_backend', 'tensorflow', 'e2e_scenario')
+    for path in glob.glob(os.path.join(root, '**', '*.py'), recursive=True):
+        tree = ast.parse(open(path).read())
+        for node in ast.walk(tree):
+            mods = []
+            if isinstance(node, ast.Import):
+                mods = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom) and node.level == 0:
+                mods = [node.module or '']
+            for m in mods:
+                assert m.split('.')[0] not in banned, (path, m)
