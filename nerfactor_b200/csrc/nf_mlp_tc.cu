@@ -24,6 +24,10 @@
 namespace {
 using namespace nftc;
 
+__device__ __forceinline__ void group_bar256(int id) {  // 256-thread named barrier
+  asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory");
+}
+
 constexpr int TC_WIDTH = 128;
 constexpr int TC_THREADS = 384;
 constexpr int TMEM_COLS = 512;
@@ -371,6 +375,303 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const TcParams p)
 }
 
 
+// ---------------------------------------------------------------------------------------------
+// Variant with EIGHT epilogue warps per worker group (NF_LVIS_EW8=1; not the default: written
+// after the round's GPU minutes were spent, to be validated and timed first thing next round).
+// Motivation: per tile and layer the tensor pipe needs ~512 cycles while a
+// 4-warp group spends ~350 issue slots per warp plus TMEM / mbarrier round trips on the epilogue
+// (tensor pipe 45 % active).  Here two warps share each TMEM lane quarter and split the 128
+// columns 64 / 64: warps 4-11 = group 0, 12-19 = group 1, `half` = which 64 columns.  Everything
+// per ROW (light direction, embedding, A_e write, final store) is done by half 0; per-point folds
+// are split (half 0: layer-0 bias, half 1: skip-layer bias); the head's dot product is reduced
+// across the halves through shared memory.  MMA issue, TMEM layout, images: as in mlp_tc_kernel.
+constexpr int TC8_THREADS = 640;
+
+template <int KIND, int BF16>
+__global__ void __launch_bounds__(TC8_THREADS, 1) mlp_tc8_kernel(const TcParams p) {
+  using SL = SmemLayout<KIND>;
+  constexpr int KE = SL::KE;
+  constexpr int NR_PAD = SL::NR_PAD;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* s_img = smem + SL::off_img;
+  float* s_aux = reinterpret_cast<float*>(smem + SL::off_aux);
+  float* s_beff = reinterpret_cast<float*>(smem + SL::off_beff);
+  float* s_e = reinterpret_cast<float*>(smem + SL::off_e);
+  float4* s_lx = reinterpret_cast<float4*>(smem + SL::off_lx);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SL::off_bar);
+  uint64_t* bar_w = bars + 0;          // weights landed
+  uint64_t* bar_a = bars + 1;          // [2] A operand ready (128 arrivals)
+  uint64_t* bar_d = bars + 3;          // [2] D accumulator ready (tcgen05.commit)
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 5);
+  float* s_red = reinterpret_cast<float*>(smem + SL::total);      // [2 groups][128] head partials
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunks = (p.L + 127) / 128;
+
+  // ---------------------------------------------------------------- set-up
+  if (threadIdx.x == 0) {
+    mbar_init(bar_w, 1);
+    mbar_init(bar_a + 0, 256); mbar_init(bar_a + 1, 256);
+    mbar_init(bar_d + 0, 1); mbar_init(bar_d + 1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(s_tmem)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int l = threadIdx.x; l < p.L; l += blockDim.x)
+    s_lx[l] = make_float4(p.lxyz[l * 3], p.lxyz[l * 3 + 1], p.lxyz[l * 3 + 2], 0.f);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+  if (threadIdx.x == 0) {
+    const uint32_t aux_bytes = (uint32_t)(SL::aux_floats * 4);
+    mbar_expect_tx(bar_w, (uint32_t)SL::img_bytes + aux_bytes);
+    // TMA bulk copies (UBLKCP): whole network -> shared memory, once per CTA
+    const uint8_t* gi = p.blob + p.off_img;
+    for (size_t o = 0; o < SL::img_bytes; o += 32768) {
+      size_t nb = SL::img_bytes - o < 32768 ? SL::img_bytes - o : 32768;
+      bulk_g2s(s_img + o, gi + o, (uint32_t)nb, bar_w);
+    }
+    const uint8_t* ga = p.blob + p.off_aux;
+    for (size_t o = 0; o < aux_bytes; o += 32768) {
+      size_t nb = aux_bytes - o < 32768 ? aux_bytes - o : 32768;
+      bulk_g2s(reinterpret_cast<uint8_t*>(s_aux) + o, ga + o, (uint32_t)nb, bar_w);
+    }
+  }
+  mbar_wait(bar_w, 0);
+
+  // unit of work = one surface point; group G takes points G, G + 2*grid, ...
+  const int n_groups = gridDim.x * 2;
+  auto group_points = [&](int g) {
+    int G = blockIdx.x * 2 + g;
+    return G < p.n ? (p.n - 1 - G) / n_groups + 1 : 0;
+  };
+
+  if (warp == 0) {
+    // =============================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(BF16, TC_WIDTH);
+      const uint32_t lbo = TC_WIDTH * 16, sbo = 128;
+      const uint32_t img0 = smem_u32(s_img);
+      // segment byte offsets inside the image: [KE | 128 | 128 | 128 | KE] x 128 x 2 B
+      const uint32_t seg_off[5] = {0u, (uint32_t)KE * 256u, (uint32_t)(KE + 128) * 256u,
+                                   (uint32_t)(KE + 256) * 256u, (uint32_t)(KE + 384) * 256u};
+      const int nt0 = group_points(0) * chunks, nt1 = group_points(1) * chunks;
+      const int nt_max = nt0 > nt1 ? nt0 : nt1;
+      uint32_t ph[2] = {0u, 0u};
+      for (int it = 0; it < nt_max; ++it) {
+        for (int layer = 0; layer < 4; ++layer) {
+          for (int g = 0; g < 2; ++g) {
+            if (it >= (g == 0 ? nt0 : nt1)) continue;
+            mbar_wait(bar_a + g, ph[g]);
+            ph[g] ^= 1u;
+            tc_fence_after();
+            const uint32_t tb = tmem_base + g * GRP_COLS;
+            const uint32_t d_t = tb + COL_D;
+            if (layer == 0) {
+#pragma unroll
+              for (int k = 0; k < KE / 16; ++k)
+                tc_mma_ts(d_t, tb + COL_AE + k * 8,
+                          make_b_desc(img0 + seg_off[0] + k * 2 * lbo, lbo, sbo), idesc, k > 0);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                tc_mma_ts(d_t, tb + COL_AH + k * 8,
+                          make_b_desc(img0 + seg_off[layer] + k * 2 * lbo, lbo, sbo), idesc, k > 0);
+              if (layer == 3) {
+#pragma unroll
+                for (int k = 0; k < KE / 16; ++k)
+                  tc_mma_ts(d_t, tb + COL_AE + k * 8,
+                            make_b_desc(img0 + seg_off[4] + k * 2 * lbo, lbo, sbo), idesc, 1u);
+              }
+            }
+            tc_commit(bar_d + g);
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================================================== workers
+    const int g = (warp - 4) >> 3;            // group 0 | 1 (8 warps each)
+    const int half = ((warp - 4) >> 2) & 1;   // which 64 of the 128 columns this warp owns
+    const int wq = warp & 3;                  // TMEM lane quarter this warp may access
+    const int t = wq * 32 + lane;             // row of the tile == TMEM lane
+    const int tg = t;                         // column / row index inside the half
+    const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
+    const uint32_t tb = tmem_base + g * GRP_COLS + lane_addr;
+    float* beff0 = s_beff + g * 256;
+    float* beff3 = beff0 + 128;
+    float* e_s = s_e + g * 64;
+    float* red = s_red + g * 128;
+    const float* Wx0 = s_aux + AUX_WX0;
+    const float* Wx3 = Wx0 + NR_PAD * 128;
+    const int G = blockIdx.x * 2 + g;
+    uint32_t phd = 0u;
+
+    for (int pt = G; pt < p.n; pt += n_groups) {
+      // ---------------------------------------------- per-point (once per L lights)
+      const f3 x = ld3(p.xyz + (size_t)pt * 3);
+      f3 fr_t, fr_b, fr_n, v_loc;
+      if (KIND == NF_MLP_LVIS) {
+        // embed(xyz_scale * xyz): embedder.py:46-47 (written by half 0)
+        if (half != 0) {
+        } else if (tg < 3) e_s[tg] = (tg == 0 ? x.x : (tg == 1 ? x.y : x.z)) * p.xyz_scale;
+        else if (tg < 3 + 3 * p.n_freqs_a) {
+          int idx = tg - 3, f = idx / 3, c = idx % 3;
+          float xv = (c == 0 ? x.x : (c == 1 ? x.y : x.z)) * p.xyz_scale;
+          float s, co;
+          sincosf(xv * (float)(1 << f), &s, &co);
+          e_s[3 + 6 * f + c] = s;
+          e_s[3 + 6 * f + 3 + c] = co;
+        }
+      } else {
+        if (half == 0 && tg < p.z_dim) e_s[tg] = p.zlat[(size_t)pt * p.z_dim + tg];
+        world2local_dev(ld3(p.normal + (size_t)pt * 3), fr_t, fr_b, fr_n);   // geom.py:119-149
+        f3 v = l2n(ld3(p.cam + (size_t)pt * 3) - x, 1e-6f);                   // shape.py:137-144
+        v_loc = mk3(dot3(fr_t, v), dot3(fr_b, v), dot3(fr_n, v));             // nerfactor.py:418
+      }
+      group_bar256(1 + g);
+      {
+        // half 0 folds the per-point columns into the layer-0 bias, half 1 into the skip layer's
+        const float* Wx = half == 0 ? Wx0 : Wx3;
+        float acc_b = s_aux[AUX_B + (half == 0 ? 0 : 3) * 128 + tg];
+        for (int k = 0; k < p.nr; ++k) acc_b = fmaf(e_s[k], Wx[k * 128 + tg], acc_b);
+        (half == 0 ? beff0 : beff3)[tg] = acc_b;
+      }
+      group_bar256(1 + g);
+
+      for (int c = 0; c < chunks; ++c) {
+        const int li = c * 128 + t;
+        const int lc = li < p.L ? li : p.L - 1;
+        // ------------------------------------------------ per-row embedding -> A_e
+        float mask = 1.f;
+        if (half == 0) {
+          float4 lp = s_lx[lc];
+          f3 d = l2n(mk3(lp.x, lp.y, lp.z) - x, 1e-6f);                       // shape.py:128-135
+          float v[KE];
+#pragma unroll
+          for (int i = 0; i < KE; ++i) v[i] = 0.f;
+          f3 q;
+          int nf;
+          if (KIND == NF_MLP_LVIS) { q = d; nf = 4; }
+          else {
+            f3 l_loc = mk3(dot3(fr_t, d), dot3(fr_b, d), dot3(fr_n, d));      // nerfactor.py:419
+            mask = l_loc.z > 0.f ? 1.f : 0.f;                                 // :429-432
+            q = dir2rusink_dev(l_loc, v_loc);                                 // geom.py:152-192
+            nf = 2;
+          }
+          v[0] = q.x; v[1] = q.y; v[2] = q.z;
+          float sx, cx, sy, cy, sz, cz;
+          sincosf(q.x, &sx, &cx); sincosf(q.y, &sy, &cy); sincosf(q.z, &sz, &cz);
+#pragma unroll
+          for (int f = 0; f < (KIND == NF_MLP_LVIS ? 4 : 2); ++f) {
+            if (f < nf) {
+              v[3 + 6 * f + 0] = sx; v[3 + 6 * f + 1] = sy; v[3 + 6 * f + 2] = sz;
+              v[3 + 6 * f + 3] = cx; v[3 + 6 * f + 4] = cy; v[3 + 6 * f + 5] = cz;
+              // double-angle step to the next octave
+              float nsx = 2.f * sx * cx, ncx = 1.f - 2.f * sx * sx;
+              float nsy = 2.f * sy * cy, ncy = 1.f - 2.f * sy * sy;
+              float nsz = 2.f * sz * cz, ncz = 1.f - 2.f * sz * sz;
+              sx = nsx; cx = ncx; sy = nsy; cy = ncy; sz = nsz; cz = ncz;
+            }
+          }
+          uint32_t pk[KE / 2];
+#pragma unroll
+          for (int i = 0; i < KE / 2; ++i) pk[i] = pack2<BF16, 0>(v[2 * i], v[2 * i + 1]);
+          if (KE == 32) { TC_ST16(tb + COL_AE, pk); }
+          else { TC_ST8(tb + COL_AE, pk); }
+        }
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(bar_a + g);
+
+        // ------------------------------------------------ layers 0..2: epilogue -> A_h
+        for (int layer = 0; layer < 3; ++layer) {
+          const float* bias = layer == 0 ? beff0 : (s_aux + AUX_B + layer * 128);
+          mbar_wait(bar_d + g, phd);
+          phd ^= 1u;
+          tc_fence_after();
+          {
+            const int c2 = half;
+            uint32_t r0[32], r1[32];
+            TC_LD32(r0, tb + COL_D + c2 * 64);
+            TC_LD32(r1, tb + COL_D + c2 * 64 + 32);
+            tc_wait_ld();
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float4 bb = *reinterpret_cast<const float4*>(bias + c2 * 64 + 4 * i);
+              pk[2 * i] = pack2<BF16, 1>(__uint_as_float(r0[4 * i]) + bb.x,
+                                             __uint_as_float(r0[4 * i + 1]) + bb.y);
+              pk[2 * i + 1] = pack2<BF16, 1>(__uint_as_float(r0[4 * i + 2]) + bb.z,
+                                                 __uint_as_float(r0[4 * i + 3]) + bb.w);
+            }
+            TC_ST16(tb + COL_AH + c2 * 32, pk);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float4 bb = *reinterpret_cast<const float4*>(bias + c2 * 64 + 32 + 4 * i);
+              pk[2 * i] = pack2<BF16, 1>(__uint_as_float(r1[4 * i]) + bb.x,
+                                             __uint_as_float(r1[4 * i + 1]) + bb.y);
+              pk[2 * i + 1] = pack2<BF16, 1>(__uint_as_float(r1[4 * i + 2]) + bb.z,
+                                                 __uint_as_float(r1[4 * i + 3]) + bb.w);
+            }
+            TC_ST16(tb + COL_AH + c2 * 32 + 16, pk);
+          }
+          tc_wait_st();
+          tc_fence_before();
+          mbar_arrive(bar_a + g);
+        }
+        // ------------------------------------------------ layer 3 + head
+        mbar_wait(bar_d + g, phd);
+        phd ^= 1u;
+        tc_fence_after();
+        float acc = 0.f;
+        {
+          const int c2 = half;
+          uint32_t r0[32], r1[32];
+          TC_LD32(r0, tb + COL_D + c2 * 64);
+          TC_LD32(r1, tb + COL_D + c2 * 64 + 32);
+          tc_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float h = fmaxf(__uint_as_float(r0[i]) + beff3[c2 * 64 + i], 0.f);
+            acc = fmaf(h, s_aux[AUX_WOUT + c2 * 64 + i], acc);
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float h = fmaxf(__uint_as_float(r1[i]) + beff3[c2 * 64 + 32 + i], 0.f);
+            acc = fmaf(h, s_aux[AUX_WOUT + c2 * 64 + 32 + i], acc);
+          }
+        }
+        // the two halves of a row meet in shared memory; half 0 finishes the row
+        if (half == 1) red[t] = acc;
+        group_bar256(1 + g);
+        if (half == 0) {
+          float o = acc + red[t] + s_aux[AUX_BOUT];
+          o = apply_act(p.out_act, o) * mask;
+          if (li < p.L) p.out[(size_t)pt * p.L + li] = o;
+        }
+      }
+    }
+  }
+
+  // ---------------------------------------------------------------- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS)
+                 : "memory");
+  }
+}
+
+
+
 // ------------------------------------------------------------------ bring-up test
 // One CTA: D[128x128] = A[128xK] * B[128xK]^T with A written to TMEM by tcgen05.st
 // (the layout the epilogue uses) and B in the swizzle-free K-major image.
@@ -519,6 +820,16 @@ int launch_tc(nf_ctx* ctx, const nf_mlp* m, const TcParams& p, cudaStream_t st) 
   int grid = ctx->sm_count;
   int need = (p.n + 1) / 2;
   if (grid > need) grid = need;
+  static const bool ew8 = [] { const char* e = getenv("NF_LVIS_EW8"); return e && e[0] == '1'; }();
+  if (ew8) {   // experimental 8-epilogue-warp variant (see mlp_tc8_kernel)
+    const size_t sm8 = SL::total + 2 * 128 * sizeof(float);
+    NF_CHECK_ARG(ctx, sm8 <= ctx->smem_optin, "shared memory budget exceeded");
+    NF_CUDA(ctx, cudaFuncSetAttribute(mlp_tc8_kernel<KIND, BF16>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm8));
+    mlp_tc8_kernel<KIND, BF16><<<grid, TC8_THREADS, sm8, st>>>(p);
+    NF_LAUNCH_CHECK(ctx);
+    return NF_OK;
+  }
   mlp_tc_kernel<KIND, BF16><<<grid, TC_THREADS, SL::total, st>>>(p);
   NF_LAUNCH_CHECK(ctx);
   return NF_OK;

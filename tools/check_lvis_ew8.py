@@ -1,0 +1,74 @@
+"""Validates and times the 8-epilogue-warp variant of the light-visibility / learned-BRDF tcgen05
+kernel (`mlp_tc8_kernel`, NF_LVIS_EW8=1; csrc/nf_mlp_tc.cu) against the default kernel.
+
+    python tools/check_lvis_ew8.py            # on a B200 (gpurun)
+
+The switch is read once per process, so each variant runs in its own subprocess on the same
+seeded inputs (640 k points x 512 lights for the timing, a ragged 203 x 200 case for edge tiles);
+prints one JSON object: max |difference| (the head's 128-term dot product is summed in two halves
+in the variant, so ~1e-7 is expected, not 0) and the two times."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+WORKER = r'''
+import json, sys, numpy as np, torch
+sys.path.insert(0, %r)
+from nerfactor_b200 import _lib, synth, config as nfconfig
+from nerfactor_b200.models.nerfactor import Model
+from nerfactor_b200.brdf.renderer import gen_light_xyz
+ctx = _lib.default_context()
+out = {}
+for tag, n, lh, lw in (('ragged', 203, 10, 20), ('full', 640000, 16, 32)):
+    params = synth.make_stage_b_params(21, 'learned', light_hw=(lh, lw))
+    m = Model(nfconfig.default_config('nerfactor', light_h=lh), params=params, ctx=ctx, precision='f16')
+    lxyz, lareas = gen_light_xyz(lh, lw)
+    m.set_lights(lxyz.reshape(-1, 3), lareas.reshape(-1)); m.light_res = (lh, lw)
+    b = synth.make_stage_b_batch(22, n, 1, fg_frac=1.0)
+    xyz = torch.as_tensor(b[6]).cuda(); nrm = torch.as_tensor(b[7]).cuda(); cam = torch.as_tensor(b[2]).cuda()
+    z = m._pred_brdf_at(xyz)
+    def t(fn, reps=3):
+        fn(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps): fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+    lv = m._pred_lvis_at(xyz)
+    sp = m._eval_brdf_at(None, None, nrm, None, z, pts=xyz, cam=cam)['spec']
+    out[tag] = {'lvis_ms': t(lambda: m._pred_lvis_at(xyz)),
+                'brdf_ms': t(lambda: m._eval_brdf_at(None, None, nrm, None, z, pts=xyz, cam=cam))}
+    sel = slice(0, min(n, 4096))
+    np.save(sys.argv[1] + '_%%s_lvis.npy' %% tag, lv[sel].cpu().numpy())
+    np.save(sys.argv[1] + '_%%s_spec.npy' %% tag, sp[sel].cpu().numpy())
+print(json.dumps(out))
+''' % ROOT
+
+
+def run(flag, prefix):
+    env = dict(os.environ, NF_LVIS_EW8=flag)
+    r = subprocess.run([sys.executable, '-c', WORKER, prefix], env=env, capture_output=True,
+                       text=True, timeout=600)
+    if r.returncode != 0:
+        return {'error': r.stderr[-600:]}
+    return json.loads([l for l in r.stdout.splitlines() if l.startswith('{')][-1])
+
+
+def main():
+    import numpy as np
+    import tempfile
+    d = tempfile.mkdtemp()
+    res = {'default': run('0', os.path.join(d, 'a')), 'ew8': run('1', os.path.join(d, 'b'))}
+    if 'error' not in res['default'] and 'error' not in res['ew8']:
+        for tag in ('ragged', 'full'):
+            for k in ('lvis', 'spec'):
+                a = np.load(os.path.join(d, 'a_%s_%s.npy' % (tag, k)))
+                b = np.load(os.path.join(d, 'b_%s_%s.npy' % (tag, k)))
+                res['maxdiff_%s_%s' % (tag, k)] = float(np.abs(a - b).max())
+    print(json.dumps(res))
+
+
+if __name__ == '__main__':
+    main()
