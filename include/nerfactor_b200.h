@@ -50,6 +50,9 @@ extern "C" {
 #define NF_PREC_F16 1  /* tcgen05 kind::f16, fp16 operands, fp32 accumulate in TMEM */
 #define NF_PREC_BF16 2 /* tcgen05 kind::f16, bf16 operands, fp32 accumulate in TMEM */
 #define NF_PREC_F16X3 3 /* tcgen05, fp16 hi/lo split of both operands, 3 MMA chains: ~fp32 */
+#define NF_PREC_F16E 4 /* nf_sigma_fwd only: NF_PREC_F16 with the positional encoding kept as an
+                          fp16 hi + lo pair (two K = 64 MMA blocks more per sample, +6.7 % tensor
+                          work); weights and hidden activations are plain fp16                  */
 
 typedef struct nf_ctx nf_ctx;
 typedef struct nf_mlp nf_mlp;

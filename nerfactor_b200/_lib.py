@@ -18,7 +18,7 @@ ERRORS = {-1: 'NF_ERR_INVALID_ARG', -2: 'NF_ERR_UNSUPPORTED', -3: 'NF_ERR_CUDA',
           -4: 'NF_ERR_NO_DEVICE'}
 ACT = {None: 0, 'relu': 1, 'sigmoid': 2, 'softplus': 3}
 KIND = {'point': 0, 'lvis': 1, 'brdf': 2, 'sigma': 3}
-PREC = {'fp32': 0, 'f16': 1, 'bf16': 2, 'f16x3': 3}
+PREC = {'fp32': 0, 'f16': 1, 'bf16': 2, 'f16x3': 3, 'f16e': 4}
 
 # every symbol include/nerfactor_b200.h declares (tests check the .so exports all)
 EXPORTS = [

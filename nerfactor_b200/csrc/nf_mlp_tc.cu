@@ -54,6 +54,7 @@ struct TcParams {
   const float* cam;      // BRDF: [n,3]
   const float* zlat;     // BRDF: [n,z_dim]
   float* out;            // [n, L]
+  int dyn_issue;         // MMA issuer serves the groups in readiness order
 };
 
 // fp32 side block layout (floats): see nf_tc_pack
@@ -173,33 +174,54 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const TcParams p)
       const int nt0 = group_points(0) * chunks, nt1 = group_points(1) * chunks;
       const int nt_max = nt0 > nt1 ? nt0 : nt1;
       uint32_t ph[2] = {0u, 0u};
-      for (int it = 0; it < nt_max; ++it) {
-        for (int layer = 0; layer < 4; ++layer) {
+      auto issue = [&](int g, int layer) {
+        const uint32_t tb = tmem_base + g * GRP_COLS;
+        const uint32_t d_t = tb + COL_D;
+        if (layer == 0) {
+#pragma unroll
+          for (int k = 0; k < KE / 16; ++k)
+            tc_mma_ts(d_t, tb + COL_AE + k * 8,
+                      make_b_desc(img0 + seg_off[0] + k * 2 * lbo, lbo, sbo), idesc, k > 0);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            tc_mma_ts(d_t, tb + COL_AH + k * 8,
+                      make_b_desc(img0 + seg_off[layer] + k * 2 * lbo, lbo, sbo), idesc, k > 0);
+          if (layer == 3) {
+#pragma unroll
+            for (int k = 0; k < KE / 16; ++k)
+              tc_mma_ts(d_t, tb + COL_AE + k * 8,
+                        make_b_desc(img0 + seg_off[4] + k * 2 * lbo, lbo, sbo), idesc, 1u);
+          }
+        }
+        tc_commit(bar_d + g);
+      };
+      if (p.dyn_issue) {
+        // serve whichever group's A operand is ready first (the groups drift apart: per-point
+        // folds, ragged last chunks), instead of strict g0 / g1 alternation
+        int done[2] = {0, 0};                       // layers issued so far per group
+        const int tot[2] = {nt0 * 4, nt1 * 4};
+        while (done[0] < tot[0] || done[1] < tot[1]) {
+#pragma unroll
           for (int g = 0; g < 2; ++g) {
-            if (it >= (g == 0 ? nt0 : nt1)) continue;
-            mbar_wait(bar_a + g, ph[g]);
-            ph[g] ^= 1u;
-            tc_fence_after();
-            const uint32_t tb = tmem_base + g * GRP_COLS;
-            const uint32_t d_t = tb + COL_D;
-            if (layer == 0) {
-#pragma unroll
-              for (int k = 0; k < KE / 16; ++k)
-                tc_mma_ts(d_t, tb + COL_AE + k * 8,
-                          make_b_desc(img0 + seg_off[0] + k * 2 * lbo, lbo, sbo), idesc, k > 0);
-            } else {
-#pragma unroll
-              for (int k = 0; k < 8; ++k)
-                tc_mma_ts(d_t, tb + COL_AH + k * 8,
-                          make_b_desc(img0 + seg_off[layer] + k * 2 * lbo, lbo, sbo), idesc, k > 0);
-              if (layer == 3) {
-#pragma unroll
-                for (int k = 0; k < KE / 16; ++k)
-                  tc_mma_ts(d_t, tb + COL_AE + k * 8,
-                            make_b_desc(img0 + seg_off[4] + k * 2 * lbo, lbo, sbo), idesc, 1u);
-              }
+            if (done[g] < tot[g] && mbar_try_wait(bar_a + g, ph[g])) {
+              ph[g] ^= 1u;
+              tc_fence_after();
+              issue(g, done[g] & 3);
+              ++done[g];
             }
-            tc_commit(bar_d + g);
+          }
+        }
+      } else {
+        for (int it = 0; it < nt_max; ++it) {
+          for (int layer = 0; layer < 4; ++layer) {
+            for (int g = 0; g < 2; ++g) {
+              if (it >= (g == 0 ? nt0 : nt1)) continue;
+              mbar_wait(bar_a + g, ph[g]);
+              ph[g] ^= 1u;
+              tc_fence_after();
+              issue(g, layer);
+            }
           }
         }
       }
@@ -464,33 +486,54 @@ __global__ void __launch_bounds__(TC8_THREADS, 1) mlp_tc8_kernel(const TcParams 
       const int nt0 = group_points(0) * chunks, nt1 = group_points(1) * chunks;
       const int nt_max = nt0 > nt1 ? nt0 : nt1;
       uint32_t ph[2] = {0u, 0u};
-      for (int it = 0; it < nt_max; ++it) {
-        for (int layer = 0; layer < 4; ++layer) {
+      auto issue = [&](int g, int layer) {
+        const uint32_t tb = tmem_base + g * GRP_COLS;
+        const uint32_t d_t = tb + COL_D;
+        if (layer == 0) {
+#pragma unroll
+          for (int k = 0; k < KE / 16; ++k)
+            tc_mma_ts(d_t, tb + COL_AE + k * 8,
+                      make_b_desc(img0 + seg_off[0] + k * 2 * lbo, lbo, sbo), idesc, k > 0);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            tc_mma_ts(d_t, tb + COL_AH + k * 8,
+                      make_b_desc(img0 + seg_off[layer] + k * 2 * lbo, lbo, sbo), idesc, k > 0);
+          if (layer == 3) {
+#pragma unroll
+            for (int k = 0; k < KE / 16; ++k)
+              tc_mma_ts(d_t, tb + COL_AE + k * 8,
+                        make_b_desc(img0 + seg_off[4] + k * 2 * lbo, lbo, sbo), idesc, 1u);
+          }
+        }
+        tc_commit(bar_d + g);
+      };
+      if (p.dyn_issue) {
+        // serve whichever group's A operand is ready first (the groups drift apart: per-point
+        // folds, ragged last chunks), instead of strict g0 / g1 alternation
+        int done[2] = {0, 0};                       // layers issued so far per group
+        const int tot[2] = {nt0 * 4, nt1 * 4};
+        while (done[0] < tot[0] || done[1] < tot[1]) {
+#pragma unroll
           for (int g = 0; g < 2; ++g) {
-            if (it >= (g == 0 ? nt0 : nt1)) continue;
-            mbar_wait(bar_a + g, ph[g]);
-            ph[g] ^= 1u;
-            tc_fence_after();
-            const uint32_t tb = tmem_base + g * GRP_COLS;
-            const uint32_t d_t = tb + COL_D;
-            if (layer == 0) {
-#pragma unroll
-              for (int k = 0; k < KE / 16; ++k)
-                tc_mma_ts(d_t, tb + COL_AE + k * 8,
-                          make_b_desc(img0 + seg_off[0] + k * 2 * lbo, lbo, sbo), idesc, k > 0);
-            } else {
-#pragma unroll
-              for (int k = 0; k < 8; ++k)
-                tc_mma_ts(d_t, tb + COL_AH + k * 8,
-                          make_b_desc(img0 + seg_off[layer] + k * 2 * lbo, lbo, sbo), idesc, k > 0);
-              if (layer == 3) {
-#pragma unroll
-                for (int k = 0; k < KE / 16; ++k)
-                  tc_mma_ts(d_t, tb + COL_AE + k * 8,
-                            make_b_desc(img0 + seg_off[4] + k * 2 * lbo, lbo, sbo), idesc, 1u);
-              }
+            if (done[g] < tot[g] && mbar_try_wait(bar_a + g, ph[g])) {
+              ph[g] ^= 1u;
+              tc_fence_after();
+              issue(g, done[g] & 3);
+              ++done[g];
             }
-            tc_commit(bar_d + g);
+          }
+        }
+      } else {
+        for (int it = 0; it < nt_max; ++it) {
+          for (int layer = 0; layer < 4; ++layer) {
+            for (int g = 0; g < 2; ++g) {
+              if (it >= (g == 0 ? nt0 : nt1)) continue;
+              mbar_wait(bar_a + g, ph[g]);
+              ph[g] ^= 1u;
+              tc_fence_after();
+              issue(g, layer);
+            }
           }
         }
       }
@@ -821,16 +864,19 @@ int launch_tc(nf_ctx* ctx, const nf_mlp* m, const TcParams& p, cudaStream_t st) 
   int need = (p.n + 1) / 2;
   if (grid > need) grid = need;
   static const bool ew8 = [] { const char* e = getenv("NF_LVIS_EW8"); return e && e[0] == '1'; }();
+  static const bool dyn = [] { const char* e = getenv("NF_LVIS_DYN"); return e && e[0] == '1'; }();
+  TcParams pd = p;
+  pd.dyn_issue = dyn ? 1 : 0;
   if (ew8) {   // experimental 8-epilogue-warp variant (see mlp_tc8_kernel)
     const size_t sm8 = SL::total + 2 * 128 * sizeof(float);
     NF_CHECK_ARG(ctx, sm8 <= ctx->smem_optin, "shared memory budget exceeded");
     NF_CUDA(ctx, cudaFuncSetAttribute(mlp_tc8_kernel<KIND, BF16>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm8));
-    mlp_tc8_kernel<KIND, BF16><<<grid, TC8_THREADS, sm8, st>>>(p);
+    mlp_tc8_kernel<KIND, BF16><<<grid, TC8_THREADS, sm8, st>>>(pd);
     NF_LAUNCH_CHECK(ctx);
     return NF_OK;
   }
-  mlp_tc_kernel<KIND, BF16><<<grid, TC_THREADS, SL::total, st>>>(p);
+  mlp_tc_kernel<KIND, BF16><<<grid, TC_THREADS, SL::total, st>>>(pd);
   NF_LAUNCH_CHECK(ctx);
   return NF_OK;
 }

@@ -30,15 +30,26 @@ constexpr int SG_W = 256, SG_DEPTH = 8, SG_SKIP = 4;
 constexpr int COL_P = 0, COL_Q = 128, COL_D0 = 256, COL_D1 = 384;
 constexpr uint32_t SG_LBO = 128 * 16, SG_SBO = 128;
 
-constexpr size_t SG_OFF_RING = 0;
-constexpr size_t SG_OFF_E = SG_OFF_RING + (size_t)SG_NSLOT * SG_SLOT_BYTES;
-constexpr size_t SG_OFF_BIAS = SG_OFF_E + 2 * SG_E_BYTES;          // [8][256] f32
-constexpr size_t SG_OFF_WOUT = SG_OFF_BIAS + 8 * 256 * 4;           // [256] f32
-constexpr size_t SG_OFF_BOUT = SG_OFF_WOUT + 256 * 4;               // [4] f32
-constexpr size_t SG_OFF_PART = SG_OFF_BOUT + 16;                    // [128] f32 head partials
-constexpr size_t SG_OFF_BAR = SG_OFF_PART + 128 * 4;
-// barriers: full[5] empty[5] d_full[2] a_ready[2] e_ready[2] e_free[2] bar_w  = 19
-constexpr size_t SG_SMEM = SG_OFF_BAR + 32 * 8;
+// Shared-memory layout of sigma_tc_kernel<.., NSLOT, ESPLIT>.  ESPLIT = 1 ("f16e"): the
+// positional encoding is kept as TWO 16-bit images, hi = rn16(e) and lo = rn16(e - hi), and
+// layer 0 / the skip layer contract both with the same weight chunk (one extra K = 64 MMA
+// block each, +6.7 % tensor work): the 2^-12 rounding of the sin / cos features -- the
+// dominant term of the fp16 error on a sharp density field, DESIGN.md section 5 -- goes away.
+// The second image pair costs 32 KB, so that mode runs with a 4-slot weight ring.
+template <int NSLOT, int ESPLIT>
+struct SgLayout {
+  static constexpr size_t off_ring = 0;
+  static constexpr size_t off_e = off_ring + (size_t)NSLOT * SG_SLOT_BYTES;   // hi images [2]
+  static constexpr size_t off_elo = off_e + 2 * SG_E_BYTES;                     // lo images [2]
+  static constexpr size_t off_bias = off_elo + (ESPLIT ? 2 * SG_E_BYTES : 0);  // [8][256] f32
+  static constexpr size_t off_wout = off_bias + 8 * 256 * 4;                    // [256] f32
+  static constexpr size_t off_bout = off_wout + 256 * 4;                        // [4] f32
+  static constexpr size_t off_part = off_bout + 16;                             // [128] f32 head partials
+  static constexpr size_t off_bar = off_part + 128 * 4;
+  // barriers: full[NSLOT] empty[NSLOT] d_full[2] a_ready[2] e_ready[2] e_free[2] bar_w
+  static constexpr size_t total = off_bar + 32 * 8;
+};
+static_assert(SgLayout<5, 0>::total <= 232448 && SgLayout<4, 1>::total <= 232448, "smem budget");
 
 struct SigmaTcParams {
   const uint8_t* blob;
@@ -58,18 +69,21 @@ struct SigmaTcParams {
 // bytes of the weight chunk for (layer, part): part 0/1 = hidden K-blocks, part 2 = input part
 __device__ __forceinline__ uint32_t part_bytes(int part) { return part == 2 ? 16384u : 32768u; }
 
-template <int BF16, int CL>
+template <int BF16, int CL, int NSLOT, int ESPLIT>
 __global__ void __launch_bounds__(SG_THREADS, 1) sigma_tc_kernel(const SigmaTcParams p) {
+  using SL = SgLayout<NSLOT, ESPLIT>;
+  constexpr int SG_NSLOT = NSLOT;       // shadows the file-level default inside this kernel
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* s_ring = smem + SG_OFF_RING;
-  uint8_t* s_e = smem + SG_OFF_E;
-  const float* s_bias = reinterpret_cast<const float*>(smem + SG_OFF_BIAS);
-  const float* s_wout = reinterpret_cast<const float*>(smem + SG_OFF_WOUT);
-  const float* s_bout = reinterpret_cast<const float*>(smem + SG_OFF_BOUT);
-  float* s_part = reinterpret_cast<float*>(smem + SG_OFF_PART);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SG_OFF_BAR);
-  uint64_t* bar_full = bars;            // [5]
-  uint64_t* bar_empty = bars + 5;       // [5]
+  uint8_t* s_ring = smem + SL::off_ring;
+  uint8_t* s_e = smem + SL::off_e;
+  uint8_t* s_elo = smem + SL::off_elo;
+  const float* s_bias = reinterpret_cast<const float*>(smem + SL::off_bias);
+  const float* s_wout = reinterpret_cast<const float*>(smem + SL::off_wout);
+  const float* s_bout = reinterpret_cast<const float*>(smem + SL::off_bout);
+  float* s_part = reinterpret_cast<float*>(smem + SL::off_part);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SL::off_bar);
+  uint64_t* bar_full = bars;            // [<= 5]
+  uint64_t* bar_empty = bars + 5;       // [<= 5]
   uint64_t* bar_dfull = bars + 10;      // [2]
   uint64_t* bar_aready = bars + 12;     // [2]
   uint64_t* bar_eready = bars + 14;     // [2]
@@ -105,7 +119,7 @@ __global__ void __launch_bounds__(SG_THREADS, 1) sigma_tc_kernel(const SigmaTcPa
   if (threadIdx.x == 0) {
     const uint32_t aux_bytes = 8 * 256 * 4 + 256 * 4 + 16;
     mbar_expect_tx(bar_w, aux_bytes);
-    bulk_g2s(smem + SG_OFF_BIAS, p.blob + p.off_aux, aux_bytes, bar_w);
+    bulk_g2s(smem + SL::off_bias, p.blob + p.off_aux, aux_bytes, bar_w);
   }
   mbar_wait(bar_w, 0);
 
@@ -140,7 +154,7 @@ __global__ void __launch_bounds__(SG_THREADS, 1) sigma_tc_kernel(const SigmaTcPa
     // ============================================================== MMA issuer
     if (lane == 0) {
       const uint32_t idesc = make_idesc(BF16, 128);
-      const uint32_t ring0 = smem_u32(s_ring), e0 = smem_u32(s_e);
+      const uint32_t ring0 = smem_u32(s_ring), e0 = smem_u32(s_e), elo0 = smem_u32(s_elo);
       uint32_t fill = 0, na[2] = {0u, 0u};
       auto wait_a = [&](int h) { mbar_wait(bar_aready + h, na[h] & 1); ++na[h]; };
       for (int it = 0; it < ntile; ++it) {
@@ -167,6 +181,13 @@ __global__ void __launch_bounds__(SG_THREADS, 1) sigma_tc_kernel(const SigmaTcPa
                   tc_mma_ss(d_t, make_b_desc(a0 + ks * 2 * SG_LBO, SG_LBO, SG_SBO),
                             make_b_desc(b0 + ks * 2 * SG_LBO, SG_LBO, SG_SBO), idesc,
                             (l == 0 && ks == 0) ? 0u : 1u);
+                if (ESPLIT) {          // + lo(e) . W with the same weight chunk
+                  const uint32_t al = elo0 + eb * SG_E_BYTES;
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks)
+                    tc_mma_ss(d_t, make_b_desc(al + ks * 2 * SG_LBO, SG_LBO, SG_SBO),
+                              make_b_desc(b0 + ks * 2 * SG_LBO, SG_LBO, SG_SBO), idesc, 1u);
+                }
               } else {
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks)
@@ -312,6 +333,22 @@ __global__ void __launch_bounds__(SG_THREADS, 1) sigma_tc_kernel(const SigmaTcPa
         q.z = pack2<BF16, 0>(v[8 * j + 4], v[8 * j + 5]);
         q.w = pack2<BF16, 0>(v[8 * j + 6], v[8 * j + 7]);
         *reinterpret_cast<uint4*>(e + ((size_t)j * 128 + t) * 16) = q;
+        if (ESPLIT) {
+          // residual of the 16-bit rounding, again as 16 bit: e = hi + lo to ~2^-22 relative
+          float r[8];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t w = i == 0 ? q.x : (i == 1 ? q.y : (i == 2 ? q.z : q.w));
+            r[2 * i] = v[8 * j + 2 * i] - unpack_lo<BF16>(w);
+            r[2 * i + 1] = v[8 * j + 2 * i + 1] - unpack_hi<BF16>(w);
+          }
+          uint4 ql;
+          ql.x = pack2<BF16, 0>(r[0], r[1]);
+          ql.y = pack2<BF16, 0>(r[2], r[3]);
+          ql.z = pack2<BF16, 0>(r[4], r[5]);
+          ql.w = pack2<BF16, 0>(r[6], r[7]);
+          *reinterpret_cast<uint4*>(s_elo + eb * SG_E_BYTES + ((size_t)j * 128 + t) * 16) = ql;
+        }
       }
       fence_proxy_async();
       mbar_arrive(bar_eready + eb);
@@ -662,9 +699,10 @@ uint16_t bf_bits(float f) {
   return b;
 }
 
-template <int BF16, int CL>
+template <int BF16, int CL, int NSLOT, int ESPLIT>
 int launch_sigma(nf_ctx* ctx, const SigmaTcParams& p, int grid, cudaStream_t st) {
-  NF_CUDA(ctx, cudaFuncSetAttribute(sigma_tc_kernel<BF16, CL>,
+  constexpr size_t SG_SMEM = SgLayout<NSLOT, ESPLIT>::total;
+  NF_CUDA(ctx, cudaFuncSetAttribute(sigma_tc_kernel<BF16, CL, NSLOT, ESPLIT>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM));
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -679,7 +717,7 @@ int launch_sigma(nf_ctx* ctx, const SigmaTcParams& p, int grid, cudaStream_t st)
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  NF_CUDA(ctx, cudaLaunchKernelEx(&cfg, sigma_tc_kernel<BF16, CL>, p));
+  NF_CUDA(ctx, cudaLaunchKernelEx(&cfg, sigma_tc_kernel<BF16, CL, NSLOT, ESPLIT>, p));
   return NF_OK;
 }
 
@@ -767,7 +805,9 @@ int nf_tc_sigma_launch(nf_ctx* ctx, const nf_mlp* m, const float* rayo, const fl
                        const float* z, int n_rays, int S, const float* bbox_host, float* sigma,
                        int precision, cudaStream_t st) {
   NF_CHECK_ARG(ctx, m->dev, "network not uploaded (call nf_mlp_upload first)");
-  NF_CHECK_ARG(ctx, precision == NF_PREC_F16 || precision == NF_PREC_BF16, "bad precision");
+  NF_CHECK_ARG(ctx, precision == NF_PREC_F16 || precision == NF_PREC_BF16 ||
+                        precision == NF_PREC_F16E, "bad precision");
+  const bool esplit = precision == NF_PREC_F16E;
   if (m->tc_bytes == 0)
     return nf_set_error(ctx, NF_ERR_UNSUPPORTED,
                         "no tcgen05 kernel for this sigma network (need 8 x 256, skip 4, F = 10); "
@@ -791,7 +831,7 @@ int nf_tc_sigma_launch(nf_ctx* ctx, const nf_mlp* m, const float* rayo, const fl
   }
   if (const char* e = getenv("NF_SIGMA_PAIR")) pair_env = atoi(e);
   const bool bf = precision == NF_PREC_BF16;
-  if (pair_env) {
+  if (pair_env && !esplit) {
     int grid2 = ctx->sm_count / 2 * 2;
     if (tiles < grid2) grid2 = (int)((tiles + 1) / 2 * 2);
     p.tiles_per_cta = (int)((tiles + grid2 - 1) / grid2);
@@ -802,7 +842,16 @@ int nf_tc_sigma_launch(nf_ctx* ctx, const nf_mlp* m, const float* rayo, const fl
   int grid = ctx->sm_count / cl * cl;
   if (tiles < grid) grid = (int)((tiles + cl - 1) / cl * cl);
   p.tiles_per_cta = (int)((tiles + grid - 1) / grid);
-  if (cl == 1) return bf ? launch_sigma<1, 1>(ctx, p, grid, st) : launch_sigma<0, 1>(ctx, p, grid, st);
-  if (cl == 2) return bf ? launch_sigma<1, 2>(ctx, p, grid, st) : launch_sigma<0, 2>(ctx, p, grid, st);
-  return bf ? launch_sigma<1, 4>(ctx, p, grid, st) : launch_sigma<0, 4>(ctx, p, grid, st);
+  // NF_PREC_F16E: hi/lo-split positional encoding (4-slot ring); NF_SIGMA_NSLOT=4 runs the
+  // plain kernels on the 4-slot ring too (tuning / A-B timing only)
+  int nslot = esplit ? 4 : 5;
+  if (const char* e = getenv("NF_SIGMA_NSLOT")) { if (atoi(e) == 4) nslot = 4; }
+#define NF_SG(B, C)                                                                         \
+  (esplit ? launch_sigma<B, C, 4, 1>(ctx, p, grid, st)                                      \
+          : (nslot == 4 ? launch_sigma<B, C, 4, 0>(ctx, p, grid, st)                        \
+                        : launch_sigma<B, C, 5, 0>(ctx, p, grid, st)))
+  if (cl == 1) return bf ? NF_SG(1, 1) : NF_SG(0, 1);
+  if (cl == 2) return bf ? NF_SG(1, 2) : NF_SG(0, 2);
+  return bf ? NF_SG(1, 4) : NF_SG(0, 4);
+#undef NF_SG
 }

@@ -105,6 +105,18 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   return d;
 }
 
+// the two 16-bit values of a pair register back as fp32 (exact)
+template <int BF16>
+__device__ __forceinline__ float unpack_lo(uint32_t w) {
+  if (BF16) return __uint_as_float(w << 16);
+  return __half2float(__ushort_as_half((unsigned short)(w & 0xFFFFu)));
+}
+template <int BF16>
+__device__ __forceinline__ float unpack_hi(uint32_t w) {
+  if (BF16) return __uint_as_float(w & 0xFFFF0000u);
+  return __half2float(__ushort_as_half((unsigned short)(w >> 16)));
+}
+
 // K-major, swizzle-free shared-memory operand descriptor (cute UMMA::SmemDescriptor):
 // core matrix = 8 rows x 16 bytes, rows 16 B apart; SBO = bytes between 8-row groups
 // along N, LBO = bytes between core matrices along K.

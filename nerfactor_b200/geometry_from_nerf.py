@@ -55,9 +55,11 @@ def compute_depth_and_normal(model, rayo, rayd, config, scene_bbox=None, precisi
     w, _, _, _, _ = _lib.composite(ctx, sigma, z, rayo, rayd, want_surf=False)
     z = _lib.gen_z_fine(ctx, z, w, n_f)
     prec = precision or model.precision
+    # the forward + input-gradient kernel has no split-encoding variant: 'f16e' -> 'f16' there
+    prec_n = {'f16e': 'f16'}.get(prec, prec)
     sigma, normal = _lib.sigma_normal_fwd(ctx, model.packed_sigma(True), rayo, rayd, z,
                                           parse_bbox(scene_bbox),
-                                          prec if prec in ('fp32', 'f16', 'bf16') else 'fp32')
+                                          prec_n if prec_n in ('fp32', 'f16', 'bf16') else 'fp32')
     _, occu, depth, _, exp_normal = _lib.composite(
         ctx, sigma, z, rayo, rayd, normal=normal, want_weights=False, want_surf=False)
     return occu, depth, exp_normal
@@ -159,8 +161,9 @@ def _parse_args(argv=None):
     ap.add_argument('--spp', type=int, default=1)
     ap.add_argument('--fps', type=int, default=12)
     ap.add_argument('--debug', action='store_true')
-    ap.add_argument('--precision', default='f16', choices=['f16', 'bf16', 'fp32'],
-                    help="'fp32' = CUDA-core kernels throughout (tight parity), else tcgen05")
+    ap.add_argument('--precision', default='f16e', choices=['f16e', 'f16', 'bf16', 'fp32'],
+                    help="'fp32' = CUDA-core kernels throughout (tight parity), else tcgen05; "
+                         "'f16e' = fp16 operands with the positional encoding as an fp16 hi + lo pair")
     return ap.parse_args(argv)
 
 

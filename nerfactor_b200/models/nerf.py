@@ -104,6 +104,7 @@ class Model(NerfVis, BaseModel):
         precision 'fp32': layer-by-layer FP32 Dense kernels on materialised activations (the
         tight-parity path); 'f16' / 'bf16': one fused tcgen05 kernel."""
         prec = precision or self.precision
+        prec = {'f16e': 'f16'}.get(prec, prec)        # colour kernel: no split-encoding variant
         if prec != 'fp32':
             return _lib.nerf_fwd(self.ctx, self.packed_nerf(use_fine), rayo, rayd, z, prec)
         from .. import autodiff as ad

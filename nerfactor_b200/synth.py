@@ -54,9 +54,15 @@ def embed_dims(n_freqs, in_dims=3):
 
 def make_stage_b_params(seed=0, brdf='microfacet', light_hw=(16, 32), width=128,
                         depth=4, skip_at=2, n_freqs_xyz=10, n_freqs_ldir=4,
-                        n_freqs_rusink=2, z_dim=3, bias_std=0.05):
+                        n_freqs_rusink=2, z_dim=3, bias_std=0.05, xyz_freq_decay=0.0):
     """Random-init NeRFactor networks (nerfactor.py:128-167, shape.py:79-94,
-    brdf.py:57-66, nerfactor_microfacet.py:108-114) + light (nerfactor.py:367-375)."""
+    brdf.py:57-66, nerfactor_microfacet.py:108-114) + light (nerfactor.py:367-375).
+
+    `xyz_freq_decay` d > 0 scales the weights that read octave f of the xyz encoding by
+    2^(-d f) (layer 0 and the skip layer): the spectrum of a *trained* network, whose outputs
+    vary smoothly with the surface point.  With d = 0 (Keras init) the outputs change by O(1)
+    when xyz moves by 2^-9, which makes any comparison across two Stage-A implementations
+    meaningless; end-to-end tests use d = 1."""
     rng = np.random.default_rng(seed)
     dx, dl, dr = embed_dims(n_freqs_xyz), embed_dims(n_freqs_ldir), \
         embed_dims(n_freqs_rusink)
@@ -77,6 +83,15 @@ def make_stage_b_params(seed=0, brdf='microfacet', light_hw=(16, 32), width=128,
         p['brdf_mlp'] = trunk(z_dim + dr)
         p['brdf_out'] = init_mlp(rng, width, [1], ['softplus'], None, bias_std)
     p['light'] = rng.uniform(0., 1., size=light_hw + (3,)).astype(np.float32)
+    if xyz_freq_decay > 0:
+        for name in ('normal_mlp', 'lvis_mlp', 'albedo_mlp', 'brdf_z_mlp'):
+            layers = p[name]['layers']
+            for li, row0 in ((0, 0), (skip_at + 1, width)):
+                W, b = layers[li]
+                W = W.copy()
+                for f in range(n_freqs_xyz):
+                    W[row0 + 3 + 6 * f:row0 + 9 + 6 * f] *= 2.0 ** (-xyz_freq_decay * f)
+                layers[li] = (W, b)
     return p
 
 
@@ -234,3 +249,39 @@ def write_merl_npz(root, names=('alum-bronze', 'blue-rubber', 'gold-paint'), n_r
                      ims=128, spp=1, rusink=r, refl=refl)
     np.savez(os.path.join(root, 'test.npz'), envmap_h=16, ims=128, spp=1, rusink=coords(n_rows))
     return list(names)
+
+
+def make_blob_nerf_params(seed=0, radius=1.0, sharpness=6.0, gain=37.3, noise=0.35,
+                          width=256, enc_depth=8, n_freqs_xyz=10):
+    """The analytic 'sphere-like' density field of SURVEY.md 8d inside the reference
+    architecture (models/nerf.py:53-71), for tests where depth has to be well-conditioned:
+
+        sigma(x) = relu(gain * carry^7 * relu(sharpness * (sum_i cos(x_i) - c)) + noise-net(x) - 1)
+
+    `sum_i cos(x_i)` is three columns of the positional encoding (octave 0), so its level set
+    through (radius, 0, 0) -- a rounded sphere -- is computed by unit 0 of layer 0; units 0 of
+    the other layers carry it to the head with a non-dyadic weight (so 16-bit operand rounding is
+    exercised at every layer), and the remaining 255 units are a random-init network whose
+    output perturbs sigma by about +-`noise` (empty space stays empty: head bias -1).  Coarse and
+    fine networks are the same field with different random parts."""
+    p = make_nerf_params(seed, width, enc_depth, n_freqs_xyz, sigma_gain=1.0, sigma_bias=0.0)
+    c = 2.0 + math.cos(radius)
+    carry = 0.973
+    for pref in ('coarse_', 'fine_'):
+        layers = p[pref + 'enc']['layers']
+        for li, (W, b) in enumerate(layers):
+            W, b = W.copy(), b.copy()
+            W[:, 0] = 0.
+            if li == 0:
+                W[6:9, 0] = sharpness                    # cos(2^0 x), cos(2^0 y), cos(2^0 z)
+                b[0] = -sharpness * c
+            else:
+                W[0, 0] = carry
+                b[0] = 0.
+            layers[li] = (W.astype(np.float32), b.astype(np.float32))
+        w_out, _ = p[pref + 'sigma_out']['layers'][0]
+        w_out = w_out.copy() * noise * 4.0
+        w_out[0, 0] = gain / carry ** (enc_depth - 1)
+        p[pref + 'sigma_out']['layers'][0] = (w_out.astype(np.float32),
+                                              np.full((1,), -1.0, np.float32))
+    return p

@@ -405,7 +405,10 @@ class NerfTrainer(Trainer):
 
     Random draws of the reference (tf.random.uniform for the stratified / importance samples,
     nerf.py:133, util/math.py:81; tf.random.normal for the density noise, nerf.py:196) are explicit
-    optional inputs (`perturb_u`, `fine_u`, `sigma_noise`), drawn with torch when not given."""
+    optional inputs (`perturb_u`, `fine_u`, `sigma_noise`), drawn with torch when not given.
+    `z_all` replays the sorted union of coarse and importance samples itself (they carry no
+    gradient): the inverse-CDF lookup is discontinuous in the coarse weights, so a comparison of
+    gradients with another implementation fixes the samples and leaves the lookup out."""
 
     def __init__(self, model, config=None, world_size=1, rank=0, precision=None):
         super().__init__(model, config, world_size, rank, precision or 'fp32')
@@ -478,7 +481,8 @@ class NerfTrainer(Trainer):
         return v0 + (u - c0) / denom * (v1 - v0)
 
     # ---- step ---------------------------------------------------------------------
-    def forward(self, flat, batch, mode='train', perturb_u=None, fine_u=None, sigma_noise=None):
+    def forward(self, flat, batch, mode='train', perturb_u=None, fine_u=None, sigma_noise=None,
+                z_all=None):
         """-> (per-ray loss [N], {'coarse': rgb, 'fine': rgb})."""
         m, dev = self.model, self.device
         views = self.views(flat)
@@ -504,15 +508,20 @@ class NerfTrainer(Trainer):
         loss, pred = mse(rgb_c), {'coarse': rgb_c, 'fine': None}
         if self.n_f > 0:
             with torch.no_grad():                                   # tf.stop_gradient, nerf.py:143
-                if fine_u is not None:
-                    u = to_device(fine_u, dev)
-                elif perturb:
-                    u = torch.rand((n, self.n_f), device=dev)
+                if z_all is not None:
+                    z_all = to_device(z_all, dev).contiguous()
+                    assert z_all.shape == (n, self.n_c + self.n_f)
                 else:
-                    u = torch.linspace(0., 1., self.n_f, device=dev)[None, :].expand(n, self.n_f)
-                z_f = self._inv_transform_sample(.5 * (z[:, 1:] + z[:, :-1]), w[:, 1:-1].detach(),
-                                                 self.n_f, u.contiguous())
-                z_all = torch.sort(torch.cat((z, z_f), -1), -1).values
+                    if fine_u is not None:
+                        u = to_device(fine_u, dev)
+                    elif perturb:
+                        u = torch.rand((n, self.n_f), device=dev)
+                    else:
+                        u = torch.linspace(0., 1., self.n_f, device=dev)[None, :].expand(n, self.n_f)
+                    z_f = self._inv_transform_sample(.5 * (z[:, 1:] + z[:, :-1]),
+                                                     w[:, 1:-1].detach(), self.n_f, u.contiguous())
+                    z_all = torch.sort(torch.cat((z, z_f), -1), -1).values
+            self.last_z_all = z_all               # sample depths of the fine pass (diagnostics)
             rgb_f, _ = self._accumulate(self._eval(views, 'fine_', rayo, rayd, z_all), z_all, rayd,
                                         sn[1])
             loss = loss + mse(rgb_f)

@@ -210,12 +210,20 @@ def run_nerf_train_gradients(seed_nerf, n_rays, out_name):
         rgb = rng.uniform(0, 1, (n_rays, 3)).astype(np.float32)
         batch = (None, None, t32(rayo), t32(rayd), t32(rgb))
         tf.random.set_seed(31337)
+        recorded = {}
+        orig_gen_z_fine = NerfModel.gen_z_fine          # record what the reference sampled
+
+        def recording_gen_z_fine(*a, **k):
+            recorded['z_all'] = orig_gen_z_fine(*a, **k)
+            return recorded['z_all']
+        NerfModel.gen_z_fine = staticmethod(recording_gen_z_fine)
         with tf.GradientTape() as tape:
             pred, gt, loss_kwargs, _ = model(batch, mode='train')
             loss_kwargs['keep_batch'] = True
             per_example_loss = model.compute_loss(pred, gt, **loss_kwargs)
             weighted_loss = tf.nn.compute_average_loss(per_example_loss,
                                                        global_batch_size=n_rays)
+        NerfModel.gen_z_fine = staticmethod(orig_gen_z_fine)
         variables = model.trainable_variables
         grads = tape.gradient(weighted_loss, variables)
         tf.random.set_seed(31337)                       # replay the draws in call order
@@ -226,6 +234,7 @@ def run_nerf_train_gradients(seed_nerf, n_rays, out_name):
         out = {'seed_nerf': seed_nerf, 'n_c': n_c, 'n_f': n_f, 'noise_std': noise_std,
                'rayo': rayo, 'rayd': rayd, 'rgb': rgb, 'perturb_u': u1.numpy(),
                'fine_u': u2.numpy(), 'noise_coarse': g1.numpy(), 'noise_fine': g2.numpy(),
+               'z_all': recorded['z_all'].detach().numpy(),
                'pred_coarse': pred['coarse'].numpy(), 'pred_fine': pred['fine'].numpy(),
                'per_example_loss': per_example_loss.numpy()}
         owner = {}

@@ -112,19 +112,35 @@ def test_nerf_trainer_vs_reference_train_step(ctx, golden_dir):
                  sigma_noise=(g['noise_coarse'], g['noise_fine']))
     with torch.no_grad():
         _, pred = tr.forward(tr.flat, batch, 'train', **draws)
+        z_mine = tr.last_z_all.cpu().numpy()
     assert np.abs(pred['coarse'].cpu().numpy() - g['pred_coarse']).max() < 1e-5
+    # own importance sampling: the inverse-CDF lookup is discontinuous in the coarse weights, so
+    # single samples may land in a neighbouring bin; the bulk must coincide with the reference's
+    assert np.median(np.abs(z_mine - g['z_all'])) < 1e-5
     d = np.abs(pred['fine'].cpu().numpy() - g['pred_fine'])
-    assert d.max() < 5e-4 and np.median(d) < 1e-5      # importance sampling: see the CPU test
-    loss, grad = tr.loss_and_grad(batch, **draws)
-    assert np.allclose(loss.cpu().numpy(), g['per_example_loss'], atol=1e-4, rtol=2e-3)
+    assert d.max() < 5e-4 and np.median(d) < 1e-5
+    # gradients: replay the reference's recorded samples (they carry no gradient, nerf.py:143), so
+    # the lookup's discontinuity is out of the comparison and the bound can be tight
+    replay = dict(draws, z_all=g['z_all'])
+    with torch.no_grad():
+        _, pred = tr.forward(tr.flat, batch, 'train', **replay)
+    assert np.abs(pred['fine'].cpu().numpy() - g['pred_fine']).max() < 2e-5
+    loss, grad = tr.loss_and_grad(batch, **replay)
+    assert np.allclose(loss.cpu().numpy(), g['per_example_loss'], atol=2e-5, rtol=1e-4)
     gv = tr.views(grad)
     keys = [k for k in g.files if k.startswith('grad/')]
     assert len(keys) == len(gv) == 48
+    worst = 0.
     for k in keys:
         _, net, li, kind = k.split('/')
         want = g[k].astype(np.float32)
         got = gv[(net, int(li), kind)].cpu().numpy()
-        assert np.abs(got - want).max() <= 5e-3 * max(np.abs(want).max(), 1e-8), k
+        # big kernels are stored as fp16 in the fixture (2^-11 of the element), else fp32
+        rel = 1e-3
+        err = np.abs(got - want).max() / max(np.abs(want).max(), 1e-8)
+        worst = max(worst, err)
+        assert err <= rel, (k, err)
+    print('nerf trainer: worst gradient error / tensor max = %.2e' % worst)
     l0 = float(tr.train_step(batch, **draws))
     for _ in range(5):
         l1 = float(tr.train_step(batch, **draws))

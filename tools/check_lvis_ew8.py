@@ -47,10 +47,10 @@ print(json.dumps(out))
 ''' % ROOT
 
 
-def run(flag, prefix):
-    env = dict(os.environ, NF_LVIS_EW8=flag)
+def run(flag, prefix, dyn='0'):
+    env = dict(os.environ, NF_LVIS_EW8=flag, NF_LVIS_DYN=dyn)
     r = subprocess.run([sys.executable, '-c', WORKER, prefix], env=env, capture_output=True,
-                       text=True, timeout=600)
+                       text=True, timeout=240)
     if r.returncode != 0:
         return {'error': r.stderr[-600:]}
     return json.loads([l for l in r.stdout.splitlines() if l.startswith('{')][-1])
@@ -60,7 +60,16 @@ def main():
     import numpy as np
     import tempfile
     d = tempfile.mkdtemp()
-    res = {'default': run('0', os.path.join(d, 'a')), 'ew8': run('1', os.path.join(d, 'b'))}
+    res = {'default': run('0', os.path.join(d, 'a')), 'ew8': run('1', os.path.join(d, 'b')),
+           'default_dyn': run('0', os.path.join(d, 'c'), '1'),
+           'ew8_dyn': run('1', os.path.join(d, 'e'), '1')}
+    for name, pre in (('default_dyn', 'c'), ('ew8_dyn', 'e')):
+        if 'error' not in res['default'] and 'error' not in res[name]:
+            for tag in ('ragged', 'full'):
+                for k in ('lvis', 'spec'):
+                    a = np.load(os.path.join(d, 'a_%s_%s.npy' % (tag, k)))
+                    b = np.load(os.path.join(d, '%s_%s_%s.npy' % (pre, tag, k)))
+                    res['maxdiff_%s_%s_%s' % (name, tag, k)] = float(np.abs(a - b).max())
     if 'error' not in res['default'] and 'error' not in res['ew8']:
         for tag in ('ragged', 'full'):
             for k in ('lvis', 'spec'):
