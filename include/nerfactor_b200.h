@@ -165,6 +165,16 @@ int nf_integrate_fwd(nf_ctx* ctx, const nf_integrate_args* args, void* stream);
 int nf_integrate_olat_fwd(nf_ctx* ctx, const nf_integrate_args* args, float olat_inten,
                           float ambient, float* rgb_olat_d, void* stream);
 
+/* Microfacet.__call__ (brdf/microfacet/microfacet.py:30-72) as a standalone op for callers that
+ * use the class directly: brdf[n, L, 3] = GGX specular (achromatic, view-side G, f0) + albedo/pi
+ * for caller-supplied directions pts2l[n, L, 3], pts2c[n, 3] and normals (all normalised inside
+ * with eps 1e-6, as the reference does).  albedo_d NULL -> ones; rough_d NULL -> default_rough.
+ * (The renderer, nf_integrate_fwd, fuses the same lobe and never builds [n, L, 3].)            */
+int nf_microfacet_brdf_fwd(nf_ctx* ctx, const float* pts2l_d, const float* pts2c_d,
+                           const float* normal_d, const float* albedo_d, const float* rough_d,
+                           int n, int n_lights, float default_rough, int lambert_only, float f0,
+                           float* brdf_d, void* stream);
+
 /* ---- Stage A: rays, sigma march, compositing --------------------------------
  * rayo/rayd[h*w, 3] (fp64 math, fp32 store, ray n = y*w + x, no half-pixel offset)
  * replaces Dataset._gen_rays nerfactor/datasets/nerf.py:172-193 (ndc=False, spp=1).
@@ -279,6 +289,12 @@ int nf_selftest_umma(nf_ctx* ctx, const float* a_d, const float* b_d, int K,
 /* Same through one CTA-pair MMA (cta_group::2): out[256,128] = a[256,K] * b[128,K]^T.   */
 int nf_selftest_umma2(nf_ctx* ctx, const float* a_d, const float* b_d, int K, float* out_d,
                       void* stream);
+
+/* TMEM read / write throughput on one SM (tcgen05.ld / .st), alone or under a concurrent
+ * tcgen05.mma stream: out_d[0] = reader cycles, out_d[1] = MMA-stream cycles (device int64[4]).
+ * mode bits: 1 loads, 2 stores, 4 MMA stream, 8 loads as .x16, 16 MMA N = 256.               */
+int nf_selftest_tmem(nf_ctx* ctx, int reader_warps, int iters, int mma_iters, int mode,
+                     long long* out_d, void* stream);
 
 #ifdef __cplusplus
 }

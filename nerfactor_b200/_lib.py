@@ -29,7 +29,7 @@ EXPORTS = [
     'nf_sigma_fwd', 'nf_sigma_normal_fwd', 'nf_mlp_attach_rgb', 'nf_nerf_fwd', 'nf_composite', 'nf_gen_z_fine',
     'nf_lvis_rays', 'nf_selftest_umma', 'nf_selftest_umma2', 'nf_dense_fwd',
     'nf_dense_fwd_workspace_bytes', 'nf_dense_bwd_workspace_bytes',
-    'nf_dense_bwd', 'nf_adam_amsgrad_step']
+    'nf_dense_bwd', 'nf_adam_amsgrad_step', 'nf_microfacet_brdf_fwd', 'nf_selftest_tmem']
 
 
 class NfError(RuntimeError):
@@ -92,6 +92,7 @@ def load_library():
     lib.nf_brdf_learned_fwd.argtypes = [vp, vp, vp, vp, vp, vp, i, vp, i, vp, i, vp]
     lib.nf_integrate_fwd.argtypes = [vp, C.POINTER(IntegrateArgs), vp]
     lib.nf_integrate_olat_fwd.argtypes = [vp, C.POINTER(IntegrateArgs), f, f, vp, vp]
+    lib.nf_microfacet_brdf_fwd.argtypes = [vp, vp, vp, vp, vp, vp, i, i, f, i, f, vp, vp]
     lib.nf_gen_rays.argtypes = [vp, C.POINTER(d), d, i, i, i, vp, vp, vp]
     lib.nf_gen_z.argtypes = [vp, f, f, i, i, i, vp, vp, vp]
     lib.nf_sigma_fwd.argtypes = [vp, vp, vp, vp, vp, i, i, C.POINTER(f), vp, i, vp]
@@ -103,6 +104,7 @@ def load_library():
     lib.nf_lvis_rays.argtypes = [vp, vp, vp, i, vp, i, vp, vp, vp, vp]
     lib.nf_selftest_umma.argtypes = [vp, vp, vp, i, i, vp, vp]
     lib.nf_selftest_umma2.argtypes = [vp, vp, vp, i, vp, vp]
+    lib.nf_selftest_tmem.argtypes = [vp, i, i, i, i, vp, vp]
     ll = C.c_longlong
     lib.nf_dense_fwd.argtypes = [vp, vp, i, vp, i, vp, vp, ll, i, i, vp, vp, i, vp]
     lib.nf_dense_fwd_workspace_bytes.argtypes = [i, i, i, i]
@@ -314,6 +316,18 @@ def integrate_olat_fwd(ctx, xyz, normal, cam, albedo, lvis, lxyz, lareas, olat_i
     return out
 
 
+def microfacet_brdf_fwd(ctx, pts2l, pts2c, normal, albedo=None, rough=None, default_rough=0.3,
+                        lambert_only=False, f0=0.91):
+    """Microfacet.__call__ (brdf/microfacet/microfacet.py:30-72) -> brdf [n, L, 3]."""
+    n, L = pts2l.shape[0], pts2l.shape[1]
+    out = torch.empty((n, L, 3), dtype=torch.float32, device=pts2l.device)
+    ctx.launch(ctx.lib.nf_microfacet_brdf_fwd(
+        ctx.h, _f32(pts2l), _f32(pts2c), _f32(normal),
+        _f32(albedo) if albedo is not None else None, _f32(rough) if rough is not None else None,
+        n, L, float(default_rough), int(bool(lambert_only)), float(f0), _f32(out), _stream()))
+    return out
+
+
 def gen_rays(ctx, c2w, cam_angle_x, h, w, normalize=False):
     c2w = np.ascontiguousarray(np.asarray(c2w, dtype=np.float64).reshape(16))
     rayo = torch.empty((h * w, 3), dtype=torch.float32, device=ctx.device)
@@ -457,6 +471,15 @@ def adam_amsgrad_step(ctx, param, grad, m, v, vhat, lr, step, beta1=0.9, beta2=0
     ctx.launch(ctx.lib.nf_adam_amsgrad_step(
         ctx.h, _f32(param), _f32(grad), _f32(m), _f32(v), _f32(vhat), param.numel(), float(lr),
         float(beta1), float(beta2), float(eps), int(step), _stream()))
+
+
+def selftest_tmem(ctx, reader_warps, iters, mma_iters, mode):
+    """-> (reader cycles, MMA-stream cycles) of the TMEM throughput microbenchmark."""
+    out = torch.zeros((4,), dtype=torch.int64, device=ctx.device)
+    ctx.launch(ctx.lib.nf_selftest_tmem(ctx.h, reader_warps, iters, mma_iters, mode, _ptr(out),
+                                       _stream()))
+    o = out.cpu().tolist()
+    return o[0], o[1]
 
 
 def selftest_umma2(ctx, a, b):

@@ -127,7 +127,7 @@ struct PointCtx2 {
   float2 npx, npy, npz;        // -point
   float2 nx, ny, nz;           // unit normal
   float2 vx, vy, vz;           // unit view direction
-  float2 a2m1;                 // alpha^2 - 1   (u = 1 + (a2 - 1) cm^2)
+  float2 a2;                   // alpha^2 (= rough^4)
   float2 k;                    // [n.v > 0] g_view a2 / (4 pi |v.n|)
   float2 f0, omf0;
   float2 lr, lg, lb;           // albedo / pi
@@ -155,10 +155,19 @@ __device__ __forceinline__ void eval_pair2(const nf_integrate_args& a, const Poi
     const float2 om2 = __fmul2_rn(om, om);
     const float2 om5 = __fmul2_rn(__fmul2_rn(om2, om2), om);
     const float2 f = __ffma2_rn(om5, c.omf0, c.f0);                             // :106-111
-    const float2 cm = __fmul2_rn(__fadd2_rn(cosv, c.cos_v), invh);              // h . n, :96
-    const float2 u = __ffma2_rn(c.a2m1, __fmul2_rn(cm, cm), bc2(1.f));
-    const float2 uu = __fmul2_rn(u, u);
-    const float2 r = make_float2(rcp_fast(uu.x), rcp_fast(uu.y));
+    // u = a2 cm^2 + (1 - cm^2) with cm = (l + v).n / |l + v|.  Near the specular peak (h -> n)
+    // 1 - cm^2 is a difference of two numbers ~1 whose rounding (6e-8) is comparable with a2
+    // itself at low roughness (a2 = rough^4 = 1.6e-3 at 0.2): formed instead from the part of
+    // l + v orthogonal to n,  u |l + v|^2 = a2 ((l + v).n)^2 + |(l + v) - ((l + v).n) n|^2.
+    const float2 hn = __fadd2_rn(cosv, c.cos_v);                                // (l + v) . n, :96
+    const float2 nhn = __fmul2_rn(hn, bc2(-1.f));
+    const float2 tx = __ffma2_rn(nhn, c.nx, hx), ty = __ffma2_rn(nhn, c.ny, hy),
+                 tz = __ffma2_rn(nhn, c.nz, hz);
+    const float2 tt = dot3_2(tx, ty, tz, tx, ty, tz);
+    const float2 U = __ffma2_rn(c.a2, __fmul2_rn(hn, hn), tt);                  // u |l + v|^2
+    const float2 hU = __fmul2_rn(hh, make_float2(rcp_fast(U.x), rcp_fast(U.y)));  // 1 / u
+    const float2 r = __fmul2_rn(hU, hU);
+    const float2 u = U;
     const float2 sp = __fmul2_rn(__fmul2_rn(f, c.k), __fmul2_rn(wl, r));
     // front-lit (which implies chi_d once n.v > 0, folded into K) and a non-degenerate lobe
     sw = make_float2(fminf(cosv.x, u.x) > 0.f ? sp.x : 0.f, fminf(cosv.y, u.y) > 0.f ? sp.y : 0.f);
@@ -232,7 +241,7 @@ __global__ void __launch_bounds__(WARPS * 32, KIND == 0 && EC == 1 ? 3 : 1) inte
         c.npx = bc2(-NF_BC(s.pt.x)); c.npy = bc2(-NF_BC(s.pt.y)); c.npz = bc2(-NF_BC(s.pt.z));
         c.nx = bc2(NF_BC(s.n1.x)); c.ny = bc2(NF_BC(s.n1.y)); c.nz = bc2(NF_BC(s.n1.z));
         c.vx = bc2(NF_BC(s.v2.x)); c.vy = bc2(NF_BC(s.v2.y)); c.vz = bc2(NF_BC(s.v2.z));
-        c.a2m1 = bc2(NF_BC(s.alpha2_sq) - 1.f);
+        c.a2 = bc2(NF_BC(s.alpha2_sq));
         c.k = bc2(NF_BC(my_k));
         c.f0 = bc2(a.f0); c.omf0 = bc2(1.f - a.f0);
         c.lr = bc2(NF_BC(s.lambert.x)); c.lg = bc2(NF_BC(s.lambert.y)); c.lb = bc2(NF_BC(s.lambert.z));
@@ -334,6 +343,53 @@ integrate_olat_kernel(const nf_integrate_args a, float inten, float ambient, flo
   }
 }
 
+// Microfacet.__call__ (brdf/microfacet/microfacet.py:30-72) as a standalone op: brdf[n, L, 3]
+// for caller-supplied directions, every step in the reference's order (this is the drop-in for
+// user code that calls the class directly; the renderer above never materialises [n, L, 3]).
+__global__ void __launch_bounds__(256)
+microfacet_brdf_kernel(const float* __restrict__ pts2l, const float* __restrict__ pts2c,
+                       const float* __restrict__ normal, const float* __restrict__ albedo,
+                       const float* __restrict__ rough, int n, int L, float default_rough,
+                       int lambert_only, float f0, float* __restrict__ out) {
+  const long long total = (long long)n * L;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx / L);
+    const f3 l = l2n(ld3(pts2l + idx * 3), 1e-6f);                 // :46
+    const f3 v = l2n(ld3(pts2c + (size_t)i * 3), 1e-6f);           // :47
+    const f3 nn = l2n(ld3(normal + (size_t)i * 3), 1e-6f);         // :48
+    const f3 alb = albedo ? ld3(albedo + (size_t)i * 3) : mk3(1.f, 1.f, 1.f);   // :40-41
+    const float r = rough ? rough[i] : default_rough;              // :42-44
+    float micro = 0.f;
+    if (!lambert_only) {
+      const f3 h = l2n(l + v, 1e-6f);                              // :51-52
+      const float om = 1.f - dot3(l, h);
+      const float om2 = om * om;
+      const float f = f0 + (1.f - f0) * (om2 * om2 * om);          // :106-111
+      const float alpha = r * r;                                   // :54
+      const float a2 = alpha * alpha;                              // alpha ** 2 (:88, :102)
+      // _get_d (:93-104)
+      const float cm = dot3(h, nn);
+      const float chi_d = cm > 0.f ? 1.f : 0.f;
+      const float cm2 = cm * cm;
+      const float tan_m = divide_no_nan(1.f - cm2, cm2);
+      const float t = a2 + tan_m;
+      const float d = divide_no_nan(a2 * chi_d, NF_PI_F * (cm2 * cm2) * (t * t));
+      // _get_g (:74-91)
+      const float cos_v = dot3(nn, v);
+      const float chi_g = divide_no_nan(dot3(h, v), cos_v) > 0.f ? 1.f : 0.f;
+      const float cv2 = fminf(fmaxf(cos_v * cos_v, 0.f), 1.f);
+      const float tan_v = fmaxf(divide_no_nan(1.f - cv2, cv2), 0.f);
+      const float g = divide_no_nan(chi_g * 2.f, 1.f + sqrtf(1.f + a2 * tan_v));
+      const float den = 4.f * fabsf(dot3(l, nn)) * fabsf(cos_v);  // :58-60
+      micro = divide_no_nan(f * g * d, den);                       // :61
+    }
+    out[idx * 3 + 0] = micro + alb.x / NF_PI_F;                    // :64-71
+    out[idx * 3 + 1] = micro + alb.y / NF_PI_F;
+    out[idx * 3 + 2] = micro + alb.z / NF_PI_F;
+  }
+}
+
 int check_args(nf_ctx* ctx, const nf_integrate_args* a) {
   NF_CHECK_ARG(ctx, a, "null args");
   NF_CHECK_ARG(ctx, a->n >= 0 && a->n_lights > 0 && a->n_lights <= 4096, "bad n / n_lights");
@@ -418,6 +474,24 @@ int nf_integrate_olat_fwd(nf_ctx* ctx, const nf_integrate_args* a, float olat_in
   int grid = ctx->sm_count * 8;
   if (grid > blocks_needed) grid = blocks_needed;
   integrate_olat_kernel<<<grid, WARPS * 32, sm, (cudaStream_t)stream>>>(*a, olat_inten, ambient, rgb_olat_d);
+  NF_LAUNCH_CHECK(ctx);
+  return NF_OK;
+}
+
+int nf_microfacet_brdf_fwd(nf_ctx* ctx, const float* pts2l_d, const float* pts2c_d,
+                           const float* normal_d, const float* albedo_d, const float* rough_d,
+                           int n, int n_lights, float default_rough, int lambert_only, float f0,
+                           float* brdf_d, void* stream) {
+  NF_CHECK_ARG(ctx, n >= 0 && n_lights > 0, "bad n / n_lights");
+  if (n == 0) return NF_OK;
+  NF_CHECK_ARG(ctx, pts2l_d && pts2c_d && normal_d && brdf_d, "null buffer");
+  const long long total = (long long)n * n_lights;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)ctx->sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  microfacet_brdf_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
+      pts2l_d, pts2c_d, normal_d, albedo_d, rough_d, n, n_lights, default_rough, lambert_only, f0,
+      brdf_d);
   NF_LAUNCH_CHECK(ctx);
   return NF_OK;
 }

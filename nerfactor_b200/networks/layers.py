@@ -25,6 +25,14 @@ class LatentCode:
         return self.z[ind]
 
     def interp(self, w1, i1, w2, i2):
-        if self.normalize:
-            raise NotImplementedError("slerp of normalised codes (geom.py:82-116)")
-        return w1 * self(i1) + w2 * self(i2)
+        """layers.py:58-67: linear interpolation, or -- codes on the unit sphere -- slerp
+        (util/geom.py:100-116; safe_acos clips its argument to [-1, 1], util/math.py:40-58)."""
+        z1, z2 = self(i1), self(i2)
+        if not self.normalize:
+            return w1 * z1 + w2 * z2
+        assert w1 + w2 == 1., "When latent codes are normalized, use weights that sum to 1"
+        omega = np.arccos(np.clip(np.sum(z1 * z2), -1., 1.))
+        if omega == 0.:                       # identical codes: the reference divides 0 / 0 here
+            return z1
+        return ((z1 * np.sin((1. - w2) * omega) + z2 * np.sin(w2 * omega)) /
+                np.sin(omega)).astype(np.float32)

@@ -3,8 +3,10 @@
 `Network` holds the Dense layers of one trunk (or one output head) exactly like
 the reference (`.layers`, in checkpoint order; `skip_at`).  The forward pass of
 the hot path does not go through `Network.__call__`: `Model._pred_*_at` hand the
-trunk + head pair to one fused CUDA kernel (embedding + Dense chain + head), so
-`__call__` on a bare Network raises instead of silently running elsewhere.
+trunk + head pair to one fused CUDA kernel (embedding + Dense chain + head).
+Calling a Network directly (`net(x)`, the reference surface, mlp.py:39-50) evaluates it
+layer by layer on the FP32 Dense kernels (`nf_dense_fwd`) for a CUDA tensor `x`; there is no
+CPU path, a CPU tensor raises.
 """
 import math
 
@@ -72,7 +74,22 @@ class Network:
         return [(l.kernel, l.bias) for l in self.layers]
 
     def __call__(self, x):
-        raise NotImplementedError(
-            "nerfactor_b200 evaluates a trunk and its head inside one fused CUDA "
-            "kernel (see Model._pred_*_at / nerfactor_b200._lib); calling a bare "
-            "Network is not part of the hot path and has no fallback")
+        """x [M, in] (CUDA, fp32) -> [M, widths[-1]], input re-concatenated after the layers in
+        `skip_at` as (y, x) (mlp.py:39-50)."""
+        return apply_layers(self.layers, x, self.skip_at)
+
+
+def apply_layers(layers, x, skip_at=None):
+    """Dense chain on the FP32 Dense kernels (nf_dense_fwd through autodiff.mlp_apply)."""
+    import torch
+    from .. import autodiff as ad
+    if not torch.is_tensor(x) or not x.is_cuda:
+        raise TypeError("Network.__call__ needs a CUDA tensor: nerfactor_b200 has no CPU path "
+                        "(the models call the fused kernels instead, see Model._pred_*_at)")
+    assert all(l.built for l in layers), "Some layers not built"
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, x.shape[-1]).float().contiguous()
+    params = [(torch.as_tensor(l.kernel).to(x.device), torch.as_tensor(l.bias).to(x.device))
+              for l in layers]
+    y = ad.mlp_apply(x2, params, [l.activation for l in layers], skip_at, 'fp32')
+    return y.reshape(*lead, y.shape[-1])

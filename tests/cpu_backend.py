@@ -205,7 +205,14 @@ def adam_amsgrad_step(ctx, param, grad, m, v, vhat, lr, step, beta1=0.9, beta2=0
     param.sub_(lr_t * m / (vhat.sqrt() + eps))
 
 
-_PATCHED = ('default_context', 'point_mlp_fwd', 'lvis_fwd', 'brdf_learned_fwd', 'integrate_fwd',
+def microfacet_brdf_fwd(ctx, pts2l, pts2c, normal, albedo=None, rough=None, default_rough=0.3,
+                        lambert_only=False, f0=0.91):
+    ctx.launches += 1
+    m = obrdf.Microfacet(default_rough=default_rough, lambert_only=lambert_only, f0=f0)
+    return m(pts2l, pts2c, normal, albedo, None if rough is None else rough.reshape(-1, 1))
+
+
+_PATCHED = ('default_context', 'microfacet_brdf_fwd', 'point_mlp_fwd', 'lvis_fwd', 'brdf_learned_fwd', 'integrate_fwd',
             'integrate_olat_fwd', 'gen_rays', 'gen_z', 'sigma_fwd', 'sigma_normal_fwd',
             'nerf_fwd', 'composite', 'gen_z_fine', 'lvis_rays', 'dense_fwd', 'dense_bwd',
             'adam_amsgrad_step')

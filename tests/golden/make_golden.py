@@ -29,10 +29,13 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
 
 
 def make_ref_pinned():
     sys.path.insert(0, '/root/reference')
+    import refpin
+    refpin.pin()      # the reference's namespace package `brdf`, not the repo-root stub
     from brdf.renderer import gen_light_xyz                      # noqa
     from third_party.nielsen2015on.coordinateFunctions import \
         DirectionsToRusink                                       # noqa
@@ -68,6 +71,8 @@ def make_ref_pinned():
 def make_ref_sphere_renderer():
     """brdf/renderer.py:23-183 as it is (NumPy, fp64)."""
     sys.path.insert(0, '/root/reference')
+    import refpin
+    refpin.pin()      # the reference's namespace package `brdf`, not the repo-root stub
     from brdf.renderer import SphereRenderer                     # noqa
     rng = np.random.default_rng(4321)
     h, ims = 8, 24

@@ -27,6 +27,8 @@ REF = '/root/reference'
 sys.path[:0] = [os.path.join(HERE, 'tfshim'), REF, os.path.join(REF, 'nerfactor'), ROOT]
 warnings.filterwarnings('ignore')
 
+import refpin  # noqa: E402
+refpin.pin()          # the reference's namespace packages (brdf, third_party), not the repo's stubs
 import tensorflow as tf  # noqa: E402  (the shim)
 import torch  # noqa: E402
 

@@ -89,7 +89,7 @@ def test_network_mirror_shapes():
     assert enc.layers[5].kernel.shape == (319, 256)                  # nerf.py:53-59
     assert Embedder(in_dims=3, log2_max_freq=9, n_freqs=10).out_dims == 63
     assert Embedder(in_dims=3, log2_max_freq=3, n_freqs=4).out_dims == 27
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(TypeError):           # no CPU path: a Network runs on CUDA tensors only
         net(np.zeros((1, 90), np.float32))
 
 

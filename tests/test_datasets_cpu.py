@@ -158,10 +158,14 @@ def test_image_helpers_roundtrip(tmp_path):
 @pytest.mark.skipif(not os.path.isdir(REF), reason='reference tree only in the build container')
 def test_against_importable_reference_helpers(tmp_path):
     sys.path.insert(0, REF)
+    sys.path.insert(0, os.path.join(HERE, 'golden'))
     try:
+        import refpin
+        refpin.pin()
         from third_party.xiuminglib import xiuminglib as xm
     finally:
         sys.path.remove(REF)
+        sys.path.remove(os.path.join(HERE, 'golden'))
     rng = np.random.default_rng(3)
     a = rng.random((20, 30, 3))
     u8 = (a * 255).astype(np.uint8)
@@ -191,10 +195,13 @@ def _reference_via_shim():
     top (their loaders / writers are NumPy underneath)."""
     import warnings
     warnings.filterwarnings('ignore')
-    paths = [os.path.join(HERE, 'golden', 'tfshim'), REF, os.path.join(REF, 'nerfactor')]
+    paths = [os.path.join(HERE, 'golden', 'tfshim'), REF, os.path.join(REF, 'nerfactor'),
+             os.path.join(HERE, 'golden')]
     for p in reversed(paths):
         if p not in sys.path:
             sys.path.insert(0, p)
+    import refpin
+    refpin.pin()          # the reference's namespace packages, not the repo-root drop-in stubs
     import tensorflow as tf
     assert tf.__version__.endswith('shim')
     return paths

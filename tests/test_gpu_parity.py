@@ -604,7 +604,9 @@ def test_integrate_kernels_vs_fp64_incl_grazing_views(ctx):
     xyz, nrm, cam = [torch.as_tensor(batch[i]) for i in (6, 7, 2)]
     lvis = torch.as_tensor(batch[8])
     alb = torch.full((n, 3), .5)
-    for rough_v, tol_packed, tol_scalar in ((0.7, 2e-6, 1e-6), (0.4, 2e-5, 5e-6), (0.2, 2e-3, 3e-4)):
+    # packed kernel: the GGX normalisation is formed from the component of l + v orthogonal to n
+    # (csrc/nf_integrate.cu), which keeps it within 1e-4 of fp64 down to roughness 0.2
+    for rough_v, tol_packed, tol_scalar in ((0.7, 2e-6, 1e-6), (0.4, 1e-5, 5e-6), (0.2, 1e-4, 3e-4)):
         rough = torch.full((n, 1), rough_v)
         c64 = cb._pair_terms(xyz.double(), nrm.double(), cam.double(), alb.double(), lvis.double(),
                              lx.double(), la.double(), rough.double(), None, 0.04, 1.0)
@@ -615,8 +617,55 @@ def test_integrate_kernels_vs_fp64_incl_grazing_views(ctx):
         white = torch.full((1, L, 3), 1e-3, device=ctx.device)
         packed = _lib.integrate_fwd(ctx, *pts, light=white, **args)[:, 0]
         scalar = _lib.integrate_olat_fwd(ctx, *pts, olat_inten=1e-3, ambient=0., **args).sum(1)
+        print('integrate vs fp64, roughness %.1f: packed %.2e  scalar %.2e'
+              % (rough_v, rel_l2(packed.cpu(), truth), rel_l2(scalar.cpu(), truth)))
         assert rel_l2(packed.cpu(), truth) < tol_packed, rough_v
         assert rel_l2(scalar.cpu(), truth) < tol_scalar, rough_v
+
+
+def test_microfacet_class_callable_vs_oracle(ctx):
+    """`Microfacet(...)(pts2l, pts2c, normal, albedo, rough)` -- the reference's class surface
+    (brdf/microfacet/microfacet.py:30-72) -- through nf_microfacet_brdf_fwd, against the oracle's
+    restatement; defaults (albedo None, rough None), lambert_only, un-normalised inputs."""
+    from nerfactor_b200.brdf.microfacet.microfacet import Microfacet
+    rng = np.random.default_rng(4)
+    n, L = 257, 33
+    pts2l = rng.standard_normal((n, L, 3)).astype(np.float32) * 3.
+    pts2c = rng.standard_normal((n, 3)).astype(np.float32)
+    nrm = rng.standard_normal((n, 3)).astype(np.float32)
+    alb = rng.uniform(0, 1, (n, 3)).astype(np.float32)
+    rough = rng.uniform(0.15, 1, (n, 1)).astype(np.float32)
+    for kw, a, r in ((dict(f0=0.04), alb, rough), (dict(), None, None),
+                     (dict(lambert_only=True), alb, None)):
+        got = Microfacet(**kw)(pts2l, pts2c, nrm, a, r).cpu()
+        t = lambda x: None if x is None else torch.as_tensor(x)
+        want = obrdf.Microfacet(**kw)(t(pts2l), t(pts2c), t(nrm), t(a), t(r))
+        assert got.shape == (n, L, 3)
+        assert rel_l2(got, want) < 2e-5, kw
+    with pytest.raises(ValueError):
+        Microfacet()(pts2l[:, 0], pts2c, nrm)
+
+
+def test_network_call_on_cuda_tensors_vs_oracle(ctx):
+    """`mlp.Network.__call__` / `seq.Network.__call__` / `Embedder.__call__` (networks/mlp.py:39-50,
+    seq.py:33-38, embedder.py:39-47) on CUDA tensors through the FP32 Dense kernels."""
+    from nerfactor_b200.networks import mlp, seq
+    from nerfactor_b200.networks.embedder import Embedder
+    rng = np.random.default_rng(9)
+    p = synth.init_mlp(rng, 27, [128] * 4, ['relu'] * 4, [2], 0.05)
+    net = mlp.Network([128] * 4, act=['relu'] * 4, skip_at=[2]).build(27).load(p)
+    head = mlp.Network([3], act=['sigmoid']).build(128)
+    emb = Embedder(in_dims=3, log2_max_freq=3, n_freqs=4)
+    x = torch.as_tensor(rng.uniform(-1, 1, (1000, 3)).astype(np.float32))
+    y = head(net(emb(x.to(ctx.device)))).cpu()
+    hp = {'layers': head.weights(), 'act': ['sigmoid'], 'skip_at': None}
+    want = onets.mlp_forward(hp, onets.mlp_forward(p, onets.embed(x, 4)))
+    assert y.shape == (1000, 3) and rel_l2(y, want) < 1e-5
+    s = seq.Network()
+    s.layers = head.layers
+    assert torch.equal(s(net(emb(x.to(ctx.device)))).cpu(), y)
+    with pytest.raises(TypeError):
+        net(emb(x))                                   # CPU tensor: no CPU path
 
 
 # ------------------------------------------------------------------ NeRF colour branch (8f.2)

@@ -39,6 +39,9 @@ def test_albedo_overrides():
 @pytest.mark.skipif(not os.path.isdir(REF), reason='reference tree only in the build container')
 def test_turbo_fit_against_reference_table():
     sys.path.insert(0, REF)
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden'))
+    import refpin
+    refpin.pin()
     try:
         from third_party.turbo_colormap import turbo_colormap_data, interpolate_or_clip
     finally:
@@ -242,6 +245,9 @@ def test_vis_batch_equals_reference_vis_batch(tmp_path, monkeypatch):
     for p in reversed(paths):
         sys.path.insert(0, p)
     try:
+        sys.path.insert(0, os.path.join(here, 'golden'))
+        import refpin
+        refpin.pin()      # the reference's namespace packages, not the repo-root drop-in stubs
         import tensorflow as tf
         assert tf.__version__.endswith('shim')
         import make_golden_tfshim as gen
