@@ -26,14 +26,22 @@ from ._visualize import NeRFactorVis
 
 class Model(NeRFactorVis, ShapeModel):
     def __init__(self, config, debug=False, params=None, ctx=None, precision='f16',
-                 config_brdf=None, test_time_jitter=False):
+                 config_brdf=None, test_time_jitter=False, allow_uninitialised_prior=False):
         # BRDF (nerfactor.py:36-42): the prior's config sits next to its checkpoint
-        # (`brdf_model_ckpt` -> `<outroot>/<xname>.ini`); without one, brdf.ini's defaults
+        # (`brdf_model_ckpt` -> `<outroot>/<xname>.ini`).  Like the reference, a configured
+        # checkpoint (or its .ini) that does not exist is an error -- a typo must not train or
+        # render with a random frozen prior.  Weights handed over explicitly (`params`, tests and
+        # the benchmark) or `allow_uninitialised_prior=True` are the only ways around a checkpoint.
         self.brdf_model_ckpt = config.get('DEFAULT', 'brdf_model_ckpt', fallback='')
-        if config_brdf is None and self.brdf_model_ckpt:
+        self._explicit_weights = params is not None or allow_uninitialised_prior
+        if config_brdf is None and self.brdf_model_ckpt and self._uses_brdf_prior:
             ini = configutil.get_config_ini(self.brdf_model_ckpt)
             if os.path.exists(ini):
                 config_brdf = ioutil.read_config(ini)
+            elif not self._explicit_weights:
+                raise FileNotFoundError(
+                    "config of the BRDF prior not found: %s (from brdf_model_ckpt = %s)"
+                    % (ini, self.brdf_model_ckpt))
         self.config_brdf = config_brdf or default_config('brdf')
         self.pred_brdf = config.getboolean('DEFAULT', 'pred_brdf')
         if not self.pred_brdf:
@@ -73,6 +81,8 @@ class Model(NeRFactorVis, ShapeModel):
             self.load_params(params)
 
     # ------------------------------------------------------------ construction
+    _uses_brdf_prior = True          # the microfacet variant has no learned prior
+
     def _init_brdf_dims(self):
         self.z_dim = self.config_brdf.getint('DEFAULT', 'z_dim')
         self.normalize_brdf_z = self.config_brdf.getboolean('DEFAULT', 'normalize_z')
@@ -90,14 +100,22 @@ class Model(NeRFactorVis, ShapeModel):
         the config exist: the frozen BRDF prior (nerfactor.py:57-60) and, for shape_mode
         'frozen' / 'finetune', the pre-trained normal / visibility MLPs (nerfactor.py:156-163)."""
         from ..util import tfckpt
-        if self.brdf_model is not None and self.brdf_model_ckpt and \
-                os.path.exists(self.brdf_model_ckpt + '.index'):
+
+        def have(ckpt, what):
+            if ckpt and os.path.exists(ckpt + '.index'):
+                return True
+            if self._explicit_weights:
+                return False               # weights come from `params` / explicit opt-out
+            raise FileNotFoundError(
+                "%s checkpoint not found: %r (.index missing); pass `params=` or "
+                "`allow_uninitialised_prior=True` to construct the model without it" % (what, ckpt))
+        if self.brdf_model is not None and have(self.brdf_model_ckpt, 'BRDF-prior (brdf_model_ckpt)'):
             restore_model(self.brdf_model, self.brdf_model_ckpt)
             n_z = np.asarray(self.brdf_model.latent_code.z).shape[0]
             if len(self.brdf_model.brdf_names) != n_z:
                 self.brdf_model.brdf_names = ['brdf_%03d' % i for i in range(n_z)]
         ckpt = self.config.get('DEFAULT', 'shape_model_ckpt', fallback='')
-        if self.shape_mode in ('frozen', 'finetune') and ckpt and os.path.exists(ckpt + '.index'):
+        if self.shape_mode in ('frozen', 'finetune') and have(ckpt, 'shape (shape_model_ckpt)'):
             params = tfckpt.params_from_checkpoint(ckpt)
             ShapeModel.load_params(self, {k: params[k] for k in (
                 'normal_mlp', 'normal_out', 'lvis_mlp', 'lvis_out')})

@@ -6,6 +6,8 @@ from .nerfactor import Model as NeRFactorModel
 
 
 class Model(NeRFactorModel):
+    _uses_brdf_prior = False                # nerfactor_microfacet.py:35-40: no brdf_model_ckpt read
+
     def _init_brdf_dims(self):
         self.z_dim = 1                      # nerfactor_microfacet.py:38
         self.normalize_brdf_z = False

@@ -31,7 +31,7 @@ class Trainer:
         self.device = model.device
         cfg = config or model.config
         self.lr0 = cfg.getfloat('DEFAULT', 'lr', fallback=5e-3)
-        self.lr_decay_steps = cfg.getint('DEFAULT', 'lr_decay_steps', fallback=500_000)
+        self.lr_decay_steps = cfg.getint('DEFAULT', 'lr_decay_steps', fallback=-1)
         self.lr_decay_rate = cfg.getfloat('DEFAULT', 'lr_decay_rate', fallback=0.1)
         self.world_size, self.rank = world_size, rank
         self.iterations = 0
@@ -128,7 +128,11 @@ class Trainer:
         self.model.weights_changed()
 
     def learning_rate(self):
-        """ExponentialDecay(lr, decay_steps, decay_rate), continuous (trainvali.py:113-117)."""
+        """ExponentialDecay(lr, decay_steps, decay_rate), continuous -- only when
+        lr_decay_steps > 0; otherwise (the reference's fallback -1) a constant rate
+        (trainvali.py:111-117)."""
+        if self.lr_decay_steps <= 0:
+            return self.lr0
         return self.lr0 * self.lr_decay_rate ** (self.iterations / self.lr_decay_steps)
 
     # ------------------------------------------------------------------ forward
