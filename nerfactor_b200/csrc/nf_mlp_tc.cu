@@ -54,7 +54,6 @@ struct TcParams {
   const float* cam;      // BRDF: [n,3]
   const float* zlat;     // BRDF: [n,z_dim]
   float* out;            // [n, L]
-  int dyn_issue;         // MMA issuer serves the groups in readiness order
 };
 
 // fp32 side block layout (floats): see nf_tc_pack
@@ -174,54 +173,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const TcParams p)
       const int nt0 = group_points(0) * chunks, nt1 = group_points(1) * chunks;
       const int nt_max = nt0 > nt1 ? nt0 : nt1;
       uint32_t ph[2] = {0u, 0u};
-      auto issue = [&](int g, int layer) {
-        const uint32_t tb = tmem_base + g * GRP_COLS;
-        const uint32_t d_t = tb + COL_D;
-        if (layer == 0) {
-#pragma unroll
-          for (int k = 0; k < KE / 16; ++k)
-            tc_mma_ts(d_t, tb + COL_AE + k * 8,
-                      make_b_desc(img0 + seg_off[0] + k * 2 * lbo, lbo, sbo), idesc, k > 0);
-        } else {
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            tc_mma_ts(d_t, tb + COL_AH + k * 8,
-                      make_b_desc(img0 + seg_off[layer] + k * 2 * lbo, lbo, sbo), idesc, k > 0);
-          if (layer == 3) {
-#pragma unroll
-            for (int k = 0; k < KE / 16; ++k)
-              tc_mma_ts(d_t, tb + COL_AE + k * 8,
-                        make_b_desc(img0 + seg_off[4] + k * 2 * lbo, lbo, sbo), idesc, 1u);
-          }
-        }
-        tc_commit(bar_d + g);
-      };
-      if (p.dyn_issue) {
-        // serve whichever group's A operand is ready first (the groups drift apart: per-point
-        // folds, ragged last chunks), instead of strict g0 / g1 alternation
-        int done[2] = {0, 0};                       // layers issued so far per group
-        const int tot[2] = {nt0 * 4, nt1 * 4};
-        while (done[0] < tot[0] || done[1] < tot[1]) {
-#pragma unroll
+      for (int it = 0; it < nt_max; ++it) {
+        for (int layer = 0; layer < 4; ++layer) {
           for (int g = 0; g < 2; ++g) {
-            if (done[g] < tot[g] && mbar_try_wait(bar_a + g, ph[g])) {
-              ph[g] ^= 1u;
-              tc_fence_after();
-              issue(g, done[g] & 3);
-              ++done[g];
+            if (it >= (g == 0 ? nt0 : nt1)) continue;
+            mbar_wait(bar_a + g, ph[g]);
+            ph[g] ^= 1u;
+            tc_fence_after();
+            const uint32_t tb = tmem_base + g * GRP_COLS;
+            const uint32_t d_t = tb + COL_D;
+            if (layer == 0) {
+#pragma unroll
+              for (int k = 0; k < KE / 16; ++k)
+                tc_mma_ts(d_t, tb + COL_AE + k * 8,
+                          make_b_desc(img0 + seg_off[0] + k * 2 * lbo, lbo, sbo), idesc, k > 0);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                tc_mma_ts(d_t, tb + COL_AH + k * 8,
+                          make_b_desc(img0 + seg_off[layer] + k * 2 * lbo, lbo, sbo), idesc, k > 0);
+              if (layer == 3) {
+#pragma unroll
+                for (int k = 0; k < KE / 16; ++k)
+                  tc_mma_ts(d_t, tb + COL_AE + k * 8,
+                            make_b_desc(img0 + seg_off[4] + k * 2 * lbo, lbo, sbo), idesc, 1u);
+              }
             }
-          }
-        }
-      } else {
-        for (int it = 0; it < nt_max; ++it) {
-          for (int layer = 0; layer < 4; ++layer) {
-            for (int g = 0; g < 2; ++g) {
-              if (it >= (g == 0 ? nt0 : nt1)) continue;
-              mbar_wait(bar_a + g, ph[g]);
-              ph[g] ^= 1u;
-              tc_fence_after();
-              issue(g, layer);
-            }
+            tc_commit(bar_d + g);
           }
         }
       }
@@ -398,26 +376,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const TcParams p)
 
 
 // ---------------------------------------------------------------------------------------------
-// Variant with EIGHT epilogue warps per worker group (NF_LVIS_EW8=1; not the default: written
-// after the round's GPU minutes were spent, to be validated and timed first thing next round).
-// Motivation: per tile and layer the tensor pipe needs ~512 cycles while a
-// 4-warp group spends ~350 issue slots per warp plus TMEM / mbarrier round trips on the epilogue
-// (tensor pipe 45 % active).  Here two warps share each TMEM lane quarter and split the 128
-// columns 64 / 64: warps 4-11 = group 0, 12-19 = group 1, `half` = which 64 columns.  Everything
-// per ROW (light direction, embedding, A_e write, final store) is done by half 0; per-point folds
-// are split (half 0: layer-0 bias, half 1: skip-layer bias); the head's dot product is reduced
-// across the halves through shared memory.  MMA issue, TMEM layout, images: as in mlp_tc_kernel.
-constexpr int TC8_THREADS = 640;
+// Version 2 (default): the bias add moves INTO the tensor-core contraction.
+//
+// Measured on B200 (profiles/r2_k2_analysis.md): in the kernel above the tensor pipe is only 45 %
+// active because a layer's epilogue (TMEM load -> +bias -> ReLU -> fp16 -> TMEM store, ~230
+// instructions per thread plus two exposed tcgen05.ld round trips of ~200 clocks each) is much
+// longer than the other group's 512-clock MMA phase it should hide behind; more epilogue warps or
+// a readiness-ordered issuer make it slower (issue contention with the MMA thread).  Here
+//   * every layer gets one extra K = 16 MMA block whose A operand is the constant row
+//     (1, 1, 0, ..) and whose B operand holds the bias as an fp16 hi + lo pair (b = hi + lo to
+//     2^-22): D = A W + 1 * b_hi + 1 * b_lo comes out of the tensor core with the bias already
+//     added in fp32.  The static biases of layers 1, 2 are part of the weight image; the folded
+//     per-point biases of layer 0 and of the skip layer are written by the group into its own
+//     4 KB shared-memory block once per surface point.
+//   * the epilogue is then just load -> cvt.relu.f16x2 -> store (~80 instructions per thread),
+//     with the second half of the accumulator in flight while the first half is converted.
+// One extra 128 x 128 x 16 MMA per layer costs 64 of ~512 clocks; the tensor pipe stays busy.
+template <int KIND>
+struct SmemLayout2 {
+  static constexpr int KE = KindCfg<KIND>::KE;
+  static constexpr int NR_PAD = KindCfg<KIND>::NR_PAD;
+  // image: [W0e KE | W1 128 | W2 128 | W3h 128 | W3e KE | bias1 16 | bias2 16] x 128 x 2 B
+  static constexpr size_t img_bytes = ((size_t)img_halves<KIND>() + 2 * 16 * 128) * 2;
+  static constexpr size_t aux_floats = AUX_WX0 + 2 * (size_t)NR_PAD * 128;
+  static constexpr size_t off_img = 0;
+  static constexpr size_t off_bdyn = img_bytes;                          // [2 groups][2][16 x 128] 16-bit
+  static constexpr size_t off_aux = off_bdyn + 2 * 2 * 4096;
+  static constexpr size_t off_e = off_aux + aux_floats * 4;              // [2 groups][64] f32
+  static constexpr size_t off_lx = off_e + 2 * 64 * 4;                   // float4 [Lmax]
+  static constexpr int LMAX = 1024;
+  static constexpr size_t off_bar = off_lx + (size_t)LMAX * 16;
+  static constexpr size_t total = off_bar + 128;
+};
+constexpr int COL_ONE = 208;       // constant A operand (1, 1, 0, ...): 8 columns
 
 template <int KIND, int BF16>
-__global__ void __launch_bounds__(TC8_THREADS, 1) mlp_tc8_kernel(const TcParams p) {
-  using SL = SmemLayout<KIND>;
+__global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p) {
+  using SL = SmemLayout2<KIND>;
   constexpr int KE = SL::KE;
   constexpr int NR_PAD = SL::NR_PAD;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* s_img = smem + SL::off_img;
+  uint8_t* s_bdyn = smem + SL::off_bdyn;
   float* s_aux = reinterpret_cast<float*>(smem + SL::off_aux);
-  float* s_beff = reinterpret_cast<float*>(smem + SL::off_beff);
   float* s_e = reinterpret_cast<float*>(smem + SL::off_e);
   float4* s_lx = reinterpret_cast<float4*>(smem + SL::off_lx);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SL::off_bar);
@@ -425,7 +426,6 @@ __global__ void __launch_bounds__(TC8_THREADS, 1) mlp_tc8_kernel(const TcParams 
   uint64_t* bar_a = bars + 1;          // [2] A operand ready (128 arrivals)
   uint64_t* bar_d = bars + 3;          // [2] D accumulator ready (tcgen05.commit)
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 5);
-  float* s_red = reinterpret_cast<float*>(smem + SL::total);      // [2 groups][128] head partials
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunks = (p.L + 127) / 128;
@@ -433,7 +433,7 @@ __global__ void __launch_bounds__(TC8_THREADS, 1) mlp_tc8_kernel(const TcParams 
   // ---------------------------------------------------------------- set-up
   if (threadIdx.x == 0) {
     mbar_init(bar_w, 1);
-    mbar_init(bar_a + 0, 256); mbar_init(bar_a + 1, 256);
+    mbar_init(bar_a + 0, 128); mbar_init(bar_a + 1, 128);
     mbar_init(bar_d + 0, 1); mbar_init(bar_d + 1, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -446,6 +446,9 @@ __global__ void __launch_bounds__(TC8_THREADS, 1) mlp_tc8_kernel(const TcParams 
   }
   for (int l = threadIdx.x; l < p.L; l += blockDim.x)
     s_lx[l] = make_float4(p.lxyz[l * 3], p.lxyz[l * 3 + 1], p.lxyz[l * 3 + 2], 0.f);
+  for (int i = threadIdx.x; i < 2 * 2 * 4096 / 4; i += blockDim.x)       // k = 2..15 rows stay zero
+    reinterpret_cast<uint32_t*>(s_bdyn)[i] = 0u;
+  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -453,7 +456,6 @@ __global__ void __launch_bounds__(TC8_THREADS, 1) mlp_tc8_kernel(const TcParams 
   if (threadIdx.x == 0) {
     const uint32_t aux_bytes = (uint32_t)(SL::aux_floats * 4);
     mbar_expect_tx(bar_w, (uint32_t)SL::img_bytes + aux_bytes);
-    // TMA bulk copies (UBLKCP): whole network -> shared memory, once per CTA
     const uint8_t* gi = p.blob + p.off_img;
     for (size_t o = 0; o < SL::img_bytes; o += 32768) {
       size_t nb = SL::img_bytes - o < 32768 ? SL::img_bytes - o : 32768;
@@ -467,7 +469,6 @@ __global__ void __launch_bounds__(TC8_THREADS, 1) mlp_tc8_kernel(const TcParams 
   }
   mbar_wait(bar_w, 0);
 
-  // unit of work = one surface point; group G takes points G, G + 2*grid, ...
   const int n_groups = gridDim.x * 2;
   auto group_points = [&](int g) {
     int G = blockIdx.x * 2 + g;
@@ -479,91 +480,81 @@ __global__ void __launch_bounds__(TC8_THREADS, 1) mlp_tc8_kernel(const TcParams 
     if (lane == 0) {
       const uint32_t idesc = make_idesc(BF16, TC_WIDTH);
       const uint32_t lbo = TC_WIDTH * 16, sbo = 128;
-      const uint32_t img0 = smem_u32(s_img);
-      // segment byte offsets inside the image: [KE | 128 | 128 | 128 | KE] x 128 x 2 B
+      const uint32_t img0 = smem_u32(s_img), bdyn0 = smem_u32(s_bdyn);
       const uint32_t seg_off[5] = {0u, (uint32_t)KE * 256u, (uint32_t)(KE + 128) * 256u,
                                    (uint32_t)(KE + 256) * 256u, (uint32_t)(KE + 384) * 256u};
+      const uint32_t bias_off[2] = {(uint32_t)(KE + 384 + KE) * 256u,
+                                    (uint32_t)(KE + 384 + KE + 16) * 256u};   // layers 1, 2
       const int nt0 = group_points(0) * chunks, nt1 = group_points(1) * chunks;
       const int nt_max = nt0 > nt1 ? nt0 : nt1;
       uint32_t ph[2] = {0u, 0u};
-      auto issue = [&](int g, int layer) {
-        const uint32_t tb = tmem_base + g * GRP_COLS;
-        const uint32_t d_t = tb + COL_D;
-        if (layer == 0) {
-#pragma unroll
-          for (int k = 0; k < KE / 16; ++k)
-            tc_mma_ts(d_t, tb + COL_AE + k * 8,
-                      make_b_desc(img0 + seg_off[0] + k * 2 * lbo, lbo, sbo), idesc, k > 0);
-        } else {
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            tc_mma_ts(d_t, tb + COL_AH + k * 8,
-                      make_b_desc(img0 + seg_off[layer] + k * 2 * lbo, lbo, sbo), idesc, k > 0);
-          if (layer == 3) {
-#pragma unroll
-            for (int k = 0; k < KE / 16; ++k)
-              tc_mma_ts(d_t, tb + COL_AE + k * 8,
-                        make_b_desc(img0 + seg_off[4] + k * 2 * lbo, lbo, sbo), idesc, 1u);
-          }
-        }
-        tc_commit(bar_d + g);
-      };
-      if (p.dyn_issue) {
-        // serve whichever group's A operand is ready first (the groups drift apart: per-point
-        // folds, ragged last chunks), instead of strict g0 / g1 alternation
-        int done[2] = {0, 0};                       // layers issued so far per group
-        const int tot[2] = {nt0 * 4, nt1 * 4};
-        while (done[0] < tot[0] || done[1] < tot[1]) {
-#pragma unroll
+      for (int it = 0; it < nt_max; ++it) {
+        for (int layer = 0; layer < 4; ++layer) {
           for (int g = 0; g < 2; ++g) {
-            if (done[g] < tot[g] && mbar_try_wait(bar_a + g, ph[g])) {
-              ph[g] ^= 1u;
-              tc_fence_after();
-              issue(g, done[g] & 3);
-              ++done[g];
+            if (it >= (g == 0 ? nt0 : nt1)) continue;
+            mbar_wait(bar_a + g, ph[g]);
+            ph[g] ^= 1u;
+            tc_fence_after();
+            const uint32_t tb = tmem_base + g * GRP_COLS;
+            const uint32_t d_t = tb + COL_D;
+            // bias block first (accumulate = 0 starts the tile from 1 * b_hi + 1 * b_lo)
+            const uint32_t bsm = (layer == 0 || layer == 3)
+                                     ? bdyn0 + (uint32_t)(g * 2 + (layer == 3 ? 1 : 0)) * 4096u
+                                     : img0 + bias_off[layer - 1];
+            tc_mma_ts(d_t, tb + COL_ONE, make_b_desc(bsm, lbo, sbo), idesc, 0u);
+            if (layer == 0) {
+#pragma unroll
+              for (int k = 0; k < KE / 16; ++k)
+                tc_mma_ts(d_t, tb + COL_AE + k * 8,
+                          make_b_desc(img0 + seg_off[0] + k * 2 * lbo, lbo, sbo), idesc, 1u);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                tc_mma_ts(d_t, tb + COL_AH + k * 8,
+                          make_b_desc(img0 + seg_off[layer] + k * 2 * lbo, lbo, sbo), idesc, 1u);
+              if (layer == 3) {
+#pragma unroll
+                for (int k = 0; k < KE / 16; ++k)
+                  tc_mma_ts(d_t, tb + COL_AE + k * 8,
+                            make_b_desc(img0 + seg_off[4] + k * 2 * lbo, lbo, sbo), idesc, 1u);
+              }
             }
-          }
-        }
-      } else {
-        for (int it = 0; it < nt_max; ++it) {
-          for (int layer = 0; layer < 4; ++layer) {
-            for (int g = 0; g < 2; ++g) {
-              if (it >= (g == 0 ? nt0 : nt1)) continue;
-              mbar_wait(bar_a + g, ph[g]);
-              ph[g] ^= 1u;
-              tc_fence_after();
-              issue(g, layer);
-            }
+            tc_commit(bar_d + g);
           }
         }
       }
     }
   } else if (warp >= 4) {
     // ================================================================== workers
-    const int g = (warp - 4) >> 3;            // group 0 | 1 (8 warps each)
-    const int half = ((warp - 4) >> 2) & 1;   // which 64 of the 128 columns this warp owns
+    const int g = (warp - 4) >> 2;            // group 0 | 1
     const int wq = warp & 3;                  // TMEM lane quarter this warp may access
     const int t = wq * 32 + lane;             // row of the tile == TMEM lane
-    const int tg = t;                         // column / row index inside the half
+    const int tg = t;                         // thread index inside the group
     const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
     const uint32_t tb = tmem_base + g * GRP_COLS + lane_addr;
-    float* beff0 = s_beff + g * 256;
-    float* beff3 = beff0 + 128;
     float* e_s = s_e + g * 64;
-    float* red = s_red + g * 128;
     const float* Wx0 = s_aux + AUX_WX0;
     const float* Wx3 = Wx0 + NR_PAD * 128;
+    // this thread's (n = tg, k = 0 | 1) pair of the group's two dynamic bias blocks
+    uint32_t* bd0 = reinterpret_cast<uint32_t*>(s_bdyn + (size_t)(g * 2 + 0) * 4096 + (size_t)tg * 16);
+    uint32_t* bd3 = reinterpret_cast<uint32_t*>(s_bdyn + (size_t)(g * 2 + 1) * 4096 + (size_t)tg * 16);
     const int G = blockIdx.x * 2 + g;
     uint32_t phd = 0u;
+    {   // constant A operand of the bias block: columns (1, 1, 0, ..., 0), written once
+      uint32_t one[8];
+      one[0] = pack2<BF16, 0>(1.f, 1.f);
+#pragma unroll
+      for (int i = 1; i < 8; ++i) one[i] = 0u;
+      TC_ST8(tb + COL_ONE, one);
+      tc_wait_st();
+    }
 
     for (int pt = G; pt < p.n; pt += n_groups) {
       // ---------------------------------------------- per-point (once per L lights)
       const f3 x = ld3(p.xyz + (size_t)pt * 3);
       f3 fr_t, fr_b, fr_n, v_loc;
       if (KIND == NF_MLP_LVIS) {
-        // embed(xyz_scale * xyz): embedder.py:46-47 (written by half 0)
-        if (half != 0) {
-        } else if (tg < 3) e_s[tg] = (tg == 0 ? x.x : (tg == 1 ? x.y : x.z)) * p.xyz_scale;
+        if (tg < 3) e_s[tg] = (tg == 0 ? x.x : (tg == 1 ? x.y : x.z)) * p.xyz_scale;
         else if (tg < 3 + 3 * p.n_freqs_a) {
           int idx = tg - 3, f = idx / 3, c = idx % 3;
           float xv = (c == 0 ? x.x : (c == 1 ? x.y : x.z)) * p.xyz_scale;
@@ -573,27 +564,35 @@ __global__ void __launch_bounds__(TC8_THREADS, 1) mlp_tc8_kernel(const TcParams 
           e_s[3 + 6 * f + 3 + c] = co;
         }
       } else {
-        if (half == 0 && tg < p.z_dim) e_s[tg] = p.zlat[(size_t)pt * p.z_dim + tg];
+        if (tg < p.z_dim) e_s[tg] = p.zlat[(size_t)pt * p.z_dim + tg];
         world2local_dev(ld3(p.normal + (size_t)pt * 3), fr_t, fr_b, fr_n);   // geom.py:119-149
         f3 v = l2n(ld3(p.cam + (size_t)pt * 3) - x, 1e-6f);                   // shape.py:137-144
         v_loc = mk3(dot3(fr_t, v), dot3(fr_b, v), dot3(fr_n, v));             // nerfactor.py:418
       }
-      group_bar256(1 + g);
+      group_bar(1 + g);
       {
-        // half 0 folds the per-point columns into the layer-0 bias, half 1 into the skip layer's
-        const float* Wx = half == 0 ? Wx0 : Wx3;
-        float acc_b = s_aux[AUX_B + (half == 0 ? 0 : 3) * 128 + tg];
-        for (int k = 0; k < p.nr; ++k) acc_b = fmaf(e_s[k], Wx[k * 128 + tg], acc_b);
-        (half == 0 ? beff0 : beff3)[tg] = acc_b;
+        // fold the per-point input columns into the biases of layer 0 and of the skip layer (fp32),
+        // then hand them to the tensor core as an fp16 / bf16 hi + lo pair
+        float a0 = s_aux[AUX_B + 0 * 128 + tg], a3 = s_aux[AUX_B + 3 * 128 + tg];
+        for (int k = 0; k < p.nr; ++k) {
+          float ev = e_s[k];
+          a0 = fmaf(ev, Wx0[k * 128 + tg], a0);
+          a3 = fmaf(ev, Wx3[k * 128 + tg], a3);
+        }
+        const uint32_t h0 = pack2<BF16, 0>(a0, 0.f), h3 = pack2<BF16, 0>(a3, 0.f);
+        const float l0 = a0 - unpack_lo<BF16>(h0), l3 = a3 - unpack_lo<BF16>(h3);
+        *bd0 = (h0 & 0xFFFFu) | (pack2<BF16, 0>(l0, 0.f) << 16);
+        *bd3 = (h3 & 0xFFFFu) | (pack2<BF16, 0>(l3, 0.f) << 16);
+        fence_proxy_async();
       }
-      group_bar256(1 + g);
+      group_bar(1 + g);
 
       for (int c = 0; c < chunks; ++c) {
         const int li = c * 128 + t;
         const int lc = li < p.L ? li : p.L - 1;
         // ------------------------------------------------ per-row embedding -> A_e
         float mask = 1.f;
-        if (half == 0) {
+        {
           float4 lp = s_lx[lc];
           f3 d = l2n(mk3(lp.x, lp.y, lp.z) - x, 1e-6f);                       // shape.py:128-135
           float v[KE];
@@ -616,7 +615,6 @@ __global__ void __launch_bounds__(TC8_THREADS, 1) mlp_tc8_kernel(const TcParams 
             if (f < nf) {
               v[3 + 6 * f + 0] = sx; v[3 + 6 * f + 1] = sy; v[3 + 6 * f + 2] = sz;
               v[3 + 6 * f + 3] = cx; v[3 + 6 * f + 4] = cy; v[3 + 6 * f + 5] = cz;
-              // double-angle step to the next octave
               float nsx = 2.f * sx * cx, ncx = 1.f - 2.f * sx * sx;
               float nsy = 2.f * sy * cy, ncy = 1.f - 2.f * sy * sy;
               float nsz = 2.f * sz * cz, ncz = 1.f - 2.f * sz * sz;
@@ -633,38 +631,35 @@ __global__ void __launch_bounds__(TC8_THREADS, 1) mlp_tc8_kernel(const TcParams 
         tc_fence_before();
         mbar_arrive(bar_a + g);
 
-        // ------------------------------------------------ layers 0..2: epilogue -> A_h
+        // ------------------------------------------------ layers 0..2: ReLU + 16-bit -> A_h
         for (int layer = 0; layer < 3; ++layer) {
-          const float* bias = layer == 0 ? beff0 : (s_aux + AUX_B + layer * 128);
           mbar_wait(bar_d + g, phd);
           phd ^= 1u;
           tc_fence_after();
-          {
-            const int c2 = half;
-            uint32_t r0[32], r1[32];
-            TC_LD32(r0, tb + COL_D + c2 * 64);
-            TC_LD32(r1, tb + COL_D + c2 * 64 + 32);
-            tc_wait_ld();
-            uint32_t pk[16];
+          uint32_t ra[32], rb[32], rc[32], rd[32];
+          TC_LD32(ra, tb + COL_D);
+          TC_LD32(rb, tb + COL_D + 32);
+          tc_wait_ld();
+          TC_LD32(rc, tb + COL_D + 64);       // second half in flight while the first converts
+          TC_LD32(rd, tb + COL_D + 96);
+          uint32_t pk[16];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float4 bb = *reinterpret_cast<const float4*>(bias + c2 * 64 + 4 * i);
-              pk[2 * i] = pack2<BF16, 1>(__uint_as_float(r0[4 * i]) + bb.x,
-                                             __uint_as_float(r0[4 * i + 1]) + bb.y);
-              pk[2 * i + 1] = pack2<BF16, 1>(__uint_as_float(r0[4 * i + 2]) + bb.z,
-                                                 __uint_as_float(r0[4 * i + 3]) + bb.w);
-            }
-            TC_ST16(tb + COL_AH + c2 * 32, pk);
+          for (int i = 0; i < 16; ++i)
+            pk[i] = pack2<BF16, 1>(__uint_as_float(ra[2 * i]), __uint_as_float(ra[2 * i + 1]));
+          TC_ST16(tb + COL_AH, pk);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float4 bb = *reinterpret_cast<const float4*>(bias + c2 * 64 + 32 + 4 * i);
-              pk[2 * i] = pack2<BF16, 1>(__uint_as_float(r1[4 * i]) + bb.x,
-                                             __uint_as_float(r1[4 * i + 1]) + bb.y);
-              pk[2 * i + 1] = pack2<BF16, 1>(__uint_as_float(r1[4 * i + 2]) + bb.z,
-                                                 __uint_as_float(r1[4 * i + 3]) + bb.w);
-            }
-            TC_ST16(tb + COL_AH + c2 * 32 + 16, pk);
-          }
+          for (int i = 0; i < 16; ++i)
+            pk[i] = pack2<BF16, 1>(__uint_as_float(rb[2 * i]), __uint_as_float(rb[2 * i + 1]));
+          TC_ST16(tb + COL_AH + 16, pk);
+          tc_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            pk[i] = pack2<BF16, 1>(__uint_as_float(rc[2 * i]), __uint_as_float(rc[2 * i + 1]));
+          TC_ST16(tb + COL_AH + 32, pk);
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            pk[i] = pack2<BF16, 1>(__uint_as_float(rd[2 * i]), __uint_as_float(rd[2 * i + 1]));
+          TC_ST16(tb + COL_AH + 48, pk);
           tc_wait_st();
           tc_fence_before();
           mbar_arrive(bar_a + g);
@@ -673,32 +668,44 @@ __global__ void __launch_bounds__(TC8_THREADS, 1) mlp_tc8_kernel(const TcParams 
         mbar_wait(bar_d + g, phd);
         phd ^= 1u;
         tc_fence_after();
-        float acc = 0.f;
+        float acc0 = 0.f, acc1 = 0.f;
         {
-          const int c2 = half;
-          uint32_t r0[32], r1[32];
-          TC_LD32(r0, tb + COL_D + c2 * 64);
-          TC_LD32(r1, tb + COL_D + c2 * 64 + 32);
+          uint32_t ra[32], rb[32], rc[32], rd[32];
+          TC_LD32(ra, tb + COL_D);
+          TC_LD32(rb, tb + COL_D + 32);
+          tc_wait_ld();
+          TC_LD32(rc, tb + COL_D + 64);
+          TC_LD32(rd, tb + COL_D + 96);
+          const float4* wo = reinterpret_cast<const float4*>(s_aux + AUX_WOUT);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 w0 = wo[i], w1 = wo[8 + i];
+            acc0 = fmaf(fmaxf(__uint_as_float(ra[4 * i + 0]), 0.f), w0.x, acc0);
+            acc1 = fmaf(fmaxf(__uint_as_float(ra[4 * i + 1]), 0.f), w0.y, acc1);
+            acc0 = fmaf(fmaxf(__uint_as_float(ra[4 * i + 2]), 0.f), w0.z, acc0);
+            acc1 = fmaf(fmaxf(__uint_as_float(ra[4 * i + 3]), 0.f), w0.w, acc1);
+            acc0 = fmaf(fmaxf(__uint_as_float(rb[4 * i + 0]), 0.f), w1.x, acc0);
+            acc1 = fmaf(fmaxf(__uint_as_float(rb[4 * i + 1]), 0.f), w1.y, acc1);
+            acc0 = fmaf(fmaxf(__uint_as_float(rb[4 * i + 2]), 0.f), w1.z, acc0);
+            acc1 = fmaf(fmaxf(__uint_as_float(rb[4 * i + 3]), 0.f), w1.w, acc1);
+          }
           tc_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float h = fmaxf(__uint_as_float(r0[i]) + beff3[c2 * 64 + i], 0.f);
-            acc = fmaf(h, s_aux[AUX_WOUT + c2 * 64 + i], acc);
-          }
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float h = fmaxf(__uint_as_float(r1[i]) + beff3[c2 * 64 + 32 + i], 0.f);
-            acc = fmaf(h, s_aux[AUX_WOUT + c2 * 64 + 32 + i], acc);
+          for (int i = 0; i < 8; ++i) {
+            const float4 w0 = wo[16 + i], w1 = wo[24 + i];
+            acc0 = fmaf(fmaxf(__uint_as_float(rc[4 * i + 0]), 0.f), w0.x, acc0);
+            acc1 = fmaf(fmaxf(__uint_as_float(rc[4 * i + 1]), 0.f), w0.y, acc1);
+            acc0 = fmaf(fmaxf(__uint_as_float(rc[4 * i + 2]), 0.f), w0.z, acc0);
+            acc1 = fmaf(fmaxf(__uint_as_float(rc[4 * i + 3]), 0.f), w0.w, acc1);
+            acc0 = fmaf(fmaxf(__uint_as_float(rd[4 * i + 0]), 0.f), w1.x, acc0);
+            acc1 = fmaf(fmaxf(__uint_as_float(rd[4 * i + 1]), 0.f), w1.y, acc1);
+            acc0 = fmaf(fmaxf(__uint_as_float(rd[4 * i + 2]), 0.f), w1.z, acc0);
+            acc1 = fmaf(fmaxf(__uint_as_float(rd[4 * i + 3]), 0.f), w1.w, acc1);
           }
         }
-        // the two halves of a row meet in shared memory; half 0 finishes the row
-        if (half == 1) red[t] = acc;
-        group_bar256(1 + g);
-        if (half == 0) {
-          float o = acc + red[t] + s_aux[AUX_BOUT];
-          o = apply_act(p.out_act, o) * mask;
-          if (li < p.L) p.out[(size_t)pt * p.L + li] = o;
-        }
+        float o = (acc0 + acc1) + s_aux[AUX_BOUT];
+        o = apply_act(p.out_act, o) * mask;
+        if (li < p.L) p.out[(size_t)pt * p.L + li] = o;
       }
     }
   }
@@ -712,7 +719,6 @@ __global__ void __launch_bounds__(TC8_THREADS, 1) mlp_tc8_kernel(const TcParams 
                  : "memory");
   }
 }
-
 
 
 // ------------------------------------------------------------------ bring-up test
@@ -856,27 +862,24 @@ uint16_t f2bf_bits(float f) {
 
 template <int KIND, int BF16>
 int launch_tc(nf_ctx* ctx, const nf_mlp* m, const TcParams& p, cudaStream_t st) {
-  using SL = SmemLayout<KIND>;
-  NF_CHECK_ARG(ctx, SL::total <= ctx->smem_optin, "shared memory budget exceeded");
-  NF_CUDA(ctx, cudaFuncSetAttribute(mlp_tc_kernel<KIND, BF16>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SL::total));
   int grid = ctx->sm_count;
   int need = (p.n + 1) / 2;
   if (grid > need) grid = need;
-  static const bool ew8 = [] { const char* e = getenv("NF_LVIS_EW8"); return e && e[0] == '1'; }();
-  static const bool dyn = [] { const char* e = getenv("NF_LVIS_DYN"); return e && e[0] == '1'; }();
-  TcParams pd = p;
-  pd.dyn_issue = dyn ? 1 : 0;
-  if (ew8) {   // experimental 8-epilogue-warp variant (see mlp_tc8_kernel)
-    const size_t sm8 = SL::total + 2 * 128 * sizeof(float);
-    NF_CHECK_ARG(ctx, sm8 <= ctx->smem_optin, "shared memory budget exceeded");
-    NF_CUDA(ctx, cudaFuncSetAttribute(mlp_tc8_kernel<KIND, BF16>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm8));
-    mlp_tc8_kernel<KIND, BF16><<<grid, TC8_THREADS, sm8, st>>>(pd);
-    NF_LAUNCH_CHECK(ctx);
-    return NF_OK;
+  // NF_LVIS_V1=1 selects the first-generation kernel (bias added in the epilogue): A / B timing
+  static const bool v1 = [] { const char* e = getenv("NF_LVIS_V1"); return e && e[0] == '1'; }();
+  if (v1) {
+    using SL = SmemLayout<KIND>;
+    NF_CHECK_ARG(ctx, SL::total <= ctx->smem_optin, "shared memory budget exceeded");
+    NF_CUDA(ctx, cudaFuncSetAttribute(mlp_tc_kernel<KIND, BF16>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SL::total));
+    mlp_tc_kernel<KIND, BF16><<<grid, TC_THREADS, SL::total, st>>>(p);
+  } else {
+    using SL = SmemLayout2<KIND>;
+    NF_CHECK_ARG(ctx, SL::total <= ctx->smem_optin, "shared memory budget exceeded");
+    NF_CUDA(ctx, cudaFuncSetAttribute(mlp_tc2_kernel<KIND, BF16>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SL::total));
+    mlp_tc2_kernel<KIND, BF16><<<grid, TC_THREADS, SL::total, st>>>(p);
   }
-  mlp_tc_kernel<KIND, BF16><<<grid, TC_THREADS, SL::total, st>>>(pd);
   NF_LAUNCH_CHECK(ctx);
   return NF_OK;
 }
@@ -912,7 +915,7 @@ int nf_tc_pack(nf_mlp* m) {
   const float* W[5];
   const float* B[5];
   for (int l = 0; l <= 4; ++l) { W[l] = d.W[l]; B[l] = d.b[l]; }
-  const size_t halves = (size_t)(KE + 384 + KE) * 128;
+  const size_t halves = (size_t)(KE + 384 + KE + 32) * 128;   // + bias blocks of layers 1, 2
   const size_t aux_floats = AUX_WX0 + 2 * (size_t)NR_PAD * 128;
   size_t base = (m->blob.size() + 255) / 256 * 256;
   m->off_tc_f16 = base;
@@ -939,6 +942,22 @@ int nf_tc_pack(nf_mlp* m) {
         imgbf[idx] = f2bf_bits(v);
       }
     seg_base += (size_t)sg.kp * 128;
+  }
+  // bias blocks (version 2): a [16 k][128 n] K-major block per static-bias layer whose rows
+  // k = 0 / 1 hold the bias as a 16-bit hi / lo pair (the A operand is the constant (1, 1, 0..))
+  for (int l = 1; l <= 2; ++l) {
+    for (int n = 0; n < 128; ++n) {
+      const float bv = B[l][n];
+      const uint16_t hi16 = f2h_bits(bv), hibf = f2bf_bits(bv);
+      __half hh; memcpy(&hh, &hi16, 2);
+      __nv_bfloat16 hb; memcpy(&hb, &hibf, 2);
+      const size_t idx = seg_base + (size_t)n * 8;      // k-group 0, row n, k = 0
+      img16[idx] = hi16;
+      img16[idx + 1] = f2h_bits(bv - __half2float(hh));
+      imgbf[idx] = hibf;
+      imgbf[idx + 1] = f2bf_bits(bv - __bfloat162float(hb));
+    }
+    seg_base += (size_t)16 * 128;
   }
   for (int l = 0; l < 4; ++l) memcpy(aux + AUX_B + l * 128, B[l], 128 * sizeof(float));
   for (int c = 0; c < 128; ++c) aux[AUX_WOUT + c] = W[4][c];  // [128][1]

@@ -66,7 +66,7 @@ def test_host_weight_packing_sizes_and_errors():
     assert lib.nf_mlp_create(None, C.byref(d), C.byref(h)) == 0
     nbytes = lib.nf_mlp_device_bytes(h)
     fp32 = sum(w.size + b.size for w, b in lv) * 4
-    tc = 2 * (32 + 384 + 32) * 128 * 2 + (644 + 2 * 64 * 128) * 4
+    tc = 2 * (32 + 384 + 32 + 32) * 128 * 2 + (644 + 2 * 64 * 128) * 4     # + bias blocks (K2 v2)
     assert fp32 + tc <= nbytes <= fp32 + tc + 16 * 256
     lib.nf_mlp_destroy(h)
     # wrong embedding spec -> invalid argument, no handle

@@ -1,7 +1,7 @@
-"""Validates and times the 8-epilogue-warp variant of the light-visibility / learned-BRDF tcgen05
-kernel (`mlp_tc8_kernel`, NF_LVIS_EW8=1; csrc/nf_mlp_tc.cu) against the default kernel.
+"""Compares and times the two generations of the light-visibility / learned-BRDF tcgen05 kernel
+(csrc/nf_mlp_tc.cu): v2 = default (bias inside the MMA), v1 = NF_LVIS_V1=1 (bias in the epilogue).
 
-    python tools/check_lvis_ew8.py            # on a B200 (gpurun)
+    python tools/check_lvis_variants.py            # on a B200 (gpurun)
 
 The switch is read once per process, so each variant runs in its own subprocess on the same
 seeded inputs (640 k points x 512 lights for the timing, a ragged 203 x 200 case for edge tiles);
@@ -47,8 +47,8 @@ print(json.dumps(out))
 ''' % ROOT
 
 
-def run(flag, prefix, dyn='0'):
-    env = dict(os.environ, NF_LVIS_EW8=flag, NF_LVIS_DYN=dyn)
+def run(flag, prefix):
+    env = dict(os.environ, NF_LVIS_V1=flag)
     r = subprocess.run([sys.executable, '-c', WORKER, prefix], env=env, capture_output=True,
                        text=True, timeout=240)
     if r.returncode != 0:
@@ -60,17 +60,8 @@ def main():
     import numpy as np
     import tempfile
     d = tempfile.mkdtemp()
-    res = {'default': run('0', os.path.join(d, 'a')), 'ew8': run('1', os.path.join(d, 'b')),
-           'default_dyn': run('0', os.path.join(d, 'c'), '1'),
-           'ew8_dyn': run('1', os.path.join(d, 'e'), '1')}
-    for name, pre in (('default_dyn', 'c'), ('ew8_dyn', 'e')):
-        if 'error' not in res['default'] and 'error' not in res[name]:
-            for tag in ('ragged', 'full'):
-                for k in ('lvis', 'spec'):
-                    a = np.load(os.path.join(d, 'a_%s_%s.npy' % (tag, k)))
-                    b = np.load(os.path.join(d, '%s_%s_%s.npy' % (pre, tag, k)))
-                    res['maxdiff_%s_%s_%s' % (name, tag, k)] = float(np.abs(a - b).max())
-    if 'error' not in res['default'] and 'error' not in res['ew8']:
+    res = {'v2': run('0', os.path.join(d, 'a')), 'v1': run('1', os.path.join(d, 'b'))}
+    if 'error' not in res['v1'] and 'error' not in res['v2']:
         for tag in ('ragged', 'full'):
             for k in ('lvis', 'spec'):
                 a = np.load(os.path.join(d, 'a_%s_%s.npy' % (tag, k)))
