@@ -182,7 +182,9 @@ def workload_config(args, sigma_prec):
                             args.imw, args.imh, args.spp, 2 * args.light_h ** 2),
             'rays_per_view': args.imh * args.imw, 'samples_per_ray': args.spp,
             'light_dirs': 2 * args.light_h ** 2, 'brdf': 'microfacet',
-            'precision': {'sigma_mlp': sigma_prec, 'lvis_mlp': 'f16 operands / f32 accum',
+            'precision': {'sigma_mlp': {'f16e': 'f16 operands (encoding as f16 hi+lo pair) / f32 accum',
+                                        'f16': 'f16 operands / f32 accum'}.get(sigma_prec, sigma_prec),
+                          'lvis_mlp': 'f16 operands / f32 accum',
                           'point_mlps': 'f16 hi/lo split x3 (fp32-accurate) / f32 accum',
                           'render': 'f32'},
             'l2_policy': 'per-step working set (lvis 1.3 GB, sigma 0.33 GB) exceeds the 126 MB L2',
@@ -204,10 +206,10 @@ def secondary_rows(ctx, nerf, kt):
     # (1) compute_depth_and_normal: 128 coarse + 320 fine samples with d sigma/dx normals
     h = w = 200
     ro, rd = _lib.gen_rays(ctx, synth.look_at_c2w(), synth.CAM_ANGLE_X, h, w, normalize=True)
-    t = kt(lambda: gfn.compute_depth_and_normal(nerf, ro, rd, cfg, precision='f16'), 2)
+    t = kt(lambda: gfn.compute_depth_and_normal(nerf, ro, rd, cfg, precision=nerf.precision), 2)
     out['stage_a_hierarchical'] = {
         'what': 'geometry_from_nerf.compute_depth_and_normal, 128 coarse + 320 fine, '
-                'tcgen05 forward + input-gradient kernel (f16 operands)',
+                'tcgen05 sigma kernel (%s) + forward / input-gradient kernel (f16)' % nerf.precision,
         'rays': h * w, 'ms': t, 'rays_per_s': h * w / (t * 1e-3)}
     h = w = 96
     ro, rd = _lib.gen_rays(ctx, synth.look_at_c2w(), synth.CAM_ANGLE_X, h, w, normalize=True)
@@ -230,9 +232,15 @@ def secondary_rows(ctx, nerf, kt):
     surf = (ro[:npts] + rd[:npts] * 3.0).contiguous()
     nrm = (-rd[:npts]).contiguous()
     t = kt(lambda: gfn.compute_light_visibility(nerf, surf, nrm, cfg, light_h=16), 2)
+    lx16, _ = gen_light_xyz(16, 32)
+    _, _, fl = _lib.lvis_rays(ctx, surf, nrm, torch.as_tensor(
+        np.asarray(lx16, np.float32).reshape(-1, 3)).to(ctx.device))
+    marched = int(fl.sum().item())                # only front-lit pairs are marched (gfn.py:205-215)
     out['stage_a_light_visibility'] = {
-        'what': 'geometry_from_nerf.compute_light_visibility, 512 lights, 128 + 320 samples/pair, f16',
-        'points': npts, 'ms': t, 'pairs_per_s': npts * 512 / (t * 1e-3)}
+        'what': 'geometry_from_nerf.compute_light_visibility, 512 lights, 128 + 320 samples per '
+                'front-lit pair, %s' % nerf.precision,
+        'points': npts, 'pairs': npts * 512, 'marched_pairs': marched, 'ms': t,
+        'marched_pairs_per_s': marched / (t * 1e-3)}
     # (3) configs[2]: learned-MERL BRDF, 1024 light dirs on a 16x32 env-map, one 200x200 view
     lm = LearnedModel(nfconfig.default_config('nerfactor'),
                       params=synth.make_stage_b_params(0, 'learned'), ctx=ctx, precision='f16')
@@ -273,6 +281,146 @@ def secondary_rows(ctx, nerf, kt):
     return out
 
 
+def timed_mode_parity(ctx, nerf, model, vr, args, sigma_prec):
+    """Measured error of the precision modes this run TIMES, against the library's own FP32
+    CUDA-core kernels (which tests/ pin to the oracle and to the reference's fixtures): the sigma
+    network on a ray subset of the benchmark view, the Stage-B networks + renderer on identical
+    surface points, and the whole chain on the well-conditioned sphere-like field with smooth
+    Stage-B networks (same construction as tests/test_gpu_stage_a_precision.py, where the same
+    chain is compared with the CPU oracle).  Outside the timed region."""
+    from nerfactor_b200 import _lib, synth, config as nfconfig
+    from nerfactor_b200 import geometry_from_nerf as gfn
+    from nerfactor_b200.models.nerf import Model as NerfModel
+    from nerfactor_b200.models.nerfactor_microfacet import Model
+    from nerfactor_b200.pipeline import ViewRenderer
+    from nerfactor_b200.brdf.renderer import gen_light_xyz
+    rl2 = lambda a, b: float((a - b).norm() / b.norm().clamp_min(1e-30))
+    out = {'reference': 'FP32 CUDA-core kernels of this library (oracle-pinned in tests/)'}
+    ro, rd = _lib.gen_rays(ctx, synth.look_at_c2w(4.0, 30.0, 30.0), synth.CAM_ANGLE_X, args.imh,
+                           args.imw, normalize=True)
+    sel = torch.linspace(0, ro.shape[0] - 1, 4096, device=ctx.device).long()
+    ro, rd = ro[sel].contiguous(), rd[sel].contiguous()
+    a_t = gfn.march_single_pass(nerf, ro, rd, args.spp, use_fine=True, precision=sigma_prec)
+    a_r = gfn.march_single_pass(nerf, ro, rd, args.spp, use_fine=True, precision='fp32')
+    dd = (a_t['depth'] - a_r['depth']).abs()
+    out['stage_a'] = {'rays': 4096, 'sigma_rel_l2': rl2(a_t['sigma'], a_r['sigma']),
+                      'depth_abs_err_median': float(dd.median()),
+                      'depth_abs_err_p99': float(torch.quantile(dd, .99)),
+                      'occupancy_abs_err_max': float((a_t['occu'] - a_r['occu']).abs().max())}
+    alpha = torch.clamp(a_r['occu'], 0., 1.)[:, None]
+    z3 = torch.zeros((4096, 3), device=ctx.device)
+    batch = (None, None, ro, rd, z3, alpha.contiguous(), (a_r['surf'] * alpha).contiguous(), z3, None)
+    p16 = model.call(batch, 'test')[0]
+    model.precision = 'fp32'
+    try:
+        p32 = model.call(batch, 'test')[0]
+    finally:
+        model.precision = 'f16'
+    out['stage_b'] = {'rays': 4096, 'rgb_rel_l2': rl2(p16['rgb'], p32['rgb']),
+                      'lvis_rel_l2': rl2(p16['lvis'], p32['lvis'])}
+    # end to end on the sphere-like field
+    lh = args.light_h
+    lxyz, lareas = gen_light_xyz(lh, 2 * lh)
+    sb = synth.make_stage_b_params(4, 'microfacet', light_hw=(lh, 2 * lh), xyz_freq_decay=1.0)
+    blob = synth.make_blob_nerf_params(5)
+    chain = {}
+    for tag, pa, pb in (('timed', sigma_prec, 'f16'), ('fp32', 'fp32', 'fp32')):
+        nm = NerfModel(nfconfig.default_config('nerf'), params=blob, ctx=ctx, precision=pa)
+        mm = Model(nfconfig.default_config('nerfactor_microfacet', light_h=lh), params=sb, ctx=ctx,
+                   precision=pb)
+        mm.set_lights(lxyz.reshape(-1, 3), lareas.reshape(-1))
+        chain[tag] = ViewRenderer(nm, mm, n_samples=args.spp, use_fine=True).render(
+            synth.look_at_c2w(), synth.CAM_ANGLE_X, 64, 64)
+    same = (chain['timed']['alpha'] > 0) == (chain['fp32']['alpha'] > 0)
+    fg = (same & (chain['fp32']['alpha'] > 0))[:, 0]
+    out['end_to_end_sphere_field'] = {
+        'what': 'camera -> %d-sample march -> Stage B -> sRGB, 64 x 64 view of the analytic '
+                'sphere-like density field, smooth Stage-B networks' % args.spp,
+        'rgb_rel_l2': rl2(chain['timed']['rgb'][fg], chain['fp32']['rgb'][fg]),
+        'foreground_rays': int(fg.sum()), 'mask_flips': int((~same).sum()),
+        'north_star_tolerance': 1e-4}
+    return out
+
+
+def multi_rank_rows(ctx, vr, model, args, dist, world, rank):
+    """Rows every rank takes part in (N = 1 too): (1) STRONG scaling -- one 800 x 800 view
+    ray-sharded over the ranks (pipeline.shard_range), image assembled with one all-gather
+    (pipeline.gather_image); (2) BASELINE configs[4] as written -- 8 novel views x 8 env-maps
+    (one integrate pass relights under all 8 probes), views split over the ranks, all images
+    gathered.  CUDA events between barriers, max over ranks."""
+    from nerfactor_b200 import synth
+    from nerfactor_b200.pipeline import shard_range, gather_image
+    n_rays = args.imh * args.imw
+
+    def timed(fn, steps=2, warmup=1):
+        for _ in range(warmup):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            t = torch.tensor([ms], device=ctx.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    out = {}
+    c2w = synth.look_at_c2w(4.0, 30.0, 30.0)
+    a, b = shard_range(n_rays, rank, world)
+
+    def strong():
+        pred = vr.render(c2w, synth.CAM_ANGLE_X, args.imh, args.imw, ray_range=(a, b))
+        return gather_image(pred['rgb'], n_rays, rank, world) if world > 1 else pred['rgb']
+    ms = timed(strong)
+    out['strong_scaling_one_view'] = {
+        'what': 'ONE %dx%d view, rays [rank] of %d contiguous shards, image all-gather inside the '
+                'timed region' % (args.imw, args.imh, world),
+        'scaling': 'strong', 'ms': ms, 'rays_per_s': n_rays / (ms * 1e-3), 'n_gpus': world}
+    # configs[4]: 8 views x 8 env-maps
+    n_views, n_maps = 8, 8
+    probes = synth.make_probes(3, n_maps, light_hw=(args.light_h, 2 * args.light_h))
+    saved = model.novel_probes
+    from collections import OrderedDict
+    model.novel_probes = OrderedDict(('probe%d' % i, torch.as_tensor(p).to(ctx.device))
+                                     for i, p in enumerate(probes))
+    mine = [v for v in range(n_views) if v % world == rank]
+    per = (n_views + world - 1) // world
+
+    def sweep():
+        imgs = []
+        for v in mine:
+            pred = vr.render(synth.look_at_c2w(4.0, 30.0 + 45.0 * v, 30.0), synth.CAM_ANGLE_X,
+                             args.imh, args.imw, relight_probes=True)
+            imgs.append(pred['rgb_probes'])                      # [n_rays, 8, 3]
+        while len(imgs) < per:                                   # ragged split: pad for the gather
+            imgs.append(torch.zeros_like(imgs[0]) if imgs else
+                        torch.zeros((n_rays, n_maps, 3), device=ctx.device))
+        local = torch.stack(imgs, 0)
+        if world > 1:
+            full = torch.empty((world,) + tuple(local.shape), device=ctx.device)
+            dist.all_gather_into_tensor(full, local)
+            return full
+        return local
+    try:
+        ms = timed(sweep, steps=1 if world == 1 else 2)
+    finally:
+        model.novel_probes = saved
+    out['config5_relight_sweep'] = {
+        'what': 'BASELINE configs[4]: %d novel views x %d env-maps at %dx%d, views split over the '
+                'ranks, NCCL all-gather of every relit image' % (n_views, n_maps, args.imw, args.imh),
+        'ms': ms, 'rays_per_s': n_views * n_rays / (ms * 1e-3),
+        'relit_images_per_s': n_views * n_maps / (ms * 1e-3), 'n_gpus': world,
+        'gathered_bytes': int(n_views * n_rays * n_maps * 3 * 4)}
+    return out
+
+
 # ------------------------------------------------------------------------ our arm
 def main():
     args = parse()
@@ -303,13 +451,9 @@ def main():
     nerf = NerfModel(nfconfig.default_config('nerf'), params=synth.make_nerf_params(0), ctx=ctx,
                      precision='f16')
     if sigma_prec == 'auto':
-        try:      # tcgen05 sigma kernel if this build has it, else the FP32 CUDA-core path
-            z = _lib.gen_z(ctx, 2., 6., 16, 128)
-            o = torch.zeros((128, 3), device=ctx.device)
-            _lib.sigma_fwd(ctx, nerf.packed_sigma(True), o, o, z, None, 'f16')
-            sigma_prec = 'f16'
-        except _lib.NfError:
-            sigma_prec = 'fp32'
+        # 'f16e' = fp16 operands with the positional encoding as an fp16 hi + lo pair: the mode
+        # whose end-to-end RGB parity is demonstrated (tests/test_gpu_stage_a_precision.py)
+        sigma_prec = 'f16e'
     nerf.precision = sigma_prec
     model = Model(nfconfig.default_config('nerfactor_microfacet', light_h=lh),
                   params=synth.make_stage_b_params(0, 'microfacet', light_hw=(lh, 2 * lh)),
@@ -390,6 +534,14 @@ def main():
     ms_e2e, _ = timed(step_e2e, args.steps, 1)
     e2e_value = world * n_rays / (ms_e2e / args.steps * 1e-3)
 
+    multi = None
+    if not args.no_secondary:
+        try:
+            multi = multi_rank_rows(ctx, vr, model, args, dist, world, rank)
+        except Exception as e:                    # context rows must not take the headline down
+            multi = {'error': repr(e)}
+            if world > 1:
+                raise
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -491,14 +643,16 @@ def main():
 
     secondary = None
     if not args.no_secondary:
-        secondary = secondary_rows(ctx, nerf, kt)
+        secondary = secondary_rows(ctx, nerf, kt) if world == 1 else {}
+        secondary.update(multi or {})
+    parity = timed_mode_parity(ctx, nerf, model, vr, args, sigma_prec)
 
     cpu = None
     if not args.no_cpu_baseline:
-        rps, dt = cpu_reference_rays_per_s(args, args.cpu_sample_rays, 1, 1)
+        rps, dt = cpu_reference_rays_per_s(args, args.cpu_sample_rays, 3, 1)
         cpu = {'value': rps, 'unit': 'rays/s', 'cores': host_cores(), 'kind': 'port',
-               'sample': '%d of %d rays, same S=%d and L=%d, 1 warm-up + 1 timed pass (%.1f s)'
-                         % (args.cpu_sample_rays, n_rays, args.spp, L, dt)}
+               'sample': '%d of %d rays, same S=%d and L=%d, 1 warm-up + 3 timed passes '
+                         '(%.1f s each)' % (args.cpu_sample_rays, n_rays, args.spp, L, dt)}
 
     line = {
         'metric': 'rays/sec', 'value': value, 'unit': 'rays/s', 'n_gpus': world,
@@ -514,6 +668,7 @@ def main():
         'rooflines': [rf_sigma, rf_lvis, rf_int, rf_point] + ([rf_int_spec] if rf_int_spec else []),
         'foreground_rays': n_fg,
         'cpu_baseline': cpu,
+        'parity': parity,
         'secondary': secondary,
     }
     print(json.dumps(line), flush=True)

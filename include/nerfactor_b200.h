@@ -252,6 +252,35 @@ int nf_lvis_rays(nf_ctx* ctx, const float* surf_d, const float* normal_d, int n_
                  const float* lxyz_d, int n_lights, float* rayo_d, float* rayd_d,
                  uint8_t* front_lit_d, void* stream);
 
+/* ---- whole ray marches in one call (intermediates in a caller-provided workspace) ----------
+ * Camera -> surface: gen_z -> sigma (coarse net) -> weights -> inverse-CDF resampling -> sigma and
+ * d sigma / dx normals (fine net) on the sorted union -> occu[n], depth[n], normal[n, 3]
+ * (= sum w, sum w z, sum w n).  Replaces compute_depth_and_normal
+ * nerfactor/geometry_from_nerf.py:249-319; n_coarse / n_fine are the ACTUAL counts (the reference
+ * adds 64 to the .ini values, :250-251).  precision as nf_sigma_fwd (NF_PREC_F16E applies to the
+ * coarse pass; the gradient kernel then runs NF_PREC_F16).  Rays are processed in chunks; the
+ * workspace holds one chunk's [c, S] buffers.                                                   */
+size_t nf_raymarch_depth_normal_workspace_bytes(int n_rays, int n_coarse, int n_fine);
+int nf_raymarch_depth_normal_fwd(nf_ctx* ctx, const nf_mlp* mlp_coarse, const nf_mlp* mlp_fine,
+                                 const float* rayo_d, const float* rayd_d, int n_rays, float near,
+                                 float far, int n_coarse, int n_fine, int lin_in_disp,
+                                 const float* bbox_host, int precision, void* workspace_d,
+                                 size_t workspace_bytes, float* occu_d, float* depth_d,
+                                 float* normal_d, void* stream);
+/* Surface -> light: lvis[n_pts, L] = 1 - sum w of the hierarchical march from surf towards every
+ * light with (surf2l . normal) > 0, 0 for back-lit pairs.  Front-lit test, compaction, both
+ * marches and the scatter run on the device.  Replaces compute_light_visibility
+ * nerfactor/geometry_from_nerf.py:177-246 (all lights at once instead of its per-light loop).
+ * NOTE: synchronises `stream` once per chunk of 2^19 pairs to read the number of front-lit pairs
+ * (it sizes the march launches) -- the one op of this library that does.                        */
+size_t nf_raymarch_lvis_workspace_bytes(int n_pts, int n_lights, int n_coarse, int n_fine);
+int nf_raymarch_lvis_fwd(nf_ctx* ctx, const nf_mlp* mlp_coarse, const nf_mlp* mlp_fine,
+                         const float* surf_d, const float* normal_d, int n_pts,
+                         const float* lxyz_d, int n_lights, float lvis_near, float lvis_far,
+                         int n_coarse, int n_fine, int lin_in_disp, const float* bbox_host,
+                         int precision, void* workspace_d, size_t workspace_bytes, float* lvis_d,
+                         void* stream);
+
 /* ---- training (config 4): Dense layers on materialised activations + optimizer ----
  * One Keras Dense of mlp.Network (nerfactor/networks/mlp.py:34, 39-50) at a time:
  *   y[m, n] = act([x1[m,k1] | x2[m,k2]] w[(k1+k2), n] + b[n])      (x2 = skip concat, k2 may be 0)

@@ -29,7 +29,9 @@ EXPORTS = [
     'nf_sigma_fwd', 'nf_sigma_normal_fwd', 'nf_mlp_attach_rgb', 'nf_nerf_fwd', 'nf_composite', 'nf_gen_z_fine',
     'nf_lvis_rays', 'nf_selftest_umma', 'nf_selftest_umma2', 'nf_dense_fwd',
     'nf_dense_fwd_workspace_bytes', 'nf_dense_bwd_workspace_bytes',
-    'nf_dense_bwd', 'nf_adam_amsgrad_step', 'nf_microfacet_brdf_fwd', 'nf_selftest_tmem']
+    'nf_dense_bwd', 'nf_adam_amsgrad_step', 'nf_microfacet_brdf_fwd', 'nf_selftest_tmem',
+    'nf_raymarch_depth_normal_workspace_bytes', 'nf_raymarch_depth_normal_fwd',
+    'nf_raymarch_lvis_workspace_bytes', 'nf_raymarch_lvis_fwd']
 
 
 class NfError(RuntimeError):
@@ -105,6 +107,14 @@ def load_library():
     lib.nf_selftest_umma.argtypes = [vp, vp, vp, i, i, vp, vp]
     lib.nf_selftest_umma2.argtypes = [vp, vp, vp, i, vp, vp]
     lib.nf_selftest_tmem.argtypes = [vp, i, i, i, i, vp, vp]
+    lib.nf_raymarch_depth_normal_workspace_bytes.argtypes = [i, i, i]
+    lib.nf_raymarch_depth_normal_workspace_bytes.restype = C.c_size_t
+    lib.nf_raymarch_depth_normal_fwd.argtypes = [vp, vp, vp, vp, vp, i, f, f, i, i, i, C.POINTER(f),
+                                                 i, vp, C.c_size_t, vp, vp, vp, vp]
+    lib.nf_raymarch_lvis_workspace_bytes.argtypes = [i, i, i, i]
+    lib.nf_raymarch_lvis_workspace_bytes.restype = C.c_size_t
+    lib.nf_raymarch_lvis_fwd.argtypes = [vp, vp, vp, vp, vp, i, vp, i, f, f, i, i, i, C.POINTER(f),
+                                         i, vp, C.c_size_t, vp, vp]
     ll = C.c_longlong
     lib.nf_dense_fwd.argtypes = [vp, vp, i, vp, i, vp, vp, ll, i, i, vp, vp, i, vp]
     lib.nf_dense_fwd_workspace_bytes.argtypes = [i, i, i, i]
@@ -115,7 +125,9 @@ def load_library():
     lib.nf_adam_amsgrad_step.argtypes = [vp, vp, vp, vp, vp, vp, ll, f, f, f, f, ll, vp]
     for name in EXPORTS:
         if name not in ('nf_last_error_string', 'nf_mlp_device_bytes',
-                        'nf_dense_bwd_workspace_bytes', 'nf_dense_fwd_workspace_bytes'):
+                        'nf_dense_bwd_workspace_bytes', 'nf_dense_fwd_workspace_bytes',
+                        'nf_raymarch_depth_normal_workspace_bytes',
+                        'nf_raymarch_lvis_workspace_bytes'):
             getattr(lib, name).restype = i
     _lib = lib
     return lib
@@ -417,6 +429,46 @@ def lvis_rays(ctx, surf, normal, lxyz):
     ctx.launch(ctx.lib.nf_lvis_rays(ctx.h, _f32(surf), _f32(normal), n, _f32(lxyz), L,
                                    _f32(rayo), _f32(rayd), _ptr(fl), _stream()))
     return rayo, rayd, fl.view(n, L)
+
+
+def raymarch_depth_normal_fwd(ctx, mlp_coarse, mlp_fine, rayo, rayd, near, far, n_coarse, n_fine,
+                              lin_in_disp=False, bbox=None, precision='f16e'):
+    """compute_depth_and_normal (gfn.py:249-319) in one C call -> (occu [n], depth [n],
+    normal [n, 3]); n_coarse / n_fine are the actual sample counts."""
+    n = rayo.shape[0]
+    dev = rayo.device
+    occu = torch.empty((n,), dtype=torch.float32, device=dev)
+    depth = torch.empty((n,), dtype=torch.float32, device=dev)
+    normal = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    nbytes = ctx.lib.nf_raymarch_depth_normal_workspace_bytes(n, n_coarse, n_fine)
+    work = torch.empty((nbytes + 256,), dtype=torch.uint8, device=dev)
+    wptr = work.data_ptr() + (-work.data_ptr()) % 256
+    n_chunks = max(1, (n + 32767) // 32768)
+    ctx.launches += 6 * n_chunks - 1
+    ctx.launch(ctx.lib.nf_raymarch_depth_normal_fwd(
+        ctx.h, mlp_coarse.h, mlp_fine.h, _f32(rayo), _f32(rayd), n, float(near), float(far),
+        int(n_coarse), int(n_fine), int(lin_in_disp), _bbox(bbox), PREC[precision],
+        C.c_void_p(wptr), nbytes, _f32(occu), _f32(depth), _f32(normal), _stream()))
+    return occu, depth, normal
+
+
+def raymarch_lvis_fwd(ctx, mlp_coarse, mlp_fine, surf, normal, lxyz, lvis_near, lvis_far,
+                      n_coarse, n_fine, lin_in_disp=False, bbox=None, precision='f16e'):
+    """compute_light_visibility (gfn.py:177-246) in one C call -> lvis_hit [m, L]."""
+    m, L = surf.shape[0], lxyz.shape[0]
+    dev = surf.device
+    lvis = torch.empty((m, L), dtype=torch.float32, device=dev)
+    if m == 0:
+        return lvis
+    nbytes = ctx.lib.nf_raymarch_lvis_workspace_bytes(m, L, n_coarse, n_fine)
+    work = torch.empty((nbytes + 256,), dtype=torch.uint8, device=dev)
+    wptr = work.data_ptr() + (-work.data_ptr()) % 256
+    ctx.launches += 8 * max(1, (m * L + (1 << 19) - 1) >> 19) - 1
+    ctx.launch(ctx.lib.nf_raymarch_lvis_fwd(
+        ctx.h, mlp_coarse.h, mlp_fine.h, _f32(surf), _f32(normal), m, _f32(lxyz), L,
+        float(lvis_near), float(lvis_far), int(n_coarse), int(n_fine), int(lin_in_disp),
+        _bbox(bbox), PREC[precision], C.c_void_p(wptr), nbytes, _f32(lvis), _stream()))
+    return lvis
 
 
 def selftest_umma(ctx, a, b, swap_lbo_sbo=False):

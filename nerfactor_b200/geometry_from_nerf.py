@@ -43,34 +43,24 @@ def march_single_pass(model, rayo, rayd, n_samples, use_fine=False, perturb_u=No
 
 
 def compute_depth_and_normal(model, rayo, rayd, config, scene_bbox=None, precision=None):
-    """geometry_from_nerf.py:249-319 -> (occu[N], exp_depth[N], exp_normal[N,3])."""
-    ctx = model.ctx
+    """geometry_from_nerf.py:249-319 -> (occu[N], exp_depth[N], exp_normal[N,3]): one call into
+    nf_raymarch_depth_normal_fwd (coarse march, inverse-CDF resampling, fine march with
+    d sigma / dx normals, compositing; all [N, S] intermediates in a workspace)."""
     n_c = 64 + config.getint('DEFAULT', 'n_samples_coarse')
     n_f = 64 + config.getint('DEFAULT', 'n_samples_fine')
     lin = config.getboolean('DEFAULT', 'lin_in_disp')
     near, far = config.getfloat('DEFAULT', 'near'), config.getfloat('DEFAULT', 'far')
-    n = rayo.shape[0]
-    z = _lib.gen_z(ctx, near, far, n_c, n, lin, None)
-    sigma = eval_sigma_mlp(model, rayo, rayd, z, False, scene_bbox, precision)
-    w, _, _, _, _ = _lib.composite(ctx, sigma, z, rayo, rayd, want_surf=False)
-    z = _lib.gen_z_fine(ctx, z, w, n_f)
     prec = precision or model.precision
-    # the forward + input-gradient kernel has no split-encoding variant: 'f16e' -> 'f16' there
-    prec_n = {'f16e': 'f16'}.get(prec, prec)
-    sigma, normal = _lib.sigma_normal_fwd(ctx, model.packed_sigma(True), rayo, rayd, z,
-                                          parse_bbox(scene_bbox),
-                                          prec_n if prec_n in ('fp32', 'f16', 'bf16') else 'fp32')
-    _, occu, depth, _, exp_normal = _lib.composite(
-        ctx, sigma, z, rayo, rayd, normal=normal, want_weights=False, want_surf=False)
-    return occu, depth, exp_normal
+    return _lib.raymarch_depth_normal_fwd(
+        model.ctx, model.packed_sigma(False), model.packed_sigma(True), rayo, rayd, near, far,
+        n_c, n_f, lin, parse_bbox(scene_bbox), prec)
 
 
 def compute_light_visibility(model, surf, normal, config, lvis_near=.1, lvis_far=1.,
-                             light_h=16, scene_bbox=None, precision=None, lxyz=None,
-                             pair_chunk=1 << 20):
-    """geometry_from_nerf.py:177-246 -> lvis_hit [M, L] (device tensor).  All lights
-    are marched together in chunks of (point, light) pairs instead of the
-    reference's 512-iteration Python loop; back-lit pairs stay 0."""
+                             light_h=16, scene_bbox=None, precision=None, lxyz=None):
+    """geometry_from_nerf.py:177-246 -> lvis_hit [M, L] (device tensor): one call into
+    nf_raymarch_lvis_fwd.  All lights are marched together in chunks of (point, light) pairs
+    instead of the reference's 512-iteration Python loop; back-lit pairs stay 0."""
     ctx = model.ctx
     n_c = 64 + config.getint('DEFAULT', 'n_samples_coarse')
     n_f = 64 + config.getint('DEFAULT', 'n_samples_fine')
@@ -78,23 +68,10 @@ def compute_light_visibility(model, surf, normal, config, lvis_near=.1, lvis_far
     if lxyz is None:
         lxyz, _ = gen_light_xyz(light_h, 2 * light_h)
     lxyz = torch.as_tensor(np.asarray(lxyz, np.float32).reshape(-1, 3)).to(ctx.device)
-    m, L = surf.shape[0], lxyz.shape[0]
-    rayo, rayd, fl = _lib.lvis_rays(ctx, surf, normal, lxyz)
-    idx = torch.nonzero(fl.reshape(-1), as_tuple=False)[:, 0]
-    lvis = torch.zeros((m * L,), dtype=torch.float32, device=ctx.device)
-    for i in range(0, idx.numel(), pair_chunk):
-        sel = idx[i:i + pair_chunk]
-        o, d = rayo.index_select(0, sel).contiguous(), rayd.index_select(0, sel).contiguous()
-        k = o.shape[0]
-        z = _lib.gen_z(ctx, lvis_near, lvis_far, n_c, k, lin, None)
-        sigma = eval_sigma_mlp(model, o, d, z, False, scene_bbox, precision)
-        w, _, _, _, _ = _lib.composite(ctx, sigma, z, o, d, want_surf=False)
-        z = _lib.gen_z_fine(ctx, z, w, n_f)
-        sigma = eval_sigma_mlp(model, o, d, z, True, scene_bbox, precision)
-        _, occu, _, _, _ = _lib.composite(ctx, sigma, z, o, d, want_weights=False,
-                                          want_surf=False)
-        lvis.index_copy_(0, sel, 1. - occu)
-    return lvis.reshape(m, L)
+    return _lib.raymarch_lvis_fwd(
+        ctx, model.packed_sigma(False), model.packed_sigma(True), surf.contiguous(),
+        normal.contiguous(), lxyz, lvis_near, lvis_far, n_c, n_f, lin, parse_bbox(scene_bbox),
+        precision or model.precision)
 
 
 def postprocess_view(occu, exp_depth, exp_normal, rayo, rayd, hw, occu_thres=0.):

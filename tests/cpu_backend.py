@@ -212,7 +212,39 @@ def microfacet_brdf_fwd(ctx, pts2l, pts2c, normal, albedo=None, rough=None, defa
     return m(pts2l, pts2c, normal, albedo, None if rough is None else rough.reshape(-1, 1))
 
 
-_PATCHED = ('default_context', 'microfacet_brdf_fwd', 'point_mlp_fwd', 'lvis_fwd', 'brdf_learned_fwd', 'integrate_fwd',
+def raymarch_depth_normal_fwd(ctx, mlp_coarse, mlp_fine, rayo, rayd, near, far, n_coarse, n_fine,
+                              lin_in_disp=False, bbox=None, precision='f16e'):
+    n = rayo.shape[0]
+    z = gen_z(ctx, near, far, n_coarse, n, lin_in_disp, None)
+    sigma = sigma_fwd(ctx, mlp_coarse, rayo, rayd, z, bbox, precision)
+    w, _, _, _, _ = composite(ctx, sigma, z, rayo, rayd, want_surf=False)
+    z = gen_z_fine(ctx, z, w, n_fine)
+    sigma, normal = sigma_normal_fwd(ctx, mlp_fine, rayo, rayd, z, bbox, 'fp32')
+    _, occu, depth, _, en = composite(ctx, sigma, z, rayo, rayd, normal=normal,
+                                      want_weights=False, want_surf=False)
+    return occu, depth, en
+
+
+def raymarch_lvis_fwd(ctx, mlp_coarse, mlp_fine, surf, normal, lxyz, lvis_near, lvis_far,
+                      n_coarse, n_fine, lin_in_disp=False, bbox=None, precision='f16e'):
+    m, L = surf.shape[0], lxyz.shape[0]
+    rayo, rayd, fl = lvis_rays(ctx, surf, normal, lxyz)
+    idx = torch.nonzero(fl.reshape(-1), as_tuple=False)[:, 0]
+    lvis = torch.zeros((m * L,), dtype=torch.float32)
+    if idx.numel():
+        o, d = rayo[idx].contiguous(), rayd[idx].contiguous()
+        z = gen_z(ctx, lvis_near, lvis_far, n_coarse, o.shape[0], lin_in_disp, None)
+        sigma = sigma_fwd(ctx, mlp_coarse, o, d, z, bbox, precision)
+        w, _, _, _, _ = composite(ctx, sigma, z, o, d, want_surf=False)
+        z = gen_z_fine(ctx, z, w, n_fine)
+        sigma = sigma_fwd(ctx, mlp_fine, o, d, z, bbox, precision)
+        _, occu, _, _, _ = composite(ctx, sigma, z, o, d, want_weights=False, want_surf=False)
+        lvis[idx] = 1. - occu
+    return lvis.reshape(m, L)
+
+
+_PATCHED = ('default_context', 'microfacet_brdf_fwd', 'raymarch_depth_normal_fwd',
+            'raymarch_lvis_fwd', 'point_mlp_fwd', 'lvis_fwd', 'brdf_learned_fwd', 'integrate_fwd',
             'integrate_olat_fwd', 'gen_rays', 'gen_z', 'sigma_fwd', 'sigma_normal_fwd',
             'nerf_fwd', 'composite', 'gen_z_fine', 'lvis_rays', 'dense_fwd', 'dense_bwd',
             'adam_amsgrad_step')
