@@ -410,7 +410,10 @@ struct SmemLayout2 {
 };
 constexpr int COL_ONE = 208;       // constant A operand (1, 1, 0, ...): 8 columns
 
-template <int KIND, int BF16>
+// KSPLIT = 1: the A operand of a hidden layer is handed over in two K-halves (two barriers per
+// layer): the next layer's bias block and first four K-steps are issued as soon as the first 64
+// accumulator columns are converted, and execute while the epilogue converts the second 64.
+template <int KIND, int BF16, int KSPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p) {
   using SL = SmemLayout2<KIND>;
   constexpr int KE = SL::KE;
@@ -423,9 +426,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
   float4* s_lx = reinterpret_cast<float4*>(smem + SL::off_lx);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SL::off_bar);
   uint64_t* bar_w = bars + 0;          // weights landed
-  uint64_t* bar_a = bars + 1;          // [2] A operand ready (128 arrivals)
+  uint64_t* bar_a = bars + 1;          // [2] A operand (first K-half) ready (128 arrivals)
   uint64_t* bar_d = bars + 3;          // [2] D accumulator ready (tcgen05.commit)
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 5);
+  uint64_t* bar_a1 = bars + 5;         // [2] second K-half of the A operand ready (KSPLIT)
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 7);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunks = (p.L + 127) / 128;
@@ -434,6 +438,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
   if (threadIdx.x == 0) {
     mbar_init(bar_w, 1);
     mbar_init(bar_a + 0, 128); mbar_init(bar_a + 1, 128);
+    mbar_init(bar_a1 + 0, 128); mbar_init(bar_a1 + 1, 128);
     mbar_init(bar_d + 0, 1); mbar_init(bar_d + 1, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -487,7 +492,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
                                     (uint32_t)(KE + 384 + KE + 16) * 256u};   // layers 1, 2
       const int nt0 = group_points(0) * chunks, nt1 = group_points(1) * chunks;
       const int nt_max = nt0 > nt1 ? nt0 : nt1;
-      uint32_t ph[2] = {0u, 0u};
+      uint32_t ph[2] = {0u, 0u}, ph1[2] = {0u, 0u};
       for (int it = 0; it < nt_max; ++it) {
         for (int layer = 0; layer < 4; ++layer) {
           for (int g = 0; g < 2; ++g) {
@@ -509,9 +514,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
                           make_b_desc(img0 + seg_off[0] + k * 2 * lbo, lbo, sbo), idesc, 1u);
             } else {
 #pragma unroll
-              for (int k = 0; k < 8; ++k)
+              for (int k = 0; k < 8; ++k) {
+                if (KSPLIT && k == 4) {            // second K-half of the A operand
+                  mbar_wait(bar_a1 + g, ph1[g]);
+                  ph1[g] ^= 1u;
+                  tc_fence_after();
+                }
                 tc_mma_ts(d_t, tb + COL_AH + k * 8,
                           make_b_desc(img0 + seg_off[layer] + k * 2 * lbo, lbo, sbo), idesc, 1u);
+              }
               if (layer == 3) {
 #pragma unroll
                 for (int k = 0; k < KE / 16; ++k)
@@ -639,9 +650,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
           uint32_t ra[32], rb[32], rc[32], rd[32];
           TC_LD32(ra, tb + COL_D);
           TC_LD32(rb, tb + COL_D + 32);
+          if (KSPLIT) {                       // the early MMAs of the next layer overwrite D:
+            TC_LD32(rc, tb + COL_D + 64);     // all of it has to be in registers first
+            TC_LD32(rd, tb + COL_D + 96);
+          }
           tc_wait_ld();
-          TC_LD32(rc, tb + COL_D + 64);       // second half in flight while the first converts
-          TC_LD32(rd, tb + COL_D + 96);
+          if (!KSPLIT) {
+            TC_LD32(rc, tb + COL_D + 64);     // second half in flight while the first converts
+            TC_LD32(rd, tb + COL_D + 96);
+          }
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i)
@@ -651,7 +668,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
           for (int i = 0; i < 16; ++i)
             pk[i] = pack2<BF16, 1>(__uint_as_float(rb[2 * i]), __uint_as_float(rb[2 * i + 1]));
           TC_ST16(tb + COL_AH + 16, pk);
-          tc_wait_ld();
+          if (KSPLIT) {
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive(bar_a + g);           // K-steps 0..3 of the next layer may start
+          } else {
+            tc_wait_ld();
+          }
 #pragma unroll
           for (int i = 0; i < 16; ++i)
             pk[i] = pack2<BF16, 1>(__uint_as_float(rc[2 * i]), __uint_as_float(rc[2 * i + 1]));
@@ -662,7 +685,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
           TC_ST16(tb + COL_AH + 48, pk);
           tc_wait_st();
           tc_fence_before();
-          mbar_arrive(bar_a + g);
+          mbar_arrive(KSPLIT ? bar_a1 + g : bar_a + g);
         }
         // ------------------------------------------------ layer 3 + head
         mbar_wait(bar_d + g, phd);
@@ -876,9 +899,17 @@ int launch_tc(nf_ctx* ctx, const nf_mlp* m, const TcParams& p, cudaStream_t st) 
   } else {
     using SL = SmemLayout2<KIND>;
     NF_CHECK_ARG(ctx, SL::total <= ctx->smem_optin, "shared memory budget exceeded");
-    NF_CUDA(ctx, cudaFuncSetAttribute(mlp_tc2_kernel<KIND, BF16>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SL::total));
-    mlp_tc2_kernel<KIND, BF16><<<grid, TC_THREADS, SL::total, st>>>(p);
+    // NF_LVIS_KSPLIT=0: hand the A operand over once per layer instead of in two K-halves
+    static const bool nosplit = [] { const char* e = getenv("NF_LVIS_KSPLIT"); return e && e[0] == '0'; }();
+    if (nosplit) {
+      NF_CUDA(ctx, cudaFuncSetAttribute(mlp_tc2_kernel<KIND, BF16, 0>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SL::total));
+      mlp_tc2_kernel<KIND, BF16, 0><<<grid, TC_THREADS, SL::total, st>>>(p);
+    } else {
+      NF_CUDA(ctx, cudaFuncSetAttribute(mlp_tc2_kernel<KIND, BF16, 1>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SL::total));
+      mlp_tc2_kernel<KIND, BF16, 1><<<grid, TC_THREADS, SL::total, st>>>(p);
+    }
   }
   NF_LAUNCH_CHECK(ctx);
   return NF_OK;
