@@ -165,6 +165,38 @@ int nf_integrate_fwd(nf_ctx* ctx, const nf_integrate_args* args, void* stream);
 int nf_integrate_olat_fwd(nf_ctx* ctx, const nf_integrate_args* args, float olat_inten,
                           float ambient, float* rgb_olat_d, void* stream);
 
+/* Fused Stage B: light-visibility network -> BRDF -> rendering equation in one call, without the
+ * [n, L] light-visibility / specular tensors resident in HBM.  Replaces, for rendering, the chain
+ * _pred_lvis_at -> _eval_brdf_at -> _render of nerfactor/models/nerfactor.py:217-226, 262-266,
+ * 315-342 (the per-point networks -- normal, albedo, roughness / z -- are evaluated before, by
+ * nf_point_mlp_fwd).  Microfacet lobe, one env-map, L <= 512, NF_PREC_F16 / BF16: ONE kernel,
+ * the integral is taken in the head epilogue of the visibility network.  Otherwise the three
+ * kernels run over point chunks whose rows stay L2-resident (workspace from the caller).
+ * lvis_d: optional [n, L] output (NULL: visibility values are not materialised at all in the
+ * single-kernel case).  rgb_d [n, E, 3].                                                      */
+typedef struct nf_stageb_args {
+  int n, n_lights, n_envmaps, envmap_pixels;
+  int brdf_kind;          /* 0 microfacet (rough_d), 1 learned lobe (z_d + mlp_brdf)            */
+  int linear2srgb, z_dim;
+  float f0, spec_scale, xyz_scale;
+  const float* xyz_d;     /* [n,3] */
+  const float* normal_d;  /* [n,3] predicted normals */
+  const float* cam_d;     /* [n,3] */
+  const float* albedo_d;  /* [n,3] */
+  const float* rough_d;   /* [n]   microfacet */
+  const float* z_d;       /* [n, z_dim] learned lobe */
+  const float* lxyz_d;    /* [L,3] */
+  const float* lareas_d;  /* [L] */
+  const float* light_d;   /* [E, envmap_pixels, 3] */
+  const int32_t* light_idx_d; /* [L] or NULL */
+  float* lvis_d;          /* [n,L] or NULL */
+  float* rgb_d;           /* [n,E,3] */
+} nf_stageb_args;
+size_t nf_stageB_fused_workspace_bytes(const nf_stageb_args* args, int precision);
+int nf_stageB_fused_fwd(nf_ctx* ctx, const nf_mlp* mlp_lvis, const nf_mlp* mlp_brdf,
+                        const nf_stageb_args* args, int precision, void* workspace_d,
+                        size_t workspace_bytes, void* stream);
+
 /* Microfacet.__call__ (brdf/microfacet/microfacet.py:30-72) as a standalone op for callers that
  * use the class directly: brdf[n, L, 3] = GGX specular (achromatic, view-side G, f0) + albedo/pi
  * for caller-supplied directions pts2l[n, L, 3], pts2c[n, 3] and normals (all normalised inside

@@ -31,7 +31,8 @@ EXPORTS = [
     'nf_dense_fwd_workspace_bytes', 'nf_dense_bwd_workspace_bytes',
     'nf_dense_bwd', 'nf_adam_amsgrad_step', 'nf_microfacet_brdf_fwd', 'nf_selftest_tmem',
     'nf_raymarch_depth_normal_workspace_bytes', 'nf_raymarch_depth_normal_fwd',
-    'nf_raymarch_lvis_workspace_bytes', 'nf_raymarch_lvis_fwd']
+    'nf_raymarch_lvis_workspace_bytes', 'nf_raymarch_lvis_fwd',
+    'nf_stageB_fused_workspace_bytes', 'nf_stageB_fused_fwd']
 
 
 class NfError(RuntimeError):
@@ -61,6 +62,17 @@ class IntegrateArgs(C.Structure):
                 ('albedo_d', C.c_void_p), ('rough_d', C.c_void_p), ('spec_d', C.c_void_p),
                 ('lvis_d', C.c_void_p), ('lxyz_d', C.c_void_p), ('lareas_d', C.c_void_p),
                 ('light_d', C.c_void_p), ('light_idx_d', C.c_void_p), ('rgb_d', C.c_void_p)]
+
+
+class StageBArgs(C.Structure):
+    _fields_ = [('n', C.c_int), ('n_lights', C.c_int), ('n_envmaps', C.c_int),
+                ('envmap_pixels', C.c_int), ('brdf_kind', C.c_int), ('linear2srgb', C.c_int),
+                ('z_dim', C.c_int), ('f0', C.c_float), ('spec_scale', C.c_float),
+                ('xyz_scale', C.c_float), ('xyz_d', C.c_void_p), ('normal_d', C.c_void_p),
+                ('cam_d', C.c_void_p), ('albedo_d', C.c_void_p), ('rough_d', C.c_void_p),
+                ('z_d', C.c_void_p), ('lxyz_d', C.c_void_p), ('lareas_d', C.c_void_p),
+                ('light_d', C.c_void_p), ('light_idx_d', C.c_void_p), ('lvis_d', C.c_void_p),
+                ('rgb_d', C.c_void_p)]
 
 
 _lib = None
@@ -111,6 +123,9 @@ def load_library():
     lib.nf_raymarch_depth_normal_workspace_bytes.restype = C.c_size_t
     lib.nf_raymarch_depth_normal_fwd.argtypes = [vp, vp, vp, vp, vp, i, f, f, i, i, i, C.POINTER(f),
                                                  i, vp, C.c_size_t, vp, vp, vp, vp]
+    lib.nf_stageB_fused_workspace_bytes.argtypes = [C.POINTER(StageBArgs), i]
+    lib.nf_stageB_fused_workspace_bytes.restype = C.c_size_t
+    lib.nf_stageB_fused_fwd.argtypes = [vp, vp, vp, C.POINTER(StageBArgs), i, vp, C.c_size_t, vp]
     lib.nf_raymarch_lvis_workspace_bytes.argtypes = [i, i, i, i]
     lib.nf_raymarch_lvis_workspace_bytes.restype = C.c_size_t
     lib.nf_raymarch_lvis_fwd.argtypes = [vp, vp, vp, vp, vp, i, vp, i, f, f, i, i, i, C.POINTER(f),
@@ -127,7 +142,7 @@ def load_library():
         if name not in ('nf_last_error_string', 'nf_mlp_device_bytes',
                         'nf_dense_bwd_workspace_bytes', 'nf_dense_fwd_workspace_bytes',
                         'nf_raymarch_depth_normal_workspace_bytes',
-                        'nf_raymarch_lvis_workspace_bytes'):
+                        'nf_raymarch_lvis_workspace_bytes', 'nf_stageB_fused_workspace_bytes'):
             getattr(lib, name).restype = i
     _lib = lib
     return lib
@@ -326,6 +341,44 @@ def integrate_olat_fwd(ctx, xyz, normal, cam, albedo, lvis, lxyz, lareas, olat_i
     ctx.launch(ctx.lib.nf_integrate_olat_fwd(ctx.h, C.byref(a), float(olat_inten),
                                             float(ambient), _f32(out), _stream()))
     return out
+
+
+def stageB_fused_fwd(ctx, mlp_lvis, xyz, normal, cam, albedo, lxyz, lareas, light, rough=None,
+                     z=None, mlp_brdf=None, light_idx=None, f0=0.04, spec_scale=1.0, xyz_scale=1.0,
+                     linear2srgb=True, precision='f16', want_lvis=False):
+    """Light-visibility net -> BRDF -> rendering equation in one C call (nf_stageB_fused_fwd).
+    light [E, P, 3] -> rgb [n, E, 3] (and lvis [n, L] when want_lvis)."""
+    lxyz, lareas = lxyz.reshape(-1, 3), lareas.reshape(-1)
+    n, L, E = xyz.shape[0], lxyz.shape[0], light.shape[0]
+    dev = xyz.device
+    rgb = torch.empty((n, E, 3), dtype=torch.float32, device=dev)
+    lvis = torch.empty((n, L), dtype=torch.float32, device=dev) if want_lvis else None
+    a = StageBArgs()
+    a.n, a.n_lights, a.n_envmaps, a.envmap_pixels = n, L, E, light.shape[1]
+    a.brdf_kind = 0 if z is None else 1
+    a.linear2srgb, a.f0, a.spec_scale, a.xyz_scale = int(linear2srgb), float(f0), float(spec_scale), float(xyz_scale)
+    a.xyz_d, a.normal_d, a.cam_d, a.albedo_d = _f32(xyz), _f32(normal), _f32(cam), _f32(albedo)
+    if z is None:
+        rough = rough.reshape(-1)
+        a.rough_d = _f32(rough)
+    else:
+        a.z_d, a.z_dim = _f32(z), z.shape[1]
+    a.lxyz_d, a.lareas_d, a.light_d = _f32(lxyz), _f32(lareas), _f32(light)
+    if light_idx is not None:
+        assert light_idx.dtype == torch.int32
+        a.light_idx_d = _ptr(light_idx)
+    a.lvis_d = _f32(lvis) if lvis is not None else None
+    a.rgb_d = _f32(rgb)
+    nbytes = ctx.lib.nf_stageB_fused_workspace_bytes(C.byref(a), PREC[precision])
+    work = torch.empty((nbytes + 256,), dtype=torch.uint8, device=dev) if nbytes else None
+    wptr = C.c_void_p(work.data_ptr() + (-work.data_ptr()) % 256) if nbytes else None
+    if nbytes:          # chunked path: 2-3 kernels per chunk of <= 32 MB rows
+        cpts = max(256, ((32 << 20) // (L * 4)) // 256 * 256)
+        ctx.launches += (2 + (z is not None)) * max(1, (n + cpts - 1) // cpts) - 1
+    ctx.launch(ctx.lib.nf_stageB_fused_fwd(
+        ctx.h, mlp_lvis.h, mlp_brdf.h if mlp_brdf is not None else None, C.byref(a),
+        PREC[precision], wptr, nbytes, _stream()))
+    return rgb, lvis
 
 
 def microfacet_brdf_fwd(ctx, pts2l, pts2c, normal, albedo=None, rough=None, default_rough=0.3,

@@ -53,7 +53,18 @@ struct TcParams {
   const float* normal;   // BRDF: [n,3]
   const float* cam;      // BRDF: [n,3]
   const float* zlat;     // BRDF: [n,z_dim]
-  float* out;            // [n, L]
+  float* out;            // [n, L]  (NULL: the light-visibility values are not materialised)
+  // ---- fused rendering equation (nf_stageB_fused_fwd: microfacet BRDF, one env-map, L <= 512)
+  const float* f_normal;   // [n,3] predicted normals
+  const float* f_cam;      // [n,3] camera position per point
+  const float* f_albedo;   // [n,3]
+  const float* f_rough;    // [n]
+  const float* f_lareas;   // [L]
+  const float* f_light;    // [P,3] env-map texels (clipped >= 0)
+  const int* f_light_idx;  // [L] light -> texel, or NULL
+  float f_f0;
+  int f_srgb;
+  float* f_rgb;            // [n,3]; NULL = plain network evaluation
 };
 
 // fp32 side block layout (floats): see nf_tc_pack
@@ -406,14 +417,14 @@ struct SmemLayout2 {
   static constexpr size_t off_lx = off_e + 2 * 64 * 4;                   // float4 [Lmax]
   static constexpr int LMAX = 1024;
   static constexpr size_t off_bar = off_lx + (size_t)LMAX * 16;
-  static constexpr size_t total = off_bar + 128;
+  static constexpr size_t off_red = off_bar + 128;                       // [2 groups][16][4] f32
+  static constexpr size_t total = off_red + 2 * 16 * 4 * 4;
 };
 constexpr int COL_ONE = 208;       // constant A operand (1, 1, 0, ...): 8 columns
 
-// KSPLIT = 1: the A operand of a hidden layer is handed over in two K-halves (two barriers per
-// layer): the next layer's bias block and first four K-steps are issued as soon as the first 64
-// accumulator columns are converted, and execute while the epilogue converts the second 64.
-template <int KIND, int BF16, int KSPLIT>
+// (Tried and removed: handing the A operand over in two K-halves so that the next layer's first
+// MMAs overlap the second half of the epilogue -- 33.1 vs 32.4 ms, profiles/r2_k2_analysis.md.)
+template <int KIND, int BF16>
 __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p) {
   using SL = SmemLayout2<KIND>;
   constexpr int KE = SL::KE;
@@ -428,8 +439,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
   uint64_t* bar_w = bars + 0;          // weights landed
   uint64_t* bar_a = bars + 1;          // [2] A operand (first K-half) ready (128 arrivals)
   uint64_t* bar_d = bars + 3;          // [2] D accumulator ready (tcgen05.commit)
-  uint64_t* bar_a1 = bars + 5;         // [2] second K-half of the A operand ready (KSPLIT)
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 7);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 5);
+  float* s_red = reinterpret_cast<float*>(smem + SL::off_red);
+  // fused rendering equation: texel * area per light in the upper half of the light table
+  const bool fuse = KIND == NF_MLP_LVIS && p.f_rgb != nullptr;
+  float4* s_lrgb = s_lx + 512;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunks = (p.L + 127) / 128;
@@ -438,7 +452,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
   if (threadIdx.x == 0) {
     mbar_init(bar_w, 1);
     mbar_init(bar_a + 0, 128); mbar_init(bar_a + 1, 128);
-    mbar_init(bar_a1 + 0, 128); mbar_init(bar_a1 + 1, 128);
     mbar_init(bar_d + 0, 1); mbar_init(bar_d + 1, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -449,8 +462,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int l = threadIdx.x; l < p.L; l += blockDim.x)
+  for (int l = threadIdx.x; l < p.L; l += blockDim.x) {
     s_lx[l] = make_float4(p.lxyz[l * 3], p.lxyz[l * 3 + 1], p.lxyz[l * 3 + 2], 0.f);
+    if (fuse) {            // light * area: rgb += brdf (lvis light) cos area, nerfactor.py:333-336
+      const float* t = p.f_light + (size_t)(p.f_light_idx ? p.f_light_idx[l] : l) * 3;
+      const float ar = p.f_lareas[l];
+      s_lrgb[l] = make_float4(t[0] * ar, t[1] * ar, t[2] * ar, 0.f);
+    }
+  }
   for (int i = threadIdx.x; i < 2 * 2 * 4096 / 4; i += blockDim.x)       // k = 2..15 rows stay zero
     reinterpret_cast<uint32_t*>(s_bdyn)[i] = 0u;
   fence_proxy_async();
@@ -492,7 +511,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
                                     (uint32_t)(KE + 384 + KE + 16) * 256u};   // layers 1, 2
       const int nt0 = group_points(0) * chunks, nt1 = group_points(1) * chunks;
       const int nt_max = nt0 > nt1 ? nt0 : nt1;
-      uint32_t ph[2] = {0u, 0u}, ph1[2] = {0u, 0u};
+      uint32_t ph[2] = {0u, 0u};
       for (int it = 0; it < nt_max; ++it) {
         for (int layer = 0; layer < 4; ++layer) {
           for (int g = 0; g < 2; ++g) {
@@ -514,15 +533,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
                           make_b_desc(img0 + seg_off[0] + k * 2 * lbo, lbo, sbo), idesc, 1u);
             } else {
 #pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                if (KSPLIT && k == 4) {            // second K-half of the A operand
-                  mbar_wait(bar_a1 + g, ph1[g]);
-                  ph1[g] ^= 1u;
-                  tc_fence_after();
-                }
+              for (int k = 0; k < 8; ++k)
                 tc_mma_ts(d_t, tb + COL_AH + k * 8,
                           make_b_desc(img0 + seg_off[layer] + k * 2 * lbo, lbo, sbo), idesc, 1u);
-              }
               if (layer == 3) {
 #pragma unroll
                 for (int k = 0; k < KE / 16; ++k)
@@ -580,6 +593,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
         f3 v = l2n(ld3(p.cam + (size_t)pt * 3) - x, 1e-6f);                   // shape.py:137-144
         v_loc = mk3(dot3(fr_t, v), dot3(fr_b, v), dot3(fr_n, v));             // nerfactor.py:418
       }
+      // fused rendering equation: this point's shading frame (every thread, same values)
+      f3 n1 = mk3(0.f, 0.f, 1.f), v2 = n1, lam = n1;
+      float a2 = 0.f, g_view = 0.f, cos_v = 0.f, abs_vn = 0.f;
+      if (fuse) {
+        n1 = l2n(l2n(ld3(p.f_normal + (size_t)pt * 3), 1e-6f), 1e-6f);     // nerfactor.py:212, microfacet.py:48
+        v2 = l2n(l2n(ld3(p.f_cam + (size_t)pt * 3) - x, 1e-6f), 1e-6f);    // shape.py:137-144, microfacet.py:47
+        const f3 alb = ld3(p.f_albedo + (size_t)pt * 3);
+        lam = mk3(alb.x / NF_PI_F, alb.y / NF_PI_F, alb.z / NF_PI_F);
+        const float rough = p.f_rough[pt];
+        const float alpha = rough * rough;                                   // microfacet.py:54
+        a2 = alpha * alpha;
+        cos_v = dot3(n1, v2);                                                // :77
+        const float cv2 = fminf(fmaxf(cos_v * cos_v, 0.f), 1.f);             // :82-84
+        const float tan2 = fmaxf(divide_no_nan(1.f - cv2, cv2), 0.f);        // :85-87
+        g_view = 2.f / (1.f + sqrtf(1.f + a2 * tan2));                       // :88-89
+        abs_vn = fabsf(cos_v);
+      }
       group_bar(1 + g);
       {
         // fold the per-point input columns into the biases of layer 0 and of the skip layer (fp32),
@@ -603,9 +633,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
         const int lc = li < p.L ? li : p.L - 1;
         // ------------------------------------------------ per-row embedding -> A_e
         float mask = 1.f;
+        f3 ldir;
         {
           float4 lp = s_lx[lc];
           f3 d = l2n(mk3(lp.x, lp.y, lp.z) - x, 1e-6f);                       // shape.py:128-135
+          ldir = d;
           float v[KE];
 #pragma unroll
           for (int i = 0; i < KE; ++i) v[i] = 0.f;
@@ -650,15 +682,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
           uint32_t ra[32], rb[32], rc[32], rd[32];
           TC_LD32(ra, tb + COL_D);
           TC_LD32(rb, tb + COL_D + 32);
-          if (KSPLIT) {                       // the early MMAs of the next layer overwrite D:
-            TC_LD32(rc, tb + COL_D + 64);     // all of it has to be in registers first
-            TC_LD32(rd, tb + COL_D + 96);
-          }
           tc_wait_ld();
-          if (!KSPLIT) {
-            TC_LD32(rc, tb + COL_D + 64);     // second half in flight while the first converts
-            TC_LD32(rd, tb + COL_D + 96);
-          }
+          TC_LD32(rc, tb + COL_D + 64);       // second half in flight while the first converts
+          TC_LD32(rd, tb + COL_D + 96);
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i)
@@ -668,13 +694,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
           for (int i = 0; i < 16; ++i)
             pk[i] = pack2<BF16, 1>(__uint_as_float(rb[2 * i]), __uint_as_float(rb[2 * i + 1]));
           TC_ST16(tb + COL_AH + 16, pk);
-          if (KSPLIT) {
-            tc_wait_st();
-            tc_fence_before();
-            mbar_arrive(bar_a + g);           // K-steps 0..3 of the next layer may start
-          } else {
-            tc_wait_ld();
-          }
+          tc_wait_ld();
 #pragma unroll
           for (int i = 0; i < 16; ++i)
             pk[i] = pack2<BF16, 1>(__uint_as_float(rc[2 * i]), __uint_as_float(rc[2 * i + 1]));
@@ -685,7 +705,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
           TC_ST16(tb + COL_AH + 48, pk);
           tc_wait_st();
           tc_fence_before();
-          mbar_arrive(KSPLIT ? bar_a1 + g : bar_a + g);
+          mbar_arrive(bar_a + g);
         }
         // ------------------------------------------------ layer 3 + head
         mbar_wait(bar_d + g, phd);
@@ -728,7 +748,56 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
         }
         float o = (acc0 + acc1) + s_aux[AUX_BOUT];
         o = apply_act(p.out_act, o) * mask;
-        if (li < p.L) p.out[(size_t)pt * p.L + li] = o;
+        if (li < p.L && p.out) p.out[(size_t)pt * p.L + li] = o;
+        if (fuse) {
+          // one term of the rendering equation (nerfactor.py:325-336) with the GGX lobe of
+          // brdf/microfacet/microfacet.py:30-111 (same reduction as nf_integrate.cu eval_pair)
+          float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+          if (li < p.L) {
+            const float cosl = dot3(ldir, n1);                               // :325
+            const float wgt = (cosl > 0.f ? o : 0.f) * cosl;                 // :329-335 (area in s_lrgb)
+            const f3 hs = ldir + v2;
+            const f3 h = hs * rsqrtf(fmaxf(dot3(hs, hs), 1e-6f));            // microfacet.py:51-52
+            const float om = 1.f - dot3(ldir, h);
+            const float om2 = om * om;
+            const float fr = p.f_f0 + (1.f - p.f_f0) * (om2 * om2 * om);     // :106-111
+            const float cm = dot3(h, n1);                                    // :96
+            const float cm2 = cm * cm;
+            const float u = fmaf(a2, cm2, 1.f - cm2);
+            const bool on = (cm > 0.f) && (dot3(h, v2) * cos_v > 0.f);       // chi_d, chi_g
+            const float den = (4.f * NF_PI_F) * (u * u) * (fabsf(cosl) * abs_vn);
+            const float spec = (on && den != 0.f) ? __fdividef(fr * (g_view * a2), den) : 0.f;
+            const float4 lc = s_lrgb[li];
+            c0 = (spec + lam.x) * (wgt * lc.x);
+            c1 = (spec + lam.y) * (wgt * lc.y);
+            c2 = (spec + lam.z) * (wgt * lc.z);
+          }
+#pragma unroll
+          for (int sft = 16; sft > 0; sft >>= 1) {
+            c0 += __shfl_xor_sync(0xffffffffu, c0, sft);
+            c1 += __shfl_xor_sync(0xffffffffu, c1, sft);
+            c2 += __shfl_xor_sync(0xffffffffu, c2, sft);
+          }
+          if (lane == 0) {          // fixed slot per (chunk, warp): summed in a fixed order below
+            float* slot = s_red + ((size_t)g * 16 + c * 4 + wq) * 4;
+            slot[0] = c0; slot[1] = c1; slot[2] = c2;
+          }
+        }
+      }
+      if (fuse) {
+        group_bar(1 + g);
+        if (tg == 0) {
+          float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+          for (int q = 0; q < chunks * 4; ++q) {
+            const float* slot = s_red + ((size_t)g * 16 + q) * 4;
+            r0 += slot[0]; r1 += slot[1]; r2 += slot[2];
+          }
+          float* orgb = p.f_rgb + (size_t)pt * 3;
+          r0 = fminf(fmaxf(r0, 0.f), 1.f); r1 = fminf(fmaxf(r1, 0.f), 1.f); r2 = fminf(fmaxf(r2, 0.f), 1.f);
+          orgb[0] = p.f_srgb ? linear2srgb_dev(r0) : r0;                     // nerfactor.py:338-339
+          orgb[1] = p.f_srgb ? linear2srgb_dev(r1) : r1;
+          orgb[2] = p.f_srgb ? linear2srgb_dev(r2) : r2;
+        }
       }
     }
   }
@@ -890,7 +959,7 @@ int launch_tc(nf_ctx* ctx, const nf_mlp* m, const TcParams& p, cudaStream_t st) 
   if (grid > need) grid = need;
   // NF_LVIS_V1=1 selects the first-generation kernel (bias added in the epilogue): A / B timing
   static const bool v1 = [] { const char* e = getenv("NF_LVIS_V1"); return e && e[0] == '1'; }();
-  if (v1) {
+  if (v1 && p.f_rgb == nullptr) {
     using SL = SmemLayout<KIND>;
     NF_CHECK_ARG(ctx, SL::total <= ctx->smem_optin, "shared memory budget exceeded");
     NF_CUDA(ctx, cudaFuncSetAttribute(mlp_tc_kernel<KIND, BF16>,
@@ -899,17 +968,9 @@ int launch_tc(nf_ctx* ctx, const nf_mlp* m, const TcParams& p, cudaStream_t st) 
   } else {
     using SL = SmemLayout2<KIND>;
     NF_CHECK_ARG(ctx, SL::total <= ctx->smem_optin, "shared memory budget exceeded");
-    // NF_LVIS_KSPLIT=0: hand the A operand over once per layer instead of in two K-halves
-    static const bool nosplit = [] { const char* e = getenv("NF_LVIS_KSPLIT"); return e && e[0] == '0'; }();
-    if (nosplit) {
-      NF_CUDA(ctx, cudaFuncSetAttribute(mlp_tc2_kernel<KIND, BF16, 0>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SL::total));
-      mlp_tc2_kernel<KIND, BF16, 0><<<grid, TC_THREADS, SL::total, st>>>(p);
-    } else {
-      NF_CUDA(ctx, cudaFuncSetAttribute(mlp_tc2_kernel<KIND, BF16, 1>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SL::total));
-      mlp_tc2_kernel<KIND, BF16, 1><<<grid, TC_THREADS, SL::total, st>>>(p);
-    }
+    NF_CUDA(ctx, cudaFuncSetAttribute(mlp_tc2_kernel<KIND, BF16>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SL::total));
+    mlp_tc2_kernel<KIND, BF16><<<grid, TC_THREADS, SL::total, st>>>(p);
   }
   NF_LAUNCH_CHECK(ctx);
   return NF_OK;
@@ -1027,6 +1088,26 @@ int nf_tc_lvis_launch(nf_ctx* ctx, const nf_mlp* m, const float* xyz, int n, flo
   if (n == 0) return NF_OK;
   p.n = n; p.L = L; p.nr = 3 * (1 + 2 * m->d.n_freqs_a); p.xyz_scale = xyz_scale;
   p.xyz = xyz; p.lxyz = lxyz; p.out = lvis;
+  return precision == NF_PREC_BF16 ? launch_tc<NF_MLP_LVIS, 1>(ctx, m, p, st)
+                                   : launch_tc<NF_MLP_LVIS, 0>(ctx, m, p, st);
+}
+
+// Light-visibility network with the rendering equation fused into the head epilogue
+// (nf_stageB_fused_fwd): rgb[n,3]; lvis may be NULL.  Microfacet lobe, one env-map, L <= 512.
+int nf_tc_lvis_render_launch(nf_ctx* ctx, const nf_mlp* m, const float* xyz, int n, float xyz_scale,
+                             const float* lxyz, int L, const float* normal, const float* cam,
+                             const float* albedo, const float* rough, const float* lareas,
+                             const float* light, const int* light_idx, float f0, int srgb,
+                             float* lvis, float* rgb, int precision, cudaStream_t st) {
+  TcParams p;
+  int rc = tc_common(ctx, m, precision, p);
+  if (rc != NF_OK) return rc;
+  NF_CHECK_ARG(ctx, L <= 512, "fused rendering needs n_lights <= 512");
+  if (n == 0) return NF_OK;
+  p.n = n; p.L = L; p.nr = 3 * (1 + 2 * m->d.n_freqs_a); p.xyz_scale = xyz_scale;
+  p.xyz = xyz; p.lxyz = lxyz; p.out = lvis;
+  p.f_normal = normal; p.f_cam = cam; p.f_albedo = albedo; p.f_rough = rough; p.f_lareas = lareas;
+  p.f_light = light; p.f_light_idx = light_idx; p.f_f0 = f0; p.f_srgb = srgb; p.f_rgb = rgb;
   return precision == NF_PREC_BF16 ? launch_tc<NF_MLP_LVIS, 1>(ctx, m, p, st)
                                    : launch_tc<NF_MLP_LVIS, 0>(ctx, m, p, st);
 }

@@ -180,18 +180,21 @@ class Model(NeRFactorVis, ShapeModel):
         """nerfactor.py:398-411."""
         return self._pred_point('brdf_z', pts)
 
-    def _eval_brdf_at(self, pts2l, pts2c, normal, albedo, brdf_prop, pts=None, cam=None):
-        """nerfactor.py:413-461.  Returns the achromatic specular lobe spec[N,L]
-        (the Lambertian term albedo/pi and learned_brdf_scale are applied inside the
-        rendering-equation kernel, nerfactor.py:460).  `pts2l` / `pts2c` are accepted
-        for signature parity; directions are rebuilt on chip from pts / cam."""
+    def _packed_brdf_mlp(self):
         if 'brdf' not in self._packed:
             trunk, head = self.brdf_model.net['brdf_mlp'], self.brdf_model.net['brdf_out']
             self._packed['brdf'] = _lib.PackedMlp(
                 self.ctx, 'brdf', trunk.weights() + head.weights(), trunk.skip_at[0],
                 'softplus', n_freqs_a=self.embedder['rusink'].n_freqs, z_dim=self.z_dim)
+        return self._packed['brdf']
+
+    def _eval_brdf_at(self, pts2l, pts2c, normal, albedo, brdf_prop, pts=None, cam=None):
+        """nerfactor.py:413-461.  Returns the achromatic specular lobe spec[N,L]
+        (the Lambertian term albedo/pi and learned_brdf_scale are applied inside the
+        rendering-equation kernel, nerfactor.py:460).  `pts2l` / `pts2c` are accepted
+        for signature parity; directions are rebuilt on chip from pts / cam."""
         spec = _lib.brdf_learned_fwd(
-            self.ctx, self._packed['brdf'], pts, normal, cam, brdf_prop.contiguous(),
+            self.ctx, self._packed_brdf_mlp(), pts, normal, cam, brdf_prop.contiguous(),
             self.lxyz.reshape(-1, 3), self.precision)
         return {'spec': spec}
 
@@ -321,6 +324,60 @@ class Model(NeRFactorVis, ShapeModel):
         for k, v in gt.items():
             to_vis['gt_' + k] = v
         return pred, gt, loss_kwargs, to_vis
+
+    # ------------------------------------------------------------ fused rendering
+    def render_rgb(self, batch, relight_probes=False, want_lvis=False):
+        """The test-mode RGB of `call` (nerfactor.py:181-313: no jitter, no edits) through the
+        fused Stage-B op nf_stageB_fused_fwd: per-point networks, then light-visibility network ->
+        BRDF -> rendering equation in one call, the [N, L] light-visibility tensor not
+        materialised (unless `want_lvis`).  Returns a dict with 'rgb', 'normal', 'albedo', 'brdf'
+        (+ 'rgb_probes', 'lvis') in the full ray shape, background rows zero -- the same values
+        `call(batch, 'test')` returns for those keys."""
+        if self.shape_mode == 'nerf':
+            raise NotImplementedError("shape_mode = 'nerf' reads lvis from the batch: use call()")
+        _, _, rayo, _, _, alpha, xyz, _, _ = batch
+        dev = self.device
+        alpha, rayo, xyz = [to_device(x, dev) for x in (alpha, rayo, xyz)]
+        ind = torch.nonzero(alpha[:, 0] > 0, as_tuple=False)[:, 0]
+        sel = lambda x: x.index_select(0, ind).contiguous()
+        rayo_m, xyz_m = sel(rayo), sel(xyz)
+        normal = mathutil.safe_l2_normalize(self._pred_normal_at(xyz_m), axis=1).contiguous()
+        albedo = self._pred_albedo_at(xyz_m).contiguous()
+        brdf_prop = self._pred_brdf_at(xyz_m)
+        if self.normalize_brdf_z:
+            brdf_prop = mathutil.safe_l2_normalize(brdf_prop, axis=1)
+        brdf_prop = brdf_prop.contiguous()
+        lights = [self.light.reshape(-1, 3)]
+        if relight_probes:
+            lights += [to_device(v, dev).reshape(-1, 3) for v in self.novel_probes.values()]
+        light = torch.stack(lights, 0).contiguous()
+        rgb_all, lvis = self._fused_stage_b(xyz_m, normal, rayo_m, albedo, brdf_prop, light,
+                                            want_lvis)
+        n = alpha.shape[0]
+
+        def scatter(v):
+            out = torch.zeros((n,) + tuple(v.shape[1:]), dtype=v.dtype, device=dev)
+            out.index_copy_(0, ind, v)
+            return out
+        out = {'rgb': scatter(rgb_all[:, 0, :]), 'normal': scatter(normal),
+               'albedo': scatter(albedo), 'brdf': scatter(brdf_prop)}
+        if relight_probes:
+            out['rgb_probes'] = scatter(rgb_all[:, 1:, :])
+        if want_lvis:
+            out['lvis'] = scatter(lvis)
+        return out
+
+    def _fused_stage_b(self, pts, normal, cam, albedo, brdf_prop, light, want_lvis):
+        """Learned-MERL lobe: latent z + the BRDF prior's network."""
+        m_lvis = self._packed_mlp('lvis', 'lvis', n_freqs_a=self.embedder['xyz'].n_freqs,
+                                  n_freqs_b=self.embedder['ldir'].n_freqs)
+        return _lib.stageB_fused_fwd(
+            self.ctx, m_lvis, pts, normal, cam, albedo, self.lxyz, self.lareas, light,
+            z=brdf_prop, mlp_brdf=self._packed_brdf_mlp(), light_idx=self.light_idx,
+            spec_scale=self.config.getfloat('DEFAULT', 'learned_brdf_scale'),
+            xyz_scale=self.xyz_scale,
+            linear2srgb=self.config.getboolean('DEFAULT', 'linear2srgb'),
+            precision=self.precision, want_lvis=want_lvis)
 
     # ------------------------------------------------------------------- loss
     def compute_loss(self, pred, gt, **kwargs):

@@ -44,19 +44,25 @@ class ViewRenderer:
                 'xyz': xyz.contiguous(), 'surf': out['surf'], 'occu': out['occu'],
                 'depth': out['depth']}
 
-    def stage_b(self, a, relight_olat=False, relight_probes=False):
+    def stage_b(self, a, relight_olat=False, relight_probes=False, fused=True):
+        """Stage B on Stage A's buffers.  `fused` (default): Model.render_rgb -- the per-point
+        networks, then nf_stageB_fused_fwd (light visibility -> BRDF -> rendering equation in one
+        call, no [N, L] tensor in HBM); the image-level outputs are the same as `Model.call`'s.
+        OLAT relighting and fused=False go through Model.call (which also returns pred['lvis'])."""
         n = a['xyz'].shape[0]
         zeros3 = torch.zeros((n, 3), device=self.ctx.device)
         batch = (None, None, a['rayo'], a['rayd'], zeros3, a['alpha'], a['xyz'], zeros3,
                  None)
+        if fused and not relight_olat and hasattr(self.model, 'render_rgb'):
+            return self.model.render_rgb(batch, relight_probes=relight_probes)
         pred, _, _, _ = self.model.call(batch, 'test', relight_olat=relight_olat,
                                         relight_probes=relight_probes)
         return pred
 
     def render(self, c2w, cam_angle_x, h, w, ray_range=None, relight_olat=False,
-               relight_probes=False):
+               relight_probes=False, fused=True):
         a = self.stage_a(c2w, cam_angle_x, h, w, ray_range)
-        pred = self.stage_b(a, relight_olat, relight_probes)
+        pred = self.stage_b(a, relight_olat, relight_probes, fused)
         pred['alpha'] = a['alpha']
         pred['xyz'] = a['xyz']
         return pred

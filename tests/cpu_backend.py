@@ -243,7 +243,18 @@ def raymarch_lvis_fwd(ctx, mlp_coarse, mlp_fine, surf, normal, lxyz, lvis_near, 
     return lvis.reshape(m, L)
 
 
-_PATCHED = ('default_context', 'microfacet_brdf_fwd', 'raymarch_depth_normal_fwd',
+def stageB_fused_fwd(ctx, mlp_lvis, xyz, normal, cam, albedo, lxyz, lareas, light, rough=None,
+                     z=None, mlp_brdf=None, light_idx=None, f0=0.04, spec_scale=1.0, xyz_scale=1.0,
+                     linear2srgb=True, precision='f16', want_lvis=False):
+    lvis = lvis_fwd(ctx, mlp_lvis, xyz, lxyz, xyz_scale, precision)
+    spec = None if z is None else brdf_learned_fwd(ctx, mlp_brdf, xyz, normal, cam, z, lxyz, precision)
+    rgb = integrate_fwd(ctx, xyz, normal, cam, albedo, lvis, lxyz, lareas, light,
+                        rough=None if rough is None else rough.reshape(-1, 1), spec=spec,
+                        light_idx=light_idx, f0=f0, spec_scale=spec_scale, linear2srgb=linear2srgb)
+    return rgb, (lvis if want_lvis else None)
+
+
+_PATCHED = ('default_context', 'microfacet_brdf_fwd', 'stageB_fused_fwd', 'raymarch_depth_normal_fwd',
             'raymarch_lvis_fwd', 'point_mlp_fwd', 'lvis_fwd', 'brdf_learned_fwd', 'integrate_fwd',
             'integrate_olat_fwd', 'gen_rays', 'gen_z', 'sigma_fwd', 'sigma_normal_fwd',
             'nerf_fwd', 'composite', 'gen_z_fine', 'lvis_rays', 'dense_fwd', 'dense_bwd',

@@ -19,7 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _header_symbols():
     src = open(os.path.join(ROOT, 'include', 'nerfactor_b200.h')).read()
     src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
-    return sorted(set(re.findall(r'\b(nf_[a-z0-9_]+)\s*\(', src)))
+    return sorted(set(re.findall(r'\b(nf_[A-Za-z0-9_]+)\s*\(', src)))
 
 
 def test_library_exports_every_header_symbol():

@@ -392,6 +392,35 @@ def test_stage_b_l512_rgb_within_1e4(ctx, brdf):
     assert rel_l2(pred['rgb_olat'].cpu().numpy()[:, :40], opred['rgb_relit']) < 1e-4
 
 
+@pytest.mark.parametrize('brdf,lh,lw,n', [('microfacet', 16, 32, 1000), ('microfacet', 10, 20, 203),
+                                          ('learned', 16, 32, 333), ('microfacet', 16, 64, 150)])
+def test_fused_stage_b_equals_model_call(ctx, brdf, lh, lw, n):
+    """Model.render_rgb (nf_stageB_fused_fwd) against Model.call on the same batch: the
+    single-kernel case (microfacet, one env-map, L <= 512: rendering equation inside the head
+    epilogue of the visibility network; ragged L = 200 too), the chunked cases (learned lobe;
+    L = 1024; several env-maps), with and without the optional lvis output -- and against the
+    oracle for RGB."""
+    m, om, _ = _stage_b(ctx, brdf, lh, lw, seed=13, precision='f16')
+    for i, p in enumerate(synth.make_probes(5, 3, light_hw=(lh, lw))):
+        m.novel_probes['p%d' % i] = p
+    batch = synth.make_stage_b_batch(31, n, lh * lw)
+    ref = m.call(batch, 'test', relight_probes=True)[0]
+    out = m.render_rgb(batch)
+    out_l = m.render_rgb(batch, want_lvis=True)
+    out_p = m.render_rgb(batch, relight_probes=True, want_lvis=True)
+    for k in ('normal', 'albedo', 'brdf'):
+        assert torch.equal(out[k], ref[k])
+    assert torch.equal(out_l['lvis'], ref['lvis']) and torch.equal(out_p['lvis'], ref['lvis'])
+    assert torch.equal(out['rgb'], out_l['rgb'])              # lvis output does not change the sums
+    assert rel_l2(out['rgb'].cpu(), ref['rgb'].cpu()) < 1e-5
+    assert rel_l2(out_p['rgb_probes'].cpu(), ref['rgb_probes'].cpu()) < 1e-5
+    assert float(out['rgb'][torch.as_tensor(batch[5][:, 0] == 0)].abs().max()) == 0.
+    opred = om.call(batch, 'test')[0]
+    assert rel_l2(out['rgb'].cpu(), opred['rgb']) < 1e-4       # north-star bar vs the oracle
+    empty = tuple(x[:0] if isinstance(x, np.ndarray) else x for x in batch)
+    assert m.render_rgb(empty)['rgb'].shape == (0, 3)
+
+
 def test_config3_learned_brdf_1024_lights_on_16x32_envmap(ctx):
     """BASELINE configs[2]: learned-MERL BRDF, L = 1024 light directions (16x64 grid) looking
     up a 16x32 HDR env-map through the nearest-pixel index map (SURVEY 8d caveat on L)."""
