@@ -115,6 +115,13 @@ int nf_point_mlp_fwd(nf_ctx* ctx, const nf_mlp* mlp, const float* xyz_d, int n,
 int nf_lvis_fwd(nf_ctx* ctx, const nf_mlp* mlp, const float* xyz_d, int n,
                 float xyz_scale, const float* lxyz_d, int n_lights, float* lvis_d,
                 int precision, void* stream);
+/* Same network, but the light directions are taken from xyz_dir[n,3] while the position encoding
+ * uses xyz[n,3]: the smoothness-loss evaluation of nerfactor/models/shape.py:170 /
+ * nerfactor.py:225, where the reference evaluates the network at the JITTERED point with the
+ * directions surf2l of the un-jittered one.  tcgen05 only (NF_PREC_F16 / NF_PREC_BF16).        */
+int nf_lvis_dirs_fwd(nf_ctx* ctx, const nf_mlp* mlp, const float* xyz_d, const float* xyz_dir_d,
+                     int n, float xyz_scale, const float* lxyz_d, int n_lights, float* lvis_d,
+                     int precision, void* stream);
 
 /* spec[n, L] = front_lit ? softplus(head(trunk(z ++ embed(rusink)))) : 0
  * with rusink = dir2rusink(R l2n(lxyz - xyz), R l2n(cam - xyz)), R = world2local(normal)

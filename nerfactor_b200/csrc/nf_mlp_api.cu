@@ -10,7 +10,8 @@ int nf_tc_point_launch(nf_ctx* ctx, const nf_mlp* m, const float* xyz, int n, fl
                        float* out, cudaStream_t st);
 // nf_mlp_tc.cu
 int nf_tc_lvis_launch(nf_ctx* ctx, const nf_mlp* m, const float* xyz, int n, float xyz_scale,
-                      const float* lxyz, int L, float* lvis, int precision, cudaStream_t st);
+                      const float* lxyz, int L, float* lvis, int precision, cudaStream_t st,
+                      const float* xyz_dir = nullptr);
 int nf_tc_sigma_launch(nf_ctx* ctx, const nf_mlp* m, const float* rayo, const float* rayd,
                        const float* z, int n_rays, int S, const float* bbox_host, float* sigma,
                        int precision, cudaStream_t st);
@@ -47,6 +48,20 @@ int nf_lvis_fwd(nf_ctx* ctx, const nf_mlp* mlp, const float* xyz_d, int n, float
                           nullptr, nullptr, nullptr, nullptr, lvis_d, (cudaStream_t)stream);
   return nf_tc_lvis_launch(ctx, mlp, xyz_d, n, xyz_scale, lxyz_d, n_lights, lvis_d, precision,
                            (cudaStream_t)stream);
+}
+
+int nf_lvis_dirs_fwd(nf_ctx* ctx, const nf_mlp* mlp, const float* xyz_d, const float* xyz_dir_d,
+                     int n, float xyz_scale, const float* lxyz_d, int n_lights, float* lvis_d,
+                     int precision, void* stream) {
+  NF_CHECK_ARG(ctx, mlp && lxyz_d && n >= 0 && n_lights > 0, "bad argument");
+  NF_CHECK_ARG(ctx, mlp->d.kind == NF_MLP_LVIS && mlp->d.out_dim == 1, "network is not NF_MLP_LVIS");
+  if (n == 0) return NF_OK;
+  NF_CHECK_ARG(ctx, xyz_d && xyz_dir_d && lvis_d, "null buffer");
+  if (precision != NF_PREC_F16 && precision != NF_PREC_BF16)
+    return nf_set_error(ctx, NF_ERR_UNSUPPORTED,
+                        "nf_lvis_dirs_fwd: tcgen05 only (NF_PREC_F16 / NF_PREC_BF16)");
+  return nf_tc_lvis_launch(ctx, mlp, xyz_d, n, xyz_scale, lxyz_d, n_lights, lvis_d, precision,
+                           (cudaStream_t)stream, xyz_dir_d);
 }
 
 int nf_brdf_learned_fwd(nf_ctx* ctx, const nf_mlp* mlp, const float* xyz_d, const float* normal_d,

@@ -49,6 +49,8 @@ struct TcParams {
   int out_act;
   float xyz_scale;
   const float* xyz;      // [n,3]
+  const float* xyz_dir;  // [n,3] or NULL: origin of the light directions when it differs from xyz
+                         // (jittered evaluation: network at xyz + noise, directions of xyz; shape.py:170)
   const float* lxyz;     // [L,3]
   const float* normal;   // BRDF: [n,3]
   const float* cam;      // BRDF: [n,3]
@@ -418,13 +420,11 @@ struct SmemLayout2 {
   static constexpr int LMAX = 1024;
   static constexpr size_t off_bar = off_lx + (size_t)LMAX * 16;
   static constexpr size_t off_red = off_bar + 128;                       // [2 groups][16][4] f32
-  static constexpr size_t total = off_red + 2 * 16 * 4 * 4;
+  static constexpr size_t off_cnt = off_red + 2 * 16 * 4 * 4;            // [2 groups][8] int: warp counts, tiles
+  static constexpr size_t off_list = off_cnt + 2 * 8 * 4;                // [2 groups][4 warps][256] u16
+  static constexpr size_t total = off_list + (KIND == NF_MLP_BRDF ? 2 * 4 * 256 * 2 : 0);
 };
-constexpr int COL_ONE = 208;       // constant A operand (1, 1, 0, ...): 8 columns
-
-// (Tried and removed: handing the A operand over in two K-halves so that the next layer's first
-// MMAs overlap the second half of the epilogue -- 33.1 vs 32.4 ms, profiles/r2_k2_analysis.md.)
-template <int KIND, int BF16>
+constexpr int COL_ONE = 208; template <int KIND, int BF16>
 __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p) {
   using SL = SmemLayout2<KIND>;
   constexpr int KE = SL::KE;
@@ -441,6 +441,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
   uint64_t* bar_d = bars + 3;          // [2] D accumulator ready (tcgen05.commit)
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 5);
   float* s_red = reinterpret_cast<float*>(smem + SL::off_red);
+  volatile int* s_cnt = reinterpret_cast<volatile int*>(smem + SL::off_cnt);   // [g][0..3] front-lit lights per warp, [g][4] tiles of the point
+  uint16_t* s_list = reinterpret_cast<uint16_t*>(smem + SL::off_list);         // BRDF: compacted front-lit light indices
   // fused rendering equation: texel * area per light in the upper half of the light table
   const bool fuse = KIND == NF_MLP_LVIS && p.f_rgb != nullptr;
   float4* s_lrgb = s_lx + 512;
@@ -509,42 +511,50 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
                                    (uint32_t)(KE + 256) * 256u, (uint32_t)(KE + 384) * 256u};
       const uint32_t bias_off[2] = {(uint32_t)(KE + 384 + KE) * 256u,
                                     (uint32_t)(KE + 384 + KE + 16) * 256u};   // layers 1, 2
-      const int nt0 = group_points(0) * chunks, nt1 = group_points(1) * chunks;
-      const int nt_max = nt0 > nt1 ? nt0 : nt1;
+      // Tiles per surface point are data-dependent for the BRDF network (only front-lit lights are
+      // evaluated: nerfactor.py:428-434), so the issuer follows the groups' hand-overs: a group
+      // publishes the tile count of a point (s_cnt[g][4]) before the point's first hand-over.
+      int pts_left[2] = {group_points(0), group_points(1)};
+      int tiles_left[2] = {0, 0}, layer_of[2] = {0, 0};
       uint32_t ph[2] = {0u, 0u};
-      for (int it = 0; it < nt_max; ++it) {
-        for (int layer = 0; layer < 4; ++layer) {
-          for (int g = 0; g < 2; ++g) {
-            if (it >= (g == 0 ? nt0 : nt1)) continue;
-            mbar_wait(bar_a + g, ph[g]);
-            ph[g] ^= 1u;
-            tc_fence_after();
-            const uint32_t tb = tmem_base + g * GRP_COLS;
-            const uint32_t d_t = tb + COL_D;
-            // bias block first (accumulate = 0 starts the tile from 1 * b_hi + 1 * b_lo)
-            const uint32_t bsm = (layer == 0 || layer == 3)
-                                     ? bdyn0 + (uint32_t)(g * 2 + (layer == 3 ? 1 : 0)) * 4096u
-                                     : img0 + bias_off[layer - 1];
-            tc_mma_ts(d_t, tb + COL_ONE, make_b_desc(bsm, lbo, sbo), idesc, 0u);
-            if (layer == 0) {
+      auto active = [&](int g) { return pts_left[g] > 0 || tiles_left[g] > 0; };
+      while (active(0) || active(1)) {
+        for (int g = 0; g < 2; ++g) {
+          if (!active(g)) continue;
+          mbar_wait(bar_a + g, ph[g]);
+          ph[g] ^= 1u;
+          tc_fence_after();
+          if (tiles_left[g] == 0) {            // first hand-over of a new point
+            tiles_left[g] = s_cnt[g * 8 + 4];
+            --pts_left[g];
+          }
+          const int layer = layer_of[g];
+          const uint32_t tb = tmem_base + g * GRP_COLS;
+          const uint32_t d_t = tb + COL_D;
+          // bias block first (accumulate = 0 starts the tile from 1 * b_hi + 1 * b_lo)
+          const uint32_t bsm = (layer == 0 || layer == 3)
+                                   ? bdyn0 + (uint32_t)(g * 2 + (layer == 3 ? 1 : 0)) * 4096u
+                                   : img0 + bias_off[layer - 1];
+          tc_mma_ts(d_t, tb + COL_ONE, make_b_desc(bsm, lbo, sbo), idesc, 0u);
+          if (layer == 0) {
+#pragma unroll
+            for (int k = 0; k < KE / 16; ++k)
+              tc_mma_ts(d_t, tb + COL_AE + k * 8,
+                        make_b_desc(img0 + seg_off[0] + k * 2 * lbo, lbo, sbo), idesc, 1u);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              tc_mma_ts(d_t, tb + COL_AH + k * 8,
+                        make_b_desc(img0 + seg_off[layer] + k * 2 * lbo, lbo, sbo), idesc, 1u);
+            if (layer == 3) {
 #pragma unroll
               for (int k = 0; k < KE / 16; ++k)
                 tc_mma_ts(d_t, tb + COL_AE + k * 8,
-                          make_b_desc(img0 + seg_off[0] + k * 2 * lbo, lbo, sbo), idesc, 1u);
-            } else {
-#pragma unroll
-              for (int k = 0; k < 8; ++k)
-                tc_mma_ts(d_t, tb + COL_AH + k * 8,
-                          make_b_desc(img0 + seg_off[layer] + k * 2 * lbo, lbo, sbo), idesc, 1u);
-              if (layer == 3) {
-#pragma unroll
-                for (int k = 0; k < KE / 16; ++k)
-                  tc_mma_ts(d_t, tb + COL_AE + k * 8,
-                            make_b_desc(img0 + seg_off[4] + k * 2 * lbo, lbo, sbo), idesc, 1u);
-              }
+                          make_b_desc(img0 + seg_off[4] + k * 2 * lbo, lbo, sbo), idesc, 1u);
             }
-            tc_commit(bar_d + g);
           }
+          tc_commit(bar_d + g);
+          if (++layer_of[g] == 4) { layer_of[g] = 0; --tiles_left[g]; }
         }
       }
     }
@@ -576,6 +586,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
     for (int pt = G; pt < p.n; pt += n_groups) {
       // ---------------------------------------------- per-point (once per L lights)
       const f3 x = ld3(p.xyz + (size_t)pt * 3);
+      const f3 xd = (KIND == NF_MLP_LVIS && p.xyz_dir) ? ld3(p.xyz_dir + (size_t)pt * 3) : x;
       f3 fr_t, fr_b, fr_n, v_loc;
       if (KIND == NF_MLP_LVIS) {
         if (tg < 3) e_s[tg] = (tg == 0 ? x.x : (tg == 1 ? x.y : x.z)) * p.xyz_scale;
@@ -626,17 +637,53 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
         *bd3 = (h3 & 0xFFFFu) | (pack2<BF16, 0>(l3, 0.f) << 16);
         fence_proxy_async();
       }
+      // tiles of this point: all lights (visibility) / only the front-lit ones (BRDF)
+      int n_rows = p.L;
+      int c0 = 0, c1 = 0, c2 = 0;                  // BRDF: cumulative front-lit counts of warps 0..2
+      if (KIND == NF_MLP_BRDF) {
+        // each warp scans a quarter of the lights, keeps the front-lit ones (l_loc.z > 0,
+        // nerfactor.py:429-432) in increasing order and zeroes the others' output (:456-458)
+        const int lq = (p.L + 3) / 4, l0 = wq * lq, l1 = min(p.L, l0 + lq);
+        uint16_t* mylist = s_list + ((size_t)g * 4 + wq) * 256;
+        int cnt = 0;
+        for (int base = l0; base < l1; base += 32) {
+          const int l = base + lane;
+          bool lit = false;
+          if (l < l1) {
+            const float4 lp = s_lx[l];
+            const f3 d = l2n(mk3(lp.x, lp.y, lp.z) - x, 1e-6f);
+            lit = dot3(fr_n, d) > 0.f;
+            if (!lit) p.out[(size_t)pt * p.L + l] = 0.f;
+          }
+          const unsigned m = __ballot_sync(0xffffffffu, lit);
+          if (lit) mylist[cnt + __popc(m & ((1u << lane) - 1u))] = (uint16_t)l;
+          cnt += __popc(m);
+        }
+        if (lane == 0) s_cnt[g * 8 + wq] = cnt;
+        group_bar(1 + g);
+        c0 = s_cnt[g * 8 + 0]; c1 = c0 + s_cnt[g * 8 + 1]; c2 = c1 + s_cnt[g * 8 + 2];
+        n_rows = c2 + s_cnt[g * 8 + 3];
+      }
+      const int n_tiles = n_rows > 0 ? (n_rows + 127) / 128 : 1;     // >= 1: the issuer expects a tile
+      if (tg == 0) s_cnt[g * 8 + 4] = n_tiles;
       group_bar(1 + g);
 
-      for (int c = 0; c < chunks; ++c) {
-        const int li = c * 128 + t;
-        const int lc = li < p.L ? li : p.L - 1;
+      for (int c = 0; c < n_tiles; ++c) {
+        int li = c * 128 + t;                     // row of the point's (compacted) light list
+        const bool row_ok = li < n_rows;
+        if (KIND == NF_MLP_BRDF) {
+          int i = row_ok ? li : (n_rows > 0 ? n_rows - 1 : 0);
+          const int seg = (i >= c0) + (i >= c1) + (i >= c2);
+          i -= seg == 0 ? 0 : (seg == 1 ? c0 : (seg == 2 ? c1 : c2));
+          li = n_rows > 0 ? (int)s_list[((size_t)g * 4 + seg) * 256 + i] : 0;
+        }
+        const int lc = KIND == NF_MLP_BRDF ? li : (li < p.L ? li : p.L - 1);
         // ------------------------------------------------ per-row embedding -> A_e
         float mask = 1.f;
         f3 ldir;
         {
           float4 lp = s_lx[lc];
-          f3 d = l2n(mk3(lp.x, lp.y, lp.z) - x, 1e-6f);                       // shape.py:128-135
+          f3 d = l2n(mk3(lp.x, lp.y, lp.z) - xd, 1e-6f);                      // shape.py:128-135
           ldir = d;
           float v[KE];
 #pragma unroll
@@ -748,12 +795,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
         }
         float o = (acc0 + acc1) + s_aux[AUX_BOUT];
         o = apply_act(p.out_act, o) * mask;
-        if (li < p.L && p.out) p.out[(size_t)pt * p.L + li] = o;
+        if (row_ok && p.out) p.out[(size_t)pt * p.L + li] = o;
         if (fuse) {
           // one term of the rendering equation (nerfactor.py:325-336) with the GGX lobe of
           // brdf/microfacet/microfacet.py:30-111 (same reduction as nf_integrate.cu eval_pair)
-          float c0 = 0.f, c1 = 0.f, c2 = 0.f;
-          if (li < p.L) {
+          float q0 = 0.f, q1 = 0.f, q2 = 0.f;
+          if (row_ok) {
             const float cosl = dot3(ldir, n1);                               // :325
             const float wgt = (cosl > 0.f ? o : 0.f) * cosl;                 // :329-335 (area in s_lrgb)
             const f3 hs = ldir + v2;
@@ -768,19 +815,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
             const float den = (4.f * NF_PI_F) * (u * u) * (fabsf(cosl) * abs_vn);
             const float spec = (on && den != 0.f) ? __fdividef(fr * (g_view * a2), den) : 0.f;
             const float4 lc = s_lrgb[li];
-            c0 = (spec + lam.x) * (wgt * lc.x);
-            c1 = (spec + lam.y) * (wgt * lc.y);
-            c2 = (spec + lam.z) * (wgt * lc.z);
+            q0 = (spec + lam.x) * (wgt * lc.x);
+            q1 = (spec + lam.y) * (wgt * lc.y);
+            q2 = (spec + lam.z) * (wgt * lc.z);
           }
 #pragma unroll
           for (int sft = 16; sft > 0; sft >>= 1) {
-            c0 += __shfl_xor_sync(0xffffffffu, c0, sft);
-            c1 += __shfl_xor_sync(0xffffffffu, c1, sft);
-            c2 += __shfl_xor_sync(0xffffffffu, c2, sft);
+            q0 += __shfl_xor_sync(0xffffffffu, q0, sft);
+            q1 += __shfl_xor_sync(0xffffffffu, q1, sft);
+            q2 += __shfl_xor_sync(0xffffffffu, q2, sft);
           }
           if (lane == 0) {          // fixed slot per (chunk, warp): summed in a fixed order below
             float* slot = s_red + ((size_t)g * 16 + c * 4 + wq) * 4;
-            slot[0] = c0; slot[1] = c1; slot[2] = c2;
+            slot[0] = q0; slot[1] = q1; slot[2] = q2;
           }
         }
       }
@@ -788,7 +835,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
         group_bar(1 + g);
         if (tg == 0) {
           float r0 = 0.f, r1 = 0.f, r2 = 0.f;
-          for (int q = 0; q < chunks * 4; ++q) {
+          for (int q = 0; q < n_tiles * 4; ++q) {
             const float* slot = s_red + ((size_t)g * 16 + q) * 4;
             r0 += slot[0]; r1 += slot[1]; r2 += slot[2];
           }
@@ -959,7 +1006,7 @@ int launch_tc(nf_ctx* ctx, const nf_mlp* m, const TcParams& p, cudaStream_t st) 
   if (grid > need) grid = need;
   // NF_LVIS_V1=1 selects the first-generation kernel (bias added in the epilogue): A / B timing
   static const bool v1 = [] { const char* e = getenv("NF_LVIS_V1"); return e && e[0] == '1'; }();
-  if (v1 && p.f_rgb == nullptr) {
+  if (v1 && p.f_rgb == nullptr && p.xyz_dir == nullptr) {
     using SL = SmemLayout<KIND>;
     NF_CHECK_ARG(ctx, SL::total <= ctx->smem_optin, "shared memory budget exceeded");
     NF_CUDA(ctx, cudaFuncSetAttribute(mlp_tc_kernel<KIND, BF16>,
@@ -1080,14 +1127,15 @@ static int tc_common(nf_ctx* ctx, const nf_mlp* m, int precision, TcParams& p) {
 }
 
 int nf_tc_lvis_launch(nf_ctx* ctx, const nf_mlp* m, const float* xyz, int n, float xyz_scale,
-                      const float* lxyz, int L, float* lvis, int precision, cudaStream_t st) {
+                      const float* lxyz, int L, float* lvis, int precision, cudaStream_t st,
+                      const float* xyz_dir) {
   TcParams p;
   int rc = tc_common(ctx, m, precision, p);
   if (rc != NF_OK) return rc;
   NF_CHECK_ARG(ctx, L <= 1024, "n_lights > 1024 not supported by the tcgen05 kernel");
   if (n == 0) return NF_OK;
   p.n = n; p.L = L; p.nr = 3 * (1 + 2 * m->d.n_freqs_a); p.xyz_scale = xyz_scale;
-  p.xyz = xyz; p.lxyz = lxyz; p.out = lvis;
+  p.xyz = xyz; p.lxyz = lxyz; p.out = lvis; p.xyz_dir = xyz_dir;
   return precision == NF_PREC_BF16 ? launch_tc<NF_MLP_LVIS, 1>(ctx, m, p, st)
                                    : launch_tc<NF_MLP_LVIS, 0>(ctx, m, p, st);
 }

@@ -174,14 +174,20 @@ class Model(ShapeVis, BaseModel):
     def _pred_lvis_jitter_at(self, pts_jitter, pts):
         """The smoothness-loss evaluation of shape.py:170 / nerfactor.py:225: the visibility net at
         the JITTERED point but with the light directions of the un-jittered one (`surf2l` is
-        computed once from `pts` in the reference).  The fused kernel derives directions from the
-        point it is given, so this runs the net layer by layer on materialised
-        [embed(x + noise) | embed(surf2l)] rows through the FP32 Dense kernels (nf_dense_fwd) --
-        train batches are 1024 rays x 512 lights.  Above JITTER_EXACT_MAX_PAIRS pairs (full-view
-        validation batches, whose NeRFactor loss ignores the jitter terms) it falls back to the
-        fused kernel: directions then follow the jittered point (<= 1e-4 in the result)."""
+        computed once from `pts` in the reference).  Tensor-core precisions: the fused kernel with
+        a separate direction origin (nf_lvis_dirs_fwd), exact semantics at any size.  'fp32': the
+        net layer by layer on materialised [embed(x + noise) | embed(surf2l)] rows through the FP32
+        Dense kernels (nf_dense_fwd) -- train batches are 1024 rays x 512 lights; above
+        JITTER_EXACT_MAX_PAIRS pairs (full-view validation batches, whose NeRFactor loss ignores
+        the jitter terms) the FP32 fused kernel, whose directions follow the jittered point
+        (<= 1e-4 in the result)."""
         lxyz = self.lxyz.reshape(-1, 3)
         n, L = pts.shape[0], lxyz.shape[0]
+        if n > 0 and self.precision != 'fp32':
+            m = self._packed_mlp('lvis', 'lvis', n_freqs_a=self.embedder['xyz'].n_freqs,
+                                 n_freqs_b=self.embedder['ldir'].n_freqs)
+            return _lib.lvis_dirs_fwd(self.ctx, m, pts_jitter.contiguous(), pts.contiguous(), lxyz,
+                                      self.xyz_scale, self.precision)
         if n == 0 or n * L > self.JITTER_EXACT_MAX_PAIRS:
             return self._pred_lvis_at(pts_jitter)
         from .. import autodiff as ad

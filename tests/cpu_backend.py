@@ -243,6 +243,19 @@ def raymarch_lvis_fwd(ctx, mlp_coarse, mlp_fine, surf, normal, lxyz, lvis_near, 
     return lvis.reshape(m, L)
 
 
+def lvis_dirs_fwd(ctx, mlp, xyz, xyz_dir, lxyz, xyz_scale=1.0, precision='f16'):
+    ctx.launches += 1
+    lxyz = lxyz.reshape(-1, 3)
+    n, L = xyz.shape[0], lxyz.shape[0]
+    if n == 0:
+        return torch.zeros((0, L))
+    surf2l = tfops.safe_l2_normalize(lxyz[None, :, :] - xyz_dir[:, None, :], 2)
+    e_xyz = onets.embed(xyz * xyz_scale, mlp.n_freqs_a)
+    x = torch.cat((e_xyz[:, None, :].expand(n, L, e_xyz.shape[1]).reshape(n * L, -1),
+                   onets.embed(surf2l.reshape(-1, 3), mlp.n_freqs_b)), -1)
+    return mlp(x).reshape(n, L)
+
+
 def stageB_fused_fwd(ctx, mlp_lvis, xyz, normal, cam, albedo, lxyz, lareas, light, rough=None,
                      z=None, mlp_brdf=None, light_idx=None, f0=0.04, spec_scale=1.0, xyz_scale=1.0,
                      linear2srgb=True, precision='f16', want_lvis=False):
@@ -254,7 +267,7 @@ def stageB_fused_fwd(ctx, mlp_lvis, xyz, normal, cam, albedo, lxyz, lareas, ligh
     return rgb, (lvis if want_lvis else None)
 
 
-_PATCHED = ('default_context', 'microfacet_brdf_fwd', 'stageB_fused_fwd', 'raymarch_depth_normal_fwd',
+_PATCHED = ('default_context', 'microfacet_brdf_fwd', 'stageB_fused_fwd', 'lvis_dirs_fwd', 'raymarch_depth_normal_fwd',
             'raymarch_lvis_fwd', 'point_mlp_fwd', 'lvis_fwd', 'brdf_learned_fwd', 'integrate_fwd',
             'integrate_olat_fwd', 'gen_rays', 'gen_z', 'sigma_fwd', 'sigma_normal_fwd',
             'nerf_fwd', 'composite', 'gen_z_fine', 'lvis_rays', 'dense_fwd', 'dense_bwd',

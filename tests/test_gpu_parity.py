@@ -421,6 +421,24 @@ def test_fused_stage_b_equals_model_call(ctx, brdf, lh, lw, n):
     assert m.render_rgb(empty)['rgb'].shape == (0, 3)
 
 
+def test_lvis_jitter_semantics_tensor_core_path(ctx):
+    """shape.py:170 / nerfactor.py:225: the jittered visibility is the network at xyz + noise with
+    the light directions of xyz.  nf_lvis_dirs_fwd (fp16 operands) against the oracle, and it
+    differs from evaluating everything at the jittered point."""
+    m, om, _ = _stage_b(ctx, 'microfacet', 10, 20, seed=3, precision='f16')
+    rng = np.random.default_rng(2)
+    xyz = torch.as_tensor(rng.uniform(-1, 1, (301, 3)).astype(np.float32))
+    noise = torch.as_tensor((0.05 * rng.standard_normal((301, 3))).astype(np.float32))
+    got = m._pred_lvis_jitter_at(dev(xyz + noise, ctx), dev(xyz, ctx)).cpu()
+    want = om.pred_lvis_at(xyz + noise, om.calc_ldir(xyz))
+    assert rel_l2(got, want) < 3e-3
+    moved = om.pred_lvis_at(xyz + noise, om.calc_ldir(xyz + noise))
+    assert rel_l2(got, moved) > 3 * rel_l2(got, want)
+    # same inputs for both origins == the plain kernel, bit for bit
+    a = m._pred_lvis_jitter_at(dev(xyz, ctx), dev(xyz, ctx))
+    assert torch.equal(a, m._pred_lvis_at(dev(xyz, ctx)))
+
+
 def test_config3_learned_brdf_1024_lights_on_16x32_envmap(ctx):
     """BASELINE configs[2]: learned-MERL BRDF, L = 1024 light directions (16x64 grid) looking
     up a 16x32 HDR env-map through the nearest-pixel index map (SURVEY 8d caveat on L)."""
