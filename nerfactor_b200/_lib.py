@@ -383,8 +383,8 @@ def stageB_fused_fwd(ctx, mlp_lvis, xyz, normal, cam, albedo, lxyz, lareas, ligh
     nbytes = ctx.lib.nf_stageB_fused_workspace_bytes(C.byref(a), PREC[precision])
     work = torch.empty((nbytes + 256,), dtype=torch.uint8, device=dev) if nbytes else None
     wptr = C.c_void_p(work.data_ptr() + (-work.data_ptr()) % 256) if nbytes else None
-    if nbytes:          # chunked path: 2-3 kernels per chunk of <= 32 MB rows
-        cpts = max(256, ((32 << 20) // (L * 4)) // 256 * 256)
+    if nbytes:          # chunked path: 2-3 kernels per chunk of <= 48 MB rows
+        cpts = max(256, ((48 << 20) // (L * 4)) // 256 * 256)
         ctx.launches += (2 + (z is not None)) * max(1, (n + cpts - 1) // cpts) - 1
     ctx.launch(ctx.lib.nf_stageB_fused_fwd(
         ctx.h, mlp_lvis.h, mlp_brdf.h if mlp_brdf is not None else None, C.byref(a),

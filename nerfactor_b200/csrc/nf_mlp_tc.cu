@@ -424,7 +424,9 @@ struct SmemLayout2 {
   static constexpr size_t off_list = off_cnt + 2 * 8 * 4;                // [2 groups][4 warps][256] u16
   static constexpr size_t total = off_list + (KIND == NF_MLP_BRDF ? 2 * 4 * 256 * 2 : 0);
 };
-constexpr int COL_ONE = 208; template <int KIND, int BF16>
+constexpr int COL_ONE = 208; // SELF = 1: no separate MMA-issuer warp -- thread 0 of a worker group issues its own group's MMAs
+// right after the group's named barrier (one hop less in the epilogue -> MMA hand-over).
+template <int KIND, int BF16, int SELF>
 __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p) {
   using SL = SmemLayout2<KIND>;
   constexpr int KE = SL::KE;
@@ -503,7 +505,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
 
   if (warp == 0) {
     // =============================================================== MMA issuer
-    if (lane == 0) {
+    if (!SELF && lane == 0) {
       const uint32_t idesc = make_idesc(BF16, TC_WIDTH);
       const uint32_t lbo = TC_WIDTH * 16, sbo = 128;
       const uint32_t img0 = smem_u32(s_img), bdyn0 = smem_u32(s_bdyn);
@@ -574,6 +576,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
     uint32_t* bd3 = reinterpret_cast<uint32_t*>(s_bdyn + (size_t)(g * 2 + 1) * 4096 + (size_t)tg * 16);
     const int G = blockIdx.x * 2 + g;
     uint32_t phd = 0u;
+    // SELF: this group's own MMA issue (same instruction sequence as the issuer warp's)
+    const uint32_t w_idesc = make_idesc(BF16, TC_WIDTH);
+    const uint32_t w_img0 = smem_u32(s_img), w_bdyn0 = smem_u32(s_bdyn);
+    auto self_issue = [&](int layer) {
+      const uint32_t lbo = TC_WIDTH * 16, sbo = 128;
+      const uint32_t tbase = tmem_base + g * GRP_COLS;
+      const uint32_t d_t = tbase + COL_D;
+      const uint32_t seg = layer == 0 ? 0u : (uint32_t)(KE + 128 * (layer - 1)) * 256u;
+      const uint32_t bsm = (layer == 0 || layer == 3)
+                               ? w_bdyn0 + (uint32_t)(g * 2 + (layer == 3 ? 1 : 0)) * 4096u
+                               : w_img0 + (uint32_t)(KE + 384 + KE + 16 * (layer - 1)) * 256u;
+      tc_mma_ts(d_t, tbase + COL_ONE, make_b_desc(bsm, lbo, sbo), w_idesc, 0u);
+      if (layer == 0) {
+#pragma unroll
+        for (int kk = 0; kk < KE / 16; ++kk)
+          tc_mma_ts(d_t, tbase + COL_AE + kk * 8, make_b_desc(w_img0 + kk * 2 * lbo, lbo, sbo), w_idesc, 1u);
+      } else {
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          tc_mma_ts(d_t, tbase + COL_AH + kk * 8, make_b_desc(w_img0 + seg + kk * 2 * lbo, lbo, sbo), w_idesc, 1u);
+        if (layer == 3) {
+#pragma unroll
+          for (int kk = 0; kk < KE / 16; ++kk)
+            tc_mma_ts(d_t, tbase + COL_AE + kk * 8,
+                      make_b_desc(w_img0 + (uint32_t)(KE + 384) * 256u + kk * 2 * lbo, lbo, sbo), w_idesc, 1u);
+        }
+      }
+      tc_commit(bar_d + g);
+    };
+    // hand the A operand of `layer` over to the tensor core
+    auto hand_over = [&](int layer) {
+      tc_fence_before();
+      if (SELF) {
+        group_bar(3 + g);
+        if (tg == 0) { tc_fence_after(); self_issue(layer); }
+      } else {
+        mbar_arrive(bar_a + g);
+      }
+    };
     {   // constant A operand of the bias block: columns (1, 1, 0, ..., 0), written once
       uint32_t one[8];
       one[0] = pack2<BF16, 0>(1.f, 1.f);
@@ -718,8 +759,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
           else { TC_ST8(tb + COL_AE, pk); }
         }
         tc_wait_st();
-        tc_fence_before();
-        mbar_arrive(bar_a + g);
+        hand_over(0);
 
         // ------------------------------------------------ layers 0..2: ReLU + 16-bit -> A_h
         for (int layer = 0; layer < 3; ++layer) {
@@ -751,8 +791,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
             pk[i] = pack2<BF16, 1>(__uint_as_float(rd[2 * i]), __uint_as_float(rd[2 * i + 1]));
           TC_ST16(tb + COL_AH + 48, pk);
           tc_wait_st();
-          tc_fence_before();
-          mbar_arrive(bar_a + g);
+          hand_over(layer + 1);
         }
         // ------------------------------------------------ layer 3 + head
         mbar_wait(bar_d + g, phd);
@@ -1015,9 +1054,17 @@ int launch_tc(nf_ctx* ctx, const nf_mlp* m, const TcParams& p, cudaStream_t st) 
   } else {
     using SL = SmemLayout2<KIND>;
     NF_CHECK_ARG(ctx, SL::total <= ctx->smem_optin, "shared memory budget exceeded");
-    NF_CUDA(ctx, cudaFuncSetAttribute(mlp_tc2_kernel<KIND, BF16>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SL::total));
-    mlp_tc2_kernel<KIND, BF16><<<grid, TC_THREADS, SL::total, st>>>(p);
+    // NF_LVIS_SELF=0: dedicated MMA-issuer warp instead of group-issued MMAs (A / B timing)
+    static const bool noself = [] { const char* e = getenv("NF_LVIS_SELF"); return e && e[0] == '0'; }();
+    if (noself) {
+      NF_CUDA(ctx, cudaFuncSetAttribute(mlp_tc2_kernel<KIND, BF16, 0>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SL::total));
+      mlp_tc2_kernel<KIND, BF16, 0><<<grid, TC_THREADS, SL::total, st>>>(p);
+    } else {
+      NF_CUDA(ctx, cudaFuncSetAttribute(mlp_tc2_kernel<KIND, BF16, 1>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SL::total));
+      mlp_tc2_kernel<KIND, BF16, 1><<<grid, TC_THREADS, SL::total, st>>>(p);
+    }
   }
   NF_LAUNCH_CHECK(ctx);
   return NF_OK;

@@ -1,12 +1,12 @@
 // nf_stageB_fused_fwd: light-visibility network -> BRDF -> rendering equation behind one call
 // (nerfactor/models/nerfactor.py:217-226, 262-266, 315-342), without the [N, L] light-visibility /
 // BRDF tensors resident in HBM:
-//   * microfacet BRDF, one env-map, L <= 512, tensor-core precision: ONE kernel -- the rendering
-//     equation is evaluated in the head epilogue of the light-visibility network
-//     (csrc/nf_mlp_tc.cu), the visibility values never leave the SM unless the caller asks for them;
-//   * otherwise (learned BRDF, several env-maps, L > 512, FP32): the same three kernels the
-//     separate entry points launch, run over point chunks small enough for the chunk's [c, L]
-//     rows to stay in the 126 MB L2 between producer and consumer (workspace from the caller).
+//   * default: the kernels the separate entry points launch, run over point chunks small enough
+//     for a chunk's [c, L] rows to stay in the 126 MB L2 between producer and consumer
+//     (workspace from the caller);
+//   * NF_STAGEB_SINGLE=1 (microfacet BRDF, one env-map, L <= 512, tensor-core precision): ONE
+//     kernel -- the rendering equation is evaluated in the head epilogue of the light-visibility
+//     network (csrc/nf_mlp_tc.cu), the visibility values never leave the SM.
 #include "nf_common.cuh"
 
 int nf_tc_lvis_render_launch(nf_ctx* ctx, const nf_mlp* m, const float* xyz, int n, float xyz_scale,
@@ -16,16 +16,22 @@ int nf_tc_lvis_render_launch(nf_ctx* ctx, const nf_mlp* m, const float* xyz, int
                              float* lvis, float* rgb, int precision, cudaStream_t st);
 
 namespace {
-// points per chunk of the chunked path: [c, L] fp32 rows of <= 32 MB (two of them for the learned BRDF)
+// points per chunk of the chunked path: [c, L] fp32 rows of <= 48 MB (two of them for the learned
+// BRDF: both stay inside the 126 MB L2 between producer and consumer)
 int chunk_points(int n, int L) {
-  long long c = (32ll << 20) / ((long long)L * 4);
+  long long c = (48ll << 20) / ((long long)L * 4);
   c = c / 256 * 256;
   if (c < 256) c = 256;
   return (int)(c < n ? c : n);
 }
 size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+// The one-kernel variant (rendering equation in the head epilogue of the visibility network) is
+// correct and keeps the visibility values on the SM, but measured SLOWER than the chunked pair
+// (38.0 vs 32.2 + 0.9 ms at 640 k x 512: the epilogue -> MMA hand-over chain of that kernel is its
+// critical path, profiles/r2_k2_analysis.md), so it is opt-in: NF_STAGEB_SINGLE=1.
 bool single_kernel(const nf_stageb_args* a, int precision) {
-  return a->brdf_kind == 0 && a->n_envmaps == 1 && a->n_lights <= 512 &&
+  static const bool want = [] { const char* e = getenv("NF_STAGEB_SINGLE"); return e && e[0] == '1'; }();
+  return want && a->brdf_kind == 0 && a->n_envmaps == 1 && a->n_lights <= 512 &&
          (precision == NF_PREC_F16 || precision == NF_PREC_BF16);
 }
 }  // namespace

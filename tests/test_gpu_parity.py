@@ -394,12 +394,16 @@ def test_stage_b_l512_rgb_within_1e4(ctx, brdf):
 
 @pytest.mark.parametrize('brdf,lh,lw,n', [('microfacet', 16, 32, 1000), ('microfacet', 10, 20, 203),
                                           ('learned', 16, 32, 333), ('microfacet', 16, 64, 150)])
-def test_fused_stage_b_equals_model_call(ctx, brdf, lh, lw, n):
+@pytest.mark.parametrize('single', [False, True])
+def test_fused_stage_b_equals_model_call(ctx, brdf, lh, lw, n, single, monkeypatch):
     """Model.render_rgb (nf_stageB_fused_fwd) against Model.call on the same batch: the
     single-kernel case (microfacet, one env-map, L <= 512: rendering equation inside the head
     epilogue of the visibility network; ragged L = 200 too), the chunked cases (learned lobe;
     L = 1024; several env-maps), with and without the optional lvis output -- and against the
     oracle for RGB."""
+    if single:                 # the variable is read once per process: only meaningful in a fresh one
+        if os.environ.get('NF_STAGEB_SINGLE') != '1':
+            pytest.skip('one-kernel variant: run with NF_STAGEB_SINGLE=1 (tools/gpu_call*.sh does)')
     m, om, _ = _stage_b(ctx, brdf, lh, lw, seed=13, precision='f16')
     for i, p in enumerate(synth.make_probes(5, 3, light_hw=(lh, lw))):
         m.novel_probes['p%d' % i] = p

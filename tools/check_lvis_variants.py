@@ -47,8 +47,8 @@ print(json.dumps(out))
 ''' % ROOT
 
 
-def run(flag, prefix, ksplit='1'):
-    env = dict(os.environ, NF_LVIS_V1=flag, NF_LVIS_KSPLIT=ksplit)
+def run(flag, prefix, self_issue='1'):
+    env = dict(os.environ, NF_LVIS_V1=flag, NF_LVIS_SELF=self_issue)
     r = subprocess.run([sys.executable, '-c', WORKER, prefix], env=env, capture_output=True,
                        text=True, timeout=200)
     if r.returncode != 0:
@@ -60,7 +60,8 @@ def main():
     import numpy as np
     import tempfile
     d = tempfile.mkdtemp()
-    res = {'v2': run('0', os.path.join(d, 'a')), 'v1': run('1', os.path.join(d, 'b'))}
+    res = {'v2': run('0', os.path.join(d, 'a')), 'v1': run('1', os.path.join(d, 'b')),
+           'v2_issuer_warp': run('0', os.path.join(d, 'c'), '0')}
     if 'error' not in res['v1'] and 'error' not in res['v2']:
         for tag in ('ragged', 'full'):
             for k in ('lvis', 'spec'):
