@@ -60,8 +60,7 @@ def main():
     import numpy as np
     import tempfile
     d = tempfile.mkdtemp()
-    res = {'v2': run('0', os.path.join(d, 'a')), 'v1': run('1', os.path.join(d, 'b')),
-           'v2_issuer_warp': run('0', os.path.join(d, 'c'), '0')}
+    res = {'v2': run('0', os.path.join(d, 'a')), 'v1': run('1', os.path.join(d, 'b'))}
     if 'error' not in res['v1'] and 'error' not in res['v2']:
         for tag in ('ragged', 'full'):
             for k in ('lvis', 'spec'):
