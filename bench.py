@@ -188,6 +188,8 @@ def workload_config(args, sigma_prec):
                           'point_mlps': 'f16 hi/lo split x3 (fp32-accurate) / f32 accum',
                           'render': 'f32'},
             'l2_policy': 'per-step working set (lvis 1.3 GB, sigma 0.33 GB) exceeds the 126 MB L2',
+            'stage_b': 'per-point networks, then nf_stageB_fused_fwd (visibility net -> GGX -> rendering '
+                       'equation over L2-resident point chunks; no [N, L] tensor kept in HBM)',
             'parallelism': 'one view per GPU (same synthetic camera on every rank) + all_gather of images '
                            '(asynchronous, overlapping the next step)'}
 
@@ -587,7 +589,14 @@ def main():
                 'achieved': n_rays * args.spp * FLOP_SIGMA / (t_sigma * 1e-3) / 1e12,
                 'peak': tensor_peak, 'unit': 'TFLOP/s', 'ms': t_sigma, 'traffic': None,
                 'algorithmic_bytes': alg_sigma}
-    rf_lvis = {'kernel': 'nf_lvis_fwd (mlp_tc_kernel f16)', 'bound': 'tensor',
+    rf_sigma_plain = None
+    if sigma_prec == 'f16e':        # context: the same kernel without the split encoding
+        t_plain = kt(lambda: _lib.sigma_fwd(ctx, nerf.packed_sigma(True), rayo, rayd, z, None, 'f16'), 3)
+        rf_sigma_plain = {'kernel': 'nf_sigma_fwd (f16, positional encoding NOT split; not the timed mode)',
+                          'bound': 'tensor', 'ms': t_plain, 'peak': tensor_peak, 'unit': 'TFLOP/s',
+                          'achieved': n_rays * args.spp * FLOP_SIGMA / (t_plain * 1e-3) / 1e12}
+        rf_sigma_plain['frac'] = rf_sigma_plain['achieved'] / tensor_peak
+    rf_lvis = {'kernel': 'nf_lvis_fwd (mlp_tc2_kernel f16)', 'bound': 'tensor',
                'achieved': n_fg * L * FLOP_LVIS / (t_lvis * 1e-3) / 1e12,
                'peak': tensor_peak, 'unit': 'TFLOP/s', 'ms': t_lvis, 'traffic': None,
                'algorithmic_bytes': alg_lvis}
@@ -626,16 +635,19 @@ def main():
             r['peak_burst'] = pk['bf16_tflops']
             r['frac_burst'] = r['achieved'] / pk['bf16_tflops']
     # DRAM bytes per launch from the committed ncu --set full capture of this exact workload
-    tpath = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
+    tpath = os.path.join(ROOT, 'profiles', 'r2_traffic.json')
+    if not os.path.exists(tpath):
+        tpath = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
         wl = tj['workload']
         if (wl['imh'], wl['imw'], wl['spp'], wl['light_dirs']) == (args.imh, args.imw, args.spp, L):
             for r, key in ((rf_sigma, 'sigma'), (rf_lvis, 'lvis'), (rf_int, 'integrate'),
                            (rf_point, 'point')):
-                if key == 'sigma' and sigma_prec == 'fp32':
+                if (key == 'sigma' and sigma_prec == 'fp32') or key not in tj['kernels']:
                     continue
                 r['traffic'] = tj['kernels'][key]['dram_bytes']
+                r['ncu_tensor_pipe_active_pct'] = tj['kernels'][key].get('tensor_pipe_active_pct')
                 r['traffic_source'] = tj['source']
     dominant = max((rf_sigma, rf_lvis, rf_int), key=lambda r: r['ms'])
     dominant = dict(dominant, peak_source=pk['source'] + ', sustained bf16 cuBLAS' if
@@ -665,7 +677,8 @@ def main():
                 'd2h_bytes_per_step': int(rgb_host.numel() * 4 + alpha_host.numel() * 4)},
         'gpu_launches': launches, 'clocks': clocks,
         'roofline': dominant,
-        'rooflines': [rf_sigma, rf_lvis, rf_int, rf_point] + ([rf_int_spec] if rf_int_spec else []),
+        'rooflines': [rf_sigma, rf_lvis, rf_int, rf_point] + ([rf_int_spec] if rf_int_spec else []) +
+                     ([rf_sigma_plain] if rf_sigma_plain else []),
         'foreground_rays': n_fg,
         'cpu_baseline': cpu,
         'parity': parity,

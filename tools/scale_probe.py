@@ -68,6 +68,27 @@ def main():
         done.record(side)
         pending[0] = done
 
+    # one-sided pushes into the peers' symmetric buffers (copy engines, no rendezvous per step)
+    symm_ok, symm_err = True, None
+    try:
+        import torch.distributed._symmetric_memory as symm
+        sbuf = symm.empty((2 * world * n, 3), dtype=torch.float32, device=ctx.device)
+        hdl = symm.rendezvous(sbuf, dist.group.WORLD)
+        step_i = [0]
+    except Exception as e:                       # API not available in this build
+        symm_ok, symm_err = False, repr(e)
+
+    def v_symm():
+        rgb = render()
+        slot = step_i[0] & 1
+        step_i[0] += 1
+        for pr in range(world):
+            dst = hdl.get_buffer(pr, (n, 3), torch.float32, (slot * world * n + rank * n) * 3)
+            dst.copy_(rgb, non_blocking=True)
+
+    def drain_symm():
+        hdl.barrier()
+
     def timed(fn, steps=6, warmup=3, drain=None):
         for _ in range(warmup):
             fn()
@@ -101,6 +122,21 @@ def main():
            'none': timed(v_none), 'async': timed(v_async, drain=drain_work),
            'sync': timed(v_sync), 'side_event': timed(v_side, drain=drain_event),
            'none_again': timed(v_none)}
+    if symm_ok:
+        try:
+            out['symm_push'] = timed(v_symm, drain=drain_symm)
+            # every rank's image must be in every rank's buffer (slot of the last step)
+            torch.cuda.synchronize()
+            dist.barrier()
+            last = (step_i[0] - 1) & 1
+            mine = render()
+            got = sbuf[last * world * n:(last + 1) * world * n].reshape(world, n, 3)
+            out['symm_push_correct'] = bool(all(torch.equal(got[r], mine) for r in range(world)))
+            out['none_third'] = timed(v_none)
+        except Exception as e:
+            out['symm_push_error'] = repr(e)
+    else:
+        out['symm_unavailable'] = symm_err
     if rank == 0:
         print(json.dumps(out), flush=True)
     dist.destroy_process_group()
