@@ -469,6 +469,20 @@ def main():
     rgb_host = torch.empty((n_rays, 3)).pin_memory()
     alpha_host = torch.empty((n_rays, 1)).pin_memory()
     gathered = torch.empty((world * n_rays, 3), device=ctx.device) if world > 1 else None
+    # N > 1: images are exchanged by one-sided pushes over NVLink peer memory (copy engines, no SM
+    # kernel, no per-step rendezvous: pipeline.PeerImageGather); NCCL all_gather is the fallback
+    peer = None
+    gather_how = 'none'
+    if world > 1:
+        gather_how = 'NCCL all_gather_into_tensor (async)'
+        if os.environ.get('NF_GATHER', 'push') == 'push':
+            try:
+                from nerfactor_b200.pipeline import PeerImageGather
+                peer = PeerImageGather(n_rays, (3,), world, rank, ctx.device)
+                gather_how = 'one-sided pushes into symmetric peer memory (NVLink, copy engines)'
+            except Exception as e:           # symmetric memory not available in this build
+                peer = None
+                gather_how += ' [symmetric memory unavailable: %r]' % (e,)
 
     # The image all-gather of step k is issued asynchronously (NCCL's own stream, after the
     # step's last kernel) and overlaps the kernels of step k + 1; the next gather -- and the end of
@@ -476,11 +490,18 @@ def main():
     pending = [None]
 
     def gather(rgb):
+        if peer is not None:
+            peer.push(rgb)
+            return
         if pending[0] is not None:
             pending[0].wait()
         pending[0] = dist.all_gather_into_tensor(gathered, rgb.contiguous(), async_op=True)
 
     def drain():
+        if peer is not None:
+            if peer.step:
+                peer.finish()
+            return
         if pending[0] is not None:
             pending[0].wait()
             pending[0] = None
@@ -671,7 +692,7 @@ def main():
         'steps': args.steps, 'warmup': max(3, args.warmup), 'ms_per_step': ms_step,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f16' if sigma_prec != 'fp32' else 'f32+f16', 'data': 'synthetic',
-        'config': workload_config(args, sigma_prec),
+        'config': dict(workload_config(args, sigma_prec), image_exchange=gather_how),
         'e2e': {'value': e2e_value, 'unit': 'rays/s',
                 'h2d_bytes_per_step': int(light_host.numel() * 4 + 16 * 8 + 8),
                 'd2h_bytes_per_step': int(rgb_host.numel() * 4 + alpha_host.numel() * 4)},

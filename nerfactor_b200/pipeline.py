@@ -97,3 +97,43 @@ def gather_image(local_rgb, n_total, rank, world):
                       device=local_rgb.device)
     dist.all_gather_into_tensor(out, pad)
     return out[:n_total]
+
+
+class PeerImageGather:
+    """Image all-gather by ONE-SIDED pushes over NVLink peer memory: every rank copies its image
+    straight into its slot of every peer's symmetric buffer (`torch.distributed._symmetric_memory`:
+    peer-mapped allocations; the copies are device-to-device memcpys on the copy engines).  No SM
+    kernel competes with the persistent one-CTA-per-SM tensor kernels of the next step and no rank
+    waits for another inside a step; `finish()` is the only rendezvous (a device-side barrier on
+    the signal pads).  Two buffers alternate, so the pushes of step k + 1 never overwrite the image
+    of step k while a consumer may still read it.  Measured at N = 2, 800 x 800 (tools/scale_probe.py):
+    111.2 ms / step vs 111.5 (NCCL all_gather, async) vs 110.3-110.6 with no exchange at all."""
+
+    def __init__(self, n_rows, row_shape, world, rank, device, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.world, self.rank, self.n = world, rank, n_rows
+        self.row_shape = tuple(row_shape)
+        self.row_elems = int(np.prod(self.row_shape)) if self.row_shape else 1
+        self.buf = symm.empty((2 * world * n_rows,) + self.row_shape, dtype=torch.float32,
+                              device=device)
+        self.hdl = symm.rendezvous(self.buf, group or dist.group.WORLD)
+        self.step = 0
+
+    def push(self, local):
+        """local [n_rows, *row_shape] (fp32, this rank's image) -> its slot on every rank."""
+        slot = self.step & 1
+        self.step += 1
+        off = (slot * self.world * self.n + self.rank * self.n) * self.row_elems
+        local = local.contiguous()
+        for pr in range(self.world):
+            dst = self.hdl.get_buffer(pr, (self.n,) + self.row_shape, torch.float32, off)
+            dst.copy_(local, non_blocking=True)
+        return slot
+
+    def finish(self):
+        """All pushes of all ranks have landed -> [world, n_rows, *row_shape] of the last step."""
+        self.hdl.barrier()
+        slot = (self.step - 1) & 1
+        return self.buf[slot * self.world * self.n:(slot + 1) * self.world * self.n].reshape(
+            (self.world, self.n) + self.row_shape)
