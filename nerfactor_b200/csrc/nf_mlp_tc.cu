@@ -405,6 +405,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const TcParams p)
 //   * the epilogue is then just load -> cvt.relu.f16x2 -> store (~80 instructions per thread),
 //     with the second half of the accumulator in flight while the first half is converted.
 // One extra 128 x 128 x 16 MMA per layer costs 64 of ~512 clocks; the tensor pipe stays busy.
+//   * software pipelining across the tiles of a point: the per-row embedding of tile c + 1 is
+//     written (second A_e buffer) while layer 3 of tile c is in the tensor pipe, and the head of
+//     tile c runs from registers AFTER layer 0 of tile c + 1 has been handed over.
 template <int KIND>
 struct SmemLayout2 {
   static constexpr int KE = KindCfg<KIND>::KE;
@@ -424,7 +427,11 @@ struct SmemLayout2 {
   static constexpr size_t off_list = off_cnt + 2 * 8 * 4;                // [2 groups][4 warps][256] u16
   static constexpr size_t total = off_list + (KIND == NF_MLP_BRDF ? 2 * 4 * 256 * 2 : 0);
 };
-constexpr int COL_ONE = 208; // SELF = 1 (learned-BRDF network): no separate MMA-issuer warp -- thread 0 of a worker group issues
+constexpr int COL_ONE = 208;       // constant A operand (1, 1, 0, ...): 8 columns
+constexpr int COL_AE1 = 216;       // second per-row embedding buffer (tiles alternate: the next
+                                   // tile's embedding is written while layer 3 still reads this one)
+
+// SELF = 1 (learned-BRDF network): no separate MMA-issuer warp -- thread 0 of a worker group issues
 // its own group's MMAs after the group's named barrier, because the number of tiles per point is
 // data-dependent there (front-lit compaction).  SELF = 0 (visibility network): warp 0 issues for both
 // groups in strict alternation (measured faster when the tile count is static: 32.4 vs 40.9 ms).
@@ -529,6 +536,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
             tc_fence_after();
             const uint32_t tb = tmem_base + g * GRP_COLS;
             const uint32_t d_t = tb + COL_D;
+            const uint32_t ae_t = tb + (((it % chunks) & 1) ? COL_AE1 : COL_AE);   // tile parity
             // bias block first (accumulate = 0 starts the tile from 1 * b_hi + 1 * b_lo)
             const uint32_t bsm = (layer == 0 || layer == 3)
                                      ? bdyn0 + (uint32_t)(g * 2 + (layer == 3 ? 1 : 0)) * 4096u
@@ -537,7 +545,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
             if (layer == 0) {
 #pragma unroll
               for (int k = 0; k < KE / 16; ++k)
-                tc_mma_ts(d_t, tb + COL_AE + k * 8,
+                tc_mma_ts(d_t, ae_t + k * 8,
                           make_b_desc(img0 + seg_off[0] + k * 2 * lbo, lbo, sbo), idesc, 1u);
             } else {
 #pragma unroll
@@ -547,7 +555,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
               if (layer == 3) {
 #pragma unroll
                 for (int k = 0; k < KE / 16; ++k)
-                  tc_mma_ts(d_t, tb + COL_AE + k * 8,
+                  tc_mma_ts(d_t, ae_t + k * 8,
                             make_b_desc(img0 + seg_off[4] + k * 2 * lbo, lbo, sbo), idesc, 1u);
               }
             }
@@ -575,10 +583,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
     // SELF: this group's own MMA issue (same instruction sequence as the issuer warp's)
     const uint32_t w_idesc = make_idesc(BF16, TC_WIDTH);
     const uint32_t w_img0 = smem_u32(s_img), w_bdyn0 = smem_u32(s_bdyn);
-    auto self_issue = [&](int layer) {
+    auto self_issue = [&](int layer, int aebuf) {
       const uint32_t lbo = TC_WIDTH * 16, sbo = 128;
       const uint32_t tbase = tmem_base + g * GRP_COLS;
       const uint32_t d_t = tbase + COL_D;
+      const uint32_t ae_t = tbase + (aebuf ? COL_AE1 : COL_AE);
       const uint32_t seg = layer == 0 ? 0u : (uint32_t)(KE + 128 * (layer - 1)) * 256u;
       const uint32_t bsm = (layer == 0 || layer == 3)
                                ? w_bdyn0 + (uint32_t)(g * 2 + (layer == 3 ? 1 : 0)) * 4096u
@@ -587,7 +596,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
       if (layer == 0) {
 #pragma unroll
         for (int kk = 0; kk < KE / 16; ++kk)
-          tc_mma_ts(d_t, tbase + COL_AE + kk * 8, make_b_desc(w_img0 + kk * 2 * lbo, lbo, sbo), w_idesc, 1u);
+          tc_mma_ts(d_t, ae_t + kk * 8, make_b_desc(w_img0 + kk * 2 * lbo, lbo, sbo), w_idesc, 1u);
       } else {
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
@@ -595,18 +604,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
         if (layer == 3) {
 #pragma unroll
           for (int kk = 0; kk < KE / 16; ++kk)
-            tc_mma_ts(d_t, tbase + COL_AE + kk * 8,
+            tc_mma_ts(d_t, ae_t + kk * 8,
                       make_b_desc(w_img0 + (uint32_t)(KE + 384) * 256u + kk * 2 * lbo, lbo, sbo), w_idesc, 1u);
         }
       }
       tc_commit(bar_d + g);
     };
     // hand the A operand of `layer` over to the tensor core
-    auto hand_over = [&](int layer) {
+    auto hand_over = [&](int layer, int aebuf) {
       tc_fence_before();
       if (SELF) {
         group_bar(3 + g);
-        if (tg == 0) { tc_fence_after(); self_issue(layer); }
+        if (tg == 0) { tc_fence_after(); self_issue(layer, aebuf); }
       } else {
         mbar_arrive(bar_a + g);
       }
@@ -705,58 +714,62 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
       if (tg == 0) s_cnt[g * 8 + 4] = n_tiles;
       group_bar(1 + g);
 
-      for (int c = 0; c < n_tiles; ++c) {
-        int li = c * 128 + t;                     // row of the point's (compacted) light list
-        const bool row_ok = li < n_rows;
+      // Row of tile c handled by this thread, and its embedding -> A_e buffer (c & 1).
+      struct RowInfo { int li; bool ok; float mask; f3 ldir; };
+      auto embed_tile = [&](int c) {
+        RowInfo r;
+        r.li = c * 128 + t;                         // row of the point's (compacted) light list
+        r.ok = r.li < n_rows;
         if (KIND == NF_MLP_BRDF) {
-          int i = row_ok ? li : (n_rows > 0 ? n_rows - 1 : 0);
+          int i = r.ok ? r.li : (n_rows > 0 ? n_rows - 1 : 0);
           const int seg = (i >= c0) + (i >= c1) + (i >= c2);
           i -= seg == 0 ? 0 : (seg == 1 ? c0 : (seg == 2 ? c1 : c2));
-          li = n_rows > 0 ? (int)s_list[((size_t)g * 4 + seg) * 256 + i] : 0;
+          r.li = n_rows > 0 ? (int)s_list[((size_t)g * 4 + seg) * 256 + i] : 0;
         }
-        const int lc = KIND == NF_MLP_BRDF ? li : (li < p.L ? li : p.L - 1);
-        // ------------------------------------------------ per-row embedding -> A_e
-        float mask = 1.f;
-        f3 ldir;
-        {
-          float4 lp = s_lx[lc];
-          f3 d = l2n(mk3(lp.x, lp.y, lp.z) - xd, 1e-6f);                      // shape.py:128-135
-          ldir = d;
-          float v[KE];
+        const int lc = KIND == NF_MLP_BRDF ? r.li : (r.li < p.L ? r.li : p.L - 1);
+        r.mask = 1.f;
+        float4 lp = s_lx[lc];
+        f3 d = l2n(mk3(lp.x, lp.y, lp.z) - xd, 1e-6f);                        // shape.py:128-135
+        r.ldir = d;
+        float v[KE];
 #pragma unroll
-          for (int i = 0; i < KE; ++i) v[i] = 0.f;
-          f3 q;
-          int nf;
-          if (KIND == NF_MLP_LVIS) { q = d; nf = 4; }
-          else {
-            f3 l_loc = mk3(dot3(fr_t, d), dot3(fr_b, d), dot3(fr_n, d));      // nerfactor.py:419
-            mask = l_loc.z > 0.f ? 1.f : 0.f;                                 // :429-432
-            q = dir2rusink_dev(l_loc, v_loc);                                 // geom.py:152-192
-            nf = 2;
-          }
-          v[0] = q.x; v[1] = q.y; v[2] = q.z;
-          float sx, cx, sy, cy, sz, cz;
-          sincosf(q.x, &sx, &cx); sincosf(q.y, &sy, &cy); sincosf(q.z, &sz, &cz);
-#pragma unroll
-          for (int f = 0; f < (KIND == NF_MLP_LVIS ? 4 : 2); ++f) {
-            if (f < nf) {
-              v[3 + 6 * f + 0] = sx; v[3 + 6 * f + 1] = sy; v[3 + 6 * f + 2] = sz;
-              v[3 + 6 * f + 3] = cx; v[3 + 6 * f + 4] = cy; v[3 + 6 * f + 5] = cz;
-              float nsx = 2.f * sx * cx, ncx = 1.f - 2.f * sx * sx;
-              float nsy = 2.f * sy * cy, ncy = 1.f - 2.f * sy * sy;
-              float nsz = 2.f * sz * cz, ncz = 1.f - 2.f * sz * sz;
-              sx = nsx; cx = ncx; sy = nsy; cy = ncy; sz = nsz; cz = ncz;
-            }
-          }
-          uint32_t pk[KE / 2];
-#pragma unroll
-          for (int i = 0; i < KE / 2; ++i) pk[i] = pack2<BF16, 0>(v[2 * i], v[2 * i + 1]);
-          if (KE == 32) { TC_ST16(tb + COL_AE, pk); }
-          else { TC_ST8(tb + COL_AE, pk); }
+        for (int i = 0; i < KE; ++i) v[i] = 0.f;
+        f3 q;
+        int nf;
+        if (KIND == NF_MLP_LVIS) { q = d; nf = 4; }
+        else {
+          f3 l_loc = mk3(dot3(fr_t, d), dot3(fr_b, d), dot3(fr_n, d));        // nerfactor.py:419
+          r.mask = l_loc.z > 0.f ? 1.f : 0.f;                                 // :429-432
+          q = dir2rusink_dev(l_loc, v_loc);                                   // geom.py:152-192
+          nf = 2;
         }
+        v[0] = q.x; v[1] = q.y; v[2] = q.z;
+        float sx, cx, sy, cy, sz, cz;
+        sincosf(q.x, &sx, &cx); sincosf(q.y, &sy, &cy); sincosf(q.z, &sz, &cz);
+#pragma unroll
+        for (int f = 0; f < (KIND == NF_MLP_LVIS ? 4 : 2); ++f) {
+          if (f < nf) {
+            v[3 + 6 * f + 0] = sx; v[3 + 6 * f + 1] = sy; v[3 + 6 * f + 2] = sz;
+            v[3 + 6 * f + 3] = cx; v[3 + 6 * f + 4] = cy; v[3 + 6 * f + 5] = cz;
+            float nsx = 2.f * sx * cx, ncx = 1.f - 2.f * sx * sx;
+            float nsy = 2.f * sy * cy, ncy = 1.f - 2.f * sy * sy;
+            float nsz = 2.f * sz * cz, ncz = 1.f - 2.f * sz * sz;
+            sx = nsx; cx = ncx; sy = nsy; cy = ncy; sz = nsz; cz = ncz;
+          }
+        }
+        uint32_t pk[KE / 2];
+#pragma unroll
+        for (int i = 0; i < KE / 2; ++i) pk[i] = pack2<BF16, 0>(v[2 * i], v[2 * i + 1]);
+        const uint32_t ae = tb + ((c & 1) ? COL_AE1 : COL_AE);
+        if (KE == 32) { TC_ST16(ae, pk); }
+        else { TC_ST8(ae, pk); }
         tc_wait_st();
-        hand_over(0);
+        return r;
+      };
 
+      RowInfo cur = embed_tile(0);
+      hand_over(0, 0);
+      for (int c = 0; c < n_tiles; ++c) {
         // ------------------------------------------------ layers 0..2: ReLU + 16-bit -> A_h
         for (int layer = 0; layer < 3; ++layer) {
           mbar_wait(bar_d + g, phd);
@@ -787,9 +800,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
             pk[i] = pack2<BF16, 1>(__uint_as_float(rd[2 * i]), __uint_as_float(rd[2 * i + 1]));
           TC_ST16(tb + COL_AH + 48, pk);
           tc_wait_st();
-          hand_over(layer + 1);
+          hand_over(layer + 1, c & 1);
         }
-        // ------------------------------------------------ layer 3 + head
+        // ------------------------------------------------ layer 3 is in flight: the NEXT tile's
+        // per-row embedding goes into the other A_e buffer now (off the critical chain)
+        const bool has_next = c + 1 < n_tiles;
+        RowInfo nxt = cur;
+        if (has_next) nxt = embed_tile(c + 1);
+        // ------------------------------------------------ layer 3 done: accumulator -> registers,
+        // hand the next tile's layer 0 over, THEN the head (it only needs the registers)
         mbar_wait(bar_d + g, phd);
         phd ^= 1u;
         tc_fence_after();
@@ -798,9 +817,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
           uint32_t ra[32], rb[32], rc[32], rd[32];
           TC_LD32(ra, tb + COL_D);
           TC_LD32(rb, tb + COL_D + 32);
-          tc_wait_ld();
           TC_LD32(rc, tb + COL_D + 64);
           TC_LD32(rd, tb + COL_D + 96);
+          tc_wait_ld();
+          if (has_next) hand_over(0, (c + 1) & 1);
           const float4* wo = reinterpret_cast<const float4*>(s_aux + AUX_WOUT);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -814,7 +834,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
             acc0 = fmaf(fmaxf(__uint_as_float(rb[4 * i + 2]), 0.f), w1.z, acc0);
             acc1 = fmaf(fmaxf(__uint_as_float(rb[4 * i + 3]), 0.f), w1.w, acc1);
           }
-          tc_wait_ld();
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float4 w0 = wo[16 + i], w1 = wo[24 + i];
@@ -828,8 +847,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
             acc1 = fmaf(fmaxf(__uint_as_float(rd[4 * i + 3]), 0.f), w1.w, acc1);
           }
         }
+        const int li = cur.li;
+        const bool row_ok = cur.ok;
+        const f3 ldir = cur.ldir;
         float o = (acc0 + acc1) + s_aux[AUX_BOUT];
-        o = apply_act(p.out_act, o) * mask;
+        o = apply_act(p.out_act, o) * cur.mask;
         if (row_ok && p.out) p.out[(size_t)pt * p.L + li] = o;
         if (fuse) {
           // one term of the rendering equation (nerfactor.py:325-336) with the GGX lobe of
@@ -865,6 +887,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
             slot[0] = q0; slot[1] = q1; slot[2] = q2;
           }
         }
+        cur = nxt;
       }
       if (fuse) {
         group_bar(1 + g);

@@ -81,6 +81,29 @@ def test_host_weight_packing_sizes_and_errors():
     lib.nf_mlp_destroy(h)
 
 
+def test_workspace_queries_are_host_only_and_consistent():
+    """`*_workspace_bytes()` of the composite ops (one query per op that needs scratch):
+    callable without a GPU, sized by the chunk the op processes at a time."""
+    lib = _lib.load_library()
+    dn = lib.nf_raymarch_depth_normal_workspace_bytes
+    # one chunk of 32768 rays: 3 [c, Sc] + 2 [c, S] + [c, S, 3] fp32 buffers
+    full = 32768 * (3 * 128 + 5 * 320) * 4
+    assert dn(640000, 128, 192) == dn(32768, 128, 192) and full <= dn(32768, 128, 192) <= full + 6 * 256
+    assert dn(100, 128, 192) < dn(32768, 128, 192)
+    lv = lib.nf_raymarch_lvis_workspace_bytes
+    assert lv(640000, 512, 128, 192) == lv(1024, 512, 128, 192)          # capped at 2^19 pairs
+    assert lv(10, 16, 128, 192) < lv(1024, 512, 128, 192)
+    a = _lib.StageBArgs()
+    a.n, a.n_lights, a.n_envmaps, a.brdf_kind = 640000, 512, 1, 0
+    one = lib.nf_stageB_fused_workspace_bytes(C.byref(a), _lib.PREC['f16'])
+    assert 0 < one <= 48 << 20                                           # one chunk of lvis rows
+    a.brdf_kind = 1
+    assert lib.nf_stageB_fused_workspace_bytes(C.byref(a), _lib.PREC['f16']) == 2 * one
+    a.lvis_d = 1                                                         # caller keeps lvis: no scratch for it
+    assert lib.nf_stageB_fused_workspace_bytes(C.byref(a), _lib.PREC['f16']) == one
+    assert lib.nf_dense_fwd_workspace_bytes(128, 128, 0, _lib.PREC['bf16']) > 0
+
+
 def test_network_mirror_shapes():
     net = mlp.Network([128] * 4, act=['relu'] * 4, skip_at=[2]).build(90)
     ks = [l.kernel.shape for l in net.layers]
