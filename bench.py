@@ -320,6 +320,13 @@ def timed_mode_parity(ctx, nerf, model, vr, args, sigma_prec):
         model.precision = 'f16'
     out['stage_b'] = {'rays': 4096, 'rgb_rel_l2': rl2(p16['rgb'], p32['rgb']),
                       'lvis_rel_l2': rl2(p16['lvis'], p32['lvis'])}
+    # the timed Stage-B path (nf_stageB_fused_fwd over point chunks) against the separate
+    # full-size kernels of Model.call, on the whole benchmark view
+    full_f = vr.render(synth.look_at_c2w(4.0, 30.0, 30.0), synth.CAM_ANGLE_X, args.imh, args.imw)
+    full_c = vr.render(synth.look_at_c2w(4.0, 30.0, 30.0), synth.CAM_ANGLE_X, args.imh, args.imw,
+                       fused=False)
+    out['stage_b']['fused_op_vs_separate_kernels_rgb_rel_l2_full_view'] = rl2(full_f['rgb'], full_c['rgb'])
+    del full_f, full_c
     # end to end on the sphere-like field
     lh = args.light_h
     lxyz, lareas = gen_light_xyz(lh, 2 * lh)
@@ -377,13 +384,31 @@ def multi_rank_rows(ctx, vr, model, args, dist, world, rank):
     c2w = synth.look_at_c2w(4.0, 30.0, 30.0)
     a, b = shard_range(n_rays, rank, world)
 
+    per = (n_rays + world - 1) // world
+    peer = None
+    if world > 1 and os.environ.get('NF_GATHER', 'push') == 'push':
+        try:
+            from nerfactor_b200.pipeline import PeerImageGather
+            peer = PeerImageGather(per, (3,), world, rank, ctx.device)
+        except Exception:
+            peer = None
+
     def strong():
         pred = vr.render(c2w, synth.CAM_ANGLE_X, args.imh, args.imw, ray_range=(a, b))
-        return gather_image(pred['rgb'], n_rays, rank, world) if world > 1 else pred['rgb']
+        if world == 1:
+            return pred['rgb']
+        if peer is None:
+            return gather_image(pred['rgb'], n_rays, rank, world)
+        rgb = pred['rgb']
+        if rgb.shape[0] < per:                    # last shard of a ragged split
+            rgb = torch.cat((rgb, torch.zeros((per - rgb.shape[0], 3), device=ctx.device)), 0)
+        peer.push(rgb)
+        return peer.finish().reshape(-1, 3)[:n_rays]      # the image is complete on every rank
     ms = timed(strong)
     out['strong_scaling_one_view'] = {
-        'what': 'ONE %dx%d view, rays [rank] of %d contiguous shards, image all-gather inside the '
-                'timed region' % (args.imw, args.imh, world),
+        'what': 'ONE %dx%d view, rays [rank] of %d contiguous shards, image assembled on every rank '
+                'inside the timed region (%s)' % (args.imw, args.imh, world,
+                                                 'peer pushes' if peer is not None else 'NCCL all-gather'),
         'scaling': 'strong', 'ms': ms, 'rays_per_s': n_rays / (ms * 1e-3), 'n_gpus': world}
     # configs[4]: 8 views x 8 env-maps
     n_views, n_maps = 8, 8

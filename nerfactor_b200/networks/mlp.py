@@ -40,8 +40,12 @@ class Dense:
         self.kernel, self.bias = kernel, bias
 
 
-class Network:
+from .base import Network as BaseNetwork
+
+
+class Network(BaseNetwork):
     def __init__(self, widths, act=None, skip_at=None):
+        super().__init__()
         depth = len(widths)
         if act is None:
             act = [None] * depth
@@ -61,17 +65,6 @@ class Network:
             if self.skip_at is not None and i in self.skip_at:
                 d = layer.units + in_dim
         return self
-
-    def load(self, mlp_dict):
-        """mlp_dict: {'layers': [(W, b), ...]} (nerfactor_b200.synth / checkpoints)."""
-        assert len(mlp_dict['layers']) == len(self.layers)
-        for layer, (w, b) in zip(self.layers, mlp_dict['layers']):
-            layer.set_weights(w, b)
-        return self
-
-    def weights(self):
-        assert all(l.built for l in self.layers), "Some layers not built"
-        return [(l.kernel, l.bias) for l in self.layers]
 
     def __call__(self, x):
         """x [M, in] (CUDA, fp32) -> [M, widths[-1]], input re-concatenated after the layers in

@@ -425,6 +425,42 @@ def test_fused_stage_b_equals_model_call(ctx, brdf, lh, lw, n, single, monkeypat
     assert m.render_rgb(empty)['rgb'].shape == (0, 3)
 
 
+def test_composite_ops_are_chunk_invariant(ctx):
+    """The one-call ops process their input in chunks (32768 rays; 2^19 (point, light) pairs;
+    <= 48 MB of visibility rows): a multi-chunk call must equal the concatenation of single-chunk
+    calls bit for bit (every ray / pair / point is independent)."""
+    from nerfactor_b200 import geometry_from_nerf as gfn
+    model = _nerf_model(ctx, 3, precision='f16e')
+    cfg = nfconfig.default_config('nerf', n_samples_coarse=-48, n_samples_fine=-52)   # 16 + 12 samples
+    ro, rd = _rays(ctx, 210, 200)                                                      # 42000 rays: 2 chunks
+    occu, depth, normal = gfn.compute_depth_and_normal(model, ro, rd, cfg)
+    k = 32768
+    for lo, hi in ((0, k), (k, ro.shape[0])):
+        o2, d2, n2 = gfn.compute_depth_and_normal(model, ro[lo:hi].contiguous(), rd[lo:hi].contiguous(), cfg)
+        assert torch.equal(occu[lo:hi], o2) and torch.equal(depth[lo:hi], d2) and torch.equal(normal[lo:hi], n2)
+    # light march: 1300 points x 512 lights = 665600 pairs (2 chunks; the boundary falls inside a point)
+    rng = np.random.default_rng(8)
+    surf = dev(rng.uniform(-1, 1, (1300, 3)).astype(np.float32), ctx)
+    nrm = rng.standard_normal((1300, 3)).astype(np.float32)
+    nrm = dev(nrm / np.linalg.norm(nrm, axis=1, keepdims=True), ctx)
+    lv = gfn.compute_light_visibility(model, surf, nrm, cfg, light_h=16)
+    for lo, hi in ((0, 700), (700, 1300)):
+        part = gfn.compute_light_visibility(model, surf[lo:hi].contiguous(), nrm[lo:hi].contiguous(), cfg,
+                                            light_h=16)
+        assert torch.equal(lv[lo:hi], part)
+    assert float(lv.min()) >= -1e-6 and float(lv.max()) <= 1. + 1e-6
+    frac_lit = float((lv != 0).float().mean())
+    assert 0.3 < frac_lit < 0.7                       # back-lit pairs stay exactly 0
+    # fused Stage B: 60000 points x 512 lights = 3 chunks of 24576 points
+    m, _, _ = _stage_b(ctx, 'microfacet', 16, 32, seed=5, precision='f16')
+    batch = synth.make_stage_b_batch(9, 60000, 1, fg_frac=1.0)
+    big = m.render_rgb(batch)['rgb']
+    ref = m.call(batch, 'test')[0]['rgb']
+    assert rel_l2(big.cpu(), ref.cpu()) < 1e-6
+    sub = tuple(x[20000:40000] if isinstance(x, np.ndarray) else x for x in batch)
+    assert torch.equal(m.render_rgb(sub)['rgb'], big[20000:40000])
+
+
 def test_lvis_jitter_semantics_tensor_core_path(ctx):
     """shape.py:170 / nerfactor.py:225: the jittered visibility is the network at xyz + noise with
     the light directions of xyz.  nf_lvis_dirs_fwd (fp16 operands) against the oracle, and it
