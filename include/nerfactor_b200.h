@@ -320,6 +320,15 @@ int nf_raymarch_lvis_fwd(nf_ctx* ctx, const nf_mlp* mlp_coarse, const nf_mlp* ml
                          int precision, void* workspace_d, size_t workspace_bytes, float* lvis_d,
                          void* stream);
 
+/* Input rows of the light-visibility network for the train step, materialised in one launch
+ * (the training path runs the network layer by layer on materialised activations):
+ *   out[(i, l), :] = [embed(xyz_scale xyz_i) | embed(l2n(lxyz_l - xyz_dir_i)) | 0 ...]  (row stride ld)
+ * replaces _calc_ldir + the two Embedder calls + tf.concat of shape.py:128-135, 213-233;
+ * xyz_dir = xyz for the clean evaluation, the un-jittered point for the jittered one (:170).   */
+int nf_lvis_inputs_fwd(nf_ctx* ctx, const float* xyz_d, const float* xyz_dir_d, int n,
+                       const float* lxyz_d, int n_lights, float xyz_scale, int n_freqs_xyz,
+                       int n_freqs_ldir, int ld, float* out_d, void* stream);
+
 /* ---- training (config 4): Dense layers on materialised activations + optimizer ----
  * One Keras Dense of mlp.Network (nerfactor/networks/mlp.py:34, 39-50) at a time:
  *   y[m, n] = act([x1[m,k1] | x2[m,k2]] w[(k1+k2), n] + b[n])      (x2 = skip concat, k2 may be 0)

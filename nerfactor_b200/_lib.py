@@ -32,7 +32,7 @@ EXPORTS = [
     'nf_dense_bwd', 'nf_adam_amsgrad_step', 'nf_microfacet_brdf_fwd', 'nf_selftest_tmem',
     'nf_raymarch_depth_normal_workspace_bytes', 'nf_raymarch_depth_normal_fwd',
     'nf_raymarch_lvis_workspace_bytes', 'nf_raymarch_lvis_fwd',
-    'nf_stageB_fused_workspace_bytes', 'nf_stageB_fused_fwd', 'nf_lvis_dirs_fwd']
+    'nf_stageB_fused_workspace_bytes', 'nf_stageB_fused_fwd', 'nf_lvis_dirs_fwd', 'nf_lvis_inputs_fwd']
 
 
 class NfError(RuntimeError):
@@ -103,6 +103,7 @@ def load_library():
     lib.nf_mlp_upload.argtypes = [vp, vp, vp, vp]
     lib.nf_point_mlp_fwd.argtypes = [vp, vp, vp, i, f, vp, i, vp]
     lib.nf_lvis_fwd.argtypes = [vp, vp, vp, i, f, vp, i, vp, i, vp]
+    lib.nf_lvis_inputs_fwd.argtypes = [vp, vp, vp, i, vp, i, f, i, i, i, vp, vp]
     lib.nf_lvis_dirs_fwd.argtypes = [vp, vp, vp, vp, i, f, vp, i, vp, i, vp]
     lib.nf_brdf_learned_fwd.argtypes = [vp, vp, vp, vp, vp, vp, i, vp, i, vp, i, vp]
     lib.nf_integrate_fwd.argtypes = [vp, C.POINTER(IntegrateArgs), vp]
@@ -286,6 +287,20 @@ def lvis_fwd(ctx, mlp, xyz, lxyz, xyz_scale=1.0, precision='f16'):
     ctx.launch(ctx.lib.nf_lvis_fwd(ctx.h, mlp.h, _f32(xyz), n, float(xyz_scale), _f32(lxyz),
                                   L, _f32(out), PREC[precision], _stream()))
     return out
+
+
+def lvis_inputs_fwd(ctx, xyz, xyz_dir, lxyz, xyz_scale, n_freqs_xyz, n_freqs_ldir):
+    """[embed(xyz_scale xyz) | embed(l2n(lxyz - xyz_dir))] rows, zero-padded to a multiple of 4
+    columns -> (rows [n * L, ld], true width)."""
+    lxyz = lxyz.reshape(-1, 3)
+    n, L = xyz.shape[0], lxyz.shape[0]
+    width = 3 * (1 + 2 * n_freqs_xyz) + 3 * (1 + 2 * n_freqs_ldir)
+    ld = (width + 3) // 4 * 4
+    out = torch.empty((n * L, ld), dtype=torch.float32, device=xyz.device)
+    ctx.launch(ctx.lib.nf_lvis_inputs_fwd(ctx.h, _f32(xyz), _f32(xyz_dir), n, _f32(lxyz), L,
+                                         float(xyz_scale), int(n_freqs_xyz), int(n_freqs_ldir),
+                                         ld, _f32(out), _stream()))
+    return out, width
 
 
 def lvis_dirs_fwd(ctx, mlp, xyz, xyz_dir, lxyz, xyz_scale=1.0, precision='f16'):

@@ -50,13 +50,16 @@ def _pad_to4(n):
     return (n + 3) // 4 * 4
 
 
-def mlp_apply(x, layers, acts, skip_at, prec='fp32'):
+def mlp_apply(x, layers, acts, skip_at, prec='fp32', in_dim=None):
     """mlp.Network.__call__ (nerfactor/networks/mlp.py:39-50) + seq.Network for the head.
     layers: [(W[in,out], b[out]), ...] torch tensors (Keras layout).  Inputs / outputs
-    whose width is not a multiple of 4 are zero-padded for the kernels (and sliced back)."""
-    in_dim = x.shape[1]
+    whose width is not a multiple of 4 are zero-padded for the kernels (and sliced back);
+    `in_dim`: true input width when `x` already arrives zero-padded to a multiple of 4."""
+    if in_dim is None:
+        in_dim = x.shape[1]
     in_pad = _pad_to4(in_dim)
-    xp = F.pad(x, (0, in_pad - in_dim)) if in_pad != in_dim else x
+    assert x.shape[1] in (in_dim, in_pad)
+    xp = F.pad(x, (0, in_pad - in_dim)) if x.shape[1] != in_pad else x
     h, h_skip = xp, None
     for i, ((w, b), act) in enumerate(zip(layers, acts)):
         n = w.shape[1]

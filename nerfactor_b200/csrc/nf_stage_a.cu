@@ -212,9 +212,62 @@ __global__ void lvis_rays_kernel(const float* __restrict__ surf, const float* __
   fl[g] = c > 0.f ? 1 : 0;
 }
 
+// Input rows of the light-visibility network for training-size batches, materialised in one
+// launch: row (i, l) = [embed(xyz_scale * xyz_i) | embed(l2n(lxyz_l - xyz_dir_i)) | 0-padding]
+// (shape.py:128-135, 213-233; embedder.py:46-47).  One thread per (row, octave-or-raw) triple.
+__global__ void __launch_bounds__(256)
+lvis_inputs_kernel(const float* __restrict__ xyz, const float* __restrict__ xyz_dir,
+                   const float* __restrict__ lxyz, long long rows, int L, float xyz_scale, int fa,
+                   int fb, int ld, float* __restrict__ out) {
+  const int per_row = (1 + fa) + (1 + fb);          // items: raw + octaves of each encoding
+  const long long total = rows * per_row;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long r = idx / per_row;
+    int item = (int)(idx % per_row);
+    const long long i = r / L;
+    const int l = (int)(r % L);
+    float* o = out + r * ld;
+    f3 v;
+    int base, k;
+    if (item < 1 + fa) {                             // position encoding
+      v = ld3(xyz + i * 3) * xyz_scale;
+      base = 0; k = item;
+    } else {                                         // light-direction encoding
+      v = l2n(ld3(lxyz + l * 3) - ld3(xyz_dir + i * 3), 1e-6f);
+      base = 3 * (1 + 2 * fa); k = item - (1 + fa);
+      if (k == 0)                                    // zero padding up to the row stride
+        for (int c = base + 3 * (1 + 2 * fb); c < ld; ++c) o[c] = 0.f;
+    }
+    if (k == 0) { o[base] = v.x; o[base + 1] = v.y; o[base + 2] = v.z; continue; }
+    const float fr = (float)(1 << (k - 1));
+    float* q = o + base + 3 + 6 * (k - 1);
+    q[0] = sinf(v.x * fr); q[1] = sinf(v.y * fr); q[2] = sinf(v.z * fr);
+    q[3] = cosf(v.x * fr); q[4] = cosf(v.y * fr); q[5] = cosf(v.z * fr);
+  }
+}
+
 }  // namespace
 
 extern "C" {
+
+int nf_lvis_inputs_fwd(nf_ctx* ctx, const float* xyz_d, const float* xyz_dir_d, int n,
+                       const float* lxyz_d, int n_lights, float xyz_scale, int n_freqs_xyz,
+                       int n_freqs_ldir, int ld, float* out_d, void* stream) {
+  NF_CHECK_ARG(ctx, xyz_d && xyz_dir_d && lxyz_d && out_d, "null argument");
+  NF_CHECK_ARG(ctx, n >= 0 && n_lights > 0 && n_freqs_xyz >= 0 && n_freqs_ldir >= 0, "bad sizes");
+  NF_CHECK_ARG(ctx, ld >= 3 * (1 + 2 * n_freqs_xyz) + 3 * (1 + 2 * n_freqs_ldir), "row stride too small");
+  const long long rows = (long long)n * n_lights;
+  if (rows == 0) return NF_OK;
+  const long long total = rows * (2 + n_freqs_xyz + n_freqs_ldir);
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)ctx->sm_count * 32;
+  if (blocks > cap) blocks = cap;
+  lvis_inputs_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
+      xyz_d, xyz_dir_d, lxyz_d, rows, n_lights, xyz_scale, n_freqs_xyz, n_freqs_ldir, ld, out_d);
+  NF_LAUNCH_CHECK(ctx);
+  return NF_OK;
+}
 
 int nf_gen_rays(nf_ctx* ctx, const double* c2w, double cam_angle_x, int h, int w,
                 int normalize, float* rayo_d, float* rayd_d, void* stream) {

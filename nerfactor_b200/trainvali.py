@@ -141,10 +141,20 @@ class Trainer:
         e = ad.embed(self.model.xyz_scale * pts, self.model.embedder['xyz'].n_freqs)
         return ad.mlp_apply(e, layers, acts, skip, self.precision)
 
-    def _lvis(self, views, pts, surf2l):
+    def _lvis(self, views, pts, surf2l, pts_dir=None):
+        """shape.py:213-237 on materialised rows.  Neither the surface points nor the light
+        directions carry gradients, so the [n L, 90] input rows ([embed(pts) | embed(surf2l)],
+        surf2l = directions of `pts_dir`: the un-jittered point for the jittered evaluation,
+        shape.py:170) are built by one kernel (nf_lvis_inputs_fwd) instead of ~30 torch ops."""
         layers, acts, skip = self.net_layers(views, 'lvis')
         n, L = surf2l.shape[0], surf2l.shape[1]
         m = self.model
+        if pts.is_cuda and not pts.requires_grad:
+            e, width = _lib.lvis_inputs_fwd(
+                self.ctx, pts.contiguous(), (pts if pts_dir is None else pts_dir).contiguous(),
+                m.lxyz.reshape(-1, 3), m.xyz_scale, m.embedder['xyz'].n_freqs,
+                m.embedder['ldir'].n_freqs)
+            return ad.mlp_apply(e, layers, acts, skip, self.precision, in_dim=width).reshape(n, L)
         e_x = ad.embed(m.xyz_scale * pts, m.embedder['xyz'].n_freqs)
         e_l = ad.embed(surf2l.reshape(-1, 3), m.embedder['ldir'].n_freqs)
         e = torch.cat((e_x[:, None, :].expand(n, L, e_x.shape[1]).reshape(n * L, -1), e_l), -1)
@@ -214,7 +224,7 @@ class Trainer:
             lvis_pred = self._lvis(views, xyz_m, surf2l)
             lvis_j = None
             if xyz_j is not None and m.lvis_smooth_weight > 0:
-                lvis_j = self._lvis(views, xyz_j, surf2l)
+                lvis_j = self._lvis(views, xyz_j, surf2l, xyz_m)
             pred = {'normal': normal_pred, 'lvis': lvis_pred}
             gt = {'normal': normal, 'lvis': lvis, 'alpha': alpha}
             loss = m.compute_loss(pred, gt, normal_jitter=normal_j, lvis_jitter=lvis_j)
@@ -228,7 +238,7 @@ class Trainer:
             normal_pred = self._point(views, 'normal', xyz_m) + 1e-6
             normal_j = None if xyz_j is None else self._point(views, 'normal', xyz_j) + 1e-6
             lvis_pred = self._lvis(views, xyz_m, surf2l)
-            lvis_j = None if xyz_j is None else self._lvis(views, xyz_j, surf2l)
+            lvis_j = None if xyz_j is None else self._lvis(views, xyz_j, surf2l, xyz_m)
         normal_pred = ad.safe_l2_normalize(normal_pred, 1)
         if normal_j is not None:
             normal_j = ad.safe_l2_normalize(normal_j, 1)
