@@ -439,6 +439,28 @@ def multi_rank_rows(ctx, vr, model, args, dist, world, rank):
         ms = timed(sweep, steps=1 if world == 1 else 2)
     finally:
         model.novel_probes = saved
+    # configs[3]: one data-parallel optimizer step (forward + backward + gradient all-reduce +
+    # AMSGrad), 1024 rays x 512 lights per rank, bf16 tensor-core Dense kernels
+    try:
+        from nerfactor_b200 import config as nfconfig
+        from nerfactor_b200.models.nerfactor import Model as LearnedModel
+        from nerfactor_b200.trainvali import Trainer
+        lm = LearnedModel(nfconfig.default_config('nerfactor'),
+                          params=synth.make_stage_b_params(0, 'learned'), ctx=ctx, precision='fp32')
+        tb = synth.make_stage_b_batch(2 + rank, 1024, 512, fg_frac=1.0)
+        tr = Trainer(lm, world_size=world, rank=rank, precision='bf16')
+        t_ms = timed(lambda: tr.train_step(tb), steps=5, warmup=3)
+        out['train_step_data_parallel'] = {
+            'what': 'BASELINE configs[3]: Trainer.train_step (learned-BRDF NeRFactor, jitter on), 1024 '
+                    'rays x 512 lights PER RANK, bf16 tcgen05 Dense kernels, one NCCL all-reduce of the '
+                    'flat gradient inside the timed region, AMSGrad',
+            'ms': t_ms, 'rays_per_s': world * 1024 / (t_ms * 1e-3), 'n_gpus': world,
+            'global_batch_rays': world * 1024}
+        del tr, lm
+    except Exception as e:
+        out['train_step_data_parallel'] = {'error': repr(e)}
+        if world > 1:
+            raise
     out['config5_relight_sweep'] = {
         'what': 'BASELINE configs[4]: %d novel views x %d env-maps at %dx%d, views split over the '
                 'ranks, NCCL all-gather of every relit image' % (n_views, n_maps, args.imw, args.imh),
