@@ -67,6 +67,7 @@ struct TcParams {
   float f_f0;
   int f_srgb;
   float* f_rgb;            // [n,3]; NULL = plain network evaluation
+  int warp_arrive;         // v2, issuer-warp mode: one elected mbarrier arrival per warp
 };
 
 // fp32 side block layout (floats): see nf_tc_pack
@@ -464,7 +465,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
   // ---------------------------------------------------------------- set-up
   if (threadIdx.x == 0) {
     mbar_init(bar_w, 1);
-    mbar_init(bar_a + 0, 128); mbar_init(bar_a + 1, 128);
+    mbar_init(bar_a + 0, p.warp_arrive ? 4 : 128); mbar_init(bar_a + 1, p.warp_arrive ? 4 : 128);
     mbar_init(bar_d + 0, 1); mbar_init(bar_d + 1, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -616,6 +617,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
       if (SELF) {
         group_bar(3 + g);
         if (tg == 0) { tc_fence_after(); self_issue(layer, aebuf); }
+      } else if (p.warp_arrive) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_a + g);
       } else {
         mbar_arrive(bar_a + g);
       }
@@ -1081,9 +1085,12 @@ int launch_tc(nf_ctx* ctx, const nf_mlp* m, const TcParams& p, cudaStream_t st) 
     using SL = SmemLayout2<KIND>;
     NF_CHECK_ARG(ctx, SL::total <= ctx->smem_optin, "shared memory budget exceeded");
     constexpr int SELF = KIND == NF_MLP_BRDF ? 1 : 0;
+    TcParams q = p;
+    q.warp_arrive = 0;
+    if (const char* e = getenv("NF_LVIS_WARP_ARRIVE")) q.warp_arrive = atoi(e) ? 1 : 0;
     NF_CUDA(ctx, cudaFuncSetAttribute(mlp_tc2_kernel<KIND, BF16, SELF>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SL::total));
-    mlp_tc2_kernel<KIND, BF16, SELF><<<grid, TC_THREADS, SL::total, st>>>(p);
+    mlp_tc2_kernel<KIND, BF16, SELF><<<grid, TC_THREADS, SL::total, st>>>(q);
   }
   NF_LAUNCH_CHECK(ctx);
   return NF_OK;

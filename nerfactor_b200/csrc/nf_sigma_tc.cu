@@ -64,6 +64,7 @@ struct SigmaTcParams {
   float bbox[6];
   int use_bbox;
   float* sigma;          // [n_rays,S]
+  int warp_arrive;       // 1: one elected mbarrier arrival per warp instead of one per thread
 };
 
 // bytes of the weight chunk for (layer, part): part 0/1 = hidden K-blocks, part 2 = input part
@@ -99,8 +100,8 @@ __global__ void __launch_bounds__(SG_THREADS, 1) sigma_tc_kernel(const SigmaTcPa
   if (threadIdx.x == 0) {
     for (int i = 0; i < SG_NSLOT; ++i) { mbar_init(bar_full + i, 1); mbar_init(bar_empty + i, CL); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(bar_dfull + i, 1); mbar_init(bar_aready + i, 256);
-      mbar_init(bar_eready + i, 128); mbar_init(bar_efree + i, 1);
+      mbar_init(bar_dfull + i, 1); mbar_init(bar_aready + i, p.warp_arrive ? 8 : 256);
+      mbar_init(bar_eready + i, p.warp_arrive ? 4 : 128); mbar_init(bar_efree + i, 1);
     }
     mbar_init(bar_w, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -264,7 +265,12 @@ __global__ void __launch_bounds__(SG_THREADS, 1) sigma_tc_kernel(const SigmaTcPa
             }
           }
           tc_fence_before();
-          mbar_arrive(bar_aready + h);
+          if (p.warp_arrive) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_aready + h);
+          } else {
+            mbar_arrive(bar_aready + h);
+          }
         }
       }
       if (ch == 1) s_part[t] = acc;
@@ -351,7 +357,12 @@ __global__ void __launch_bounds__(SG_THREADS, 1) sigma_tc_kernel(const SigmaTcPa
         }
       }
       fence_proxy_async();
-      mbar_arrive(bar_eready + eb);
+      if (p.warp_arrive) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_eready + eb);
+      } else {
+        mbar_arrive(bar_eready + eb);
+      }
     }
   }
 
@@ -830,6 +841,7 @@ int nf_tc_sigma_launch(nf_ctx* ctx, const nf_mlp* m, const float* rayo, const fl
     if (cl_env != 1 && cl_env != 2 && cl_env != 4) cl_env = 2;
   }
   if (const char* e = getenv("NF_SIGMA_PAIR")) pair_env = atoi(e);
+  if (const char* e = getenv("NF_SIGMA_WARP_ARRIVE")) p.warp_arrive = atoi(e) ? 1 : 0;
   const bool bf = precision == NF_PREC_BF16;
   if (pair_env && !esplit) {
     int grid2 = ctx->sm_count / 2 * 2;

@@ -47,8 +47,8 @@ print(json.dumps(out))
 ''' % ROOT
 
 
-def run(flag, prefix, self_issue='1'):
-    env = dict(os.environ, NF_LVIS_V1=flag, NF_LVIS_SELF=self_issue)
+def run(flag, prefix, self_issue='1', **extra):
+    env = dict(os.environ, NF_LVIS_V1=flag, NF_LVIS_SELF=self_issue, **extra)
     r = subprocess.run([sys.executable, '-c', WORKER, prefix], env=env, capture_output=True,
                        text=True, timeout=200)
     if r.returncode != 0:
@@ -60,7 +60,13 @@ def main():
     import numpy as np
     import tempfile
     d = tempfile.mkdtemp()
-    res = {'v2': run('0', os.path.join(d, 'a')), 'v1': run('1', os.path.join(d, 'b'))}
+    res = {'v2': run('0', os.path.join(d, 'a')), 'v1': run('1', os.path.join(d, 'b')),
+           'v2_warp_arrive': run('0', os.path.join(d, 'c'), NF_LVIS_WARP_ARRIVE='1')}
+    if 'error' not in res['v2_warp_arrive'] and 'error' not in res['v2']:
+        for tag in ('ragged', 'full'):
+            a = np.load(os.path.join(d, 'a_%s_lvis.npy' % tag))
+            c = np.load(os.path.join(d, 'c_%s_lvis.npy' % tag))
+            res['maxdiff_warp_arrive_%s_lvis' % tag] = float(np.abs(a - c).max())
     if 'error' not in res['v1'] and 'error' not in res['v2']:
         for tag in ('ragged', 'full'):
             for k in ('lvis', 'spec'):

@@ -42,10 +42,9 @@ def main():
     s32 = _lib.sigma_fwd(ctx, mlp, ro[:k].contiguous(), rd[:k].contiguous(), z[:k].contiguous(),
                          None, 'fp32')
     out = {}
-    for name, prec, env in (('f16_ring5_cl2', 'f16', {}), ('f16_ring4_cl2', 'f16', {'NF_SIGMA_NSLOT': '4'}),
-                            ('f16e_ring4_cl2', 'f16e', {}), ('f16e_ring4_cl1', 'f16e', {'NF_SIGMA_CLUSTER': '1'}),
-                            ('f16e_ring4_cl4', 'f16e', {'NF_SIGMA_CLUSTER': '4'}),
-                            ('f16_ring5_cl4', 'f16', {'NF_SIGMA_CLUSTER': '4'})):
+    for name, prec, env in (('f16_ring5_cl2', 'f16', {}), ('f16e_ring4_cl2', 'f16e', {}),
+                            ('f16_warp_arrive', 'f16', {'NF_SIGMA_WARP_ARRIVE': '1'}),
+                            ('f16e_warp_arrive', 'f16e', {'NF_SIGMA_WARP_ARRIVE': '1'})):
         for kk, v in env.items():
             os.environ[kk] = v
         try:
