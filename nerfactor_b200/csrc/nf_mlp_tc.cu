@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const TcParams p)
 
   if (warp == 0) {
     // =============================================================== MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = make_idesc(BF16, TC_WIDTH);
       const uint32_t lbo = TC_WIDTH * 16, sbo = 128;
       const uint32_t img0 = smem_u32(s_img);
@@ -515,7 +515,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
 
   if (warp == 0) {
     // =============================================================== MMA issuer
-    if (!SELF && lane == 0) {
+    if (!SELF && elect_one()) {
       const uint32_t idesc = make_idesc(BF16, TC_WIDTH);
       const uint32_t lbo = TC_WIDTH * 16, sbo = 128;
       const uint32_t img0 = smem_u32(s_img), bdyn0 = smem_u32(s_bdyn);
@@ -616,7 +616,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
       tc_fence_before();
       if (SELF) {
         group_bar(3 + g);
-        if (tg == 0) { tc_fence_after(); self_issue(layer, aebuf); }
+        if (tg < 32 && elect_one()) { tc_fence_after(); self_issue(layer, aebuf); }
       } else if (p.warp_arrive) {
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_a + g);

@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(NR_THREADS, 1) nerf_tc_kernel(const NerfTcPara
     }
   } else if (warp == 0) {
     // ============================================================== MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = make_idesc(BF16, 128);
       const uint32_t ring0 = smem_u32(s_ring), e0 = smem_u32(s_e), v0 = smem_u32(s_v);
       uint32_t fill = 0, na[2] = {0u, 0u};

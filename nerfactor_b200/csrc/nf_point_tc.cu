@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) point_tc_kernel(const PointTcPa
     }
   } else if (warp == 0) {
     // ============================================================== MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = make_idesc(0, 128);
       const uint32_t ring0 = smem_u32(s_ring), e0 = smem_u32(s_e);
       uint32_t fill = 0, na = 0;

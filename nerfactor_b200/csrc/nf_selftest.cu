@@ -55,7 +55,7 @@ tmem_bw_kernel(int reader_warps, int iters, int mma_iters, int mode, long long* 
   tc_fence_after();
   const long long t0 = clock64();
   if (warp == 0) {
-    if ((mode & 4) && lane == 0) {
+    if ((mode & 4) && elect_one()) {
       const int n = (mode & 16) ? 256 : 128;
       const uint32_t idesc = make_idesc(0, n);
       const uint32_t lbo = 128 * 16, sbo = 128;

@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) sigma_grad_tc_kernel(const Grad
     }
   } else if (warp == 0) {
     // ============================================================== MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = make_idesc(BF16, 128);
       const uint32_t idesc64 = make_idesc(BF16, 64);
       const uint32_t ring0 = smem_u32(s_ring), e0 = smem_u32(s_e);

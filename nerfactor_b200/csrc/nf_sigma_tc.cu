@@ -65,7 +65,15 @@ struct SigmaTcParams {
   int use_bbox;
   float* sigma;          // [n_rays,S]
   int warp_arrive;       // 1: one elected mbarrier arrival per warp instead of one per thread
+  long long* dbg;        // NF_SIGMA_DBG: clock64 stamps of CTA 0, tile 2 ([8 layers][2][6]), else NULL
 };
+__device__ __forceinline__ long long clk64() {
+  long long c;
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(c));
+  return c;
+}
+#define SG_STAMP(l, h, k)                                                                   \
+  do { if (p.dbg && blockIdx.x == 0 && it == 2) p.dbg[((l) * 2 + (h)) * 6 + (k)] = clk64(); } while (0)
 
 // bytes of the weight chunk for (layer, part): part 0/1 = hidden K-blocks, part 2 = input part
 __device__ __forceinline__ uint32_t part_bytes(int part) { return part == 2 ? 16384u : 32768u; }
@@ -153,7 +161,7 @@ __global__ void __launch_bounds__(SG_THREADS, 1) sigma_tc_kernel(const SigmaTcPa
     }
   } else if (warp == 0) {
     // ============================================================== MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = make_idesc(BF16, 128);
       const uint32_t ring0 = smem_u32(s_ring), e0 = smem_u32(s_e), elo0 = smem_u32(s_elo);
       uint32_t fill = 0, na[2] = {0u, 0u};
@@ -170,7 +178,7 @@ __global__ void __launch_bounds__(SG_THREADS, 1) sigma_tc_kernel(const SigmaTcPa
               const int part = l == 0 ? 2 : pi;
               // operand / accumulator hazards
               if (l == 0) { if (it > 0) wait_a(h); }
-              else if (h == 0 && part < 2) wait_a(part);
+              else if (h == 0 && part < 2) { wait_a(part); SG_STAMP(l, part, 1); }
               const uint32_t slot = fill % SG_NSLOT;
               mbar_wait(bar_full + slot, (fill / SG_NSLOT) & 1);
               tc_fence_after();
@@ -201,6 +209,7 @@ __global__ void __launch_bounds__(SG_THREADS, 1) sigma_tc_kernel(const SigmaTcPa
               ++fill;
             }
             tc_commit(bar_dfull + h);
+            SG_STAMP(l, h, 0);
           }
           if (l == SG_SKIP + 1) tc_commit(bar_efree + eb);   // embedding buffer consumed
         }
@@ -225,11 +234,13 @@ __global__ void __launch_bounds__(SG_THREADS, 1) sigma_tc_kernel(const SigmaTcPa
           mbar_wait(bar_dfull + h, nd[h] & 1);
           ++nd[h];
           tc_fence_after();
+          if (threadIdx.x == 64) SG_STAMP(l, h, 2);
           const float* bias = s_bias + l * 256 + h * 128 + ch * 64;
           uint32_t r0[32], r1[32];
           TC_LD32(r0, tb + (h ? COL_D1 : COL_D0) + ch * 64);
           TC_LD32(r1, tb + (h ? COL_D1 : COL_D0) + ch * 64 + 32);
           tc_wait_ld();
+          if (threadIdx.x == 64) SG_STAMP(l, h, 3);
           if (l < SG_DEPTH - 1) {
             uint32_t pk[16];
 #pragma unroll
@@ -251,6 +262,7 @@ __global__ void __launch_bounds__(SG_THREADS, 1) sigma_tc_kernel(const SigmaTcPa
             }
             TC_ST16(xout + h * 64 + ch * 32 + 16, pk);
             tc_wait_st();
+            if (threadIdx.x == 64) SG_STAMP(l, h, 4);
           } else {
             const float* wo = s_wout + h * 128 + ch * 64;
 #pragma unroll
@@ -271,6 +283,7 @@ __global__ void __launch_bounds__(SG_THREADS, 1) sigma_tc_kernel(const SigmaTcPa
           } else {
             mbar_arrive(bar_aready + h);
           }
+          if (threadIdx.x == 64) SG_STAMP(l, h, 5);
         }
       }
       if (ch == 1) s_part[t] = acc;
@@ -487,7 +500,7 @@ __global__ void __launch_bounds__(SG_THREADS, 1) sigma_tc2_kernel(const SigmaTcP
     }
   } else if (warp == 0) {
     // ============================================================== MMA issuer (leader CTA)
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = make_idesc_mn(BF16, 256, 128);
       const uint32_t ring0 = smem_u32(s_ring), e0 = smem_u32(s_e);
       uint32_t fill = 0, na[2] = {0u, 0u};
@@ -858,12 +871,29 @@ int nf_tc_sigma_launch(nf_ctx* ctx, const nf_mlp* m, const float* rayo, const fl
   // plain kernels on the 4-slot ring too (tuning / A-B timing only)
   int nslot = esplit ? 4 : 5;
   if (const char* e = getenv("NF_SIGMA_NSLOT")) { if (atoi(e) == 4) nslot = 4; }
+  const char* dbg_path = getenv("NF_SIGMA_DBG");
+  if (dbg_path) {
+    NF_CUDA(ctx, cudaMalloc(&p.dbg, 96 * sizeof(long long)));
+    NF_CUDA(ctx, cudaMemsetAsync(p.dbg, 0, 96 * sizeof(long long), st));
+  }
+  auto dump_dbg = [&](int rc) {
+    if (!dbg_path) return rc;
+    long long h[96];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, p.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(p.dbg);
+    if (FILE* f = fopen(dbg_path, "w")) {
+      for (int i = 0; i < 96; ++i) fprintf(f, "%lld%c", h[i], i % 6 == 5 ? '\n' : ' ');
+      fclose(f);
+    }
+    return rc;
+  };
 #define NF_SG(B, C)                                                                         \
   (esplit ? launch_sigma<B, C, 4, 1>(ctx, p, grid, st)                                      \
           : (nslot == 4 ? launch_sigma<B, C, 4, 0>(ctx, p, grid, st)                        \
                         : launch_sigma<B, C, 5, 0>(ctx, p, grid, st)))
-  if (cl == 1) return bf ? NF_SG(1, 1) : NF_SG(0, 1);
-  if (cl == 2) return bf ? NF_SG(1, 2) : NF_SG(0, 2);
-  return bf ? NF_SG(1, 4) : NF_SG(0, 4);
+  if (cl == 1) return dump_dbg(bf ? NF_SG(1, 1) : NF_SG(0, 1));
+  if (cl == 2) return dump_dbg(bf ? NF_SG(1, 2) : NF_SG(0, 2));
+  return dump_dbg(bf ? NF_SG(1, 4) : NF_SG(0, 4));
 #undef NF_SG
 }

@@ -8,6 +8,16 @@ namespace nftc {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
+// One thread of a CONVERGED warp.  Issue tcgen05.mma / commit under `if (elect_one())`, not under
+// `if (lane == 0)`: with a data-dependent predicate the compiler cannot know that a single thread
+// is active and wraps every UTCHMMA in an ELECT / BRA.U.ANY serialisation loop (12 SASS
+// instructions and ~85 clocks per MMA -- more than the 64 clocks a 128 x 128 x 16 MMA executes, so
+// the issuing thread, not the tensor pipe, was the limiter; profiles/r2_issue_bound.md).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }

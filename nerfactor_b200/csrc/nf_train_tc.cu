@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) rowgemm_tc_kernel(const RowGemm
 
   if (warp == 0) {
     // ============================================================== MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = make_idesc(BF16, Np);
       const uint32_t a0 = smem_u32(s_a), w0 = smem_u32(s_w);
       const uint32_t lbo_b = (uint32_t)Np * 16;
@@ -442,7 +442,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgradPara
   const int mblocks = KpW / 128;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = make_idesc_major(BF16, Nz, 1, 1);
       // MN-major, swizzle-free (cute UMMA canonical layout ((T,1,m),(8,k)):((1,T,SBO),(1T,LBO))):
       // 8 (MN) x 8 (K) core matrix with MN contiguous (16 B) and K rows 16 B apart.  Here K =

@@ -43,8 +43,10 @@ def main():
                          None, 'fp32')
     out = {}
     for name, prec, env in (('f16_ring5_cl2', 'f16', {}), ('f16e_ring4_cl2', 'f16e', {}),
-                            ('f16_warp_arrive', 'f16', {'NF_SIGMA_WARP_ARRIVE': '1'}),
-                            ('f16e_warp_arrive', 'f16e', {'NF_SIGMA_WARP_ARRIVE': '1'})):
+                            ('f16_ring5_cl1', 'f16', {'NF_SIGMA_CLUSTER': '1'}),
+                            ('f16_ring5_cl4', 'f16', {'NF_SIGMA_CLUSTER': '4'}),
+                            ('f16_pair', 'f16', {'NF_SIGMA_PAIR': '1'}),
+                            ('bf16_ring5_cl2', 'bf16', {})):
         for kk, v in env.items():
             os.environ[kk] = v
         try:
