@@ -198,6 +198,15 @@ typedef struct nf_stageb_args {
   const int32_t* light_idx_d; /* [L] or NULL */
   float* lvis_d;          /* [n,L] or NULL */
   float* rgb_d;           /* [n,E,3] */
+  int lvis_all_lights;    /* only read when lvis_d is NULL (visibility not an output) and the
+                           * precision is NF_PREC_F16 / NF_PREC_BF16.  0 (default): the visibility
+                           * network runs on the FRONT-LIT lights of every point only, the ones with
+                           * cos(normal, light) > -1e-5 -- nerfactor.py:329-330 multiplies the
+                           * visibility of every other light by zero, so rgb_d is unchanged; the
+                           * learned BRDF is evaluated on front-lit pairs only in the reference
+                           * itself (nerfactor.py:429-458).  1: evaluate it for every light.
+                           * 2: front-lit lights only even with lvis_d given -- lvis_d then holds
+                           * front_lit * visibility, the `lvis` of nerfactor.py:330.                 */
 } nf_stageb_args;
 size_t nf_stageB_fused_workspace_bytes(const nf_stageb_args* args, int precision);
 int nf_stageB_fused_fwd(nf_ctx* ctx, const nf_mlp* mlp_lvis, const nf_mlp* mlp_brdf,

@@ -72,7 +72,7 @@ class StageBArgs(C.Structure):
                 ('cam_d', C.c_void_p), ('albedo_d', C.c_void_p), ('rough_d', C.c_void_p),
                 ('z_d', C.c_void_p), ('lxyz_d', C.c_void_p), ('lareas_d', C.c_void_p),
                 ('light_d', C.c_void_p), ('light_idx_d', C.c_void_p), ('lvis_d', C.c_void_p),
-                ('rgb_d', C.c_void_p)]
+                ('rgb_d', C.c_void_p), ('lvis_all_lights', C.c_int)]
 
 
 _lib = None
@@ -371,9 +371,11 @@ def integrate_olat_fwd(ctx, xyz, normal, cam, albedo, lvis, lxyz, lareas, olat_i
 
 def stageB_fused_fwd(ctx, mlp_lvis, xyz, normal, cam, albedo, lxyz, lareas, light, rough=None,
                      z=None, mlp_brdf=None, light_idx=None, f0=0.04, spec_scale=1.0, xyz_scale=1.0,
-                     linear2srgb=True, precision='f16', want_lvis=False):
+                     linear2srgb=True, precision='f16', want_lvis=False, all_lights=False):
     """Light-visibility net -> BRDF -> rendering equation in one C call (nf_stageB_fused_fwd).
-    light [E, P, 3] -> rgb [n, E, 3] (and lvis [n, L] when want_lvis)."""
+    light [E, P, 3] -> rgb [n, E, 3] (and lvis [n, L] when want_lvis).  Without `want_lvis` the
+    visibility network only runs on the front-lit lights of each point (the renderer multiplies
+    the others by zero, nerfactor.py:329-330) unless `all_lights`."""
     lxyz, lareas = lxyz.reshape(-1, 3), lareas.reshape(-1)
     n, L, E = xyz.shape[0], lxyz.shape[0], light.shape[0]
     dev = xyz.device
@@ -395,6 +397,7 @@ def stageB_fused_fwd(ctx, mlp_lvis, xyz, normal, cam, albedo, lxyz, lareas, ligh
         a.light_idx_d = _ptr(light_idx)
     a.lvis_d = _f32(lvis) if lvis is not None else None
     a.rgb_d = _f32(rgb)
+    a.lvis_all_lights = 2 if all_lights == 'front_lit' else int(bool(all_lights))
     nbytes = ctx.lib.nf_stageB_fused_workspace_bytes(C.byref(a), PREC[precision])
     work = torch.empty((nbytes + 256,), dtype=torch.uint8, device=dev) if nbytes else None
     wptr = C.c_void_p(work.data_ptr() + (-work.data_ptr()) % 256) if nbytes else None

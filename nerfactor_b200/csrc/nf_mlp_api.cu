@@ -11,7 +11,7 @@ int nf_tc_point_launch(nf_ctx* ctx, const nf_mlp* m, const float* xyz, int n, fl
 // nf_mlp_tc.cu
 int nf_tc_lvis_launch(nf_ctx* ctx, const nf_mlp* m, const float* xyz, int n, float xyz_scale,
                       const float* lxyz, int L, float* lvis, int precision, cudaStream_t st,
-                      const float* xyz_dir = nullptr);
+                      const float* xyz_dir = nullptr, const float* cull_normal = nullptr);
 int nf_tc_sigma_launch(nf_ctx* ctx, const nf_mlp* m, const float* rayo, const float* rayd,
                        const float* z, int n_rays, int S, const float* bbox_host, float* sigma,
                        int precision, cudaStream_t st);

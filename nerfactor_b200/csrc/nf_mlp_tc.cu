@@ -67,7 +67,8 @@ struct TcParams {
   float f_f0;
   int f_srgb;
   float* f_rgb;            // [n,3]; NULL = plain network evaluation
-  int warp_arrive;         // v2, issuer-warp mode: one elected mbarrier arrival per warp
+  const float* cull_normal;  // visibility network, CULL = 1: [n,3] shading normals -- only the
+                             // lights with cos(normal, light) > -1e-5 are evaluated, the others get 0
 };
 
 // fp32 side block layout (floats): see nf_tc_pack
@@ -426,7 +427,7 @@ struct SmemLayout2 {
   static constexpr size_t off_red = off_bar + 128;                       // [2 groups][16][4] f32
   static constexpr size_t off_cnt = off_red + 2 * 16 * 4 * 4;            // [2 groups][8] int: warp counts, tiles
   static constexpr size_t off_list = off_cnt + 2 * 8 * 4;                // [2 groups][4 warps][256] u16
-  static constexpr size_t total = off_list + (KIND == NF_MLP_BRDF ? 2 * 4 * 256 * 2 : 0);
+  static constexpr size_t total = off_list + 2 * 4 * 256 * 2;
 };
 constexpr int COL_ONE = 208;       // constant A operand (1, 1, 0, ...): 8 columns
 constexpr int COL_AE1 = 216;       // second per-row embedding buffer (tiles alternate: the next
@@ -435,9 +436,15 @@ constexpr int COL_AE1 = 216;       // second per-row embedding buffer (tiles alt
 // SELF = 1 (learned-BRDF network): no separate MMA-issuer warp -- thread 0 of a worker group issues
 // its own group's MMAs after the group's named barrier, because the number of tiles per point is
 // data-dependent there (front-lit compaction).  SELF = 0 (visibility network): warp 0 issues for both
-// groups in strict alternation (measured faster when the tile count is static: 32.4 vs 40.9 ms).
-template <int KIND, int BF16, int SELF>
+// groups in strict alternation (measured faster: 32.4 vs 40.9 ms).  The issuer does not know how
+// many tiles a group will run: it serves hand-overs (layer 0, 1, 2, 3, 0, ... of running tile
+// k = 0, 1, ...) until the group raises its `done` flag with a last arrival.
+// CULL = 1: only the front-lit lights of a point become tile rows (always for the BRDF network,
+// nerfactor.py:429-458; for the visibility network when the caller only needs the rendered colour:
+// nerfactor.py:329-330 multiplies the visibility of every other light by zero).
+template <int KIND, int BF16, int SELF, int CULL>
 __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p) {
+  static_assert(KIND != NF_MLP_BRDF || CULL == 1, "the BRDF network always runs on the front-lit lights");
   using SL = SmemLayout2<KIND>;
   constexpr int KE = SL::KE;
   constexpr int NR_PAD = SL::NR_PAD;
@@ -465,7 +472,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
   // ---------------------------------------------------------------- set-up
   if (threadIdx.x == 0) {
     mbar_init(bar_w, 1);
-    mbar_init(bar_a + 0, p.warp_arrive ? 4 : 128); mbar_init(bar_a + 1, p.warp_arrive ? 4 : 128);
+    mbar_init(bar_a + 0, 128); mbar_init(bar_a + 1, 128);
     mbar_init(bar_d + 0, 1); mbar_init(bar_d + 1, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -486,6 +493,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
   }
   for (int i = threadIdx.x; i < 2 * 2 * 4096 / 4; i += blockDim.x)       // k = 2..15 rows stay zero
     reinterpret_cast<uint32_t*>(s_bdyn)[i] = 0u;
+  if (threadIdx.x < 16) s_cnt[threadIdx.x] = 0;                            // incl. the `done` flags [g][5]
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -519,49 +527,53 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
       const uint32_t idesc = make_idesc(BF16, TC_WIDTH);
       const uint32_t lbo = TC_WIDTH * 16, sbo = 128;
       const uint32_t img0 = smem_u32(s_img), bdyn0 = smem_u32(s_bdyn);
-      const uint32_t seg_off[5] = {0u, (uint32_t)KE * 256u, (uint32_t)(KE + 128) * 256u,
-                                   (uint32_t)(KE + 256) * 256u, (uint32_t)(KE + 384) * 256u};
-      const uint32_t bias_off[2] = {(uint32_t)(KE + 384 + KE) * 256u,
-                                    (uint32_t)(KE + 384 + KE + 16) * 256u};   // layers 1, 2
-      // (SELF = 0 only: the tile count per point is static here -- the visibility network
-      // evaluates all lights of every point.)
-      const int nt0 = group_points(0) * chunks, nt1 = group_points(1) * chunks;
-      const int nt_max = nt0 > nt1 ? nt0 : nt1;
-      uint32_t ph[2] = {0u, 0u};
-      for (int it = 0; it < nt_max; ++it) {
-        for (int layer = 0; layer < 4; ++layer) {
-          for (int g = 0; g < 2; ++g) {
-            if (it >= (g == 0 ? nt0 : nt1)) continue;
-            mbar_wait(bar_a + g, ph[g]);
-            ph[g] ^= 1u;
-            tc_fence_after();
-            const uint32_t tb = tmem_base + g * GRP_COLS;
-            const uint32_t d_t = tb + COL_D;
-            const uint32_t ae_t = tb + (((it % chunks) & 1) ? COL_AE1 : COL_AE);   // tile parity
-            // bias block first (accumulate = 0 starts the tile from 1 * b_hi + 1 * b_lo)
-            const uint32_t bsm = (layer == 0 || layer == 3)
-                                     ? bdyn0 + (uint32_t)(g * 2 + (layer == 3 ? 1 : 0)) * 4096u
-                                     : img0 + bias_off[layer - 1];
-            tc_mma_ts(d_t, tb + COL_ONE, make_b_desc(bsm, lbo, sbo), idesc, 0u);
-            if (layer == 0) {
+      // image segments [W0e | W1 | W2 | W3h | W3e | bias1 | bias2]: byte offsets computed, NOT
+      // looked up in local arrays -- nvcc 12.9 overlapped two dynamically indexed constant local
+      // arrays on the stack here (seg_off[1] and bias_off[1] shared a slot: wrong B operands)
+      auto seg_off = [](int layer) { return layer == 0 ? 0u : (uint32_t)(KE + 128 * (layer - 1)) * 256u; };
+      auto bias_off = [](int layer) { return (uint32_t)(KE + 384 + KE + 16 * (layer - 1)) * 256u; };
+      constexpr uint32_t seg_w3e = (uint32_t)(KE + 384) * 256u;
+      // running state per group: next layer, running tile index (its parity selects the A_e buffer)
+      bool live[2] = {true, true};
+      uint32_t ph[2] = {0u, 0u}, tile[2] = {0u, 0u};
+      int layer_of[2] = {0, 0};
+      while (live[0] || live[1]) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          if (!live[g]) continue;
+          mbar_wait(bar_a + g, ph[g]);
+          ph[g] ^= 1u;
+          if (s_cnt[g * 8 + 5]) { live[g] = false; continue; }      // the group's last arrival
+          tc_fence_after();
+          const int layer = layer_of[g];
+          const uint32_t tb = tmem_base + g * GRP_COLS;
+          const uint32_t d_t = tb + COL_D;
+          const uint32_t ae_t = tb + ((tile[g] & 1u) ? COL_AE1 : COL_AE);
+          // bias block first (accumulate = 0 starts the tile from 1 * b_hi + 1 * b_lo)
+          const uint32_t bsm = (layer == 0 || layer == 3)
+                                   ? bdyn0 + (uint32_t)(g * 2 + (layer == 3 ? 1 : 0)) * 4096u
+                                   : img0 + bias_off(layer);
+          tc_mma_ts(d_t, tb + COL_ONE, make_b_desc(bsm, lbo, sbo), idesc, 0u);
+          if (layer == 0) {
+#pragma unroll
+            for (int k = 0; k < KE / 16; ++k)
+              tc_mma_ts(d_t, ae_t + k * 8,
+                        make_b_desc(img0 + k * 2 * lbo, lbo, sbo), idesc, 1u);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              tc_mma_ts(d_t, tb + COL_AH + k * 8,
+                        make_b_desc(img0 + seg_off(layer) + k * 2 * lbo, lbo, sbo), idesc, 1u);
+            if (layer == 3) {
 #pragma unroll
               for (int k = 0; k < KE / 16; ++k)
                 tc_mma_ts(d_t, ae_t + k * 8,
-                          make_b_desc(img0 + seg_off[0] + k * 2 * lbo, lbo, sbo), idesc, 1u);
-            } else {
-#pragma unroll
-              for (int k = 0; k < 8; ++k)
-                tc_mma_ts(d_t, tb + COL_AH + k * 8,
-                          make_b_desc(img0 + seg_off[layer] + k * 2 * lbo, lbo, sbo), idesc, 1u);
-              if (layer == 3) {
-#pragma unroll
-                for (int k = 0; k < KE / 16; ++k)
-                  tc_mma_ts(d_t, ae_t + k * 8,
-                            make_b_desc(img0 + seg_off[4] + k * 2 * lbo, lbo, sbo), idesc, 1u);
-              }
+                          make_b_desc(img0 + seg_w3e + k * 2 * lbo, lbo, sbo), idesc, 1u);
             }
-            tc_commit(bar_d + g);
           }
+          tc_commit(bar_d + g);
+          if (layer == 3) { layer_of[g] = 0; ++tile[g]; }
+          else layer_of[g] = layer + 1;
         }
       }
     }
@@ -581,6 +593,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
     uint32_t* bd3 = reinterpret_cast<uint32_t*>(s_bdyn + (size_t)(g * 2 + 1) * 4096 + (size_t)tg * 16);
     const int G = blockIdx.x * 2 + g;
     uint32_t phd = 0u;
+    int tile0 = 0;                              // tiles this group has run before the current point
     // SELF: this group's own MMA issue (same instruction sequence as the issuer warp's)
     const uint32_t w_idesc = make_idesc(BF16, TC_WIDTH);
     const uint32_t w_img0 = smem_u32(s_img), w_bdyn0 = smem_u32(s_bdyn);
@@ -617,9 +630,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
       if (SELF) {
         group_bar(3 + g);
         if (tg < 32 && elect_one()) { tc_fence_after(); self_issue(layer, aebuf); }
-      } else if (p.warp_arrive) {
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_a + g);
       } else {
         mbar_arrive(bar_a + g);
       }
@@ -690,9 +700,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
       // tiles of this point: all lights (visibility) / only the front-lit ones (BRDF)
       int n_rows = p.L;
       int c0 = 0, c1 = 0, c2 = 0;                  // BRDF: cumulative front-lit counts of warps 0..2
-      if (KIND == NF_MLP_BRDF) {
+      if (CULL) {
         // each warp scans a quarter of the lights, keeps the front-lit ones (l_loc.z > 0,
-        // nerfactor.py:429-432) in increasing order and zeroes the others' output (:456-458)
+        // nerfactor.py:429-432) in increasing order and zeroes the others' output (:456-458);
+        // visibility network: cos(shading normal, light) > -1e-5, a superset of the renderer's
+        // cos > 0 (nerfactor.py:325-330) whatever the rounding of its own cosine
+        f3 cn = fr_n;
+        if (KIND == NF_MLP_LVIS) cn = l2n(l2n(ld3(p.cull_normal + (size_t)pt * 3), 1e-6f), 1e-6f);
         const int lq = (p.L + 3) / 4, l0 = wq * lq, l1 = min(p.L, l0 + lq);
         uint16_t* mylist = s_list + ((size_t)g * 4 + wq) * 256;
         int cnt = 0;
@@ -702,7 +716,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
           if (l < l1) {
             const float4 lp = s_lx[l];
             const f3 d = l2n(mk3(lp.x, lp.y, lp.z) - x, 1e-6f);
-            lit = dot3(fr_n, d) > 0.f;
+            lit = KIND == NF_MLP_LVIS ? dot3(cn, d) > -1e-5f : dot3(cn, d) > 0.f;
             if (!lit) p.out[(size_t)pt * p.L + l] = 0.f;
           }
           const unsigned m = __ballot_sync(0xffffffffu, lit);
@@ -714,7 +728,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
         c0 = s_cnt[g * 8 + 0]; c1 = c0 + s_cnt[g * 8 + 1]; c2 = c1 + s_cnt[g * 8 + 2];
         n_rows = c2 + s_cnt[g * 8 + 3];
       }
-      const int n_tiles = n_rows > 0 ? (n_rows + 127) / 128 : 1;     // >= 1: the issuer expects a tile
+      // BRDF network: at least one (possibly empty) tile, as before; visibility: none if unlit
+      const int n_tiles = (n_rows > 0 || KIND == NF_MLP_BRDF) ? (n_rows > 0 ? (n_rows + 127) / 128 : 1) : 0;
       if (tg == 0) s_cnt[g * 8 + 4] = n_tiles;
       group_bar(1 + g);
 
@@ -724,13 +739,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
         RowInfo r;
         r.li = c * 128 + t;                         // row of the point's (compacted) light list
         r.ok = r.li < n_rows;
-        if (KIND == NF_MLP_BRDF) {
+        if (CULL) {
           int i = r.ok ? r.li : (n_rows > 0 ? n_rows - 1 : 0);
           const int seg = (i >= c0) + (i >= c1) + (i >= c2);
           i -= seg == 0 ? 0 : (seg == 1 ? c0 : (seg == 2 ? c1 : c2));
           r.li = n_rows > 0 ? (int)s_list[((size_t)g * 4 + seg) * 256 + i] : 0;
         }
-        const int lc = KIND == NF_MLP_BRDF ? r.li : (r.li < p.L ? r.li : p.L - 1);
+        const int lc = CULL ? r.li : (r.li < p.L ? r.li : p.L - 1);
         r.mask = 1.f;
         float4 lp = s_lx[lc];
         f3 d = l2n(mk3(lp.x, lp.y, lp.z) - xd, 1e-6f);                        // shape.py:128-135
@@ -764,15 +779,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
         uint32_t pk[KE / 2];
 #pragma unroll
         for (int i = 0; i < KE / 2; ++i) pk[i] = pack2<BF16, 0>(v[2 * i], v[2 * i + 1]);
-        const uint32_t ae = tb + ((c & 1) ? COL_AE1 : COL_AE);
+        const uint32_t ae = tb + (((tile0 + c) & 1) ? COL_AE1 : COL_AE);
         if (KE == 32) { TC_ST16(ae, pk); }
         else { TC_ST8(ae, pk); }
         tc_wait_st();
         return r;
       };
 
-      RowInfo cur = embed_tile(0);
-      hand_over(0, 0);
+      RowInfo cur;
+      if (n_tiles > 0) {
+        cur = embed_tile(0);
+        hand_over(0, tile0 & 1);
+      }
       for (int c = 0; c < n_tiles; ++c) {
         // ------------------------------------------------ layers 0..2: ReLU + 16-bit -> A_h
         for (int layer = 0; layer < 3; ++layer) {
@@ -804,7 +822,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
             pk[i] = pack2<BF16, 1>(__uint_as_float(rd[2 * i]), __uint_as_float(rd[2 * i + 1]));
           TC_ST16(tb + COL_AH + 48, pk);
           tc_wait_st();
-          hand_over(layer + 1, c & 1);
+          hand_over(layer + 1, (tile0 + c) & 1);
         }
         // ------------------------------------------------ layer 3 is in flight: the NEXT tile's
         // per-row embedding goes into the other A_e buffer now (off the critical chain)
@@ -827,7 +845,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
           TC_LD32(rc, tb + COL_D + 64);
           TC_LD32(rd, tb + COL_D + 96);
           tc_wait_ld();
-          if (has_next) hand_over(0, (c + 1) & 1);
+          if (has_next) hand_over(0, (tile0 + c + 1) & 1);
           const float4* wo = reinterpret_cast<const float4*>(s_aux + AUX_WOUT);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -896,10 +914,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
         }
         if (!PIPE && c + 1 < n_tiles) {          // plain order: embedding, then layer 0
           nxt = embed_tile(c + 1);
-          hand_over(0, (c + 1) & 1);
+          hand_over(0, (tile0 + c + 1) & 1);
         }
         cur = nxt;
       }
+      tile0 += n_tiles;
       if (fuse) {
         group_bar(1 + g);
         if (tg == 0) {
@@ -916,6 +935,454 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
         }
       }
     }
+    if (!SELF) {                    // tell the issuer warp that this group has no more tiles
+      if (tg == 0) s_cnt[g * 8 + 5] = 1;
+      mbar_arrive(bar_a + g);
+    }
+  }
+
+  // ---------------------------------------------------------------- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS)
+                 : "memory");
+  }
+}
+
+
+// =====================================================================================
+// Version 3 of the light-visibility kernel: everything that happens once per surface POINT is
+// taken off the workers' critical path.
+// Measured on B200 (profiles/r2_k2_analysis.md, section 4): in version 2 the per-point phase --
+// 63-term fold of the positional encoding of xyz into two 128-wide biases, hi/lo split, the first
+// tile's per-row embedding -- costs about as much as 1.4 tiles and both worker groups sit in it
+// with the tensor pipe idle (cutting the tiles per point from 4 to 3 by front-lit culling did not
+// shorten the kernel at all).  Here
+//   * warps 1 and 2 (idle so far) are PREFETCHERS, one per worker group: they run one point ahead,
+//     fold the next point's biases into the second of two shared-memory bias buffers, build the
+//     front-lit light list (CULL) and publish a small record; full/free mbarriers per buffer;
+//   * the workers run a flat stream of tiles: the embedding of the next tile -- also when it
+//     belongs to the next point -- is written under layer 3 of the current one;
+//   * the issuer learns which bias buffer a tile uses from a two-slot table the group fills in
+//     before it hands layer 0 over; a dynamic bias block is 2 KB (k = 0..7) + a shared 2 KB of
+//     zeros for k = 8..15, reached through the descriptor's leading-dimension offset.
+// Light positions are read from global memory (L1-resident 12 KB) instead of a shared table.
+struct SmemLayout3 {
+  static constexpr int KE = KindCfg<NF_MLP_LVIS>::KE;
+  static constexpr int NR_PAD = KindCfg<NF_MLP_LVIS>::NR_PAD;
+  static constexpr int LMAX = 1024;
+  static constexpr size_t img_bytes = ((size_t)img_halves<NF_MLP_LVIS>() + 2 * 16 * 128) * 2;
+  static constexpr size_t aux_floats = AUX_WX0 + 2 * (size_t)NR_PAD * 128;
+  static constexpr size_t off_img = 0;
+  static constexpr size_t off_bdyn = img_bytes;                  // [2 g][2 buf][2 layer] x 2048 B
+  static constexpr size_t off_zero = off_bdyn + 8 * 2048;        // 2048 B of zeros (k = 8..15)
+  static constexpr size_t off_aux = off_zero + 2048;
+  static constexpr size_t off_rec = off_aux + aux_floats * 4;    // [2 g][2 buf] x 16 B: xd[3], n_rows
+  static constexpr size_t off_list = off_rec + 4 * 16;           // [2 g][2 buf][LMAX] u16
+  static constexpr size_t off_es = off_list + 4 * (size_t)LMAX * 2;   // [2 prefetchers][64] f32
+  static constexpr size_t off_bar = off_es + 2 * 64 * 4;         // 13 barriers + tmem pointer
+  static constexpr size_t off_flag = off_bar + 128;              // int: done[2], tile->buffer [2][2]
+  static constexpr size_t total = off_flag + 32;
+};
+static_assert(SmemLayout3::total <= 232448, "shared memory budget");
+
+template <int BF16, int CULL>
+__global__ void __launch_bounds__(TC_THREADS, 1) lvis_tc3_kernel(const TcParams p) {
+  using SL = SmemLayout3;
+  constexpr int KE = SL::KE;
+  constexpr int NR_PAD = SL::NR_PAD;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* s_img = smem + SL::off_img;
+  uint8_t* s_bdyn = smem + SL::off_bdyn;
+  float* s_aux = reinterpret_cast<float*>(smem + SL::off_aux);
+  float* s_rec = reinterpret_cast<float*>(smem + SL::off_rec);
+  uint16_t* s_list = reinterpret_cast<uint16_t*>(smem + SL::off_list);
+  float* s_es = reinterpret_cast<float*>(smem + SL::off_es);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SL::off_bar);
+  uint64_t* bar_w = bars + 0;          // weights landed
+  uint64_t* bar_a = bars + 1;          // [2] A operand ready (128 arrivals)
+  uint64_t* bar_d = bars + 3;          // [2] D accumulator ready (tcgen05.commit)
+  uint64_t* rec_full = bars + 5;       // [2 g][2 buf] record + biases of a point published
+  uint64_t* rec_free = bars + 9;       // [2 g][2 buf] the group is done with that point
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 13);
+  volatile int* s_flag = reinterpret_cast<volatile int*>(smem + SL::off_flag);   // [0..1] done, [2 + 2 g + (tile & 1)] buffer
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---------------------------------------------------------------- set-up
+  if (threadIdx.x == 0) {
+    mbar_init(bar_w, 1);
+    mbar_init(bar_a + 0, 128); mbar_init(bar_a + 1, 128);
+    mbar_init(bar_d + 0, 1); mbar_init(bar_d + 1, 1);
+    for (int i = 0; i < 4; ++i) { mbar_init(rec_full + i, 1); mbar_init(rec_free + i, 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(s_tmem)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < (8 * 2048 + 2048) / 4; i += blockDim.x)      // k = 2..15 rows stay zero
+    reinterpret_cast<uint32_t*>(s_bdyn)[i] = 0u;
+  if (threadIdx.x < 8) s_flag[threadIdx.x] = 0;
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+  if (threadIdx.x == 0) {
+    const uint32_t aux_bytes = (uint32_t)(SL::aux_floats * 4);
+    mbar_expect_tx(bar_w, (uint32_t)SL::img_bytes + aux_bytes);
+    const uint8_t* gi = p.blob + p.off_img;
+    for (size_t o = 0; o < SL::img_bytes; o += 32768) {
+      size_t nb = SL::img_bytes - o < 32768 ? SL::img_bytes - o : 32768;
+      bulk_g2s(s_img + o, gi + o, (uint32_t)nb, bar_w);
+    }
+    const uint8_t* ga = p.blob + p.off_aux;
+    for (size_t o = 0; o < aux_bytes; o += 32768) {
+      size_t nb = aux_bytes - o < 32768 ? aux_bytes - o : 32768;
+      bulk_g2s(reinterpret_cast<uint8_t*>(s_aux) + o, ga + o, (uint32_t)nb, bar_w);
+    }
+  }
+  mbar_wait(bar_w, 0);
+  const int n_groups = gridDim.x * 2;
+
+  if (warp == 0) {
+    // =============================================================== MMA issuer
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc(BF16, TC_WIDTH);
+      const uint32_t lbo = TC_WIDTH * 16, sbo = 128;
+      const uint32_t img0 = smem_u32(s_img), bdyn0 = smem_u32(s_bdyn);
+      const uint32_t zero0 = smem_u32(smem + SL::off_zero);
+      auto seg_off = [](int layer) { return layer == 0 ? 0u : (uint32_t)(KE + 128 * (layer - 1)) * 256u; };
+      auto bias_off = [](int layer) { return (uint32_t)(KE + 384 + KE + 16 * (layer - 1)) * 256u; };
+      constexpr uint32_t seg_w3e = (uint32_t)(KE + 384) * 256u;
+      bool live[2] = {true, true};
+      uint32_t ph[2] = {0u, 0u}, tile[2] = {0u, 0u};
+      int layer_of[2] = {0, 0}, buf_of[2] = {0, 0};
+      while (live[0] || live[1]) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          if (!live[g]) continue;
+          mbar_wait(bar_a + g, ph[g]);
+          ph[g] ^= 1u;
+          if (s_flag[g]) { live[g] = false; continue; }      // the group's last arrival
+          tc_fence_after();
+          const int layer = layer_of[g];
+          if (layer == 0) buf_of[g] = s_flag[2 + 2 * g + (int)(tile[g] & 1u)];
+          const uint32_t tb = tmem_base + g * GRP_COLS;
+          const uint32_t d_t = tb + COL_D;
+          const uint32_t ae_t = tb + ((tile[g] & 1u) ? COL_AE1 : COL_AE);
+          // bias block first (accumulate = 0 starts the tile from 1 * b_hi + 1 * b_lo)
+          if (layer == 0 || layer == 3) {
+            const uint32_t bsm = bdyn0 + (uint32_t)((g * 2 + buf_of[g]) * 2 + (layer == 3 ? 1 : 0)) * 2048u;
+            tc_mma_ts(d_t, tb + COL_ONE, make_b_desc(bsm, zero0 - bsm, sbo), idesc, 0u);
+          } else {
+            tc_mma_ts(d_t, tb + COL_ONE, make_b_desc(img0 + bias_off(layer), lbo, sbo), idesc, 0u);
+          }
+          if (layer == 0) {
+#pragma unroll
+            for (int k = 0; k < KE / 16; ++k)
+              tc_mma_ts(d_t, ae_t + k * 8, make_b_desc(img0 + k * 2 * lbo, lbo, sbo), idesc, 1u);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              tc_mma_ts(d_t, tb + COL_AH + k * 8,
+                        make_b_desc(img0 + seg_off(layer) + k * 2 * lbo, lbo, sbo), idesc, 1u);
+            if (layer == 3) {
+#pragma unroll
+              for (int k = 0; k < KE / 16; ++k)
+                tc_mma_ts(d_t, ae_t + k * 8,
+                          make_b_desc(img0 + seg_w3e + k * 2 * lbo, lbo, sbo), idesc, 1u);
+            }
+          }
+          tc_commit(bar_d + g);
+          if (layer == 3) { layer_of[g] = 0; ++tile[g]; }
+          else layer_of[g] = layer + 1;
+        }
+      }
+    }
+  } else if (warp == 1 || warp == 2) {
+    // ============================================================ per-point prefetcher of group g
+    const int g = warp - 1;
+    const int G = blockIdx.x * 2 + g;
+    float* es = s_es + g * 64;
+    const float* Wx0 = s_aux + AUX_WX0;
+    const float* Wx3 = Wx0 + NR_PAD * 128;
+    int i = 0;
+    for (int pt = G; pt < p.n; pt += n_groups, ++i) {
+      const int b = i & 1;
+      if (i >= 2) mbar_wait(rec_free + g * 2 + b, (uint32_t)((i >> 1) - 1) & 1u);
+      const f3 x = ld3(p.xyz + (size_t)pt * 3);
+      // positional encoding of xyz (embedder.py:46-47), fp32
+      if (lane < 3) es[lane] = (lane == 0 ? x.x : (lane == 1 ? x.y : x.z)) * p.xyz_scale;
+      for (int idx = lane; idx < 3 * p.n_freqs_a; idx += 32) {
+        const int fq = idx / 3, c = idx % 3;
+        const float xv = (c == 0 ? x.x : (c == 1 ? x.y : x.z)) * p.xyz_scale;
+        float sn, cs;
+        sincosf(xv * (float)(1 << fq), &sn, &cs);
+        es[3 + 6 * fq + c] = sn;
+        es[3 + 6 * fq + 3 + c] = cs;
+      }
+      __syncwarp();
+      // fold the per-point input columns into the biases of layer 0 and of the skip layer (fp32):
+      // four output columns per lane
+      float4 a0 = *reinterpret_cast<const float4*>(s_aux + AUX_B + 0 * 128 + 4 * lane);
+      float4 a3 = *reinterpret_cast<const float4*>(s_aux + AUX_B + 3 * 128 + 4 * lane);
+#pragma unroll 4
+      for (int k = 0; k < p.nr; ++k) {
+        const float ev = es[k];
+        const float4 w0 = *reinterpret_cast<const float4*>(Wx0 + k * 128 + 4 * lane);
+        const float4 w3 = *reinterpret_cast<const float4*>(Wx3 + k * 128 + 4 * lane);
+        a0.x = fmaf(ev, w0.x, a0.x); a0.y = fmaf(ev, w0.y, a0.y);
+        a0.z = fmaf(ev, w0.z, a0.z); a0.w = fmaf(ev, w0.w, a0.w);
+        a3.x = fmaf(ev, w3.x, a3.x); a3.y = fmaf(ev, w3.y, a3.y);
+        a3.z = fmaf(ev, w3.z, a3.z); a3.w = fmaf(ev, w3.w, a3.w);
+      }
+      // 16-bit hi + lo pair per column: rows k = 0 / 1 of the bias block ((k/8) 2048 + n 16 + (k%8) 2)
+      uint8_t* blk0 = s_bdyn + (size_t)((g * 2 + b) * 2 + 0) * 2048;
+      uint8_t* blk3 = s_bdyn + (size_t)((g * 2 + b) * 2 + 1) * 2048;
+      const float v0[4] = {a0.x, a0.y, a0.z, a0.w}, v3[4] = {a3.x, a3.y, a3.z, a3.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int col = 4 * lane + j;
+        const uint32_t h0 = pack2<BF16, 0>(v0[j], 0.f), h3 = pack2<BF16, 0>(v3[j], 0.f);
+        const float l0 = v0[j] - unpack_lo<BF16>(h0), l3 = v3[j] - unpack_lo<BF16>(h3);
+        *reinterpret_cast<uint32_t*>(blk0 + (size_t)col * 16) = (h0 & 0xFFFFu) | (pack2<BF16, 0>(l0, 0.f) << 16);
+        *reinterpret_cast<uint32_t*>(blk3 + (size_t)col * 16) = (h3 & 0xFFFFu) | (pack2<BF16, 0>(l3, 0.f) << 16);
+      }
+      int n_rows = p.L;
+      if (CULL) {
+        // front-lit lights in increasing order; the others' output is zero (nerfactor.py:329-330).
+        // cos(shading normal, light) > -1e-5: a superset of the renderer's cos > 0 whatever the
+        // rounding of its own cosine
+        const f3 cn = l2n(l2n(ld3(p.cull_normal + (size_t)pt * 3), 1e-6f), 1e-6f);
+        uint16_t* list = s_list + (size_t)(g * 2 + b) * SL::LMAX;
+        int cnt = 0;
+        for (int base = 0; base < p.L; base += 32) {
+          const int l = base + lane;
+          bool lit = false;
+          if (l < p.L) {
+            const f3 d = l2n(ld3(p.lxyz + (size_t)l * 3) - x, 1e-6f);
+            lit = dot3(cn, d) > -1e-5f;
+            if (!lit) p.out[(size_t)pt * p.L + l] = 0.f;
+          }
+          const unsigned m = __ballot_sync(0xffffffffu, lit);
+          if (lit) list[cnt + __popc(m & ((1u << lane) - 1u))] = (uint16_t)l;
+          cnt += __popc(m);
+        }
+        n_rows = cnt;
+      }
+      if (lane == 0) {
+        const f3 xd = p.xyz_dir ? ld3(p.xyz_dir + (size_t)pt * 3) : x;
+        float* rec = s_rec + (size_t)(g * 2 + b) * 4;
+        rec[0] = xd.x; rec[1] = xd.y; rec[2] = xd.z; rec[3] = __int_as_float(n_rows);
+      }
+      fence_proxy_async();           // the bias blocks are read by the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(rec_full + g * 2 + b);
+    }
+  } else if (warp >= 4) {
+    // ================================================================== workers
+    const int g = (warp - 4) >> 2;            // group 0 | 1
+    const int wq = warp & 3;                  // TMEM lane quarter this warp may access
+    const int t = wq * 32 + lane;             // row of the tile == TMEM lane == thread of the group
+    const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
+    const uint32_t tb = tmem_base + g * GRP_COLS + lane_addr;
+    const int G = blockIdx.x * 2 + g;
+    uint32_t phd = 0u;
+    {   // constant A operand of the bias block: columns (1, 1, 0, ..., 0), written once
+      uint32_t one[8];
+      one[0] = pack2<BF16, 0>(1.f, 1.f);
+#pragma unroll
+      for (int i = 1; i < 8; ++i) one[i] = 0u;
+      TC_ST8(tb + COL_ONE, one);
+      tc_wait_st();
+    }
+    struct PointState { int pt, b, n_rows, n_tiles; f3 xd; };
+    struct RowInfo { int li; bool ok; };
+    // record of the group's i-th point (published by the prefetcher); false past the last point
+    auto acquire = [&](int i, PointState& s) {
+      s.pt = G + i * n_groups;
+      if (s.pt >= p.n) return false;
+      s.b = i & 1;
+      mbar_wait(rec_full + g * 2 + s.b, (uint32_t)(i >> 1) & 1u);
+      const float* rec = s_rec + (size_t)(g * 2 + s.b) * 4;
+      s.xd = mk3(rec[0], rec[1], rec[2]);
+      s.n_rows = __float_as_int(rec[3]);
+      s.n_tiles = (s.n_rows + 127) / 128;
+      return true;
+    };
+    // first point from sequence index i on that has a tile; points without one are released here
+    // (named barrier: every thread has read the record before the prefetcher may overwrite it)
+    auto next_nonempty = [&](int& i, PointState& s) {
+      for (;;) {
+        if (!acquire(i, s)) return false;
+        if (s.n_tiles > 0) return true;
+        group_bar(1 + g);
+        if (t == 0) mbar_arrive(rec_free + g * 2 + s.b);
+        ++i;
+      }
+    };
+    // row `t` of tile c of point s, and its embedding -> A_e buffer `aebuf`
+    auto embed_tile = [&](const PointState& s, int c, int aebuf) {
+      RowInfo r;
+      const int row = c * 128 + t;
+      r.ok = row < s.n_rows;
+      const int rr = r.ok ? row : s.n_rows - 1;
+      r.li = CULL ? (int)s_list[(size_t)(g * 2 + s.b) * SL::LMAX + rr] : rr;
+      const f3 d = l2n(ld3(p.lxyz + (size_t)r.li * 3) - s.xd, 1e-6f);            // shape.py:128-135
+      float v[KE];
+#pragma unroll
+      for (int i = 0; i < KE; ++i) v[i] = 0.f;
+      v[0] = d.x; v[1] = d.y; v[2] = d.z;
+      float sx, cx, sy, cy, sz, cz;
+      sincosf(d.x, &sx, &cx); sincosf(d.y, &sy, &cy); sincosf(d.z, &sz, &cz);
+#pragma unroll
+      for (int fq = 0; fq < 4; ++fq) {
+        v[3 + 6 * fq + 0] = sx; v[3 + 6 * fq + 1] = sy; v[3 + 6 * fq + 2] = sz;
+        v[3 + 6 * fq + 3] = cx; v[3 + 6 * fq + 4] = cy; v[3 + 6 * fq + 5] = cz;
+        const float nsx = 2.f * sx * cx, ncx = 1.f - 2.f * sx * sx;
+        const float nsy = 2.f * sy * cy, ncy = 1.f - 2.f * sy * sy;
+        const float nsz = 2.f * sz * cz, ncz = 1.f - 2.f * sz * sz;
+        sx = nsx; cx = ncx; sy = nsy; cy = ncy; sz = nsz; cz = ncz;
+      }
+      uint32_t pk[KE / 2];
+#pragma unroll
+      for (int i = 0; i < KE / 2; ++i) pk[i] = pack2<BF16, 0>(v[2 * i], v[2 * i + 1]);
+      TC_ST16(tb + (aebuf ? COL_AE1 : COL_AE), pk);
+      tc_wait_st();
+      return r;
+    };
+    // layer 0 of running tile `tile` (bias buffer b) is ready for the tensor core
+    auto hand_over_tile = [&](int tile, int b) {
+      if (t == 0) s_flag[2 + 2 * g + (tile & 1)] = b;
+      tc_fence_before();
+      mbar_arrive(bar_a + g);
+    };
+
+    int pi = 0, c = 0, tile = 0;
+    PointState cur;
+    RowInfo rcur;
+    bool have = next_nonempty(pi, cur);
+    if (have) {
+      rcur = embed_tile(cur, 0, 0);
+      hand_over_tile(0, cur.b);
+    }
+    while (have) {
+      // ------------------------------------------------ layers 0..2: ReLU + 16-bit -> A_h
+      for (int layer = 0; layer < 3; ++layer) {
+        mbar_wait(bar_d + g, phd);
+        phd ^= 1u;
+        tc_fence_after();
+        uint32_t ra[32], rb[32], rc[32], rd[32];
+        TC_LD32(ra, tb + COL_D);
+        TC_LD32(rb, tb + COL_D + 32);
+        tc_wait_ld();
+        TC_LD32(rc, tb + COL_D + 64);       // second half in flight while the first converts
+        TC_LD32(rd, tb + COL_D + 96);
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          pk[i] = pack2<BF16, 1>(__uint_as_float(ra[2 * i]), __uint_as_float(ra[2 * i + 1]));
+        TC_ST16(tb + COL_AH, pk);
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          pk[i] = pack2<BF16, 1>(__uint_as_float(rb[2 * i]), __uint_as_float(rb[2 * i + 1]));
+        TC_ST16(tb + COL_AH + 16, pk);
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          pk[i] = pack2<BF16, 1>(__uint_as_float(rc[2 * i]), __uint_as_float(rc[2 * i + 1]));
+        TC_ST16(tb + COL_AH + 32, pk);
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          pk[i] = pack2<BF16, 1>(__uint_as_float(rd[2 * i]), __uint_as_float(rd[2 * i + 1]));
+        TC_ST16(tb + COL_AH + 48, pk);
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(bar_a + g);
+      }
+      // ------------------------------------------------ layer 3 is in flight: the NEXT tile (of
+      // this point or of the next one that has any) gets its embedding now
+      PointState nx = cur;
+      int nc = c + 1, npi = pi;
+      bool nhave = true, skip_empty = false;
+      if (nc >= cur.n_tiles) {
+        // only the DIRECTLY following point may be looked at here: the one after it uses the bias
+        // buffer of the current point, which is released further down
+        nc = 0;
+        npi = pi + 1;
+        nhave = acquire(npi, nx);
+        if (nhave && nx.n_tiles == 0) { skip_empty = true; nhave = false; }
+      }
+      RowInfo rn = rcur;
+      if (nhave) rn = embed_tile(nx, nc, (tile + 1) & 1);
+      // ------------------------------------------------ layer 3 done: accumulator -> registers,
+      // hand the next tile's layer 0 over, THEN the head (it only needs the registers)
+      mbar_wait(bar_d + g, phd);
+      phd ^= 1u;
+      tc_fence_after();
+      float acc0 = 0.f, acc1 = 0.f;
+      {
+        uint32_t ra[32], rb[32], rc[32], rd[32];
+        TC_LD32(ra, tb + COL_D);
+        TC_LD32(rb, tb + COL_D + 32);
+        TC_LD32(rc, tb + COL_D + 64);
+        TC_LD32(rd, tb + COL_D + 96);
+        tc_wait_ld();
+        // every MMA that reads this point's bias buffer has completed
+        if ((!nhave || npi != pi) && t == 0) mbar_arrive(rec_free + g * 2 + cur.b);
+        if (nhave) hand_over_tile(tile + 1, nx.b);
+        const float4* wo = reinterpret_cast<const float4*>(s_aux + AUX_WOUT);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 w0 = wo[i], w1 = wo[8 + i];
+          acc0 = fmaf(fmaxf(__uint_as_float(ra[4 * i + 0]), 0.f), w0.x, acc0);
+          acc1 = fmaf(fmaxf(__uint_as_float(ra[4 * i + 1]), 0.f), w0.y, acc1);
+          acc0 = fmaf(fmaxf(__uint_as_float(ra[4 * i + 2]), 0.f), w0.z, acc0);
+          acc1 = fmaf(fmaxf(__uint_as_float(ra[4 * i + 3]), 0.f), w0.w, acc1);
+          acc0 = fmaf(fmaxf(__uint_as_float(rb[4 * i + 0]), 0.f), w1.x, acc0);
+          acc1 = fmaf(fmaxf(__uint_as_float(rb[4 * i + 1]), 0.f), w1.y, acc1);
+          acc0 = fmaf(fmaxf(__uint_as_float(rb[4 * i + 2]), 0.f), w1.z, acc0);
+          acc1 = fmaf(fmaxf(__uint_as_float(rb[4 * i + 3]), 0.f), w1.w, acc1);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 w0 = wo[16 + i], w1 = wo[24 + i];
+          acc0 = fmaf(fmaxf(__uint_as_float(rc[4 * i + 0]), 0.f), w0.x, acc0);
+          acc1 = fmaf(fmaxf(__uint_as_float(rc[4 * i + 1]), 0.f), w0.y, acc1);
+          acc0 = fmaf(fmaxf(__uint_as_float(rc[4 * i + 2]), 0.f), w0.z, acc0);
+          acc1 = fmaf(fmaxf(__uint_as_float(rc[4 * i + 3]), 0.f), w0.w, acc1);
+          acc0 = fmaf(fmaxf(__uint_as_float(rd[4 * i + 0]), 0.f), w1.x, acc0);
+          acc1 = fmaf(fmaxf(__uint_as_float(rd[4 * i + 1]), 0.f), w1.y, acc1);
+          acc0 = fmaf(fmaxf(__uint_as_float(rd[4 * i + 2]), 0.f), w1.z, acc0);
+          acc1 = fmaf(fmaxf(__uint_as_float(rd[4 * i + 3]), 0.f), w1.w, acc1);
+        }
+      }
+      const float o = apply_act(p.out_act, (acc0 + acc1) + s_aux[AUX_BOUT]);
+      if (rcur.ok) p.out[(size_t)cur.pt * p.L + rcur.li] = o;
+      if (skip_empty) {
+        // the following point has no tile: release it and search on without overlap (no buffer
+        // is held at this moment)
+        group_bar(1 + g);
+        if (t == 0) mbar_arrive(rec_free + g * 2 + nx.b);
+        npi = pi + 2;
+        nhave = next_nonempty(npi, nx);
+        if (nhave) {
+          rn = embed_tile(nx, 0, (tile + 1) & 1);
+          hand_over_tile(tile + 1, nx.b);
+        }
+      }
+      cur = nx; c = nc; pi = npi; rcur = rn; ++tile; have = nhave;
+    }
+    // tell the issuer warp that this group has no more tiles
+    if (t == 0) s_flag[g] = 1;
+    mbar_arrive(bar_a + g);
   }
 
   // ---------------------------------------------------------------- teardown
@@ -1082,15 +1549,36 @@ int launch_tc(nf_ctx* ctx, const nf_mlp* m, const TcParams& p, cudaStream_t st) 
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SL::total));
     mlp_tc_kernel<KIND, BF16><<<grid, TC_THREADS, SL::total, st>>>(p);
   } else {
+    // NF_LVIS_V2=1: the version-2 kernel for the visibility network too (A / B timing)
+    static const bool v2 = [] { const char* e = getenv("NF_LVIS_V2"); return e && e[0] == '1'; }();
+    if (KIND == NF_MLP_LVIS && p.f_rgb == nullptr && !v2) {
+      using S3 = SmemLayout3;
+      NF_CHECK_ARG(ctx, S3::total <= ctx->smem_optin, "shared memory budget exceeded");
+      if (p.cull_normal) {
+        NF_CUDA(ctx, cudaFuncSetAttribute(lvis_tc3_kernel<BF16, 1>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S3::total));
+        lvis_tc3_kernel<BF16, 1><<<grid, TC_THREADS, S3::total, st>>>(p);
+      } else {
+        NF_CUDA(ctx, cudaFuncSetAttribute(lvis_tc3_kernel<BF16, 0>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S3::total));
+        lvis_tc3_kernel<BF16, 0><<<grid, TC_THREADS, S3::total, st>>>(p);
+      }
+      NF_LAUNCH_CHECK(ctx);
+      return NF_OK;
+    }
     using SL = SmemLayout2<KIND>;
     NF_CHECK_ARG(ctx, SL::total <= ctx->smem_optin, "shared memory budget exceeded");
     constexpr int SELF = KIND == NF_MLP_BRDF ? 1 : 0;
-    TcParams q = p;
-    q.warp_arrive = 0;
-    if (const char* e = getenv("NF_LVIS_WARP_ARRIVE")) q.warp_arrive = atoi(e) ? 1 : 0;
-    NF_CUDA(ctx, cudaFuncSetAttribute(mlp_tc2_kernel<KIND, BF16, SELF>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SL::total));
-    mlp_tc2_kernel<KIND, BF16, SELF><<<grid, TC_THREADS, SL::total, st>>>(q);
+    if (KIND == NF_MLP_BRDF || p.cull_normal) {
+      NF_CUDA(ctx, cudaFuncSetAttribute(mlp_tc2_kernel<KIND, BF16, SELF, 1>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SL::total));
+      mlp_tc2_kernel<KIND, BF16, SELF, 1><<<grid, TC_THREADS, SL::total, st>>>(p);
+    } else {
+      constexpr int C0 = KIND == NF_MLP_BRDF ? 1 : 0;     // (never taken for the BRDF network)
+      NF_CUDA(ctx, cudaFuncSetAttribute(mlp_tc2_kernel<KIND, BF16, SELF, C0>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SL::total));
+      mlp_tc2_kernel<KIND, BF16, SELF, C0><<<grid, TC_THREADS, SL::total, st>>>(p);
+    }
   }
   NF_LAUNCH_CHECK(ctx);
   return NF_OK;
@@ -1201,14 +1689,14 @@ static int tc_common(nf_ctx* ctx, const nf_mlp* m, int precision, TcParams& p) {
 
 int nf_tc_lvis_launch(nf_ctx* ctx, const nf_mlp* m, const float* xyz, int n, float xyz_scale,
                       const float* lxyz, int L, float* lvis, int precision, cudaStream_t st,
-                      const float* xyz_dir) {
+                      const float* xyz_dir, const float* cull_normal) {
   TcParams p;
   int rc = tc_common(ctx, m, precision, p);
   if (rc != NF_OK) return rc;
   NF_CHECK_ARG(ctx, L <= 1024, "n_lights > 1024 not supported by the tcgen05 kernel");
   if (n == 0) return NF_OK;
   p.n = n; p.L = L; p.nr = 3 * (1 + 2 * m->d.n_freqs_a); p.xyz_scale = xyz_scale;
-  p.xyz = xyz; p.lxyz = lxyz; p.out = lvis; p.xyz_dir = xyz_dir;
+  p.xyz = xyz; p.lxyz = lxyz; p.out = lvis; p.xyz_dir = xyz_dir; p.cull_normal = cull_normal;
   return precision == NF_PREC_BF16 ? launch_tc<NF_MLP_LVIS, 1>(ctx, m, p, st)
                                    : launch_tc<NF_MLP_LVIS, 0>(ctx, m, p, st);
 }

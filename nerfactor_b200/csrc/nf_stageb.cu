@@ -15,6 +15,10 @@ int nf_tc_lvis_render_launch(nf_ctx* ctx, const nf_mlp* m, const float* xyz, int
                              const float* light, const int* light_idx, float f0, int srgb,
                              float* lvis, float* rgb, int precision, cudaStream_t st);
 
+int nf_tc_lvis_launch(nf_ctx* ctx, const nf_mlp* m, const float* xyz, int n, float xyz_scale,
+                      const float* lxyz, int L, float* lvis, int precision, cudaStream_t st,
+                      const float* xyz_dir, const float* cull_normal);
+
 namespace {
 // points per chunk of the chunked path: [c, L] fp32 rows of <= 48 MB (two of them for the learned
 // BRDF: both stay inside the 126 MB L2 between producer and consumer)
@@ -56,6 +60,8 @@ int nf_stageB_fused_fwd(nf_ctx* ctx, const nf_mlp* mlp_lvis, const nf_mlp* mlp_b
                         a->light_d && a->rgb_d, "null buffer");
   NF_CHECK_ARG(ctx, a->brdf_kind == 0 ? a->rough_d != nullptr : (a->z_d != nullptr && mlp_brdf != nullptr),
                "missing rough_d / (z_d, mlp_brdf)");
+  NF_CHECK_ARG(ctx, mlp_lvis->d.kind == NF_MLP_LVIS && mlp_lvis->d.out_dim == 1,
+               "mlp_lvis is not NF_MLP_LVIS");
   cudaStream_t st = (cudaStream_t)stream;
   if (single_kernel(a, precision))
     return nf_tc_lvis_render_launch(ctx, mlp_lvis, a->xyz_d, a->n, a->xyz_scale, a->lxyz_d, a->n_lights,
@@ -74,8 +80,16 @@ int nf_stageB_fused_fwd(nf_ctx* ctx, const nf_mlp* mlp_lvis, const nf_mlp* mlp_b
   for (int p0 = 0; p0 < a->n; p0 += c_max) {
     const int c = a->n - p0 < c_max ? a->n - p0 : c_max;
     float* lv = a->lvis_d ? a->lvis_d + (size_t)p0 * L : lvis_ws;
-    int rc = nf_lvis_fwd(ctx, mlp_lvis, a->xyz_d + (size_t)p0 * 3, c, a->xyz_scale, a->lxyz_d, L, lv,
-                         precision, stream);
+    // the visibility tensor is not an output: only the lights the renderer does not multiply by
+    // zero (nerfactor.py:329-330) go through the network (see nf_stageb_args.lvis_all_lights)
+    const bool front_lit_only = (a->lvis_all_lights == 2 || (!a->lvis_d && a->lvis_all_lights == 0)) &&
+                                (precision == NF_PREC_F16 || precision == NF_PREC_BF16);
+    int rc = front_lit_only
+                 ? nf_tc_lvis_launch(ctx, mlp_lvis, a->xyz_d + (size_t)p0 * 3, c, a->xyz_scale,
+                                     a->lxyz_d, L, lv, precision, st, nullptr,
+                                     a->normal_d + (size_t)p0 * 3)
+                 : nf_lvis_fwd(ctx, mlp_lvis, a->xyz_d + (size_t)p0 * 3, c, a->xyz_scale, a->lxyz_d,
+                               L, lv, precision, stream);
     if (rc != NF_OK) return rc;
     if (a->brdf_kind == 1) {
       rc = nf_brdf_learned_fwd(ctx, mlp_brdf, a->xyz_d + (size_t)p0 * 3, a->normal_d + (size_t)p0 * 3,

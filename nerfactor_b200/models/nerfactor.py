@@ -326,11 +326,14 @@ class Model(NeRFactorVis, ShapeModel):
         return pred, gt, loss_kwargs, to_vis
 
     # ------------------------------------------------------------ fused rendering
-    def render_rgb(self, batch, relight_probes=False, want_lvis=False):
+    def render_rgb(self, batch, relight_probes=False, want_lvis=False, all_lights=False):
         """The test-mode RGB of `call` (nerfactor.py:181-313: no jitter, no edits) through the
         fused Stage-B op nf_stageB_fused_fwd: per-point networks, then light-visibility network ->
         BRDF -> rendering equation in one call, the [N, L] light-visibility tensor not
-        materialised (unless `want_lvis`).  Returns a dict with 'rgb', 'normal', 'albedo', 'brdf'
+        materialised (unless `want_lvis`).  When it is not an output, the visibility network only
+        runs on the lights facing the shading normal -- the renderer multiplies the visibility of
+        all others by zero (nerfactor.py:329-330), so 'rgb' does not change; `all_lights=True`
+        evaluates it for every light anyway.  Returns a dict with 'rgb', 'normal', 'albedo', 'brdf'
         (+ 'rgb_probes', 'lvis') in the full ray shape, background rows zero -- the same values
         `call(batch, 'test')` returns for those keys."""
         if self.shape_mode == 'nerf':
@@ -352,7 +355,7 @@ class Model(NeRFactorVis, ShapeModel):
             lights += [to_device(v, dev).reshape(-1, 3) for v in self.novel_probes.values()]
         light = torch.stack(lights, 0).contiguous()
         rgb_all, lvis = self._fused_stage_b(xyz_m, normal, rayo_m, albedo, brdf_prop, light,
-                                            want_lvis)
+                                            want_lvis, all_lights)
         n = alpha.shape[0]
 
         def scatter(v):
@@ -367,7 +370,7 @@ class Model(NeRFactorVis, ShapeModel):
             out['lvis'] = scatter(lvis)
         return out
 
-    def _fused_stage_b(self, pts, normal, cam, albedo, brdf_prop, light, want_lvis):
+    def _fused_stage_b(self, pts, normal, cam, albedo, brdf_prop, light, want_lvis, all_lights=False):
         """Learned-MERL lobe: latent z + the BRDF prior's network."""
         m_lvis = self._packed_mlp('lvis', 'lvis', n_freqs_a=self.embedder['xyz'].n_freqs,
                                   n_freqs_b=self.embedder['ldir'].n_freqs)
@@ -377,7 +380,7 @@ class Model(NeRFactorVis, ShapeModel):
             spec_scale=self.config.getfloat('DEFAULT', 'learned_brdf_scale'),
             xyz_scale=self.xyz_scale,
             linear2srgb=self.config.getboolean('DEFAULT', 'linear2srgb'),
-            precision=self.precision, want_lvis=want_lvis)
+            precision=self.precision, want_lvis=want_lvis, all_lights=all_lights)
 
     # ------------------------------------------------------------------- loss
     def compute_loss(self, pred, gt, **kwargs):

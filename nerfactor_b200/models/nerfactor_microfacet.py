@@ -39,7 +39,7 @@ class Model(NeRFactorModel):
     def _brdf_kernel_args(self, brdf):
         return {'rough': brdf['rough'], 'f0': brdf['microfacet'].f0}
 
-    def _fused_stage_b(self, pts, normal, cam, albedo, brdf_prop, light, want_lvis):
+    def _fused_stage_b(self, pts, normal, cam, albedo, brdf_prop, light, want_lvis, all_lights=False):
         """GGX lobe: with one env-map and <= 512 lights this is ONE kernel (the rendering equation
         runs in the head epilogue of the light-visibility network)."""
         from .. import _lib
@@ -50,4 +50,4 @@ class Model(NeRFactorModel):
             rough=brdf_prop, light_idx=self.light_idx,
             f0=self.config.getfloat('DEFAULT', 'fresnel_f0'), xyz_scale=self.xyz_scale,
             linear2srgb=self.config.getboolean('DEFAULT', 'linear2srgb'),
-            precision=self.precision, want_lvis=want_lvis)
+            precision=self.precision, want_lvis=want_lvis, all_lights=all_lights)

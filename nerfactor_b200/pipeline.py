@@ -44,25 +44,28 @@ class ViewRenderer:
                 'xyz': xyz.contiguous(), 'surf': out['surf'], 'occu': out['occu'],
                 'depth': out['depth']}
 
-    def stage_b(self, a, relight_olat=False, relight_probes=False, fused=True):
+    def stage_b(self, a, relight_olat=False, relight_probes=False, fused=True, all_lights=False):
         """Stage B on Stage A's buffers.  `fused` (default): Model.render_rgb -- the per-point
         networks, then nf_stageB_fused_fwd (light visibility -> BRDF -> rendering equation in one
         call, no [N, L] tensor in HBM); the image-level outputs are the same as `Model.call`'s.
-        OLAT relighting and fused=False go through Model.call (which also returns pred['lvis'])."""
+        OLAT relighting and fused=False go through Model.call (which also returns pred['lvis']).
+        In the fused path the visibility network skips the lights facing away from the shading
+        normal (zero weight in the renderer, nerfactor.py:329-330) unless `all_lights`."""
         n = a['xyz'].shape[0]
         zeros3 = torch.zeros((n, 3), device=self.ctx.device)
         batch = (None, None, a['rayo'], a['rayd'], zeros3, a['alpha'], a['xyz'], zeros3,
                  None)
         if fused and not relight_olat and hasattr(self.model, 'render_rgb'):
-            return self.model.render_rgb(batch, relight_probes=relight_probes)
+            return self.model.render_rgb(batch, relight_probes=relight_probes,
+                                         all_lights=all_lights)
         pred, _, _, _ = self.model.call(batch, 'test', relight_olat=relight_olat,
                                         relight_probes=relight_probes)
         return pred
 
     def render(self, c2w, cam_angle_x, h, w, ray_range=None, relight_olat=False,
-               relight_probes=False, fused=True):
+               relight_probes=False, fused=True, all_lights=False):
         a = self.stage_a(c2w, cam_angle_x, h, w, ray_range)
-        pred = self.stage_b(a, relight_olat, relight_probes, fused)
+        pred = self.stage_b(a, relight_olat, relight_probes, fused, all_lights)
         pred['alpha'] = a['alpha']
         pred['xyz'] = a['xyz']
         return pred

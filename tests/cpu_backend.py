@@ -258,7 +258,7 @@ def lvis_dirs_fwd(ctx, mlp, xyz, xyz_dir, lxyz, xyz_scale=1.0, precision='f16'):
 
 def stageB_fused_fwd(ctx, mlp_lvis, xyz, normal, cam, albedo, lxyz, lareas, light, rough=None,
                      z=None, mlp_brdf=None, light_idx=None, f0=0.04, spec_scale=1.0, xyz_scale=1.0,
-                     linear2srgb=True, precision='f16', want_lvis=False):
+                     linear2srgb=True, precision='f16', want_lvis=False, all_lights=False):
     lvis = lvis_fwd(ctx, mlp_lvis, xyz, lxyz, xyz_scale, precision)
     spec = None if z is None else brdf_learned_fwd(ctx, mlp_brdf, xyz, normal, cam, z, lxyz, precision)
     rgb = integrate_fwd(ctx, xyz, normal, cam, albedo, lvis, lxyz, lareas, light,

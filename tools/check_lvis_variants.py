@@ -1,5 +1,7 @@
 """Compares and times the two generations of the light-visibility / learned-BRDF tcgen05 kernel
-(csrc/nf_mlp_tc.cu): v2 = default (bias inside the MMA), v1 = NF_LVIS_V1=1 (bias in the epilogue).
+(csrc/nf_mlp_tc.cu): v3 = default for the visibility network (per-point work on prefetch warps),
+v2 = NF_LVIS_V2=1 (bias inside the MMA; default for the BRDF network), v1 = NF_LVIS_V1=1 (bias in the
+epilogue).
 
     python tools/check_lvis_variants.py            # on a B200 (gpurun)
 
@@ -47,8 +49,8 @@ print(json.dumps(out))
 ''' % ROOT
 
 
-def run(flag, prefix, self_issue='1', **extra):
-    env = dict(os.environ, NF_LVIS_V1=flag, NF_LVIS_SELF=self_issue, **extra)
+def run(flag, prefix, **extra):
+    env = dict(os.environ, NF_LVIS_V1=flag, **extra)
     r = subprocess.run([sys.executable, '-c', WORKER, prefix], env=env, capture_output=True,
                        text=True, timeout=200)
     if r.returncode != 0:
@@ -60,19 +62,17 @@ def main():
     import numpy as np
     import tempfile
     d = tempfile.mkdtemp()
-    res = {'v2': run('0', os.path.join(d, 'a')), 'v1': run('1', os.path.join(d, 'b')),
-           'v2_warp_arrive': run('0', os.path.join(d, 'c'), NF_LVIS_WARP_ARRIVE='1')}
-    if 'error' not in res['v2_warp_arrive'] and 'error' not in res['v2']:
-        for tag in ('ragged', 'full'):
-            a = np.load(os.path.join(d, 'a_%s_lvis.npy' % tag))
-            c = np.load(os.path.join(d, 'c_%s_lvis.npy' % tag))
-            res['maxdiff_warp_arrive_%s_lvis' % tag] = float(np.abs(a - c).max())
-    if 'error' not in res['v1'] and 'error' not in res['v2']:
+    res = {'v3': run('0', os.path.join(d, 'c')),
+           'v2': run('0', os.path.join(d, 'a'), NF_LVIS_V2='1'), 'v1': run('1', os.path.join(d, 'b'))}
+    if all('error' not in res[k] for k in ('v1', 'v2', 'v3')):
         for tag in ('ragged', 'full'):
             for k in ('lvis', 'spec'):
                 a = np.load(os.path.join(d, 'a_%s_%s.npy' % (tag, k)))
                 b = np.load(os.path.join(d, 'b_%s_%s.npy' % (tag, k)))
-                res['maxdiff_%s_%s' % (tag, k)] = float(np.abs(a - b).max())
+                res['maxdiff_v2_v1_%s_%s' % (tag, k)] = float(np.abs(a - b).max())
+            a = np.load(os.path.join(d, 'a_%s_lvis.npy' % tag))
+            c = np.load(os.path.join(d, 'c_%s_lvis.npy' % tag))
+            res['maxdiff_v3_v2_%s_lvis' % tag] = float(np.abs(a - c).max())
     print(json.dumps(res))
 
 
