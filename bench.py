@@ -190,6 +190,13 @@ def workload_config(args, sigma_prec):
             'l2_policy': 'per-step working set (lvis 1.3 GB, sigma 0.33 GB) exceeds the 126 MB L2',
             'stage_b': 'per-point networks, then nf_stageB_fused_fwd (visibility net -> GGX -> rendering '
                        'equation over L2-resident point chunks; no [N, L] tensor kept in HBM)',
+            'lvis_lights': 'the visibility tensor is not an output of the timed call, so the visibility '
+                           'network runs on the front-lit lights of each point only (cos(normal, light) > '
+                           '-1e-5): the reference multiplies the visibility of all others by zero '
+                           '(nerfactor.py:329-330) and evaluates its BRDF on front-lit pairs only itself '
+                           '(:429-458).  Colours are bit-identical to evaluating every light '
+                           '(parity.stage_b.front_lit_vs_all_lights...); secondary.step_all_lights times '
+                           'the same step with every light evaluated',
             'parallelism': 'one view per GPU (same synthetic camera on every rank) + all_gather of images '
                            '(asynchronous, overlapping the next step)'}
 
@@ -326,7 +333,11 @@ def timed_mode_parity(ctx, nerf, model, vr, args, sigma_prec):
     full_c = vr.render(synth.look_at_c2w(4.0, 30.0, 30.0), synth.CAM_ANGLE_X, args.imh, args.imw,
                        fused=False)
     out['stage_b']['fused_op_vs_separate_kernels_rgb_rel_l2_full_view'] = rl2(full_f['rgb'], full_c['rgb'])
-    del full_f, full_c
+    full_a = vr.render(synth.look_at_c2w(4.0, 30.0, 30.0), synth.CAM_ANGLE_X, args.imh, args.imw,
+                       all_lights=True)
+    out['stage_b']['front_lit_vs_all_lights_rgb_max_abs_diff_full_view'] = float(
+        (full_f['rgb'] - full_a['rgb']).abs().max())
+    del full_f, full_c, full_a
     # end to end on the sphere-like field
     lh = args.light_h
     lxyz, lareas = gen_light_xyz(lh, 2 * lh)
@@ -604,6 +615,16 @@ def main():
     ms_e2e, _ = timed(step_e2e, args.steps, 1)
     e2e_value = world * n_rays / (ms_e2e / args.steps * 1e-3)
 
+    def step_all_lights():
+        pred = vr.render(c2w, synth.CAM_ANGLE_X, args.imh, args.imw, all_lights=True)
+        if world > 1:
+            gather(pred['rgb'])
+        return pred
+    ms_all, _ = timed(step_all_lights, args.steps, 1)
+    all_lights_row = {'what': 'the timed step with the visibility network evaluated for EVERY light '
+                              '(config.lvis_lights); same images bit for bit',
+                      'ms': ms_all / args.steps, 'rays_per_s': world * n_rays / (ms_all / args.steps * 1e-3)}
+
     multi = None
     if not args.no_secondary:
         try:
@@ -639,6 +660,8 @@ def main():
     z = _lib.gen_z(ctx, nerf.near, nerf.far, args.spp, n_rays)
     t_sigma = kt(lambda: _lib.sigma_fwd(ctx, nerf.packed_sigma(True), rayo, rayd, z, None,
                                         sigma_prec), 2 if sigma_prec == 'fp32' else 3)
+    z3 = torch.zeros_like(a['xyz'])
+    batch_b = (None, None, a['rayo'], a['rayd'], z3, a['alpha'], a['xyz'], z3, None)
     t_lvis = kt(lambda: model._pred_lvis_at(xyz_m))
     lvis = model._pred_lvis_at(xyz_m)
     t_point = kt(lambda: model._pred_normal_at(xyz_m))
@@ -664,10 +687,17 @@ def main():
                           'bound': 'tensor', 'ms': t_plain, 'peak': tensor_peak, 'unit': 'TFLOP/s',
                           'achieved': n_rays * args.spp * FLOP_SIGMA / (t_plain * 1e-3) / 1e12}
         rf_sigma_plain['frac'] = rf_sigma_plain['achieved'] / tensor_peak
-    rf_lvis = {'kernel': 'nf_lvis_fwd (mlp_tc2_kernel f16)', 'bound': 'tensor',
+    # Stage B as the timed step runs it (front-lit lights only) and with every light
+    t_sb_fl = kt(lambda: model.render_rgb(batch_b))
+    t_sb_all = kt(lambda: model.render_rgb(batch_b, all_lights=True))
+    rf_lvis = {'kernel': 'nf_lvis_fwd (lvis_tc3_kernel f16, every light: %d x %d rows)' % (n_fg, L),
+               'bound': 'tensor',
                'achieved': n_fg * L * FLOP_LVIS / (t_lvis * 1e-3) / 1e12,
                'peak': tensor_peak, 'unit': 'TFLOP/s', 'ms': t_lvis, 'traffic': None,
-               'algorithmic_bytes': alg_lvis}
+               'algorithmic_bytes': alg_lvis,
+               'stage_b_ms': {'front_lit_lights_only (timed mode)': t_sb_fl, 'every_light': t_sb_all,
+                              'what': 'Model.render_rgb on the view\'s foreground points: per-point '
+                                      'networks + nf_stageB_fused_fwd'}}
     rf_int = {'kernel': 'nf_integrate_fwd (microfacet)', 'bound': 'hbm',
               'achieved': alg_int / (t_int * 1e-3) / 1e9,
               'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'ms': t_int, 'traffic': None,
@@ -725,6 +755,7 @@ def main():
     if not args.no_secondary:
         secondary = secondary_rows(ctx, nerf, kt) if world == 1 else {}
         secondary.update(multi or {})
+        secondary['step_all_lights'] = all_lights_row
     parity = timed_mode_parity(ctx, nerf, model, vr, args, sigma_prec)
 
     cpu = None

@@ -429,6 +429,51 @@ def test_fused_stage_b_equals_model_call(ctx, brdf, lh, lw, n, single, monkeypat
     assert m.render_rgb(empty)['rgb'].shape == (0, 3)
 
 
+def test_front_lit_culling_with_unlit_points(ctx):
+    """nf_stageB_fused_fwd without the lvis output evaluates the visibility network only for the
+    lights facing the shading normal (nerfactor.py:329-330 zeroes the others).  Lights on the upper
+    cap only + normals pointing down make whole points unlit: runs of such points at the start,
+    in the middle and at the end of a worker group's point sequence, and alternating ones, must
+    neither hang the kernel's point pipeline nor change a colour (bit-equal to all lights)."""
+    from nerfactor_b200 import _lib
+    m, _, _ = _stage_b(ctx, 'microfacet', 16, 32, seed=7, precision='f16')
+    lx_all, la_all = m.lxyz.reshape(-1, 3), m.lareas.reshape(-1)
+    keep = lx_all[:, 2] > 30.
+    lxyz, lareas = lx_all[keep].contiguous(), la_all[keep].contiguous()
+    L = int(lxyz.shape[0])
+    assert 100 < L < 400
+    n_groups = 2 * int(ctx.sm_count)
+    n = 6 * n_groups
+    rng = np.random.default_rng(17)
+    seq, grp = np.arange(n) // n_groups, np.arange(n) % n_groups
+    unlit = ((grp % 4 == 0) & np.isin(seq, (1, 2))) | ((grp % 4 == 1) & np.isin(seq, (0, 1))) | \
+            ((grp % 4 == 2) & np.isin(seq, (4, 5))) | ((grp % 4 == 3) & (seq % 2 == 0))
+    nrm = rng.standard_normal((n, 3)).astype(np.float32)
+    nrm[:, 2] = np.abs(nrm[:, 2]) + 0.5
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    nrm[unlit] = (0., 0., -1.)
+    xyz = dev(rng.uniform(-.5, .5, (n, 3)).astype(np.float32), ctx)
+    normal = dev(nrm, ctx)
+    cam = dev((rng.standard_normal((n, 3)) * .1 + (0., 0., 4.)).astype(np.float32), ctx)
+    albedo = dev(rng.uniform(.1, .9, (n, 3)).astype(np.float32), ctx)
+    rough = dev(rng.uniform(.2, .8, (n,)).astype(np.float32), ctx)
+    light = dev(rng.uniform(0., 2., (1, L, 3)).astype(np.float32), ctx)
+    mlp = m._packed_mlp('lvis', 'lvis', n_freqs_a=m.embedder['xyz'].n_freqs,
+                        n_freqs_b=m.embedder['ldir'].n_freqs)
+    run = lambda **kw: _lib.stageB_fused_fwd(ctx, mlp, xyz, normal, cam, albedo, lxyz, lareas, light,
+                                             rough=rough, precision='f16', **kw)
+    rgb_c, _ = run()
+    rgb_a, _ = run(all_lights=True)
+    rgb_f, lv_f = run(want_lvis=True, all_lights='front_lit')
+    rgb_l, lv = run(want_lvis=True)
+    assert torch.equal(rgb_c, rgb_a) and torch.equal(rgb_f, rgb_a) and torch.equal(rgb_l, rgb_a)
+    u = torch.as_tensor(unlit, device=lv.device)
+    assert float(lv_f[u].abs().max()) == 0. and float(rgb_c[u].abs().max()) == 0.
+    nz = lv_f != 0
+    assert 0.2 < float(nz[~u].float().mean()) <= 1.
+    assert torch.equal(lv_f[nz], lv[nz])
+
+
 def test_composite_ops_are_chunk_invariant(ctx):
     """The one-call ops process their input in chunks (32768 rays; 2^19 (point, light) pairs;
     <= 48 MB of visibility rows): a multi-chunk call must equal the concatenation of single-chunk
