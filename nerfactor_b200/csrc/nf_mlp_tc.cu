@@ -954,45 +954,55 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
 
 // =====================================================================================
 // Version 3 of the light-visibility kernel: everything that happens once per surface POINT is
-// taken off the workers' critical path.
+// taken off the workers' critical path, and a tile is 128 rows of the group's ROW STREAM, not of
+// one point.
 // Measured on B200 (profiles/r2_k2_analysis.md, section 4): in version 2 the per-point phase --
 // 63-term fold of the positional encoding of xyz into two 128-wide biases, hi/lo split, the first
 // tile's per-row embedding -- costs about as much as 1.4 tiles and both worker groups sit in it
 // with the tensor pipe idle (cutting the tiles per point from 4 to 3 by front-lit culling did not
-// shorten the kernel at all).  Here
-//   * warps 1 and 2 (idle so far) are PREFETCHERS, one per worker group: they run one point ahead,
-//     fold the next point's biases into the second of two shared-memory bias buffers, build the
-//     front-lit light list (CULL) and publish a small record; full/free mbarriers per buffer;
-//   * the workers run a flat stream of tiles: the embedding of the next tile -- also when it
-//     belongs to the next point -- is written under layer 3 of the current one;
-//   * the issuer learns which bias buffer a tile uses from a two-slot table the group fills in
-//     before it hands layer 0 over; a dynamic bias block is 2 KB (k = 0..7) + a shared 2 KB of
-//     zeros for k = 8..15, reached through the descriptor's leading-dimension offset.
+// shorten that kernel at all).  Here
+//   * warps 1 and 2 (idle so far) are PREFETCHERS, one per worker group: they run ahead of the
+//     group, fold the next points' biases, build the front-lit light list (CULL) and publish a
+//     small record per point; four record buffers per group with full / free mbarriers;
+//   * the rows of a group form one stream -- the (front-lit) lights of its points one after the
+//     other -- cut into tiles of 128: a tile may end one point and start the next (at most two
+//     points per tile), so ~260 front-lit lights cost 2.03 tiles per point instead of 3;
+//   * the per-point biases of layer 0 and of the skip layer sit in ONE 2 KB block per layer: point
+//     number i owns rows k = 2 (i % 4), 2 (i % 4) + 1 (hi, lo) of it, and every tile row selects
+//     its point through its own "ones" operand ((1, 1) at that position, zeros elsewhere), written
+//     together with the row's light-direction embedding.  The static bias blocks of layers 1, 2
+//     repeat (hi, lo) at all four positions.  k = 8..15 is a shared 2 KB block of zeros reached
+//     through the descriptor's leading-dimension offset;
+//   * the embedding of the next tile is written under layer 3 of the current one, also across a
+//     point boundary; the issuer serves hand-overs and needs no per-tile information.
 // Light positions are read from global memory (L1-resident 12 KB) instead of a shared table.
 struct SmemLayout3 {
   static constexpr int KE = KindCfg<NF_MLP_LVIS>::KE;
   static constexpr int NR_PAD = KindCfg<NF_MLP_LVIS>::NR_PAD;
   static constexpr int LMAX = 1024;
+  static constexpr int NBUF = 4;                                 // point records in flight per group
   static constexpr size_t img_bytes = ((size_t)img_halves<NF_MLP_LVIS>() + 2 * 16 * 128) * 2;
   static constexpr size_t aux_floats = AUX_WX0 + 2 * (size_t)NR_PAD * 128;
   static constexpr size_t off_img = 0;
-  static constexpr size_t off_bdyn = img_bytes;                  // [2 g][2 buf][2 layer] x 2048 B
-  static constexpr size_t off_zero = off_bdyn + 8 * 2048;        // 2048 B of zeros (k = 8..15)
+  static constexpr size_t off_bdyn = img_bytes;                  // [2 g][2 layer] x 2048 B
+  static constexpr size_t off_zero = off_bdyn + 4 * 2048;        // 2048 B of zeros (k = 8..15)
   static constexpr size_t off_aux = off_zero + 2048;
-  static constexpr size_t off_rec = off_aux + aux_floats * 4;    // [2 g][2 buf] x 16 B: xd[3], n_rows
-  static constexpr size_t off_list = off_rec + 4 * 16;           // [2 g][2 buf][LMAX] u16
-  static constexpr size_t off_es = off_list + 4 * (size_t)LMAX * 2;   // [2 prefetchers][64] f32
-  static constexpr size_t off_bar = off_es + 2 * 64 * 4;         // 13 barriers + tmem pointer
-  static constexpr size_t off_flag = off_bar + 128;              // int: done[2], tile->buffer [2][2]
-  static constexpr size_t total = off_flag + 32;
+  static constexpr size_t off_rec = off_aux + aux_floats * 4;    // [2 g][NBUF] x 16 B: xd[3], n_rows
+  static constexpr size_t off_list = off_rec + 2 * NBUF * 16;    // [2 g][NBUF][LMAX] u16
+  static constexpr size_t off_es = off_list + 2 * NBUF * (size_t)LMAX * 2;   // [2 prefetchers][64] f32
+  static constexpr size_t off_bar = off_es + 2 * 64 * 4;         // 5 + 16 barriers + tmem pointer
+  static constexpr size_t off_flag = off_bar + 192;              // int: done[2]
+  static constexpr size_t total = off_flag + 16;
 };
 static_assert(SmemLayout3::total <= 232448, "shared memory budget");
+constexpr int COL_ONE1 = 232;      // second "ones" operand (tiles alternate, like COL_AE / COL_AE1)
 
 template <int BF16, int CULL>
 __global__ void __launch_bounds__(TC_THREADS, 1) lvis_tc3_kernel(const TcParams p) {
   using SL = SmemLayout3;
   constexpr int KE = SL::KE;
   constexpr int NR_PAD = SL::NR_PAD;
+  constexpr int NBUF = SL::NBUF;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* s_img = smem + SL::off_img;
   uint8_t* s_bdyn = smem + SL::off_bdyn;
@@ -1004,10 +1014,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lvis_tc3_kernel(const TcParams 
   uint64_t* bar_w = bars + 0;          // weights landed
   uint64_t* bar_a = bars + 1;          // [2] A operand ready (128 arrivals)
   uint64_t* bar_d = bars + 3;          // [2] D accumulator ready (tcgen05.commit)
-  uint64_t* rec_full = bars + 5;       // [2 g][2 buf] record + biases of a point published
-  uint64_t* rec_free = bars + 9;       // [2 g][2 buf] the group is done with that point
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 13);
-  volatile int* s_flag = reinterpret_cast<volatile int*>(smem + SL::off_flag);   // [0..1] done, [2 + 2 g + (tile & 1)] buffer
+  uint64_t* rec_full = bars + 5;       // [2 g][NBUF] record + biases of a point published
+  uint64_t* rec_free = bars + 5 + 2 * NBUF;   // [2 g][NBUF] the group is done with that point
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 5 + 4 * NBUF);
+  volatile int* s_flag = reinterpret_cast<volatile int*>(smem + SL::off_flag);   // [g] done
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -1016,7 +1026,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lvis_tc3_kernel(const TcParams 
     mbar_init(bar_w, 1);
     mbar_init(bar_a + 0, 128); mbar_init(bar_a + 1, 128);
     mbar_init(bar_d + 0, 1); mbar_init(bar_d + 1, 1);
-    for (int i = 0; i < 4; ++i) { mbar_init(rec_full + i, 1); mbar_init(rec_free + i, 1); }
+    for (int i = 0; i < 2 * NBUF; ++i) { mbar_init(rec_full + i, 1); mbar_init(rec_free + i, 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -1026,9 +1036,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lvis_tc3_kernel(const TcParams 
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < (8 * 2048 + 2048) / 4; i += blockDim.x)      // k = 2..15 rows stay zero
+  for (int i = threadIdx.x; i < (4 * 2048 + 2048) / 4; i += blockDim.x)
     reinterpret_cast<uint32_t*>(s_bdyn)[i] = 0u;
-  if (threadIdx.x < 8) s_flag[threadIdx.x] = 0;
+  if (threadIdx.x < 4) s_flag[threadIdx.x] = 0;
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -1063,7 +1073,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lvis_tc3_kernel(const TcParams 
       constexpr uint32_t seg_w3e = (uint32_t)(KE + 384) * 256u;
       bool live[2] = {true, true};
       uint32_t ph[2] = {0u, 0u}, tile[2] = {0u, 0u};
-      int layer_of[2] = {0, 0}, buf_of[2] = {0, 0};
+      int layer_of[2] = {0, 0};
       while (live[0] || live[1]) {
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
@@ -1073,16 +1083,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lvis_tc3_kernel(const TcParams 
           if (s_flag[g]) { live[g] = false; continue; }      // the group's last arrival
           tc_fence_after();
           const int layer = layer_of[g];
-          if (layer == 0) buf_of[g] = s_flag[2 + 2 * g + (int)(tile[g] & 1u)];
           const uint32_t tb = tmem_base + g * GRP_COLS;
           const uint32_t d_t = tb + COL_D;
           const uint32_t ae_t = tb + ((tile[g] & 1u) ? COL_AE1 : COL_AE);
+          const uint32_t one_t = tb + ((tile[g] & 1u) ? COL_ONE1 : COL_ONE);
           // bias block first (accumulate = 0 starts the tile from 1 * b_hi + 1 * b_lo)
           if (layer == 0 || layer == 3) {
-            const uint32_t bsm = bdyn0 + (uint32_t)((g * 2 + buf_of[g]) * 2 + (layer == 3 ? 1 : 0)) * 2048u;
-            tc_mma_ts(d_t, tb + COL_ONE, make_b_desc(bsm, zero0 - bsm, sbo), idesc, 0u);
+            const uint32_t bsm = bdyn0 + (uint32_t)(g * 2 + (layer == 3 ? 1 : 0)) * 2048u;
+            tc_mma_ts(d_t, one_t, make_b_desc(bsm, zero0 - bsm, sbo), idesc, 0u);
           } else {
-            tc_mma_ts(d_t, tb + COL_ONE, make_b_desc(img0 + bias_off(layer), lbo, sbo), idesc, 0u);
+            tc_mma_ts(d_t, one_t, make_b_desc(img0 + bias_off(layer), lbo, sbo), idesc, 0u);
           }
           if (layer == 0) {
 #pragma unroll
@@ -1115,8 +1125,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lvis_tc3_kernel(const TcParams 
     const float* Wx3 = Wx0 + NR_PAD * 128;
     int i = 0;
     for (int pt = G; pt < p.n; pt += n_groups, ++i) {
-      const int b = i & 1;
-      if (i >= 2) mbar_wait(rec_free + g * 2 + b, (uint32_t)((i >> 1) - 1) & 1u);
+      const int b = i & (NBUF - 1);
+      if (i >= NBUF) mbar_wait(rec_free + g * NBUF + b, (uint32_t)((i / NBUF) - 1) & 1u);
       const f3 x = ld3(p.xyz + (size_t)pt * 3);
       // positional encoding of xyz (embedder.py:46-47), fp32
       if (lane < 3) es[lane] = (lane == 0 ? x.x : (lane == 1 ? x.y : x.z)) * p.xyz_scale;
@@ -1143,9 +1153,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lvis_tc3_kernel(const TcParams 
         a3.x = fmaf(ev, w3.x, a3.x); a3.y = fmaf(ev, w3.y, a3.y);
         a3.z = fmaf(ev, w3.z, a3.z); a3.w = fmaf(ev, w3.w, a3.w);
       }
-      // 16-bit hi + lo pair per column: rows k = 0 / 1 of the bias block ((k/8) 2048 + n 16 + (k%8) 2)
-      uint8_t* blk0 = s_bdyn + (size_t)((g * 2 + b) * 2 + 0) * 2048;
-      uint8_t* blk3 = s_bdyn + (size_t)((g * 2 + b) * 2 + 1) * 2048;
+      __syncwarp();                    // es is rewritten for the next point
+      // 16-bit hi + lo pair per column into rows k = 2 b, 2 b + 1 of the group's bias block of
+      // that layer (element (n, k) at n 16 + k 2 bytes)
+      uint8_t* blk0 = s_bdyn + (size_t)(g * 2 + 0) * 2048 + (size_t)b * 4;
+      uint8_t* blk3 = s_bdyn + (size_t)(g * 2 + 1) * 2048 + (size_t)b * 4;
       const float v0[4] = {a0.x, a0.y, a0.z, a0.w}, v3[4] = {a3.x, a3.y, a3.z, a3.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -1161,7 +1173,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lvis_tc3_kernel(const TcParams 
         // cos(shading normal, light) > -1e-5: a superset of the renderer's cos > 0 whatever the
         // rounding of its own cosine
         const f3 cn = l2n(l2n(ld3(p.cull_normal + (size_t)pt * 3), 1e-6f), 1e-6f);
-        uint16_t* list = s_list + (size_t)(g * 2 + b) * SL::LMAX;
+        uint16_t* list = s_list + (size_t)(g * NBUF + b) * SL::LMAX;
         int cnt = 0;
         for (int base = 0; base < p.L; base += 32) {
           const int l = base + lane;
@@ -1179,12 +1191,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lvis_tc3_kernel(const TcParams 
       }
       if (lane == 0) {
         const f3 xd = p.xyz_dir ? ld3(p.xyz_dir + (size_t)pt * 3) : x;
-        float* rec = s_rec + (size_t)(g * 2 + b) * 4;
+        float* rec = s_rec + (size_t)(g * NBUF + b) * 4;
         rec[0] = xd.x; rec[1] = xd.y; rec[2] = xd.z; rec[3] = __int_as_float(n_rows);
       }
       fence_proxy_async();           // the bias blocks are read by the tensor core (async proxy)
       __syncwarp();
-      if (lane == 0) mbar_arrive(rec_full + g * 2 + b);
+      if (lane == 0) mbar_arrive(rec_full + g * NBUF + b);
     }
   } else if (warp >= 4) {
     // ================================================================== workers
@@ -1195,46 +1207,76 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lvis_tc3_kernel(const TcParams 
     const uint32_t tb = tmem_base + g * GRP_COLS + lane_addr;
     const int G = blockIdx.x * 2 + g;
     uint32_t phd = 0u;
-    {   // constant A operand of the bias block: columns (1, 1, 0, ..., 0), written once
-      uint32_t one[8];
-      one[0] = pack2<BF16, 0>(1.f, 1.f);
-#pragma unroll
-      for (int i = 1; i < 8; ++i) one[i] = 0u;
-      TC_ST8(tb + COL_ONE, one);
-      tc_wait_st();
-    }
-    struct PointState { int pt, b, n_rows, n_tiles; f3 xd; };
-    struct RowInfo { int li; bool ok; };
-    // record of the group's i-th point (published by the prefetcher); false past the last point
+    struct PointState { int pt, b, n_rows; f3 xd; };
+    // a tile: rows [a_start, a_start + a_cnt) of point a, then the first b_cnt rows of the next point
+    struct Tile { PointState a, b; int a_start, a_cnt, b_cnt; bool a_last, b_last; };
+    struct RowInfo { int pt, li; bool ok; };
+    // record of the group's i-th point (published by the prefetcher); false past the last point.
+    // Waiting again for a record that is still held returns at once.
     auto acquire = [&](int i, PointState& s) {
       s.pt = G + i * n_groups;
       if (s.pt >= p.n) return false;
-      s.b = i & 1;
-      mbar_wait(rec_full + g * 2 + s.b, (uint32_t)(i >> 1) & 1u);
-      const float* rec = s_rec + (size_t)(g * 2 + s.b) * 4;
+      s.b = i & (NBUF - 1);
+      mbar_wait(rec_full + g * NBUF + s.b, (uint32_t)(i / NBUF) & 1u);
+      const float* rec = s_rec + (size_t)(g * NBUF + s.b) * 4;
       s.xd = mk3(rec[0], rec[1], rec[2]);
       s.n_rows = __float_as_int(rec[3]);
-      s.n_tiles = (s.n_rows + 127) / 128;
       return true;
     };
-    // first point from sequence index i on that has a tile; points without one are released here
-    // (named barrier: every thread has read the record before the prefetcher may overwrite it)
-    auto next_nonempty = [&](int& i, PointState& s) {
+    // head of the row stream: point number hp, of which hoff rows are consumed (hs valid if hvalid)
+    int hp = 0, hoff = 0;
+    bool hvalid = false;
+    PointState hs;
+    // next tile of the stream: 1 = built, 0 = the stream has ended, -1 = `overlap` was set and the
+    // next point has no row (it can only be released once every thread has seen that, which needs
+    // a barrier the caller does not want under a running layer)
+    auto build = [&](bool overlap, Tile& T) {
       for (;;) {
-        if (!acquire(i, s)) return false;
-        if (s.n_tiles > 0) return true;
-        group_bar(1 + g);
-        if (t == 0) mbar_arrive(rec_free + g * 2 + s.b);
-        ++i;
+        if (!hvalid) {
+          if (!acquire(hp, hs)) return 0;
+          hvalid = true;
+          hoff = 0;
+        }
+        if (hs.n_rows > hoff) break;
+        if (overlap) return -1;
+        group_bar(1 + g);                               // every thread has read the record
+        if (t == 0) mbar_arrive(rec_free + g * NBUF + hs.b);
+        ++hp;
+        hvalid = false;
       }
+      T.a = hs; T.b = hs;
+      T.a_start = hoff;
+      T.a_cnt = min(128, hs.n_rows - hoff);
+      T.b_cnt = 0;
+      T.a_last = false; T.b_last = false;
+      hoff += T.a_cnt;
+      if (hoff == hs.n_rows) {                          // this tile ends point a
+        T.a_last = true;
+        ++hp;
+        hvalid = false;
+        if (T.a_cnt < 128 && acquire(hp, hs)) {         // room for the first rows of the next one
+          hvalid = true;
+          hoff = 0;
+          if (hs.n_rows > 0) {
+            T.b = hs;
+            T.b_cnt = min(128 - T.a_cnt, hs.n_rows);
+            hoff = T.b_cnt;
+            if (hoff == hs.n_rows) { T.b_last = true; ++hp; hvalid = false; }
+          }     // (a point without rows stays the head: the next build releases it)
+        }
+      }
+      return 1;
     };
-    // row `t` of tile c of point s, and its embedding -> A_e buffer `aebuf`
-    auto embed_tile = [&](const PointState& s, int c, int aebuf) {
+    // row `t` of tile T: its light-direction embedding and its "ones" operand -> buffers `par`
+    auto embed_tile = [&](const Tile& T, int par) {
       RowInfo r;
-      const int row = c * 128 + t;
-      r.ok = row < s.n_rows;
-      const int rr = r.ok ? row : s.n_rows - 1;
-      r.li = CULL ? (int)s_list[(size_t)(g * 2 + s.b) * SL::LMAX + rr] : rr;
+      const bool in_a = t < T.a_cnt;
+      const PointState& s = in_a ? T.a : T.b;
+      r.ok = t < T.a_cnt + T.b_cnt;
+      int row = in_a ? T.a_start + t : t - T.a_cnt;
+      if (!r.ok) row = T.b_cnt > 0 ? T.b_cnt - 1 : T.a_start + T.a_cnt - 1;     // any valid row
+      r.pt = s.pt;
+      r.li = CULL ? (int)s_list[(size_t)(g * NBUF + s.b) * SL::LMAX + row] : row;
       const f3 d = l2n(ld3(p.lxyz + (size_t)r.li * 3) - s.xd, 1e-6f);            // shape.py:128-135
       float v[KE];
 #pragma unroll
@@ -1254,24 +1296,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lvis_tc3_kernel(const TcParams 
       uint32_t pk[KE / 2];
 #pragma unroll
       for (int i = 0; i < KE / 2; ++i) pk[i] = pack2<BF16, 0>(v[2 * i], v[2 * i + 1]);
-      TC_ST16(tb + (aebuf ? COL_AE1 : COL_AE), pk);
+      TC_ST16(tb + (par ? COL_AE1 : COL_AE), pk);
+      // (1, 1) at k = 2 b, 2 b + 1: this row takes the bias pair of ITS point
+      uint32_t one[8];
+      const uint32_t pair = pack2<BF16, 0>(1.f, 1.f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) one[i] = (i == s.b) ? pair : 0u;
+      TC_ST8(tb + (par ? COL_ONE1 : COL_ONE), one);
       tc_wait_st();
       return r;
     };
-    // layer 0 of running tile `tile` (bias buffer b) is ready for the tensor core
-    auto hand_over_tile = [&](int tile, int b) {
-      if (t == 0) s_flag[2 + 2 * g + (tile & 1)] = b;
+    auto hand_over = [&]() {
       tc_fence_before();
       mbar_arrive(bar_a + g);
     };
 
-    int pi = 0, c = 0, tile = 0;
-    PointState cur;
+    int tile = 0;
+    Tile cur;
     RowInfo rcur;
-    bool have = next_nonempty(pi, cur);
+    bool have = build(false, cur) == 1;
     if (have) {
-      rcur = embed_tile(cur, 0, 0);
-      hand_over_tile(0, cur.b);
+      rcur = embed_tile(cur, 0);
+      hand_over();
     }
     while (have) {
       // ------------------------------------------------ layers 0..2: ReLU + 16-bit -> A_h
@@ -1304,24 +1350,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lvis_tc3_kernel(const TcParams 
           pk[i] = pack2<BF16, 1>(__uint_as_float(rd[2 * i]), __uint_as_float(rd[2 * i + 1]));
         TC_ST16(tb + COL_AH + 48, pk);
         tc_wait_st();
-        tc_fence_before();
-        mbar_arrive(bar_a + g);
+        hand_over();
       }
-      // ------------------------------------------------ layer 3 is in flight: the NEXT tile (of
-      // this point or of the next one that has any) gets its embedding now
-      PointState nx = cur;
-      int nc = c + 1, npi = pi;
-      bool nhave = true, skip_empty = false;
-      if (nc >= cur.n_tiles) {
-        // only the DIRECTLY following point may be looked at here: the one after it uses the bias
-        // buffer of the current point, which is released further down
-        nc = 0;
-        npi = pi + 1;
-        nhave = acquire(npi, nx);
-        if (nhave && nx.n_tiles == 0) { skip_empty = true; nhave = false; }
-      }
+      // ------------------------------------------------ layer 3 is in flight: the NEXT tile of the
+      // stream gets its embedding now
+      Tile nx = cur;
+      int st = build(true, nx);
       RowInfo rn = rcur;
-      if (nhave) rn = embed_tile(nx, nc, (tile + 1) & 1);
+      if (st == 1) rn = embed_tile(nx, (tile + 1) & 1);
       // ------------------------------------------------ layer 3 done: accumulator -> registers,
       // hand the next tile's layer 0 over, THEN the head (it only needs the registers)
       mbar_wait(bar_d + g, phd);
@@ -1335,9 +1371,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lvis_tc3_kernel(const TcParams 
         TC_LD32(rc, tb + COL_D + 64);
         TC_LD32(rd, tb + COL_D + 96);
         tc_wait_ld();
-        // every MMA that reads this point's bias buffer has completed
-        if ((!nhave || npi != pi) && t == 0) mbar_arrive(rec_free + g * 2 + cur.b);
-        if (nhave) hand_over_tile(tile + 1, nx.b);
+        // every MMA that reads the bias rows of a point this tile ends has completed
+        if (t == 0) {
+          if (cur.a_last) mbar_arrive(rec_free + g * NBUF + cur.a.b);
+          if (cur.b_cnt > 0 && cur.b_last) mbar_arrive(rec_free + g * NBUF + cur.b.b);
+        }
+        if (st == 1) hand_over();
         const float4* wo = reinterpret_cast<const float4*>(s_aux + AUX_WOUT);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -1365,20 +1404,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lvis_tc3_kernel(const TcParams 
         }
       }
       const float o = apply_act(p.out_act, (acc0 + acc1) + s_aux[AUX_BOUT]);
-      if (rcur.ok) p.out[(size_t)cur.pt * p.L + rcur.li] = o;
-      if (skip_empty) {
-        // the following point has no tile: release it and search on without overlap (no buffer
-        // is held at this moment)
-        group_bar(1 + g);
-        if (t == 0) mbar_arrive(rec_free + g * 2 + nx.b);
-        npi = pi + 2;
-        nhave = next_nonempty(npi, nx);
-        if (nhave) {
-          rn = embed_tile(nx, 0, (tile + 1) & 1);
-          hand_over_tile(tile + 1, nx.b);
+      if (rcur.ok) p.out[(size_t)rcur.pt * p.L + rcur.li] = o;
+      if (st == -1) {
+        // the following point has no row: release it and go on without overlap (the tile just
+        // finished has released the points it ended; at most the stream head is still held)
+        st = build(false, nx);
+        if (st == 1) {
+          rn = embed_tile(nx, (tile + 1) & 1);
+          hand_over();
         }
       }
-      cur = nx; c = nc; pi = npi; rcur = rn; ++tile; have = nhave;
+      cur = nx; rcur = rn; ++tile; have = st == 1;
     }
     // tell the issuer warp that this group has no more tiles
     if (t == 0) s_flag[g] = 1;
@@ -1394,7 +1430,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lvis_tc3_kernel(const TcParams 
                  : "memory");
   }
 }
-
 
 // ------------------------------------------------------------------ bring-up test
 // One CTA: D[128x128] = A[128xK] * B[128xK]^T with A written to TMEM by tcgen05.st
@@ -1652,10 +1687,15 @@ int nf_tc_pack(nf_mlp* m) {
       __half hh; memcpy(&hh, &hi16, 2);
       __nv_bfloat16 hb; memcpy(&hb, &hibf, 2);
       const size_t idx = seg_base + (size_t)n * 8;      // k-group 0, row n, k = 0
-      img16[idx] = hi16;
-      img16[idx + 1] = f2h_bits(bv - __half2float(hh));
-      imgbf[idx] = hibf;
-      imgbf[idx + 1] = f2bf_bits(bv - __bfloat162float(hb));
+      // (hi, lo) at k = 0, 1 -- and repeated at k = 2..7 for the version-3 visibility kernel, whose
+      // "ones" operand has its (1, 1) at k = 2 j, 2 j + 1 for a row of point j mod 4 (the other
+      // kernels' ones operand is (1, 1, 0, ...): the copies meet zeros there)
+      for (int j = 0; j < 4; ++j) {
+        img16[idx + 2 * j] = hi16;
+        img16[idx + 2 * j + 1] = f2h_bits(bv - __half2float(hh));
+        imgbf[idx + 2 * j] = hibf;
+        imgbf[idx + 2 * j + 1] = f2bf_bits(bv - __bfloat162float(hb));
+      }
     }
     seg_base += (size_t)16 * 128;
   }
