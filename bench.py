@@ -695,6 +695,12 @@ def main():
                'achieved': n_fg * L * FLOP_LVIS / (t_lvis * 1e-3) / 1e12,
                'peak': tensor_peak, 'unit': 'TFLOP/s', 'ms': t_lvis, 'traffic': None,
                'algorithmic_bytes': alg_lvis,
+               'executed_tflops': n_fg * L * 131328 / (t_lvis * 1e-3) / 1e12,
+               'note': 'achieved = the reference\'s FLOPs per (point, light) pair / time; the kernel '
+                       'EXECUTES 131 328 per pair (the xyz part of the input is folded into a '
+                       'per-point bias once per point: -22 % of the K; the bias rides in the MMA as '
+                       'a K = 16 block: +12.5 %), which is why `frac` can exceed 1 against the '
+                       'sustained cuBLAS figure',
                'stage_b_ms': {'front_lit_lights_only (timed mode)': t_sb_fl, 'every_light': t_sb_all,
                               'what': 'Model.render_rgb on the view\'s foreground points: per-point '
                                       'networks + nf_stageB_fused_fwd'}}

@@ -23,8 +23,8 @@ def main(raw, out):
         v = num(r[col[name]])
         return None if v is None else v * scale[units[col[name]]]
 
-    pick = {'sigma': 'sigma_tc_kernel', 'lvis': 'mlp_tc2_kernel<1', 'point': 'point_tc_kernel',
-            'integrate': 'integrate_kernel<1, 0>'}
+    pick = {'sigma': 'sigma_tc_kernel', 'lvis': 'lvis_tc3_kernel<0, 0>', 'point': 'point_tc_kernel',
+            'integrate': 'integrate_kernel<1, 0>', 'lvis_front_lit_chunk': 'lvis_tc3_kernel<0, 1>'}
     kernels = {}
     for key, pat in pick.items():
         for r in data:
