@@ -360,6 +360,36 @@ int nf_dense_bwd(nf_ctx* ctx, const float* x1_d, int k1, const float* x2_d, int 
                  const float* w_d, const float* y_d, const float* dy_d, long long m, int n,
                  int act, float* dx1_d, float* dx2_d, float* dw_d, float* db_d, void* work_d,
                  int precision, void* stream);
+/* ---- whole-network forward / backward of the train step (the `*_bwd` counterparts of the
+ * per-network forward ops).  One call runs every Dense of an mlp.Network
+ * (nerfactor/networks/mlp.py:39-50: `depth - 1` hidden layers, the input re-concatenated as
+ * [h | x] in front of layer `skip_layer`, + the seq.Network head) and what tape.gradient
+ * (nerfactor/trainvali.py:278-285) computes for it.  Activations stay 16-bit rows inside
+ * `workspace_d` (nf_mlp_chain_workspace_bytes; the SAME workspace must be passed to the backward
+ * call, untouched in between).  x_d [rows, in_dim] (in_dim % 4 == 0: pad with zero columns and zero
+ * weight rows), y_d [rows, width[depth-1]] (head width % 4 == 0: pad W / b with zero columns);
+ * hidden widths % 16 == 0, every layer input <= 256 columns; NF_PREC_F16 / NF_PREC_BF16 only.
+ * Backward: dy_d like y_d; dx_d [rows, in_dim] or NULL; dw_d[l] / db_d[l] (Keras layout; the
+ * skip layer's W is [width[skip-1] + in_dim, width[skip]]) are ACCUMULATED INTO (+=), NULL
+ * entries / NULL arrays are skipped.  Replaces the per-layer nf_dense_fwd / nf_dense_bwd sequence
+ * for networks of this shape; numbers agree with it up to the rounding of the bias-gradient sums. */
+#define NF_CHAIN_MAX 8
+typedef struct nf_mlp_chain {
+  int depth;                     /* Dense layers incl. the head, 2..NF_CHAIN_MAX */
+  int in_dim;
+  int skip_layer;                /* index of the layer fed with [h | x]; 0 = no skip */
+  int width[NF_CHAIN_MAX];
+  int act[NF_CHAIN_MAX];         /* NF_ACT_* */
+  const float* w[NF_CHAIN_MAX];  /* device, fp32 */
+  const float* b[NF_CHAIN_MAX];
+} nf_mlp_chain;
+size_t nf_mlp_chain_workspace_bytes(const nf_mlp_chain* chain, long long rows);
+int nf_mlp_chain_fwd(nf_ctx* ctx, const nf_mlp_chain* chain, const float* x_d, long long rows,
+                     float* y_d, void* workspace_d, int precision, void* stream);
+int nf_mlp_chain_bwd(nf_ctx* ctx, const nf_mlp_chain* chain, long long rows, const float* y_d,
+                     const float* dy_d, float* dx_d, float* const* dw_d, float* const* db_d,
+                     void* workspace_d, int precision, void* stream);
+
 /* One AMSGrad-Adam update of a flat parameter buffer: tf.keras.optimizers.Adam(lr, amsgrad=True)
  * as configured at nerfactor/trainvali.py:110-127 (beta1 .9, beta2 .999, epsilon 1e-7);
  * `step` is the 1-based iteration count, `lr` the already-decayed learning rate.          */

@@ -29,7 +29,8 @@ EXPORTS = [
     'nf_sigma_fwd', 'nf_sigma_normal_fwd', 'nf_mlp_attach_rgb', 'nf_nerf_fwd', 'nf_composite', 'nf_gen_z_fine',
     'nf_lvis_rays', 'nf_selftest_umma', 'nf_selftest_umma2', 'nf_dense_fwd',
     'nf_dense_fwd_workspace_bytes', 'nf_dense_bwd_workspace_bytes',
-    'nf_dense_bwd', 'nf_adam_amsgrad_step', 'nf_microfacet_brdf_fwd', 'nf_selftest_tmem',
+    'nf_dense_bwd', 'nf_mlp_chain_workspace_bytes', 'nf_mlp_chain_fwd', 'nf_mlp_chain_bwd',
+    'nf_adam_amsgrad_step', 'nf_microfacet_brdf_fwd', 'nf_selftest_tmem',
     'nf_raymarch_depth_normal_workspace_bytes', 'nf_raymarch_depth_normal_fwd',
     'nf_raymarch_lvis_workspace_bytes', 'nf_raymarch_lvis_fwd',
     'nf_stageB_fused_workspace_bytes', 'nf_stageB_fused_fwd', 'nf_lvis_dirs_fwd', 'nf_lvis_inputs_fwd']
@@ -75,6 +76,15 @@ class StageBArgs(C.Structure):
                 ('rgb_d', C.c_void_p), ('lvis_all_lights', C.c_int)]
 
 
+CHAIN_MAX = 8
+
+
+class MlpChain(C.Structure):
+    _fields_ = [('depth', C.c_int), ('in_dim', C.c_int), ('skip_layer', C.c_int),
+                ('width', C.c_int * CHAIN_MAX), ('act', C.c_int * CHAIN_MAX),
+                ('w', C.c_void_p * CHAIN_MAX), ('b', C.c_void_p * CHAIN_MAX)]
+
+
 _lib = None
 
 
@@ -101,6 +111,11 @@ def load_library():
     lib.nf_mlp_device_bytes.argtypes = [vp]
     lib.nf_mlp_device_bytes.restype = C.c_size_t
     lib.nf_mlp_upload.argtypes = [vp, vp, vp, vp]
+    lib.nf_mlp_chain_workspace_bytes.argtypes = [C.POINTER(MlpChain), C.c_longlong]
+    lib.nf_mlp_chain_workspace_bytes.restype = C.c_size_t
+    lib.nf_mlp_chain_fwd.argtypes = [vp, C.POINTER(MlpChain), vp, C.c_longlong, vp, vp, i, vp]
+    lib.nf_mlp_chain_bwd.argtypes = [vp, C.POINTER(MlpChain), C.c_longlong, vp, vp, vp,
+                                     C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), vp, i, vp]
     lib.nf_point_mlp_fwd.argtypes = [vp, vp, vp, i, f, vp, i, vp]
     lib.nf_lvis_fwd.argtypes = [vp, vp, vp, i, f, vp, i, vp, i, vp]
     lib.nf_lvis_inputs_fwd.argtypes = [vp, vp, vp, i, vp, i, f, i, i, i, vp, vp]
@@ -598,6 +613,59 @@ def dense_bwd(ctx, x1, x2, w, y, dy, act, need_dx1, need_dx2, precision='fp32'):
         _f32(dx2) if dx2 is not None else None, _f32(dw), _f32(db), _ptr(work), PREC[precision],
         _stream()))
     return dx1, dx2, dw, db
+
+
+def _chain_struct(ws, bs, acts, skip_layer, in_dim):
+    ch = MlpChain()
+    ch.depth, ch.in_dim, ch.skip_layer = len(ws), int(in_dim), int(skip_layer)
+    for l, (w, b, a) in enumerate(zip(ws, bs, acts)):
+        ch.width[l], ch.act[l] = int(w.shape[1]), ACT[a]
+        ch.w[l], ch.b[l] = w.data_ptr(), b.data_ptr()
+    return ch
+
+
+def mlp_chain_supported(in_dim, widths, n_rows_in):
+    """Shapes nf_mlp_chain_fwd / _bwd take (include/nerfactor_b200.h): widths[-1] is the head."""
+    if not 2 <= len(widths) <= CHAIN_MAX or in_dim % 4 or widths[-1] % 4:
+        return False
+    k0p = (in_dim + 15) // 16 * 16
+    if any(w % 16 or w > 256 for w in widths[:-1]) or k0p > 256:
+        return False
+    return all(k <= 256 for k in n_rows_in)
+
+
+def mlp_chain_fwd(ctx, x, ws, bs, acts, skip_layer, precision='bf16'):
+    """Whole mlp.Network forward in one call (nf_mlp_chain_fwd).  ws[l] [in_l, width_l] (the skip
+    layer's [width + in_dim, width]), all fp32 contiguous.  -> (y [rows, width[-1]], workspace):
+    the workspace holds the 16-bit activations the backward call needs."""
+    rows, in_dim = x.shape
+    ch = _chain_struct(ws, bs, acts, skip_layer, in_dim)
+    nbytes = ctx.lib.nf_mlp_chain_workspace_bytes(C.byref(ch), rows)
+    if rows and not nbytes:
+        raise NfError('nf_mlp_chain: unsupported network shape')
+    work = torch.empty((max(nbytes, 16),), dtype=torch.uint8, device=x.device)
+    y = torch.empty((rows, ws[-1].shape[1]), dtype=torch.float32, device=x.device)
+    ctx.launches += 2 * len(ws)
+    ctx.launch(ctx.lib.nf_mlp_chain_fwd(ctx.h, C.byref(ch), _f32(x), rows, _f32(y), _ptr(work),
+                                        PREC[precision], _stream()))
+    return y, work
+
+
+def mlp_chain_bwd(ctx, ws, bs, acts, skip_layer, in_dim, y, dy, work, need_dx, precision='bf16'):
+    """-> (dx | None, [dw_l], [db_l]) for the network nf_mlp_chain_fwd just ran on `work`."""
+    rows = y.shape[0]
+    dev = y.device
+    ch = _chain_struct(ws, bs, acts, skip_layer, in_dim)
+    dx = torch.empty((rows, in_dim), dtype=torch.float32, device=dev) if need_dx else None
+    dws = [torch.zeros_like(w) for w in ws]
+    dbs = [torch.zeros_like(b) for b in bs]
+    pw = (C.c_void_p * CHAIN_MAX)(*([t.data_ptr() for t in dws] + [None] * (CHAIN_MAX - len(ws))))
+    pb = (C.c_void_p * CHAIN_MAX)(*([t.data_ptr() for t in dbs] + [None] * (CHAIN_MAX - len(bs))))
+    ctx.launches += 6 * len(ws)
+    ctx.launch(ctx.lib.nf_mlp_chain_bwd(ctx.h, C.byref(ch), rows, _f32(y), _f32(dy),
+                                        _f32(dx) if dx is not None else None, pw, pb, _ptr(work),
+                                        PREC[precision], _stream()))
+    return dx, dws, dbs
 
 
 def adam_amsgrad_step(ctx, param, grad, m, v, vhat, lr, step, beta1=0.9, beta2=0.999,

@@ -10,6 +10,8 @@ autograd Functions.  Forward values equal the fused inference kernels' (same for
 """
 import math
 
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -17,6 +19,10 @@ from . import _lib
 
 
 # ------------------------------------------------------------------ Dense layers
+
+# NF_MLP_CHAIN=0: layer-by-layer Dense calls (fp32 activations in HBM) also for tensor-core precisions
+CHAIN = os.environ.get('NF_MLP_CHAIN', '1') != '0'
+
 
 class DenseFn(torch.autograd.Function):
     """act([x1 | x2] @ w + b) through nf_dense_fwd / nf_dense_bwd.  `prec`: 'fp32' (CUDA
@@ -46,6 +52,38 @@ class DenseFn(torch.autograd.Function):
         return dx1, dx2, dw, db, None, None
 
 
+class MlpChainFn(torch.autograd.Function):
+    """A whole mlp.Network (hidden layers + head) through nf_mlp_chain_fwd / nf_mlp_chain_bwd: one
+    call each way, activations kept as 16-bit rows in a private workspace.  Arguments after `prec`:
+    w0, b0, w1, b1, ... (already padded the way mlp_apply pads them)."""
+
+    @staticmethod
+    def forward(ctx, x, acts, skip_layer, prec, *wb):
+        c = _lib.default_context()
+        x = x.contiguous()
+        ws = [t.contiguous() for t in wb[0::2]]
+        bs = [t.contiguous() for t in wb[1::2]]
+        ws = [w.clone() if w.data_ptr() % 16 else w for w in ws]
+        y, work = _lib.mlp_chain_fwd(c, x, ws, bs, acts, skip_layer, prec)
+        ctx.save_for_backward(y, *ws, *bs)
+        ctx.work = work                 # the library's private workspace (not an autograd variable)
+        ctx.acts, ctx.skip_layer, ctx.prec, ctx.in_dim, ctx.nl = acts, skip_layer, prec, x.shape[1], len(ws)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        y, work = ctx.saved_tensors[0], ctx.work
+        ws = list(ctx.saved_tensors[1:1 + ctx.nl])
+        bs = list(ctx.saved_tensors[1 + ctx.nl:])
+        c = _lib.default_context()
+        dx, dws, dbs = _lib.mlp_chain_bwd(c, ws, bs, ctx.acts, ctx.skip_layer, ctx.in_dim, y,
+                                          dy.contiguous(), work, ctx.needs_input_grad[0], ctx.prec)
+        grads = []
+        for dw, db in zip(dws, dbs):
+            grads += [dw, db]
+        return (dx, None, None, None) + tuple(grads)
+
+
 def _pad_to4(n):
     return (n + 3) // 4 * 4
 
@@ -60,6 +98,28 @@ def mlp_apply(x, layers, acts, skip_at, prec='fp32', in_dim=None):
     in_pad = _pad_to4(in_dim)
     assert x.shape[1] in (in_dim, in_pad)
     xp = F.pad(x, (0, in_pad - in_dim)) if x.shape[1] != in_pad else x
+    widths = [_pad_to4(w.shape[1]) for w, _ in layers]
+    skips = sorted(skip_at) if skip_at is not None else []
+    if (prec in ('bf16', 'f16') and CHAIN and len(skips) <= 1 and (not skips or skips[0] + 1 < len(layers))
+            and _lib.mlp_chain_supported(in_pad, widths, [in_pad] + [
+                widths[i] + (in_pad if skips and i == skips[0] else 0) for i in range(len(layers) - 1)])):
+        # one call for the whole network; weights padded exactly as in the layer-by-layer path below
+        wb = []
+        for i, (w, b) in enumerate(layers):
+            n, n_pad = w.shape[1], widths[i]
+            if skips and i == skips[0] + 1:
+                wh, wx = w[:w.shape[0] - in_dim], w[w.shape[0] - in_dim:]
+                wfull = torch.cat((wh, F.pad(wx, (0, 0, 0, in_pad - in_dim))), 0)
+            elif i == 0:
+                wfull = F.pad(w, (0, 0, 0, in_pad - in_dim)) if in_pad != in_dim else w
+            else:
+                wfull = w
+            if n_pad != n:
+                wfull, b = F.pad(wfull, (0, n_pad - n)), F.pad(b, (0, n_pad - n))
+            wb += [wfull, b]
+        y = MlpChainFn.apply(xp, tuple(acts), skips[0] + 1 if skips else 0, prec, *wb)
+        n_out = layers[-1][0].shape[1]
+        return y[:, :n_out] if y.shape[1] != n_out else y
     h, h_skip = xp, None
     for i, ((w, b), act) in enumerate(zip(layers, acts)):
         n = w.shape[1]

@@ -85,10 +85,12 @@ __global__ void wimg_kernel(const float* __restrict__ w, int n, int k1, int k1p,
 // ---------------------------------------------------------------- dz = dy * act'(y), colsum
 // dz16[m][Nz] (Nz = n rounded up to 16, pad columns zero); part[block][n] = column sums of the
 // fp32 products over the block's rows.
-template <int BF16>
+// IN16 = 1 (chain mode): y and dy are 16-bit rows y16[m][ldy] / dy16[m][lddy] (dz16 may alias dy16).
+template <int BF16, int IN16>
 __global__ void __launch_bounds__(256) act_bwd_colsum_kernel(
     const float* __restrict__ y, const float* __restrict__ dy, long long m, int n, int Nz, int act,
-    long long rows_per_block, uint16_t* __restrict__ dz16, float* __restrict__ part) {
+    long long rows_per_block, uint16_t* dz16, float* __restrict__ part,
+    const uint16_t* __restrict__ y16, int ldy, const uint16_t* dy16, int lddy) {
   __shared__ float4 red[256];
   const int n4 = n >> 2;
   const int rp = 256 / n4;                       // rows per pass
@@ -99,8 +101,16 @@ __global__ void __launch_bounds__(256) act_bwd_colsum_kernel(
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (active) {
     for (long long r = r0 + rl; r < r1; r += rp) {
-      const float4 yy = *reinterpret_cast<const float4*>(y + r * n + cq * 4);
-      const float4 dd = *reinterpret_cast<const float4*>(dy + r * n + cq * 4);
+      float4 yy, dd;
+      if (IN16) {
+        const uint2 a = *reinterpret_cast<const uint2*>(y16 + r * ldy + cq * 4);
+        const uint2 b = *reinterpret_cast<const uint2*>(dy16 + r * lddy + cq * 4);
+        yy = make_float4(unpack_lo<BF16>(a.x), unpack_hi<BF16>(a.x), unpack_lo<BF16>(a.y), unpack_hi<BF16>(a.y));
+        dd = make_float4(unpack_lo<BF16>(b.x), unpack_hi<BF16>(b.x), unpack_lo<BF16>(b.y), unpack_hi<BF16>(b.y));
+      } else {
+        yy = *reinterpret_cast<const float4*>(y + r * n + cq * 4);
+        dd = *reinterpret_cast<const float4*>(dy + r * n + cq * 4);
+      }
       float4 z;
       z.x = dd.x * act_grad_tc(act, yy.x);
       z.y = dd.y * act_grad_tc(act, yy.y);
@@ -162,9 +172,16 @@ struct RowGemmParams {
   const float* bias; int nbias; int act;
   float* out1; int n1, ldo1;           // image columns [0, n1) -> out1
   float* out2; int n2, ldo2, col2;     // image columns [col2, col2 + n2) -> out2
+  uint16_t* out16; int ldo16;          // O16 = 1: image columns [0, n1) -> 16-bit rows instead of out1
+  int stages;                          // A-operand images in flight (2..4, as shared memory allows)
   long long rows;
   long long tiles;
 };
+__device__ __forceinline__ void stg256u(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y),
+               "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
 
 // 256-bit global accesses (sm_100: LDG/STG.256) halve the LSU wavefronts of the one-row-per-lane
 // access pattern these kernels use
@@ -218,7 +235,9 @@ __device__ __forceinline__ uint4 pack8(const float4& a, const float4& b) {
 // TMEM lane quarter)
 constexpr int RG_THREADS = 544;
 
-template <int BF16, int A16>
+// O16 = 1 (chain mode): the result columns [0, n1) are stored as 16-bit rows (out16), rounded the
+// way the next layer's operand image would round them anyway.
+template <int BF16, int A16, int O16>
 __global__ void __launch_bounds__(RG_THREADS, 1) rowgemm_tc_kernel(const RowGemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int Kp = p.Kp, Np = p.Np;
@@ -226,20 +245,19 @@ __global__ void __launch_bounds__(RG_THREADS, 1) rowgemm_tc_kernel(const RowGemm
   const uint32_t abytes = (uint32_t)Kp * 128 * 2;
   uint8_t* s_w = smem;
   uint8_t* s_a = smem + wbytes;
-  float* s_bias = reinterpret_cast<float*>(s_a + 2 * abytes);
+  const int S = p.stages;         // the loaders run up to S - 1 tiles ahead of the tensor pipe
+  float* s_bias = reinterpret_cast<float*>(s_a + (size_t)S * abytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 256);
-  uint64_t* a_full = bars;        // [2] 256 loader arrivals
-  uint64_t* a_empty = bars + 2;   // [2] commit
-  uint64_t* d_full = bars + 4;    // [2] commit
-  uint64_t* d_empty = bars + 6;   // [2] 256 epilogue arrivals
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* a_full = bars;        // [4] 256 loader arrivals
+  uint64_t* a_empty = bars + 4;   // [4] commit
+  uint64_t* d_full = bars + 8;    // [2] commit
+  uint64_t* d_empty = bars + 10;  // [2] 256 epilogue arrivals
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 12);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(a_full + i, 256); mbar_init(a_empty + i, 1);
-      mbar_init(d_full + i, 1); mbar_init(d_empty + i, 256);
-    }
+    for (int i = 0; i < 4; ++i) { mbar_init(a_full + i, 256); mbar_init(a_empty + i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(d_full + i, 1); mbar_init(d_empty + i, 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -269,14 +287,15 @@ __global__ void __launch_bounds__(RG_THREADS, 1) rowgemm_tc_kernel(const RowGemm
       const uint32_t lbo_b = (uint32_t)Np * 16;
       for (long long it = 0; it < ntile; ++it) {
         const int buf = (int)(it & 1);
-        mbar_wait(a_full + buf, (uint32_t)(it >> 1) & 1);
+        const int sa = (int)(it % S);
+        mbar_wait(a_full + sa, (uint32_t)(it / S) & 1);
         if (it >= 2) mbar_wait(d_empty + buf, (uint32_t)((it >> 1) - 1) & 1);
         tc_fence_after();
         const uint32_t d_t = tmem_base + buf * 256;
         for (int ks = 0; ks < Kp / 16; ++ks)
-          tc_mma_ss(d_t, make_b_desc(a0 + buf * abytes + ks * 2 * 2048, 2048, 128),
+          tc_mma_ss(d_t, make_b_desc(a0 + sa * abytes + ks * 2 * 2048, 2048, 128),
                     make_b_desc(w0 + ks * 2 * lbo_b, lbo_b, 128), idesc, ks > 0 ? 1u : 0u);
-        tc_commit(a_empty + buf);
+        tc_commit(a_empty + sa);
         tc_commit(d_full + buf);
       }
     }
@@ -291,23 +310,40 @@ __global__ void __launch_bounds__(RG_THREADS, 1) rowgemm_tc_kernel(const RowGemm
     rs.v1 = !A16 && (p.ld1 % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.x1) & 31) == 0);
     rs.v2 = !A16 && p.x2 && (p.ld2 % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.x2) & 31) == 0);
     for (long long it = 0; it < ntile; ++it) {
-      const int buf = (int)(it & 1);
+      const int buf = (int)(it % S);
       const long long row = (it * gridDim.x + blockIdx.x) * 128 + t;
       const bool valid = row < p.rows;
-      if (it >= 2) mbar_wait(a_empty + buf, (uint32_t)((it >> 1) - 1) & 1);
+      if (it >= S) mbar_wait(a_empty + buf, (uint32_t)((it / S) - 1) & 1);
       uint8_t* img = s_a + (size_t)buf * abytes + (size_t)t * 16;
       if (A16) {
-        const uint16_t* src = p.a16 + row * p.lda16;
-        for (int kg0 = kg_lo; kg0 < kg_hi; kg0 += 8) {
-          uint4 v[8];
+        // a warp instruction covers 8 rows x 4 sixteen-byte chunks: 64 contiguous bytes per row
+        // from global memory (full sectors), 128 contiguous bytes per quarter warp into the image
+        const int lw = lt >> 5, r8 = lane & 7, kq = lane >> 3;
+        uint8_t* imgb = s_a + (size_t)buf * abytes;
+        const long long tile_row0 = (it * gridDim.x + blockIdx.x) * 128;
+        for (int kg0 = 0; kg0 < KG; kg0 += 16) {
+          uint4 v[2][4];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            v[j] = make_uint4(0u, 0u, 0u, 0u);
-            if (valid && kg0 + j < kg_hi) v[j] = __ldg(reinterpret_cast<const uint4*>(src + (kg0 + j) * 8));
+          for (int rsub = 0; rsub < 2; ++rsub) {
+            const int tr = lw * 16 + rsub * 8 + r8;
+            const long long grow = tile_row0 + tr;
+            const uint16_t* src = p.a16 + grow * p.lda16;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int kg = kg0 + 4 * j + kq;
+              v[rsub][j] = make_uint4(0u, 0u, 0u, 0u);
+              if (grow < p.rows && kg < KG) v[rsub][j] = __ldg(reinterpret_cast<const uint4*>(src + kg * 8));
+            }
           }
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (kg0 + j < kg_hi) *reinterpret_cast<uint4*>(img + (size_t)(kg0 + j) * 2048) = v[j];
+          for (int rsub = 0; rsub < 2; ++rsub) {
+            const int tr = lw * 16 + rsub * 8 + r8;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int kg = kg0 + 4 * j + kq;
+              if (kg < KG) *reinterpret_cast<uint4*>(imgb + (size_t)kg * 2048 + (size_t)tr * 16) = v[rsub][j];
+            }
+          }
         }
       } else {
         rs.s1 = p.x1 + row * p.ld1;
@@ -359,7 +395,9 @@ __global__ void __launch_bounds__(RG_THREADS, 1) rowgemm_tc_kernel(const RowGemm
               o[q].z = apply_act(p.act, __uint_as_float(r[8 * j + 4 * q + 2]) + s_bias[c + 4 * q + 2]);
               o[q].w = apply_act(p.act, __uint_as_float(r[8 * j + 4 * q + 3]) + s_bias[c + 4 * q + 3]);
             }
-            if (c + 8 <= p.n1) {
+            if (O16 && c + 8 <= p.n1) {
+              *reinterpret_cast<uint4*>(p.out16 + row * p.ldo16 + c) = pack8<BF16>(o[0], o[1]);
+            } else if (c + 8 <= p.n1) {
               if (w1) stg256(p.out1 + row * p.ldo1 + c, o[0], o[1]);
               else if (p.out1) {
                 *reinterpret_cast<float4*>(p.out1 + row * p.ldo1 + c) = o[0];
@@ -401,11 +439,12 @@ struct WgradParams {
   int n;                               // real output columns
   float* part;                         // [gridDim.x][(k1 + k2) * n]
   long long rows, tiles;
+  const uint16_t* x16; int ldx16;      // X16 = 1: the input as 16-bit rows covering the Kp image columns
 };
 
 constexpr int WG_THREADS = 288;        // warp 0 MMA, warps 1-8 loaders (+ final epilogue)
 
-template <int BF16>
+template <int BF16, int X16>
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int KpW = p.KpW, Nz = p.Nz;
@@ -479,6 +518,53 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgradPara
       const long long row = (it * gridDim.x + blockIdx.x) * 128 + t;
       const bool valid = row < p.rows;
       if (it >= 2) mbar_wait(empty + buf, (uint32_t)((it >> 1) - 1) & 1);
+      if (X16) {
+        // both operands are 16-bit rows: plain copies, 8 rows x 4 sixteen-byte chunks per warp
+        // instruction (64 contiguous bytes per row from global memory)
+        const int lw = lt >> 5, r8 = lane & 7, kq = lane >> 3;
+        uint8_t* xb = s_x + (size_t)buf * xbytes;
+        uint8_t* zb = s_z + (size_t)buf * zbytes;
+        const long long tile_row0 = (it * gridDim.x + blockIdx.x) * 128;
+#pragma unroll
+        for (int rsub = 0; rsub < 2; ++rsub) {
+          const int tr = lw * 16 + rsub * 8 + r8;
+          const long long grow = tile_row0 + tr;
+          const bool ok = grow < p.rows;
+          const uint16_t* xs = p.x16 + grow * p.ldx16;
+          const uint16_t* zs2 = p.dz16 + grow * Nz;
+          for (int kg0 = 0; kg0 < KG; kg0 += 16) {
+            uint4 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int kg = kg0 + 4 * j + kq;
+              v[j] = make_uint4(0u, 0u, 0u, 0u);
+              if (ok && kg < KG) v[j] = __ldg(reinterpret_cast<const uint4*>(xs + kg * 8));
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int kg = kg0 + 4 * j + kq;
+              if (kg < KG) *reinterpret_cast<uint4*>(xb + (size_t)kg * 2048 + (size_t)tr * 16) = v[j];
+            }
+          }
+          for (int g0 = 0; g0 < ZG; g0 += 16) {
+            uint4 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int zg = g0 + 4 * j + kq;
+              v[j] = make_uint4(0u, 0u, 0u, 0u);
+              if (ok && zg < ZG) v[j] = __ldg(reinterpret_cast<const uint4*>(zs2 + zg * 8));
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int zg = g0 + 4 * j + kq;
+              if (zg < ZG) *reinterpret_cast<uint4*>(zb + (size_t)zg * 2048 + (size_t)tr * 16) = v[j];
+            }
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(full + buf);
+        continue;
+      }
       uint8_t* xi = s_x + (size_t)buf * xbytes + (size_t)t * 16;
       uint8_t* zi = s_z + (size_t)buf * zbytes + (size_t)t * 16;
       rs.s1 = p.x1 + row * p.ld1;
@@ -571,6 +657,15 @@ inline TcDims tc_dims(int k1, int k2, int n) {
   return d;
 }
 constexpr size_t RG_SMEM_EXTRA = 256 * 4 + 16 * 8;
+// shared memory of rowgemm_tc_kernel and how many A-operand images fit (2..4): weight image
+// wk x wn, A images of ak columns (x 128 rows x 2 B)
+inline size_t rg_smem(int wk, int wn, int ak, int* stages) {
+  const size_t wbytes = (size_t)wk * wn * 2, ab = (size_t)ak * 256;
+  long long S = ((long long)200 * 1024 - (long long)wbytes - (long long)RG_SMEM_EXTRA) / (long long)ab;
+  S = S < 2 ? 2 : (S > 4 ? 4 : S);
+  *stages = (int)S;
+  return wbytes + (size_t)S * ab + RG_SMEM_EXTRA;
+}
 constexpr int COLSUM_BLOCKS = 592;
 
 }  // namespace
@@ -615,10 +710,10 @@ static int dense_tc_fwd_t(nf_ctx* ctx, const float* x1, int k1, const float* x2,
   p.wimg = img; p.Kp = d.Kp; p.Np = d.Nz; p.bias = b; p.nbias = n; p.act = act;
   p.out1 = y; p.n1 = n; p.ldo1 = n;
   p.rows = m; p.tiles = (m + 127) / 128;
-  const size_t smb = (size_t)d.Kp * d.Nz * 2 + 2 * (size_t)d.Kp * 256 + RG_SMEM_EXTRA;
+  const size_t smb = rg_smem(d.Kp, d.Nz, d.Kp, &p.stages);
   const int grid = (int)std::min<long long>(ctx->sm_count, p.tiles);
-  NF_CUDA(ctx, cudaFuncSetAttribute(rowgemm_tc_kernel<BF16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb));
-  rowgemm_tc_kernel<BF16, 0><<<grid, RG_THREADS, smb, st>>>(p);
+  NF_CUDA(ctx, cudaFuncSetAttribute(rowgemm_tc_kernel<BF16, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb));
+  rowgemm_tc_kernel<BF16, 0, 0><<<grid, RG_THREADS, smb, st>>>(p);
   NF_LAUNCH_CHECK(ctx);
   return NF_OK;
 }
@@ -640,7 +735,7 @@ static int dense_tc_bwd_t(nf_ctx* ctx, const float* x1, int k1, const float* x2,
   // dz (16 bit) + bias gradient
   const long long rpb = (m + COLSUM_BLOCKS - 1) / COLSUM_BLOCKS;
   const int cblocks = (int)((m + rpb - 1) / rpb);
-  act_bwd_colsum_kernel<BF16><<<cblocks, 256, 0, st>>>(y, dy, m, n, d.Nz, act, rpb, dz16, cpart);
+  act_bwd_colsum_kernel<BF16, 0><<<cblocks, 256, 0, st>>>(y, dy, m, n, d.Nz, act, rpb, dz16, cpart, nullptr, 0, nullptr, 0);
   NF_LAUNCH_CHECK(ctx);
   if (db) {
     reduce_partials_kernel<<<(n + RP_OUT - 1) / RP_OUT, RP_OUT * RP_SLICES, 0, st>>>(cpart, cblocks, n, n, db);
@@ -660,9 +755,9 @@ static int dense_tc_bwd_t(nf_ctx* ctx, const float* x1, int k1, const float* x2,
     p.out1 = dx1; p.n1 = k1; p.ldo1 = k1;
     p.out2 = dx2; p.n2 = k2; p.ldo2 = k2; p.col2 = d.k1p;
     p.rows = m; p.tiles = tiles;
-    const size_t smb = (size_t)d.Kp * d.Nz * 2 + 2 * (size_t)d.Nz * 256 + RG_SMEM_EXTRA;
-    NF_CUDA(ctx, cudaFuncSetAttribute(rowgemm_tc_kernel<BF16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb));
-    rowgemm_tc_kernel<BF16, 1><<<grid, RG_THREADS, smb, st>>>(p);
+    const size_t smb = rg_smem(d.Kp, d.Nz, d.Nz, &p.stages);
+    NF_CUDA(ctx, cudaFuncSetAttribute(rowgemm_tc_kernel<BF16, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb));
+    rowgemm_tc_kernel<BF16, 1, 0><<<grid, RG_THREADS, smb, st>>>(p);
     NF_LAUNCH_CHECK(ctx);
   }
   if (dw) {
@@ -672,8 +767,8 @@ static int dense_tc_bwd_t(nf_ctx* ctx, const float* x1, int k1, const float* x2,
     q.k1p = d.k1p; q.Kp = d.Kp; q.KpW = d.KpW; q.dz16 = dz16; q.Nz = d.Nz; q.n = n;
     q.part = wpart; q.rows = m; q.tiles = tiles;
     const size_t smb = 2 * (size_t)(d.KpW + d.Nz) * 256 + 128;
-    NF_CUDA(ctx, cudaFuncSetAttribute(wgrad_tc_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb));
-    wgrad_tc_kernel<BF16><<<grid, WG_THREADS, smb, st>>>(q);
+    NF_CUDA(ctx, cudaFuncSetAttribute(wgrad_tc_kernel<BF16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb));
+    wgrad_tc_kernel<BF16, 0><<<grid, WG_THREADS, smb, st>>>(q);
     NF_LAUNCH_CHECK(ctx);
     const int count = (k1 + k2) * n;
     reduce_partials_kernel<<<(count + RP_OUT - 1) / RP_OUT, RP_OUT * RP_SLICES, 0, st>>>(wpart, grid, count, count, dw);
@@ -697,3 +792,259 @@ int nf_dense_tc_bwd(nf_ctx* ctx, const float* x1, int k1, const float* x2, int k
              ? dense_tc_bwd_t<1>(ctx, x1, k1, x2, k2, w, y, dy, m, n, act, dx1, dx2, dw, db, work, st)
              : dense_tc_bwd_t<0>(ctx, x1, k1, x2, k2, w, y, dy, m, n, act, dx1, dx2, dw, db, work, st);
 }
+
+
+// =====================================================================================
+// Whole-network forward / backward for the train step (SURVEY 8b "*_bwd counterparts"): one C call
+// runs every Dense of an mlp.Network (nerfactor/networks/mlp.py:39-50 + the seq.Network head) and
+// keeps the activations between the layers -- and between forward and backward -- as 16-BIT rows
+// in a caller-provided workspace.  The operand images of the per-layer kernels round activations
+// to 16 bit anyway, so the numbers match the layer-by-layer path (nf_dense_fwd / nf_dense_bwd with
+// fp32 activations) up to the rounding of the bias-gradient column sums; the HBM traffic per
+// hidden layer drops from 4 + 4 to 2 + 2 bytes per activation.
+namespace {
+
+template <int BF16>
+__global__ void cvt16_kernel(const float* __restrict__ x, long long rows, int k, int kp,
+                             uint16_t* __restrict__ d1, int ld1, uint16_t* __restrict__ d2, int ld2,
+                             int off2) {
+  const int groups = kp / 8;
+  const long long total = rows * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / groups;
+    const int c = (int)(i % groups) * 8;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (c + j < k) ? x[r * k + c + j] : 0.f;
+    uint4 q;
+    q.x = pack2<BF16, 0>(v[0], v[1]); q.y = pack2<BF16, 0>(v[2], v[3]);
+    q.z = pack2<BF16, 0>(v[4], v[5]); q.w = pack2<BF16, 0>(v[6], v[7]);
+    *reinterpret_cast<uint4*>(d1 + r * ld1 + c) = q;
+    if (d2) *reinterpret_cast<uint4*>(d2 + r * ld2 + off2 + c) = q;
+  }
+}
+
+__global__ void axpy_kernel(const float* __restrict__ a, float* __restrict__ y, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    y[i] += a[i];
+}
+
+struct ChainPlan {
+  int depth, in_dim, k0p, skip;               // skip = index of the layer fed with [h | x], 0 = none
+  int width[NF_CHAIN_MAX], nz[NF_CHAIN_MAX];  // output columns, rounded up to 16
+  int ld[NF_CHAIN_MAX];                       // row stride of the 16-bit output buffer of hidden layer l
+  size_t off_x0, off_h[NF_CHAIN_MAX];         // saved activations
+  size_t off_dh[2], off_dzh, off_img, off_cpart, off_wpart, off_dxs, total;
+};
+
+bool chain_plan(const nf_mlp_chain* c, long long rows, int sm_count, ChainPlan& P) {
+  if (!c || c->depth < 2 || c->depth > NF_CHAIN_MAX || c->in_dim < 4 || c->in_dim % 4) return false;
+  P.depth = c->depth; P.in_dim = c->in_dim; P.k0p = rup(c->in_dim, 16); P.skip = c->skip_layer;
+  if (P.skip < 0 || P.skip >= c->depth) return false;
+  size_t off = 0;
+  P.off_x0 = off; off += rup256((size_t)rows * P.k0p * 2);
+  int max_k = P.k0p, max_n = 16;
+  for (int l = 0; l < c->depth; ++l) {
+    P.width[l] = c->width[l];
+    P.nz[l] = rup(c->width[l], 16);
+    const bool hidden = l < c->depth - 1;
+    if (hidden && (c->width[l] % 16 || c->width[l] > 256)) return false;      // 16-bit rows need whole chunks
+    if (!hidden && c->width[l] % 4) return false;
+    P.ld[l] = P.nz[l] + ((P.skip && l == P.skip - 1) ? P.k0p : 0);
+    P.off_h[l] = off;
+    if (hidden) off += rup256((size_t)rows * P.ld[l] * 2);
+    const int kin = l == 0 ? P.k0p : P.ld[l - 1];
+    if (kin > 256 || P.nz[l] > 256) return false;
+    max_k = std::max(max_k, kin); max_n = std::max(max_n, P.nz[l]);
+  }
+  P.off_dh[0] = off; off += rup256((size_t)rows * 256 * 2);
+  P.off_dh[1] = off; off += rup256((size_t)rows * 256 * 2);
+  P.off_dzh = off; off += rup256((size_t)rows * P.nz[c->depth - 1] * 2);
+  P.off_img = off; off += rup256((size_t)max_k * max_n * 2);
+  P.off_cpart = off; off += rup256((size_t)COLSUM_BLOCKS * 256 * 4);
+  P.off_wpart = off; off += rup256((size_t)sm_count * (size_t)max_k * max_n * 4);
+  P.off_dxs = off; off += rup256((size_t)rows * c->in_dim * 4);
+  P.total = off;
+  return true;
+}
+
+template <int BF16>
+int chain_fwd_t(nf_ctx* ctx, const nf_mlp_chain* c, const ChainPlan& P, const float* x,
+                long long rows, float* y, uint8_t* ws, cudaStream_t st) {
+  uint16_t* x0 = reinterpret_cast<uint16_t*>(ws + P.off_x0);
+  uint16_t* hskip = P.skip ? reinterpret_cast<uint16_t*>(ws + P.off_h[P.skip - 1]) : nullptr;
+  const long long tiles = (rows + 127) / 128;
+  const int grid = (int)std::min<long long>(ctx->sm_count, tiles);
+  cvt16_kernel<BF16><<<(unsigned)std::min<long long>((rows * (P.k0p / 8) + 255) / 256, 4096), 256, 0, st>>>(
+      x, rows, P.in_dim, P.k0p, x0, P.k0p, hskip, P.skip ? P.ld[P.skip - 1] : 0,
+      P.skip ? P.nz[P.skip - 1] : 0);
+  NF_LAUNCH_CHECK(ctx);
+  uint16_t* img = reinterpret_cast<uint16_t*>(ws + P.off_img);
+  for (int l = 0; l < P.depth; ++l) {
+    const bool hidden = l < P.depth - 1;
+    const bool sk = P.skip && l == P.skip;
+    const int k1 = l == 0 ? P.in_dim : P.width[l - 1];
+    const int k2 = sk ? P.in_dim : 0;
+    const TcDims d = tc_dims(k1, k2, P.width[l]);
+    wimg_kernel<BF16><<<64, 256, 0, st>>>(c->w[l], P.width[l], k1, d.k1p, k2, d.Kp, d.Nz, 0, img);
+    NF_LAUNCH_CHECK(ctx);
+    RowGemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.a16 = l == 0 ? x0 : reinterpret_cast<uint16_t*>(ws + P.off_h[l - 1]);
+    p.lda16 = l == 0 ? P.k0p : P.ld[l - 1];
+    p.k1p = d.k1p; p.wimg = img; p.Kp = d.Kp; p.Np = d.Nz;
+    p.bias = c->b[l]; p.nbias = P.width[l]; p.act = c->act[l];
+    p.n1 = P.width[l];
+    p.rows = rows; p.tiles = tiles;
+    const size_t smb = rg_smem(d.Kp, d.Nz, d.Kp, &p.stages);
+    if (hidden) {
+      p.out16 = reinterpret_cast<uint16_t*>(ws + P.off_h[l]); p.ldo16 = P.ld[l];
+      NF_CUDA(ctx, cudaFuncSetAttribute(rowgemm_tc_kernel<BF16, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb));
+      rowgemm_tc_kernel<BF16, 1, 1><<<grid, RG_THREADS, smb, st>>>(p);
+    } else {
+      p.out1 = y; p.ldo1 = P.width[l];
+      NF_CUDA(ctx, cudaFuncSetAttribute(rowgemm_tc_kernel<BF16, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb));
+      rowgemm_tc_kernel<BF16, 1, 0><<<grid, RG_THREADS, smb, st>>>(p);
+    }
+    NF_LAUNCH_CHECK(ctx);
+  }
+  return NF_OK;
+}
+
+template <int BF16>
+int chain_bwd_t(nf_ctx* ctx, const nf_mlp_chain* c, const ChainPlan& P, long long rows,
+                const float* y, const float* dy, float* dx, float* const* dw, float* const* db,
+                uint8_t* ws, cudaStream_t st) {
+  const long long tiles = (rows + 127) / 128;
+  const int grid = (int)std::min<long long>(ctx->sm_count, tiles);
+  uint16_t* x0 = reinterpret_cast<uint16_t*>(ws + P.off_x0);
+  uint16_t* img = reinterpret_cast<uint16_t*>(ws + P.off_img);
+  float* cpart = reinterpret_cast<float*>(ws + P.off_cpart);
+  float* wpart = reinterpret_cast<float*>(ws + P.off_wpart);
+  float* dxs = reinterpret_cast<float*>(ws + P.off_dxs);
+  const long long rpb = (rows + COLSUM_BLOCKS - 1) / COLSUM_BLOCKS;
+  const int cblocks = (int)((rows + rpb - 1) / rpb);
+  int cur = 0;                                      // dh[cur]: gradient w.r.t. the output of layer l
+  for (int l = P.depth - 1; l >= 0; --l) {
+    const bool hidden = l < P.depth - 1;
+    const bool sk = P.skip && l == P.skip;
+    const int n = P.width[l];
+    const int k1 = l == 0 ? P.in_dim : P.width[l - 1];
+    const int k2 = sk ? P.in_dim : 0;
+    const TcDims d = tc_dims(k1, k2, n);
+    // dz = dy * act'(y) as 16 bit (+ bias gradient): hidden layers in place in dh[cur]
+    uint16_t* dz16;
+    if (hidden) {
+      dz16 = reinterpret_cast<uint16_t*>(ws + P.off_dh[cur]);
+      const uint16_t* h = reinterpret_cast<const uint16_t*>(ws + P.off_h[l]);
+      act_bwd_colsum_kernel<BF16, 1><<<cblocks, 256, 0, st>>>(nullptr, nullptr, rows, n, d.Nz, c->act[l], rpb,
+                                                              dz16, cpart, h, P.ld[l], dz16, d.Nz);
+    } else {
+      dz16 = reinterpret_cast<uint16_t*>(ws + P.off_dzh);
+      act_bwd_colsum_kernel<BF16, 0><<<cblocks, 256, 0, st>>>(y, dy, rows, n, d.Nz, c->act[l], rpb, dz16,
+                                                              cpart, nullptr, 0, nullptr, 0);
+    }
+    NF_LAUNCH_CHECK(ctx);
+    if (db && db[l]) {
+      reduce_partials_kernel<<<(n + RP_OUT - 1) / RP_OUT, RP_OUT * RP_SLICES, 0, st>>>(cpart, cblocks, n, n, db[l]);
+      NF_LAUNCH_CHECK(ctx);
+    }
+    // weight gradient: [x1 | x2]^T dz with the 16-bit input rows of the forward pass
+    if (dw && dw[l]) {
+      WgradParams q;
+      memset(&q, 0, sizeof(q));
+      q.k1 = k1; q.k2 = k2; q.k1p = d.k1p; q.Kp = d.Kp; q.KpW = d.KpW; q.dz16 = dz16; q.Nz = d.Nz; q.n = n;
+      q.x16 = l == 0 ? x0 : reinterpret_cast<const uint16_t*>(ws + P.off_h[l - 1]);
+      q.ldx16 = l == 0 ? P.k0p : P.ld[l - 1];
+      q.part = wpart; q.rows = rows; q.tiles = tiles;
+      const size_t smb = 2 * (size_t)(d.KpW + d.Nz) * 256 + 128;
+      NF_CUDA(ctx, cudaFuncSetAttribute(wgrad_tc_kernel<BF16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb));
+      wgrad_tc_kernel<BF16, 1><<<grid, WG_THREADS, smb, st>>>(q);
+      NF_LAUNCH_CHECK(ctx);
+      const int count = (k1 + k2) * n;
+      reduce_partials_kernel<<<(count + RP_OUT - 1) / RP_OUT, RP_OUT * RP_SLICES, 0, st>>>(wpart, grid, count, count, dw[l]);
+      NF_LAUNCH_CHECK(ctx);
+    }
+    // data gradient: dz W^T -> 16-bit rows for the layer below (fp32 for the network input)
+    if (l > 0 || dx) {
+      wimg_kernel<BF16><<<64, 256, 0, st>>>(c->w[l], n, k1, d.k1p, k2, d.Kp, d.Nz, 1, img);
+      NF_LAUNCH_CHECK(ctx);
+      RowGemmParams p;
+      memset(&p, 0, sizeof(p));
+      p.a16 = dz16; p.lda16 = d.Nz; p.wimg = img;
+      p.Kp = d.Nz; p.Np = d.Kp; p.act = NF_ACT_NONE;
+      p.rows = rows; p.tiles = tiles;
+      const size_t smb = rg_smem(d.Kp, d.Nz, d.Nz, &p.stages);
+      if (l == 0) {
+        p.out1 = dx; p.n1 = k1; p.ldo1 = k1;
+        NF_CUDA(ctx, cudaFuncSetAttribute(rowgemm_tc_kernel<BF16, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb));
+        rowgemm_tc_kernel<BF16, 1, 0><<<grid, RG_THREADS, smb, st>>>(p);
+      } else {
+        p.out16 = reinterpret_cast<uint16_t*>(ws + P.off_dh[cur ^ 1]); p.ldo16 = P.nz[l - 1]; p.n1 = k1;
+        if (sk && dx) { p.out2 = dxs; p.n2 = k2; p.ldo2 = k2; p.col2 = d.k1p; }
+        NF_CUDA(ctx, cudaFuncSetAttribute(rowgemm_tc_kernel<BF16, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb));
+        rowgemm_tc_kernel<BF16, 1, 1><<<grid, RG_THREADS, smb, st>>>(p);
+      }
+      NF_LAUNCH_CHECK(ctx);
+      cur ^= 1;
+    }
+  }
+  if (dx && P.skip) {                                  // dx += the skip layer's input part
+    const long long total = rows * P.in_dim;
+    axpy_kernel<<<(unsigned)std::min<long long>((total + 255) / 256, 8192), 256, 0, st>>>(dxs, dx, total);
+    NF_LAUNCH_CHECK(ctx);
+  }
+  return NF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t nf_mlp_chain_workspace_bytes(const nf_mlp_chain* chain, long long rows) {
+  ChainPlan P;
+  if (rows <= 0 || !chain_plan(chain, rows, 160, P)) return 0;
+  return P.total;
+}
+
+int nf_mlp_chain_fwd(nf_ctx* ctx, const nf_mlp_chain* chain, const float* x_d, long long rows,
+                     float* y_d, void* workspace_d, int precision, void* stream) {
+  NF_CHECK_ARG(ctx, chain && rows >= 0, "bad argument");
+  NF_CHECK_ARG(ctx, precision == NF_PREC_F16 || precision == NF_PREC_BF16,
+               "nf_mlp_chain_fwd: tensor-core precisions only (NF_PREC_F16 / NF_PREC_BF16)");
+  if (rows == 0) return NF_OK;
+  ChainPlan P;
+  if (!chain_plan(chain, rows, 160, P))
+    return nf_set_error(ctx, NF_ERR_UNSUPPORTED,
+                        "nf_mlp_chain: hidden widths must be multiples of 16 and <= 256, layer inputs "
+                        "<= 256 columns, 2 <= depth <= 8");
+  NF_CHECK_ARG(ctx, x_d && y_d && workspace_d, "null buffer");
+  for (int l = 0; l < chain->depth; ++l) NF_CHECK_ARG(ctx, chain->w[l] && chain->b[l], "null weights");
+  NF_CHECK_ARG(ctx, ctx->sm_count <= 160, "unexpected SM count");
+  return precision == NF_PREC_BF16
+             ? chain_fwd_t<1>(ctx, chain, P, x_d, rows, y_d, (uint8_t*)workspace_d, (cudaStream_t)stream)
+             : chain_fwd_t<0>(ctx, chain, P, x_d, rows, y_d, (uint8_t*)workspace_d, (cudaStream_t)stream);
+}
+
+int nf_mlp_chain_bwd(nf_ctx* ctx, const nf_mlp_chain* chain, long long rows, const float* y_d,
+                     const float* dy_d, float* dx_d, float* const* dw_d, float* const* db_d,
+                     void* workspace_d, int precision, void* stream) {
+  NF_CHECK_ARG(ctx, chain && rows >= 0, "bad argument");
+  NF_CHECK_ARG(ctx, precision == NF_PREC_F16 || precision == NF_PREC_BF16,
+               "nf_mlp_chain_bwd: tensor-core precisions only (NF_PREC_F16 / NF_PREC_BF16)");
+  if (rows == 0) return NF_OK;
+  ChainPlan P;
+  if (!chain_plan(chain, rows, 160, P))
+    return nf_set_error(ctx, NF_ERR_UNSUPPORTED, "nf_mlp_chain: unsupported network shape");
+  NF_CHECK_ARG(ctx, y_d && dy_d && workspace_d, "null buffer");
+  NF_CHECK_ARG(ctx, ctx->sm_count <= 160, "unexpected SM count");
+  return precision == NF_PREC_BF16
+             ? chain_bwd_t<1>(ctx, chain, P, rows, y_d, dy_d, dx_d, dw_d, db_d, (uint8_t*)workspace_d,
+                              (cudaStream_t)stream)
+             : chain_bwd_t<0>(ctx, chain, P, rows, y_d, dy_d, dx_d, dw_d, db_d, (uint8_t*)workspace_d,
+                              (cudaStream_t)stream);
+}
+
+}  // extern "C"

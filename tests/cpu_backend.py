@@ -195,6 +195,46 @@ def dense_bwd(ctx, x1, x2, w, y, dy, act, need_dx1, need_dx2, precision='fp32'):
             x.t() @ dz, dz.sum(0))
 
 
+def _act_fwd(z, act):
+    if act == 'relu':
+        return torch.relu(z)
+    if act == 'sigmoid':
+        return torch.sigmoid(z)
+    if act == 'softplus':
+        return torch.nn.functional.softplus(z)
+    return z
+
+
+def mlp_chain_fwd(ctx, x, ws, bs, acts, skip_layer, precision='bf16'):
+    """CPU double of nf_mlp_chain_fwd: the `workspace` is the list of layer inputs / outputs."""
+    ctx.launches += 1
+    h, saved = x, []
+    for l, (w, b, a) in enumerate(zip(ws, bs, acts)):
+        xin = torch.cat((h, x), 1) if (skip_layer and l == skip_layer) else h
+        h = _act_fwd(xin @ w + b, a)
+        saved.append((xin, h))
+    return h, saved
+
+
+def mlp_chain_bwd(ctx, ws, bs, acts, skip_layer, in_dim, y, dy, work, need_dx, precision='bf16'):
+    ctx.launches += 1
+    dws, dbs = [None] * len(ws), [None] * len(ws)
+    dh, dx_skip = dy, None
+    for l in range(len(ws) - 1, -1, -1):
+        xin, out = work[l]
+        a = acts[l]
+        dz = dh * ((out > 0).to(dh.dtype) if a == 'relu' else out * (1 - out) if a == 'sigmoid'
+                   else (1 - torch.exp(-out)) if a == 'softplus' else 1.)
+        dws[l], dbs[l] = xin.t() @ dz, dz.sum(0)
+        dxin = dz @ ws[l].t()
+        if skip_layer and l == skip_layer:
+            dh, dx_skip = dxin[:, :xin.shape[1] - in_dim], dxin[:, xin.shape[1] - in_dim:]
+        else:
+            dh = dxin
+    dx = (dh + dx_skip if dx_skip is not None else dh).contiguous() if need_dx else None
+    return dx, dws, dbs
+
+
 def adam_amsgrad_step(ctx, param, grad, m, v, vhat, lr, step, beta1=0.9, beta2=0.999, eps=1e-7):
     """Keras Adam(amsgrad=True), trainvali.py:110-127."""
     ctx.launches += 1
@@ -271,7 +311,7 @@ _PATCHED = ('default_context', 'microfacet_brdf_fwd', 'stageB_fused_fwd', 'lvis_
             'raymarch_lvis_fwd', 'point_mlp_fwd', 'lvis_fwd', 'brdf_learned_fwd', 'integrate_fwd',
             'integrate_olat_fwd', 'gen_rays', 'gen_z', 'sigma_fwd', 'sigma_normal_fwd',
             'nerf_fwd', 'composite', 'gen_z_fine', 'lvis_rays', 'dense_fwd', 'dense_bwd',
-            'adam_amsgrad_step')
+            'mlp_chain_fwd', 'mlp_chain_bwd', 'adam_amsgrad_step')
 
 
 def install(monkeypatch):

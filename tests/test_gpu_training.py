@@ -308,3 +308,42 @@ def test_checkpoint_save_resume_and_restore_model(ctx, tmp_path):
     p1, _, _, _ = m1.call(batch, 'test')
     p2, _, _, _ = m2.call(batch, 'test')
     assert torch.equal(p1['rgb'], p2['rgb'])
+
+
+@pytest.mark.parametrize('case', [(3000, 90, (128, 128, 128, 128, 1), (2,), 'bf16', True),
+                                  (1029, 18, (128, 128, 128, 128, 1), (2,), 'bf16', True),
+                                  (700, 63, (128, 128, 3), None, 'f16', False),
+                                  (260, 24, (64, 256, 128, 4), (0,), 'bf16', True)])
+def test_mlp_chain_matches_layer_by_layer(ctx, case, monkeypatch):
+    """nf_mlp_chain_fwd / _bwd (one call per network, 16-bit activations in a private workspace)
+    against the layer-by-layer nf_dense_fwd / nf_dense_bwd path (fp32 activations in HBM) it
+    replaces: the operand images round the activations to 16 bit in both, so the forward values
+    agree to the last fp32 bit or two and the gradients to ~1e-3 (bias-gradient sums are taken over
+    16-bit instead of fp32 products); ragged row counts, input widths that need padding, a skip
+    connection, input gradient on and off."""
+    from nerfactor_b200 import autodiff as ad
+    rows, in_dim, widths, skip_at, prec, need_dx = case
+    g = torch.Generator(device='cpu').manual_seed(rows)
+    x = torch.randn((rows, in_dim), generator=g).cuda().requires_grad_(need_dx)
+    layers, k = [], in_dim
+    for i, n in enumerate(widths):
+        kin = k + (in_dim if (skip_at and i - 1 in skip_at) else 0)
+        w = (torch.randn((kin, n), generator=g) * (1.5 / np.sqrt(kin))).cuda().requires_grad_(True)
+        b = (torch.randn((n,), generator=g) * 0.1).cuda().requires_grad_(True)
+        layers.append((w, b))
+        k = n
+    acts = ['relu'] * (len(widths) - 1) + ['sigmoid']
+    dy = torch.randn((rows, widths[-1]), generator=g).cuda()
+    outs = {}
+    for chain in (True, False):
+        monkeypatch.setattr(ad, 'CHAIN', chain)
+        y = ad.mlp_apply(x, layers, acts, skip_at, prec)
+        ins = [t for wb in layers for t in wb] + ([x] if need_dx else [])
+        outs[chain] = (y.detach().clone(), [t.clone() for t in torch.autograd.grad(y, ins, dy)])
+    ya, ga = outs[True]
+    yb, gb = outs[False]
+    assert ya.shape == yb.shape == (rows, widths[-1])
+    assert float((ya - yb).abs().max()) <= 2e-6
+    worst = max(rel_l2(a.cpu(), b.cpu()) for a, b in zip(ga, gb))
+    print('mlp chain vs layer-by-layer: worst gradient rel-L2 %.2e' % worst)
+    assert worst < 3e-3
