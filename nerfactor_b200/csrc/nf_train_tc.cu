@@ -20,6 +20,7 @@
 #include "nf_common.cuh"
 #include "nf_tc_ptx.cuh"
 #include <algorithm>
+#include <type_traits>
 #include <cstdlib>
 
 namespace {
@@ -309,6 +310,60 @@ __global__ void __launch_bounds__(RG_THREADS, 1) rowgemm_tc_kernel(const RowGemm
     rs.k1 = p.k1; rs.k1p = p.k1p; rs.k2 = p.k2;
     rs.v1 = !A16 && (p.ld1 % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.x1) & 31) == 0);
     rs.v2 = !A16 && p.x2 && (p.ld2 % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.x2) & 31) == 0);
+    // 16-bit rows: a warp instruction covers 8 rows x 4 sixteen-byte chunks (64 contiguous bytes per
+    // row from global memory, 128 contiguous bytes per quarter warp into the image).  With <= 16
+    // chunks per row the loads of tile it + 1 are issued BEFORE the image of tile it is written: the
+    // global-memory latency of one tile hides behind the previous one (it was paid once per tile).
+    const int lw = lt >> 5, r8 = lane & 7, kq = lane >> 3;
+    auto load16 = [&](long long it, int kg0, uint4 (&v)[2][4]) {
+      const long long tile_row0 = (it * gridDim.x + blockIdx.x) * 128;
+#pragma unroll
+      for (int rsub = 0; rsub < 2; ++rsub) {
+        const long long grow = tile_row0 + lw * 16 + rsub * 8 + r8;
+        const uint16_t* src = p.a16 + grow * p.lda16;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int kg = kg0 + 4 * j + kq;
+          v[rsub][j] = make_uint4(0u, 0u, 0u, 0u);
+          if (grow < p.rows && kg < KG) v[rsub][j] = __ldg(reinterpret_cast<const uint4*>(src + kg * 8));
+        }
+      }
+    };
+    auto store16 = [&](uint8_t* imgb, int kg0, const uint4 (&v)[2][4]) {
+#pragma unroll
+      for (int rsub = 0; rsub < 2; ++rsub) {
+        const int tr = lw * 16 + rsub * 8 + r8;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int kg = kg0 + 4 * j + kq;
+          if (kg < KG) *reinterpret_cast<uint4*>(imgb + (size_t)kg * 2048 + (size_t)tr * 16) = v[rsub][j];
+        }
+      }
+    };
+    if (A16 && KG <= 16) {
+      uint4 va[2][4], vb[2][4];
+      if (ntile > 0) load16(0, 0, va);
+      for (long long it = 0; it < ntile; it += 2) {
+        // even tile from va (prefetch odd into vb), odd tile from vb (prefetch next even into va)
+        if (it + 1 < ntile) load16(it + 1, 0, vb);
+        {
+          const int buf = (int)(it % S);
+          if (it >= S) mbar_wait(a_empty + buf, (uint32_t)((it / S) - 1) & 1);
+          store16(s_a + (size_t)buf * abytes, 0, va);
+          fence_proxy_async();
+          mbar_arrive(a_full + buf);
+        }
+        if (it + 1 < ntile) {
+          if (it + 2 < ntile) load16(it + 2, 0, va);
+          const long long i1 = it + 1;
+          const int buf = (int)(i1 % S);
+          if (i1 >= S) mbar_wait(a_empty + buf, (uint32_t)((i1 / S) - 1) & 1);
+          store16(s_a + (size_t)buf * abytes, 0, vb);
+          fence_proxy_async();
+          mbar_arrive(a_full + buf);
+        }
+      }
+    } else
     for (long long it = 0; it < ntile; ++it) {
       const int buf = (int)(it % S);
       const long long row = (it * gridDim.x + blockIdx.x) * 128 + t;
@@ -316,34 +371,11 @@ __global__ void __launch_bounds__(RG_THREADS, 1) rowgemm_tc_kernel(const RowGemm
       if (it >= S) mbar_wait(a_empty + buf, (uint32_t)((it / S) - 1) & 1);
       uint8_t* img = s_a + (size_t)buf * abytes + (size_t)t * 16;
       if (A16) {
-        // a warp instruction covers 8 rows x 4 sixteen-byte chunks: 64 contiguous bytes per row
-        // from global memory (full sectors), 128 contiguous bytes per quarter warp into the image
-        const int lw = lt >> 5, r8 = lane & 7, kq = lane >> 3;
         uint8_t* imgb = s_a + (size_t)buf * abytes;
-        const long long tile_row0 = (it * gridDim.x + blockIdx.x) * 128;
         for (int kg0 = 0; kg0 < KG; kg0 += 16) {
           uint4 v[2][4];
-#pragma unroll
-          for (int rsub = 0; rsub < 2; ++rsub) {
-            const int tr = lw * 16 + rsub * 8 + r8;
-            const long long grow = tile_row0 + tr;
-            const uint16_t* src = p.a16 + grow * p.lda16;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int kg = kg0 + 4 * j + kq;
-              v[rsub][j] = make_uint4(0u, 0u, 0u, 0u);
-              if (grow < p.rows && kg < KG) v[rsub][j] = __ldg(reinterpret_cast<const uint4*>(src + kg * 8));
-            }
-          }
-#pragma unroll
-          for (int rsub = 0; rsub < 2; ++rsub) {
-            const int tr = lw * 16 + rsub * 8 + r8;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int kg = kg0 + 4 * j + kq;
-              if (kg < KG) *reinterpret_cast<uint4*>(imgb + (size_t)kg * 2048 + (size_t)tr * 16) = v[rsub][j];
-            }
-          }
+          load16(it, kg0, v);
+          store16(imgb, kg0, v);
         }
       } else {
         rs.s1 = p.x1 + row * p.ld1;
@@ -373,51 +405,68 @@ __global__ void __launch_bounds__(RG_THREADS, 1) rowgemm_tc_kernel(const RowGemm
     const uint32_t tb = tmem_base + ((uint32_t)(wq * 32) << 16);
     const bool w1 = p.out1 && (p.ldo1 % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.out1) & 31) == 0);
     const bool w2 = p.out2 && (p.ldo2 % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.out2) & 31) == 0);
-    for (long long it = 0; it < ntile; ++it) {
-      const int buf = (int)(it & 1);
-      const long long row = (it * gridDim.x + blockIdx.x) * 128 + t;
-      const bool valid = row < p.rows;
-      mbar_wait(d_full + buf, (uint32_t)(it >> 1) & 1);
-      tc_fence_after();
-      for (int c0 = ch * 16; c0 < Np; c0 += 32) {
-        uint32_t r[16];
-        TC_LD16(r, tb + buf * 256 + c0);
-        tc_wait_ld();
-        if (valid) {
+    // The activation is a run-time argument but fixed for the launch: the tile loop is instantiated
+    // once per kind (with `apply_act(p.act, ..)` per element the compiler inlined the sigmoid and
+    // softplus code 64 times per tile row behind uniform branches -- 1 300 SASS instructions of
+    // epilogue, which bounded the kernel at ~9 k clocks per 128-row tile; profiles/r2_rowgemm.md).
+    auto run = [&](auto act_c) {
+      constexpr int ACT = decltype(act_c)::value;
+      for (long long it = 0; it < ntile; ++it) {
+        const int buf = (int)(it & 1);
+        const long long row = (it * gridDim.x + blockIdx.x) * 128 + t;
+        const bool valid = row < p.rows;
+        mbar_wait(d_full + buf, (uint32_t)(it >> 1) & 1);
+        tc_fence_after();
+        for (int c0 = ch * 16; c0 < Np; c0 += 32) {
+          uint32_t r[16];
+          TC_LD16(r, tb + buf * 256 + c0);
+          float4 bb[4];
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const int c = c0 + 8 * j;
-            float4 o[2];
+          for (int q = 0; q < 4; ++q) bb[q] = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * q);
+          tc_wait_ld();
+          if (valid) {
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              o[q].x = apply_act(p.act, __uint_as_float(r[8 * j + 4 * q + 0]) + s_bias[c + 4 * q + 0]);
-              o[q].y = apply_act(p.act, __uint_as_float(r[8 * j + 4 * q + 1]) + s_bias[c + 4 * q + 1]);
-              o[q].z = apply_act(p.act, __uint_as_float(r[8 * j + 4 * q + 2]) + s_bias[c + 4 * q + 2]);
-              o[q].w = apply_act(p.act, __uint_as_float(r[8 * j + 4 * q + 3]) + s_bias[c + 4 * q + 3]);
-            }
-            if (O16 && c + 8 <= p.n1) {
-              *reinterpret_cast<uint4*>(p.out16 + row * p.ldo16 + c) = pack8<BF16>(o[0], o[1]);
-            } else if (c + 8 <= p.n1) {
-              if (w1) stg256(p.out1 + row * p.ldo1 + c, o[0], o[1]);
-              else if (p.out1) {
-                *reinterpret_cast<float4*>(p.out1 + row * p.ldo1 + c) = o[0];
-                *reinterpret_cast<float4*>(p.out1 + row * p.ldo1 + c + 4) = o[1];
+            for (int j = 0; j < 2; ++j) {
+              const int c = c0 + 8 * j;
+              float4 o[2];
+#pragma unroll
+              for (int q = 0; q < 2; ++q) {
+                const float4 bq = bb[2 * j + q];
+                o[q].x = apply_act(ACT, __uint_as_float(r[8 * j + 4 * q + 0]) + bq.x);
+                o[q].y = apply_act(ACT, __uint_as_float(r[8 * j + 4 * q + 1]) + bq.y);
+                o[q].z = apply_act(ACT, __uint_as_float(r[8 * j + 4 * q + 2]) + bq.z);
+                o[q].w = apply_act(ACT, __uint_as_float(r[8 * j + 4 * q + 3]) + bq.w);
               }
-            } else if (c + 4 <= p.n1) {
-              if (p.out1) *reinterpret_cast<float4*>(p.out1 + row * p.ldo1 + c) = o[0];
-            } else if (p.out2 && c >= p.col2 && c < p.col2 + p.n2) {
-              const int d = c - p.col2;
-              if (d + 8 <= p.n2 && w2) stg256(p.out2 + row * p.ldo2 + d, o[0], o[1]);
-              else {
-                *reinterpret_cast<float4*>(p.out2 + row * p.ldo2 + d) = o[0];
-                if (d + 8 <= p.n2) *reinterpret_cast<float4*>(p.out2 + row * p.ldo2 + d + 4) = o[1];
+              if (O16 && c + 8 <= p.n1) {
+                *reinterpret_cast<uint4*>(p.out16 + row * p.ldo16 + c) = pack8<BF16>(o[0], o[1]);
+              } else if (c + 8 <= p.n1) {
+                if (w1) stg256(p.out1 + row * p.ldo1 + c, o[0], o[1]);
+                else if (p.out1) {
+                  *reinterpret_cast<float4*>(p.out1 + row * p.ldo1 + c) = o[0];
+                  *reinterpret_cast<float4*>(p.out1 + row * p.ldo1 + c + 4) = o[1];
+                }
+              } else if (c + 4 <= p.n1) {
+                if (p.out1) *reinterpret_cast<float4*>(p.out1 + row * p.ldo1 + c) = o[0];
+              } else if (p.out2 && c >= p.col2 && c < p.col2 + p.n2) {
+                const int d = c - p.col2;
+                if (d + 8 <= p.n2 && w2) stg256(p.out2 + row * p.ldo2 + d, o[0], o[1]);
+                else {
+                  *reinterpret_cast<float4*>(p.out2 + row * p.ldo2 + d) = o[0];
+                  if (d + 8 <= p.n2) *reinterpret_cast<float4*>(p.out2 + row * p.ldo2 + d + 4) = o[1];
+                }
               }
             }
           }
         }
+        tc_fence_before();
+        mbar_arrive(d_empty + buf);
       }
-      tc_fence_before();
-      mbar_arrive(d_empty + buf);
+    };
+    switch (p.act) {
+      case NF_ACT_RELU: run(std::integral_constant<int, NF_ACT_RELU>{}); break;
+      case NF_ACT_SIGMOID: run(std::integral_constant<int, NF_ACT_SIGMOID>{}); break;
+      case NF_ACT_SOFTPLUS: run(std::integral_constant<int, NF_ACT_SOFTPLUS>{}); break;
+      default: run(std::integral_constant<int, NF_ACT_NONE>{}); break;
     }
   }
   tc_fence_before();
@@ -513,53 +562,77 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgradPara
     rs.k1 = p.k1; rs.k1p = p.k1p; rs.k2 = p.k2;
     rs.v1 = (p.ld1 % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.x1) & 31) == 0);
     rs.v2 = p.x2 && (p.ld2 % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.x2) & 31) == 0);
+    // 16-bit operands (X16): plain copies, 8 rows x 4 sixteen-byte chunks per warp instruction (64
+    // contiguous bytes per row from global memory); with <= 16 chunks per row in both operands the
+    // loads of tile it + 1 are in flight while tile it is written to shared memory.
+    const int lw = lt >> 5, r8 = lane & 7, kq = lane >> 3;
+    auto wload = [&](long long it, const uint16_t* base, int ld, int G, int g0, uint4 (&v)[2][4]) {
+      const long long tile_row0 = (it * gridDim.x + blockIdx.x) * 128;
+#pragma unroll
+      for (int rsub = 0; rsub < 2; ++rsub) {
+        const long long grow = tile_row0 + lw * 16 + rsub * 8 + r8;
+        const uint16_t* src = base + grow * ld;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int kg = g0 + 4 * j + kq;
+          v[rsub][j] = make_uint4(0u, 0u, 0u, 0u);
+          if (grow < p.rows && kg < G) v[rsub][j] = __ldg(reinterpret_cast<const uint4*>(src + kg * 8));
+        }
+      }
+    };
+    auto wstore = [&](uint8_t* img, int G, int g0, const uint4 (&v)[2][4]) {
+#pragma unroll
+      for (int rsub = 0; rsub < 2; ++rsub) {
+        const int tr = lw * 16 + rsub * 8 + r8;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int kg = g0 + 4 * j + kq;
+          if (kg < G) *reinterpret_cast<uint4*>(img + (size_t)kg * 2048 + (size_t)tr * 16) = v[rsub][j];
+        }
+      }
+    };
+    if (X16 && KG <= 16 && ZG <= 16) {
+      uint4 xa[2][4], za[2][4], xb[2][4], zb2[2][4];
+      if (ntile > 0) { wload(0, p.x16, p.ldx16, KG, 0, xa); wload(0, p.dz16, Nz, ZG, 0, za); }
+      for (long long it = 0; it < ntile; it += 2) {
+        if (it + 1 < ntile) { wload(it + 1, p.x16, p.ldx16, KG, 0, xb); wload(it + 1, p.dz16, Nz, ZG, 0, zb2); }
+        {
+          const int buf = (int)(it & 1);
+          if (it >= 2) mbar_wait(empty + buf, (uint32_t)((it >> 1) - 1) & 1);
+          wstore(s_x + (size_t)buf * xbytes, KG, 0, xa);
+          wstore(s_z + (size_t)buf * zbytes, ZG, 0, za);
+          fence_proxy_async();
+          mbar_arrive(full + buf);
+        }
+        if (it + 1 < ntile) {
+          if (it + 2 < ntile) { wload(it + 2, p.x16, p.ldx16, KG, 0, xa); wload(it + 2, p.dz16, Nz, ZG, 0, za); }
+          const long long i1 = it + 1;
+          const int buf = (int)(i1 & 1);
+          if (i1 >= 2) mbar_wait(empty + buf, (uint32_t)((i1 >> 1) - 1) & 1);
+          wstore(s_x + (size_t)buf * xbytes, KG, 0, xb);
+          wstore(s_z + (size_t)buf * zbytes, ZG, 0, zb2);
+          fence_proxy_async();
+          mbar_arrive(full + buf);
+        }
+      }
+    } else
     for (long long it = 0; it < ntile; ++it) {
       const int buf = (int)(it & 1);
       const long long row = (it * gridDim.x + blockIdx.x) * 128 + t;
       const bool valid = row < p.rows;
       if (it >= 2) mbar_wait(empty + buf, (uint32_t)((it >> 1) - 1) & 1);
       if (X16) {
-        // both operands are 16-bit rows: plain copies, 8 rows x 4 sixteen-byte chunks per warp
-        // instruction (64 contiguous bytes per row from global memory)
-        const int lw = lt >> 5, r8 = lane & 7, kq = lane >> 3;
         uint8_t* xb = s_x + (size_t)buf * xbytes;
         uint8_t* zb = s_z + (size_t)buf * zbytes;
-        const long long tile_row0 = (it * gridDim.x + blockIdx.x) * 128;
-#pragma unroll
-        for (int rsub = 0; rsub < 2; ++rsub) {
-          const int tr = lw * 16 + rsub * 8 + r8;
-          const long long grow = tile_row0 + tr;
-          const bool ok = grow < p.rows;
-          const uint16_t* xs = p.x16 + grow * p.ldx16;
-          const uint16_t* zs2 = p.dz16 + grow * Nz;
-          for (int kg0 = 0; kg0 < KG; kg0 += 16) {
-            uint4 v[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int kg = kg0 + 4 * j + kq;
-              v[j] = make_uint4(0u, 0u, 0u, 0u);
-              if (ok && kg < KG) v[j] = __ldg(reinterpret_cast<const uint4*>(xs + kg * 8));
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int kg = kg0 + 4 * j + kq;
-              if (kg < KG) *reinterpret_cast<uint4*>(xb + (size_t)kg * 2048 + (size_t)tr * 16) = v[j];
-            }
-          }
-          for (int g0 = 0; g0 < ZG; g0 += 16) {
-            uint4 v[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int zg = g0 + 4 * j + kq;
-              v[j] = make_uint4(0u, 0u, 0u, 0u);
-              if (ok && zg < ZG) v[j] = __ldg(reinterpret_cast<const uint4*>(zs2 + zg * 8));
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int zg = g0 + 4 * j + kq;
-              if (zg < ZG) *reinterpret_cast<uint4*>(zb + (size_t)zg * 2048 + (size_t)tr * 16) = v[j];
-            }
-          }
+        for (int g0 = 0; g0 < KG; g0 += 16) {
+          uint4 v[2][4];
+          wload(it, p.x16, p.ldx16, KG, g0, v);
+          wstore(xb, KG, g0, v);
+        }
+        for (int g0 = 0; g0 < ZG; g0 += 16) {
+          uint4 v[2][4];
+          wload(it, p.dz16, Nz, ZG, g0, v);
+          wstore(zb, ZG, g0, v);
         }
         fence_proxy_async();
         mbar_arrive(full + buf);
