@@ -976,33 +976,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc2_kernel(const TcParams p
 //   * the embedding of the next tile is written under layer 3 of the current one, also across a
 //     point boundary; the issuer serves hand-overs and needs no per-tile information.
 // Light positions are read from global memory (L1-resident 12 KB) instead of a shared table.
+template <int KIND>
 struct SmemLayout3 {
-  static constexpr int KE = KindCfg<NF_MLP_LVIS>::KE;
-  static constexpr int NR_PAD = KindCfg<NF_MLP_LVIS>::NR_PAD;
+  static constexpr int KE = KindCfg<KIND>::KE;
+  static constexpr int NR_PAD = KindCfg<KIND>::NR_PAD;
   static constexpr int LMAX = 1024;
   static constexpr int NBUF = 4;                                 // point records in flight per group
-  static constexpr size_t img_bytes = ((size_t)img_halves<NF_MLP_LVIS>() + 2 * 16 * 128) * 2;
+  static constexpr int REC_F = KIND == NF_MLP_BRDF ? 16 : 4;     // floats per point record
+  static constexpr size_t img_bytes = ((size_t)img_halves<KIND>() + 2 * 16 * 128) * 2;
   static constexpr size_t aux_floats = AUX_WX0 + 2 * (size_t)NR_PAD * 128;
   static constexpr size_t off_img = 0;
   static constexpr size_t off_bdyn = img_bytes;                  // [2 g][2 layer] x 2048 B
   static constexpr size_t off_zero = off_bdyn + 4 * 2048;        // 2048 B of zeros (k = 8..15)
   static constexpr size_t off_aux = off_zero + 2048;
-  static constexpr size_t off_rec = off_aux + aux_floats * 4;    // [2 g][NBUF] x 16 B: xd[3], n_rows
-  static constexpr size_t off_list = off_rec + 2 * NBUF * 16;    // [2 g][NBUF][LMAX] u16
+  static constexpr size_t off_rec = off_aux + aux_floats * 4;    // [2 g][NBUF] records (REC_F floats)
+  static constexpr size_t off_list = off_rec + 2 * NBUF * REC_F * 4;   // [2 g][NBUF][LMAX] u16
   static constexpr size_t off_es = off_list + 2 * NBUF * (size_t)LMAX * 2;   // [2 prefetchers][64] f32
   static constexpr size_t off_bar = off_es + 2 * 64 * 4;         // 5 + 16 barriers + tmem pointer
   static constexpr size_t off_flag = off_bar + 192;              // int: done[2]
   static constexpr size_t total = off_flag + 16;
 };
-static_assert(SmemLayout3::total <= 232448, "shared memory budget");
+static_assert(SmemLayout3<NF_MLP_LVIS>::total <= 232448 && SmemLayout3<NF_MLP_BRDF>::total <= 232448,
+              "shared memory budget");
 constexpr int COL_ONE1 = 232;      // second "ones" operand (tiles alternate, like COL_AE / COL_AE1)
 
-template <int BF16, int CULL>
-__global__ void __launch_bounds__(TC_THREADS, 1) lvis_tc3_kernel(const TcParams p) {
-  using SL = SmemLayout3;
+// KIND = NF_MLP_BRDF (always CULL): the per-point record carries the shading frame and the local view
+// direction, the fold runs over the latent code z, the per-row embedding is the Rusinkiewicz triple
+// (nerfactor.py:413-457) -- everything else is the same machinery.
+template <int KIND, int BF16, int CULL>
+__device__ __forceinline__ void tc3_body(const TcParams& p) {
+  static_assert(KIND != NF_MLP_BRDF || CULL == 1, "the BRDF network always runs on the front-lit lights");
+  using SL = SmemLayout3<KIND>;
   constexpr int KE = SL::KE;
   constexpr int NR_PAD = SL::NR_PAD;
   constexpr int NBUF = SL::NBUF;
+  constexpr int REC_F = SL::REC_F;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* s_img = smem + SL::off_img;
   uint8_t* s_bdyn = smem + SL::off_bdyn;
@@ -1128,15 +1136,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lvis_tc3_kernel(const TcParams 
       const int b = i & (NBUF - 1);
       if (i >= NBUF) mbar_wait(rec_free + g * NBUF + b, (uint32_t)((i / NBUF) - 1) & 1u);
       const f3 x = ld3(p.xyz + (size_t)pt * 3);
-      // positional encoding of xyz (embedder.py:46-47), fp32
-      if (lane < 3) es[lane] = (lane == 0 ? x.x : (lane == 1 ? x.y : x.z)) * p.xyz_scale;
-      for (int idx = lane; idx < 3 * p.n_freqs_a; idx += 32) {
-        const int fq = idx / 3, c = idx % 3;
-        const float xv = (c == 0 ? x.x : (c == 1 ? x.y : x.z)) * p.xyz_scale;
-        float sn, cs;
-        sincosf(xv * (float)(1 << fq), &sn, &cs);
-        es[3 + 6 * fq + c] = sn;
-        es[3 + 6 * fq + 3 + c] = cs;
+      f3 fr_t = mk3(1.f, 0.f, 0.f), fr_b = mk3(0.f, 1.f, 0.f), fr_n = mk3(0.f, 0.f, 1.f), v_loc = fr_n;
+      if (KIND == NF_MLP_LVIS) {
+        // positional encoding of xyz (embedder.py:46-47), fp32
+        if (lane < 3) es[lane] = (lane == 0 ? x.x : (lane == 1 ? x.y : x.z)) * p.xyz_scale;
+        for (int idx = lane; idx < 3 * p.n_freqs_a; idx += 32) {
+          const int fq = idx / 3, c = idx % 3;
+          const float xv = (c == 0 ? x.x : (c == 1 ? x.y : x.z)) * p.xyz_scale;
+          float sn, cs;
+          sincosf(xv * (float)(1 << fq), &sn, &cs);
+          es[3 + 6 * fq + c] = sn;
+          es[3 + 6 * fq + 3 + c] = cs;
+        }
+      } else {
+        // latent code z of the point; shading frame and local view direction
+        if (lane < p.z_dim) es[lane] = p.zlat[(size_t)pt * p.z_dim + lane];
+        world2local_dev(ld3(p.normal + (size_t)pt * 3), fr_t, fr_b, fr_n);   // geom.py:119-149
+        const f3 v = l2n(ld3(p.cam + (size_t)pt * 3) - x, 1e-6f);             // shape.py:137-144
+        v_loc = mk3(dot3(fr_t, v), dot3(fr_b, v), dot3(fr_n, v));             // nerfactor.py:418
       }
       __syncwarp();
       // fold the per-point input columns into the biases of layer 0 and of the skip layer (fp32):
@@ -1172,7 +1189,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lvis_tc3_kernel(const TcParams 
         // front-lit lights in increasing order; the others' output is zero (nerfactor.py:329-330).
         // cos(shading normal, light) > -1e-5: a superset of the renderer's cos > 0 whatever the
         // rounding of its own cosine
-        const f3 cn = l2n(l2n(ld3(p.cull_normal + (size_t)pt * 3), 1e-6f), 1e-6f);
+        // (BRDF network: l_loc.z > 0 exactly, nerfactor.py:429-432, unlit outputs zero :456-458)
+        const f3 cn = KIND == NF_MLP_BRDF ? fr_n
+                                          : l2n(l2n(ld3(p.cull_normal + (size_t)pt * 3), 1e-6f), 1e-6f);
         uint16_t* list = s_list + (size_t)(g * NBUF + b) * SL::LMAX;
         int cnt = 0;
         for (int base = 0; base < p.L; base += 32) {
@@ -1180,7 +1199,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lvis_tc3_kernel(const TcParams 
           bool lit = false;
           if (l < p.L) {
             const f3 d = l2n(ld3(p.lxyz + (size_t)l * 3) - x, 1e-6f);
-            lit = dot3(cn, d) > -1e-5f;
+            lit = KIND == NF_MLP_BRDF ? dot3(cn, d) > 0.f : dot3(cn, d) > -1e-5f;
             if (!lit) p.out[(size_t)pt * p.L + l] = 0.f;
           }
           const unsigned m = __ballot_sync(0xffffffffu, lit);
@@ -1190,9 +1209,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lvis_tc3_kernel(const TcParams 
         n_rows = cnt;
       }
       if (lane == 0) {
-        const f3 xd = p.xyz_dir ? ld3(p.xyz_dir + (size_t)pt * 3) : x;
-        float* rec = s_rec + (size_t)(g * NBUF + b) * 4;
+        const f3 xd = (KIND == NF_MLP_LVIS && p.xyz_dir) ? ld3(p.xyz_dir + (size_t)pt * 3) : x;
+        float* rec = s_rec + (size_t)(g * NBUF + b) * REC_F;
         rec[0] = xd.x; rec[1] = xd.y; rec[2] = xd.z; rec[3] = __int_as_float(n_rows);
+        if (KIND == NF_MLP_BRDF) {
+          rec[4] = fr_t.x; rec[5] = fr_t.y; rec[6] = fr_t.z;
+          rec[7] = fr_b.x; rec[8] = fr_b.y; rec[9] = fr_b.z;
+          rec[10] = fr_n.x; rec[11] = fr_n.y; rec[12] = fr_n.z;
+          rec[13] = v_loc.x; rec[14] = v_loc.y; rec[15] = v_loc.z;
+        }
       }
       fence_proxy_async();           // the bias blocks are read by the tensor core (async proxy)
       __syncwarp();
@@ -1207,7 +1232,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lvis_tc3_kernel(const TcParams 
     const uint32_t tb = tmem_base + g * GRP_COLS + lane_addr;
     const int G = blockIdx.x * 2 + g;
     uint32_t phd = 0u;
-    struct PointState { int pt, b, n_rows; f3 xd; };
+    struct PointState { int pt, b, n_rows; f3 xd, fr_t, fr_b, fr_n, v_loc; };
     // a tile: rows [a_start, a_start + a_cnt) of point a, then the first b_cnt rows of the next point
     struct Tile { PointState a, b; int a_start, a_cnt, b_cnt; bool a_last, b_last; };
     struct RowInfo { int pt, li; bool ok; };
@@ -1218,9 +1243,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lvis_tc3_kernel(const TcParams 
       if (s.pt >= p.n) return false;
       s.b = i & (NBUF - 1);
       mbar_wait(rec_full + g * NBUF + s.b, (uint32_t)(i / NBUF) & 1u);
-      const float* rec = s_rec + (size_t)(g * NBUF + s.b) * 4;
+      const float* rec = s_rec + (size_t)(g * NBUF + s.b) * REC_F;
       s.xd = mk3(rec[0], rec[1], rec[2]);
       s.n_rows = __float_as_int(rec[3]);
+      if (KIND == NF_MLP_BRDF) {
+        s.fr_t = mk3(rec[4], rec[5], rec[6]);
+        s.fr_b = mk3(rec[7], rec[8], rec[9]);
+        s.fr_n = mk3(rec[10], rec[11], rec[12]);
+        s.v_loc = mk3(rec[13], rec[14], rec[15]);
+      }
       return true;
     };
     // head of the row stream: point number hp, of which hoff rows are consumed (hs valid if hvalid)
@@ -1278,14 +1309,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lvis_tc3_kernel(const TcParams 
       r.pt = s.pt;
       r.li = CULL ? (int)s_list[(size_t)(g * NBUF + s.b) * SL::LMAX + row] : row;
       const f3 d = l2n(ld3(p.lxyz + (size_t)r.li * 3) - s.xd, 1e-6f);            // shape.py:128-135
+      f3 q = d;
+      if (KIND == NF_MLP_BRDF) {
+        const f3 l_loc = mk3(dot3(s.fr_t, d), dot3(s.fr_b, d), dot3(s.fr_n, d));  // nerfactor.py:419
+        q = dir2rusink_dev(l_loc, s.v_loc);                                       // geom.py:152-192
+      }
       float v[KE];
 #pragma unroll
       for (int i = 0; i < KE; ++i) v[i] = 0.f;
-      v[0] = d.x; v[1] = d.y; v[2] = d.z;
+      v[0] = q.x; v[1] = q.y; v[2] = q.z;
       float sx, cx, sy, cy, sz, cz;
-      sincosf(d.x, &sx, &cx); sincosf(d.y, &sy, &cy); sincosf(d.z, &sz, &cz);
+      sincosf(q.x, &sx, &cx); sincosf(q.y, &sy, &cy); sincosf(q.z, &sz, &cz);
 #pragma unroll
-      for (int fq = 0; fq < 4; ++fq) {
+      for (int fq = 0; fq < (KIND == NF_MLP_LVIS ? 4 : 2); ++fq) {
         v[3 + 6 * fq + 0] = sx; v[3 + 6 * fq + 1] = sy; v[3 + 6 * fq + 2] = sz;
         v[3 + 6 * fq + 3] = cx; v[3 + 6 * fq + 4] = cy; v[3 + 6 * fq + 5] = cz;
         const float nsx = 2.f * sx * cx, ncx = 1.f - 2.f * sx * sx;
@@ -1296,7 +1332,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lvis_tc3_kernel(const TcParams 
       uint32_t pk[KE / 2];
 #pragma unroll
       for (int i = 0; i < KE / 2; ++i) pk[i] = pack2<BF16, 0>(v[2 * i], v[2 * i + 1]);
-      TC_ST16(tb + (par ? COL_AE1 : COL_AE), pk);
+      if (KE == 32) { TC_ST16(tb + (par ? COL_AE1 : COL_AE), pk); }
+      else { TC_ST8(tb + (par ? COL_AE1 : COL_AE), pk); }
       // (1, 1) at k = 2 b, 2 b + 1: this row takes the bias pair of ITS point
       uint32_t one[8];
       const uint32_t pair = pack2<BF16, 0>(1.f, 1.f);
@@ -1429,6 +1466,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) lvis_tc3_kernel(const TcParams 
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS)
                  : "memory");
   }
+}
+
+template <int BF16, int CULL>
+__global__ void __launch_bounds__(TC_THREADS, 1) lvis_tc3_kernel(const TcParams p) {
+  tc3_body<NF_MLP_LVIS, BF16, CULL>(p);
+}
+template <int BF16>
+__global__ void __launch_bounds__(TC_THREADS, 1) brdf_tc3_kernel(const TcParams p) {
+  tc3_body<NF_MLP_BRDF, BF16, 1>(p);
 }
 
 // ------------------------------------------------------------------ bring-up test
@@ -1586,8 +1632,20 @@ int launch_tc(nf_ctx* ctx, const nf_mlp* m, const TcParams& p, cudaStream_t st) 
   } else {
     // NF_LVIS_V2=1: the version-2 kernel for the visibility network too (A / B timing)
     static const bool v2 = [] { const char* e = getenv("NF_LVIS_V2"); return e && e[0] == '1'; }();
+    // the learned-BRDF network runs on the version-3 machinery too (27.0 -> 20.6 ms at 640 k x 512,
+    // bit-identical); NF_BRDF_V3=0 selects the version-2 kernel (group-issued MMAs) for A / B timing
+    static const bool b3 = [] { const char* e = getenv("NF_BRDF_V3"); return !(e && e[0] == '0'); }();
+    if (KIND == NF_MLP_BRDF && b3) {
+      using S3 = SmemLayout3<NF_MLP_BRDF>;
+      NF_CHECK_ARG(ctx, S3::total <= ctx->smem_optin, "shared memory budget exceeded");
+      NF_CUDA(ctx, cudaFuncSetAttribute(brdf_tc3_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)S3::total));
+      brdf_tc3_kernel<BF16><<<grid, TC_THREADS, S3::total, st>>>(p);
+      NF_LAUNCH_CHECK(ctx);
+      return NF_OK;
+    }
     if (KIND == NF_MLP_LVIS && p.f_rgb == nullptr && !v2) {
-      using S3 = SmemLayout3;
+      using S3 = SmemLayout3<NF_MLP_LVIS>;
       NF_CHECK_ARG(ctx, S3::total <= ctx->smem_optin, "shared memory budget exceeded");
       if (p.cull_normal) {
         NF_CUDA(ctx, cudaFuncSetAttribute(lvis_tc3_kernel<BF16, 1>,

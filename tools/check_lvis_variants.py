@@ -64,6 +64,12 @@ def main():
     d = tempfile.mkdtemp()
     res = {'v3': run('0', os.path.join(d, 'c')),
            'v2': run('0', os.path.join(d, 'a'), NF_LVIS_V2='1'), 'v1': run('1', os.path.join(d, 'b'))}
+    res['brdf_v2'] = run('0', os.path.join(d, 'e'), NF_BRDF_V3='0')
+    if 'error' not in res['brdf_v2'] and 'error' not in res['v3']:
+        for tag in ('ragged', 'full'):
+            c = np.load(os.path.join(d, 'c_%s_spec.npy' % tag))
+            e = np.load(os.path.join(d, 'e_%s_spec.npy' % tag))
+            res['maxdiff_brdf_v3_v2_%s_spec' % tag] = float(np.abs(c - e).max())
     if all('error' not in res[k] for k in ('v1', 'v2', 'v3')):
         for tag in ('ragged', 'full'):
             for k in ('lvis', 'spec'):
