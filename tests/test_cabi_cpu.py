@@ -102,6 +102,25 @@ def test_workspace_queries_are_host_only_and_consistent():
     a.lvis_d = 1                                                         # caller keeps lvis: no scratch for it
     assert lib.nf_stageB_fused_workspace_bytes(C.byref(a), _lib.PREC['f16']) == one
     assert lib.nf_dense_fwd_workspace_bytes(128, 128, 0, _lib.PREC['bf16']) > 0
+    # whole-network train calls: 16-bit activations of every hidden layer + backward scratch
+    def chain(in_dim, widths, skip):
+        ch = _lib.MlpChain()
+        ch.depth, ch.in_dim, ch.skip_layer = len(widths), in_dim, skip
+        for l, w in enumerate(widths):
+            ch.width[l] = w
+        return ch
+    rows = 524288
+    wsb = lib.nf_mlp_chain_workspace_bytes
+    full = wsb(C.byref(chain(92, (128, 128, 128, 128, 4), 3)), rows)
+    saved = rows * 2 * (96 + 3 * 128 + (128 + 96))               # x0 + four hidden outputs (one with [h | x])
+    assert saved < full < saved + rows * (2 * 256 * 2 + 16 * 2 + 92 * 4) + (64 << 20)
+    assert wsb(C.byref(chain(92, (128, 128, 128, 128, 4), 0)), rows) < full          # no skip: narrower buffer
+    assert wsb(C.byref(chain(90, (128, 128, 4), 0)), rows) == 0                      # in_dim not a multiple of 4
+    assert wsb(C.byref(chain(92, (100, 128, 4), 0)), rows) == 0                      # hidden width not a multiple of 16
+    assert wsb(C.byref(chain(92, (128, 128, 3), 0)), rows) == 0                      # head not padded to 4
+    assert wsb(C.byref(chain(92, (128,), 0)), rows) == 0                             # needs >= 2 layers
+    assert _lib.mlp_chain_supported(92, [128, 128, 128, 128, 4], [92, 128, 128, 224, 128])
+    assert not _lib.mlp_chain_supported(92, [128, 512, 4], [92, 128, 512])
 
 
 def test_network_mirror_shapes():
