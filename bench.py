@@ -781,6 +781,10 @@ def main():
                 'h2d_bytes_per_step': int(light_host.numel() * 4 + 16 * 8 + 8),
                 'd2h_bytes_per_step': int(rgb_host.numel() * 4 + alpha_host.numel() * 4)},
         'gpu_launches': launches, 'clocks': clocks,
+        # the same step with the visibility network evaluated for every light instead of the
+        # front-lit ones (config.lvis_lights): identical images, more tensor work
+        'every_light': {'value': all_lights_row['rays_per_s'], 'unit': 'rays/s',
+                        'ms_per_step': all_lights_row['ms']},
         'roofline': dominant,
         'rooflines': [rf_sigma, rf_lvis, rf_int, rf_point] + ([rf_int_spec] if rf_int_spec else []) +
                      ([rf_sigma_plain] if rf_sigma_plain else []),
